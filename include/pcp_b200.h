@@ -1,0 +1,181 @@
+/* pcp_b200.h -- C ABI of the B200-native propagation engine.
+ *
+ * This is the drop-in boundary for libpcp's hot path: everything at and below
+ * `Consistency::consistency` (reference src/libpcp/kernel/consistency.rs:17-19,
+ * implemented by src/libpcp/propagation/store.rs:240-258 and reached from
+ * src/libpcp/search/space.rs:41-43) runs on the device behind these entry points.
+ * The host search (libpcp::search) keeps driving branching and calls in here once
+ * per search node.  INTEGRATION.md shows the Rust `extern "C"` block and the
+ * `GpuCStore` shim that binds these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer argument is caller-owned and
+ *     borrowed for the duration of the call; outputs go to caller buffers.
+ *   - return value: PCP_OK or a negative error code.  A contract violation that
+ *     panics in the reference (assert!) returns PCP_ERR_INVALID and leaves the
+ *     engine unchanged.  Inconsistency is NOT an error: it is reported through
+ *     *status == PCP_FALSE, exactly like `consistency() -> SKleene::False`.
+ *   - one engine handle per host thread, bound to one CUDA device and one
+ *     stream; a handle is not thread-safe, distinct handles are independent.
+ *   - there is no CPU fallback: pcp_engine_create fails with PCP_ERR_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef PCP_B200_H
+#define PCP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCP_OK 0
+#define PCP_ERR_INVALID (-1)     /* contract violation (a panic in the reference)   */
+#define PCP_ERR_CUDA (-2)        /* CUDA runtime / launch failure, or no device       */
+#define PCP_ERR_NOMEM (-3)       /* host or device allocation failed                  */
+#define PCP_ERR_UNSUPPORTED (-4) /* propagator/view that has no device lowering       */
+
+/* trilean::SKleene as returned by Consistency::consistency. */
+#define PCP_FALSE (-1)
+#define PCP_UNKNOWN 0
+#define PCP_TRUE 1
+
+typedef struct pcp_engine pcp_engine;
+
+/* A view over the variable store (reference src/libpcp/term/):
+ *   var >= 0            Identity(var)            (term/identity.rs:47-70), off == 0
+ *   var >= 0, off != 0  Addition(Identity, off)  (term/addition.rs:80-110; nested
+ *                       additions fold into one offset)
+ *   var == -1           Constant(off)            (term/constant.rs:43-68)
+ *   var <= -2           Sum view #(-2 - var) + off  (term/sum.rs:56-92), see
+ *                       pcp_sum_alloc.                                              */
+typedef struct pcp_operand {
+  int32_t var;
+  int32_t off;
+} pcp_operand;
+
+#define PCP_VAR_CONSTANT (-1)
+#define PCP_VAR_SUM(sum_id) (-2 - (sum_id))
+
+/* Propagator kinds (reference src/libpcp/propagators/, src/libpcp/logic/). */
+enum pcp_prop_kind {
+  PCP_X_LESS_Y = 0,           /* cmp/x_less_y.rs:67-117; 2 operands (x, y)            */
+  PCP_X_NEQ_Y = 1,            /* cmp/x_neq_y.rs:66-104; 2 operands                    */
+  PCP_X_EQ_Y = 2,             /* cmp/x_eq_y.rs:67-116; 2 operands                     */
+  PCP_X_GREATER_Y_PLUS_Z = 3, /* cmp/x_greater_y_plus_z.rs:75-128; 3 operands         */
+  PCP_X_LESS_Y_PLUS_Z = 4,    /* cmp/x_less_y_plus_z.rs:75-128; 3 operands            */
+  PCP_X_EQ_Y_PLUS_Z = 5,      /* cmp/x_eq_y_plus_z.rs:26-105; 3 operands              */
+  PCP_DISTINCT = 6,           /* distinct.rs:69-126; n >= 1 operands                  */
+  PCP_DISJ2_X_EQ_Y_PLUS_Z = 7 /* logic/disjunction.rs:77-129 over two XEqYPlusZ;
+                                 6 operands (x1,y1,z1,x2,y2,z2)                       */
+};
+#define PCP_NUM_KINDS 8
+
+/* Engine configuration (the reference configures through type aliases only:
+ * propagation/mod.rs:33-34, variable/mod.rs:35-38). */
+#define PCP_FLAG_INCREMENTAL 1u /* skip the schedule-everything first sweep when the
+                                   engine can prove the restored state was a fixpoint
+                                   (same domains/status; fewer propagations than
+                                   store.rs:144-149)                                  */
+typedef struct pcp_config {
+  int32_t device;      /* CUDA device ordinal                                        */
+  uint32_t flags;      /* PCP_FLAG_*                                                 */
+  uint32_t max_labels; /* capacity of the label stack (0 = default 4096)             */
+  uint32_t reserved;
+} pcp_config;
+
+/* Counters the reference lacks (no propagation counter exists). */
+typedef struct pcp_stats {
+  uint64_t propagations; /* propagator evaluations (propagate + is_subsumed), this call */
+  uint32_t iterations;   /* device fixpoint iterations (1 = first sweep was quiescent)  */
+  uint32_t active_props; /* propagators still active (not entailed) after the call      */
+  float kernel_ms;       /* device time of the fixpoint kernel (CUDA events); 0 unless
+                            timing was enabled with pcp_set_timing                      */
+  uint32_t reserved;
+} pcp_stats;
+
+int pcp_engine_create(const pcp_config* cfg, pcp_engine** out);
+void pcp_engine_destroy(pcp_engine* e);
+const char* pcp_last_error(const pcp_engine* e);
+int pcp_set_timing(pcp_engine* e, int32_t enabled);
+
+/* VStore::alloc (variable/store.rs:135-140): n new variables with domains
+ * [lo[i], hi[i]]; an empty domain is a contract violation (store.rs:136). */
+int pcp_vars_alloc(pcp_engine* e, const int32_t* lo, const int32_t* hi, int32_t n, int32_t* first_idx);
+
+/* Sum::new (term/sum.rs:28-32): registers a sum view over `n` (var, off) terms. */
+int pcp_sum_alloc(pcp_engine* e, const pcp_operand* terms, int32_t n, int32_t* sum_id);
+
+/* Store::alloc (propagation/store.rs:223-230): appends one propagator, marks it
+ * active and returns its index. */
+int pcp_prop_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops, int32_t* idx);
+
+/* The same for `n_props` propagators of one kind with `n_ops` operands each,
+ * operands laid out prop-major (model upload: millions of descriptors). */
+int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops,
+                    int64_t n_props, int32_t* first_idx);
+
+/* Consistency::consistency (propagation/store.rs:247-257): runs the propagation
+ * fixpoint on the device.  *status is PCP_FALSE / PCP_UNKNOWN / PCP_TRUE. */
+int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats /* may be NULL */);
+
+/* Index<usize> on the variable store (variable/store.rs:175-181), batched. */
+int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32_t* hi);
+
+/* MonotonicUpdate::update (variable/store.rs:151-166): *ok = 0 when [lo,hi] is
+ * empty (store untouched); widening is a contract violation. */
+int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* ok);
+
+/* The `active` bit set of the constraint store (propagation/store.rs:34). */
+int pcp_active_read(pcp_engine* e, int32_t first, int32_t n, uint8_t* out);
+
+/* Snapshot::label / Snapshot::restore (kernel/restoration.rs:20-30) of the pair
+ * (vstore, cstore) as in search/recomputation/no_recomputation.rs:49-61:
+ * restore brings back the domains, truncates the propagators to the labelled
+ * length and restores `active` (propagation/store.rs:312-323).  Labels are
+ * plain values; restoring a label invalidates the labels taken after it. */
+int pcp_label(pcp_engine* e, uint64_t* label);
+int pcp_restore(pcp_engine* e, uint64_t label);
+
+int pcp_num_vars(const pcp_engine* e, int32_t* n);
+int pcp_num_props(const pcp_engine* e, int32_t* n);
+
+/* ---- host search driver (callers of the path) ------------------
+ * OneSolution/AllSolution o StopNode o [BranchAndBound o] Propagation o
+ * Brancher(var_sel, val_sel, distributor) as in search/mod.rs:45-52, executed
+ * node by node against the entry points above. */
+typedef struct pcp_search_config {
+  uint64_t node_limit;   /* StopNode (search/stop_node.rs:54-61); 0 = unlimited      */
+  int32_t all_solutions; /* AllSolution (search/engine/all_solution.rs:41-50)        */
+  int32_t var_sel;       /* 0 FirstSmallestVar, 1 InputOrder                          */
+  int32_t val_sel;       /* 0 MiddleVal, 1 MinVal                                     */
+  int32_t distributor;   /* 0 BinarySplit, 1 Enumerate                                */
+  int32_t bb_mode;       /* 0 none, 1 minimize, 2 maximize (search/branch_and_bound.rs) */
+  int32_t bb_var;
+  int32_t trace_domains; /* 1: also copy lo/hi of every non-failed node into the trace */
+  int32_t reserved;
+} pcp_search_config;
+
+typedef struct pcp_search_result {
+  int32_t status;          /* 1 Satisfiable, -1 Unsatisfiable, 2 EndOfSearch          */
+  int32_t has_bb_value;
+  int32_t bb_value;
+  int32_t reserved;
+  uint64_t num_nodes, num_solution, num_failed_node, num_prune; /* search/statistics.rs:19-53 */
+  uint64_t propagations;
+  uint64_t iterations;
+  double seconds;          /* host wall clock of the whole search                     */
+  double kernel_seconds;   /* sum of device fixpoint kernel times (if timing enabled) */
+} pcp_search_result;
+
+/* Per-node trace (optional): status[i] in {-1,0,1}; hash[i] = FNV-1a over the
+ * (lo,hi) words of all domains after the node's fixpoint (0 for failed nodes);
+ * lo/hi (if trace_domains) hold num_vars entries per node. */
+int pcp_search_run(pcp_engine* e, const pcp_search_config* cfg, pcp_search_result* res,
+                   int32_t* trace_status, uint64_t* trace_hash, int32_t* trace_lo,
+                   int32_t* trace_hi, uint64_t trace_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCP_B200_H */

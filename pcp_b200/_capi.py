@@ -1,0 +1,229 @@
+"""ctypes binding of the C ABI declared in include/pcp_b200.h.
+
+`bind(lib, prefix)` attaches argtypes/restypes; `EngineBase` is the thin Python mirror of
+the reference's store surface (VStore::alloc, Store::alloc, Consistency::consistency,
+Snapshot::label/restore) on top of those symbols.  The symbol prefix is a parameter only
+so that the test-side oracle (oracle/oracle_api.py), which exports the same shapes under
+`pcpo_`, can reuse the glue; the product always binds `pcp_` from libpcp_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+FALSE, UNKNOWN, TRUE = -1, 0, 1
+
+ERRORS = {0: "OK", -1: "PCP_ERR_INVALID", -2: "PCP_ERR_CUDA", -3: "PCP_ERR_NOMEM", -4: "PCP_ERR_UNSUPPORTED"}
+
+
+class PcpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERRORS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class ContractViolation(PcpError):
+    """A call that panics in the reference (assert!) -- PCP_ERR_INVALID."""
+
+
+class Operand(C.Structure):
+    _fields_ = [("var", C.c_int32), ("off", C.c_int32)]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("max_labels", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("propagations", C.c_uint64), ("iterations", C.c_uint32), ("active_props", C.c_uint32),
+                ("kernel_ms", C.c_float), ("reserved", C.c_uint32)]
+
+
+class SearchConfig(C.Structure):
+    _fields_ = [("node_limit", C.c_uint64), ("all_solutions", C.c_int32), ("var_sel", C.c_int32),
+                ("val_sel", C.c_int32), ("distributor", C.c_int32), ("bb_mode", C.c_int32),
+                ("bb_var", C.c_int32), ("trace_domains", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SearchResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("has_bb_value", C.c_int32), ("bb_value", C.c_int32),
+                ("reserved", C.c_int32), ("num_nodes", C.c_uint64), ("num_solution", C.c_uint64),
+                ("num_failed_node", C.c_uint64), ("num_prune", C.c_uint64), ("propagations", C.c_uint64),
+                ("iterations", C.c_uint64), ("seconds", C.c_double), ("kernel_seconds", C.c_double)]
+
+
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+_opp = C.POINTER(Operand)
+
+# name -> (restype, argtypes) without the engine-handle-specific create/destroy
+_COMMON = {
+    "engine_destroy": (None, [C.c_void_p]),
+    "last_error": (C.c_char_p, [C.c_void_p]),
+    "vars_alloc": (C.c_int, [C.c_void_p, _i32p, _i32p, C.c_int32, _i32p]),
+    "sum_alloc": (C.c_int, [C.c_void_p, _opp, C.c_int32, _i32p]),
+    "prop_alloc": (C.c_int, [C.c_void_p, C.c_int32, _opp, C.c_int32, _i32p]),
+    "props_alloc": (C.c_int, [C.c_void_p, C.c_int32, _opp, C.c_int32, C.c_int64, _i32p]),
+    "consistency": (C.c_int, [C.c_void_p, _i32p, C.POINTER(Stats)]),
+    "domains_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p]),
+    "var_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p]),
+    "active_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _u8p]),
+    "label": (C.c_int, [C.c_void_p, _u64p]),
+    "restore": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "num_vars": (C.c_int, [C.c_void_p, _i32p]),
+    "num_props": (C.c_int, [C.c_void_p, _i32p]),
+    "search_run": (C.c_int, [C.c_void_p, C.POINTER(SearchConfig), C.POINTER(SearchResult), _i32p, _u64p,
+                             _i32p, _i32p, C.c_uint64]),
+}
+
+
+def bind(lib: C.CDLL, prefix: str) -> None:
+    for name, (res, args) in _COMMON.items():
+        fn = getattr(lib, prefix + name)  # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+
+
+def _ops_array(ops) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(ops, dtype=np.int32))
+    assert a.shape[-1] == 2, "operands are (var, off) pairs"
+    return a
+
+
+class EngineBase:
+    """Python mirror of the store surface; subclasses provide `_lib`, `_prefix`, `_h`."""
+
+    _lib: C.CDLL
+    _prefix: str
+    _h: Optional[C.c_void_p]
+
+    def _fn(self, name):
+        return getattr(self._lib, self._prefix + name)
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            msg = self._fn("last_error")(self._h)
+            msg = msg.decode() if msg else ""
+            raise (ContractViolation if rc == -1 else PcpError)(rc, msg)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._fn("engine_destroy")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # --- VStore::alloc (variable/store.rs:135-140)
+    def vars_alloc(self, lo, hi) -> int:
+        lo = np.ascontiguousarray(np.asarray(lo, dtype=np.int32).reshape(-1))
+        hi = np.ascontiguousarray(np.asarray(hi, dtype=np.int32).reshape(-1))
+        assert lo.shape == hi.shape
+        first = C.c_int32(-1)
+        self._check(self._fn("vars_alloc")(self._h, lo.ctypes.data_as(_i32p), hi.ctypes.data_as(_i32p),
+                                           lo.shape[0], C.byref(first)))
+        return first.value
+
+    # --- Sum::new (term/sum.rs:28-32)
+    def sum_alloc(self, terms) -> int:
+        a = _ops_array(terms).reshape(-1, 2)
+        sid = C.c_int32(-1)
+        self._check(self._fn("sum_alloc")(self._h, a.ctypes.data_as(_opp), a.shape[0], C.byref(sid)))
+        return sid.value
+
+    # --- Store::alloc (propagation/store.rs:223-230)
+    def prop_alloc(self, kind: int, ops) -> int:
+        a = _ops_array(ops).reshape(-1, 2)
+        idx = C.c_int32(-1)
+        self._check(self._fn("prop_alloc")(self._h, kind, a.ctypes.data_as(_opp), a.shape[0], C.byref(idx)))
+        return idx.value
+
+    def props_alloc(self, kind: int, ops) -> int:
+        a = _ops_array(ops)
+        assert a.ndim == 3
+        first = C.c_int32(-1)
+        self._check(self._fn("props_alloc")(self._h, kind, a.ctypes.data_as(_opp), a.shape[1], a.shape[0],
+                                            C.byref(first)))
+        return first.value
+
+    # --- Consistency::consistency (propagation/store.rs:247-257)
+    def consistency(self) -> Tuple[int, Stats]:
+        st = C.c_int32(0)
+        stats = Stats()
+        self._check(self._fn("consistency")(self._h, C.byref(st), C.byref(stats)))
+        return st.value, stats
+
+    def domains(self, first: int = 0, n: Optional[int] = None) -> Tuple[np.ndarray, np.ndarray]:
+        if n is None:
+            n = self.num_vars - first
+        lo = np.empty(n, np.int32)
+        hi = np.empty(n, np.int32)
+        self._check(self._fn("domains_read")(self._h, first, n, lo.ctypes.data_as(_i32p), hi.ctypes.data_as(_i32p)))
+        return lo, hi
+
+    # --- MonotonicUpdate::update (variable/store.rs:151-166)
+    def var_update(self, idx: int, lo: int, hi: int) -> bool:
+        ok = C.c_int32(0)
+        self._check(self._fn("var_update")(self._h, idx, lo, hi, C.byref(ok)))
+        return bool(ok.value)
+
+    def active(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        if n is None:
+            n = self.num_props - first
+        out = np.empty(n, np.uint8)
+        self._check(self._fn("active_read")(self._h, first, n, out.ctypes.data_as(_u8p)))
+        return out
+
+    # --- Snapshot (kernel/restoration.rs:20-30)
+    def label(self) -> int:
+        l = C.c_uint64(0)
+        self._check(self._fn("label")(self._h, C.byref(l)))
+        return l.value
+
+    def restore(self, label: int) -> None:
+        self._check(self._fn("restore")(self._h, label))
+
+    @property
+    def num_vars(self) -> int:
+        n = C.c_int32(0)
+        self._check(self._fn("num_vars")(self._h, C.byref(n)))
+        return n.value
+
+    @property
+    def num_props(self) -> int:
+        n = C.c_int32(0)
+        self._check(self._fn("num_props")(self._h, C.byref(n)))
+        return n.value
+
+    # --- search driver (search/mod.rs:45-52 and friends)
+    def search(self, node_limit: int = 0, all_solutions: bool = False, var_sel: int = 0, val_sel: int = 0,
+               distributor: int = 0, bb_mode: int = 0, bb_var: int = 0, trace: int = 0,
+               trace_domains: bool = False):
+        cfg = SearchConfig(node_limit, int(all_solutions), var_sel, val_sel, distributor, bb_mode, bb_var,
+                           int(trace_domains), 0)
+        res = SearchResult()
+        V = self.num_vars
+        t_status = np.zeros(trace, np.int32)
+        t_hash = np.zeros(trace, np.uint64)
+        t_lo = np.zeros((trace, V) if trace_domains else (0, V), np.int32)
+        t_hi = np.zeros((trace, V) if trace_domains else (0, V), np.int32)
+        self._check(self._fn("search_run")(
+            self._h, C.byref(cfg), C.byref(res), t_status.ctypes.data_as(_i32p), t_hash.ctypes.data_as(_u64p),
+            t_lo.ctypes.data_as(_i32p), t_hi.ctypes.data_as(_i32p), trace))
+        n = int(min(trace, res.num_nodes))
+        tr = {"status": t_status[:n], "hash": t_hash[:n]}
+        if trace_domains:
+            tr["lo"], tr["hi"] = t_lo[:n], t_hi[:n]
+        return res, tr
