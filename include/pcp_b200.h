@@ -81,7 +81,9 @@ typedef struct pcp_config {
   int32_t device;      /* CUDA device ordinal                                        */
   uint32_t flags;      /* PCP_FLAG_*                                                 */
   uint32_t max_labels; /* capacity of the label stack (0 = default 4096)             */
-  uint32_t reserved;
+  uint32_t tail_limit; /* propagators allocated after the reactor CSR was built are kept in
+                          a tail that every launch evaluates; the CSR is rebuilt when the
+                          tail exceeds this (0 = default 4096)                        */
 } pcp_config;
 
 /* Counters the reference lacks (no propagation counter exists). */

@@ -33,7 +33,7 @@ class Operand(C.Structure):
 
 
 class Config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("max_labels", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("device", C.c_int32), ("flags", C.c_uint32), ("max_labels", C.c_uint32), ("tail_limit", C.c_uint32)]
 
 
 class Stats(C.Structure):

@@ -1,0 +1,886 @@
+// pcp_engine.cu -- host side of the B200 propagation engine and its C ABI
+// (include/pcp_b200.h).  The engine handle owns every device allocation; the reference's
+// constraint store (src/libpcp/propagation/store.rs:32-37) and variable store
+// (src/libpcp/variable/store.rs:29-33) map to:
+//
+//   domains        int2 dom[V] = (lo, hi) per variable, in HBM, preceded by a 64-byte
+//                  result header so that status + domains come back in one D2H copy
+//   propagators    per-family descriptor arrays (binary 16 B, ternary 16 B + 8 B planes,
+//                  2-way disjunction 48 B, n-ary Distinct as CSR of operands)
+//   active         one bit per propagator and family (store.rs:34) + a trail of the
+//                  propagators entailed so far (restored by label, store.rs:319-323)
+//   reactor        static CSR var -> propagator refs (reactors/indexed_deps.rs:23-27),
+//                  built once per model; propagators allocated later form a short tail
+//   labels         copy stack of the domain array (variable/memory/copy_memory.rs:141-151)
+//
+// There is no CPU path: without a usable CUDA device pcp_engine_create fails.
+#include "../../include/pcp_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pcp_device.cuh"
+
+using namespace pcpd;
+
+namespace {
+
+struct Error {
+  int code;
+  std::string msg;
+};
+#define PCP_FAIL(code, msg) throw Error{code, msg}
+#define PCP_REQUIRE(cond, msg) \
+  do { if (!(cond)) PCP_FAIL(PCP_ERR_INVALID, msg); } while (0)
+#define CUDA_CHECK(expr)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      PCP_FAIL(_e == cudaErrorMemoryAllocation ? PCP_ERR_NOMEM : PCP_ERR_CUDA,                \
+               std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+  } while (0)
+
+// Growable device array with a host-known logical size.
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t n, cudaStream_t st, bool keep = true, size_t keep_n = 0) {
+    if (n <= cap) return;
+    size_t ncap = std::max<size_t>(n, cap + cap / 2 + 64);
+    T* q = nullptr;
+    CUDA_CHECK(cudaMalloc(&q, ncap * sizeof(T)));
+    if (p) {
+      if (keep && keep_n) CUDA_CHECK(cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      cudaFree(p);
+    }
+    p = q;
+    cap = ncap;
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct HostFamily {
+  std::vector<int4> desc;   // BIN: n, TER: n, DJ: 3n
+  std::vector<int2> descB;  // TER only
+  size_t n = 0;
+  size_t n_static = 0;      // covered by the CSR
+  size_t uploaded = 0;      // descriptors [0, uploaded) are on the device
+  size_t active_set = 0;    // active bits [0, active_set) are initialised on the device
+  DevBuf<int4> d_desc;
+  DevBuf<int2> d_descB;
+  DevBuf<uint32_t> d_active, d_stamp;
+  int width() const { return width_; }
+  int width_ = 1;
+};
+
+struct LabelRec {
+  size_t n_fam[4];
+  size_t n_nary_ops;
+  size_t n_props;
+  unsigned trail_len;
+  bool at_fixpoint;
+};
+
+}  // namespace
+
+struct pcp_engine {
+  int device = 0;
+  uint32_t flags = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timing = false;
+  int num_sms = 0;
+  int max_smem_optin = 0;
+  std::string err;
+
+  // variables
+  std::vector<int2> h_dom_pending;  // variables allocated but not yet uploaded
+  size_t V = 0, V_uploaded = 0;
+  char* d_block = nullptr;          // [Result | dom ...]
+  size_t block_cap_vars = 0;
+  char* h_block = nullptr;          // pinned mirror of d_block
+  size_t h_block_cap_vars = 0;
+  bool mirror_valid = false;        // h_block domains == device domains
+
+  // propagators
+  HostFamily fam[3];                // BIN, TER, DJ
+  std::vector<int> h_nary_ptr{0};
+  std::vector<int2> h_nary_ops;
+  size_t n_nary = 0, nary_uploaded = 0, nary_active_set = 0;
+  int nary_max_k = 0;
+  DevBuf<int> d_nary_ptr;
+  DevBuf<int2> d_nary_ops;
+  DevBuf<uint32_t> d_nary_active;
+  std::vector<uint32_t> prop_ref;   // global propagator index -> (family, slot)
+  std::vector<std::vector<pcp_operand>> sums;
+
+  // reactor CSR
+  DevBuf<int> d_adj_ptr;
+  DevBuf<uint32_t> d_adj;
+  bool csr_built = false;
+  size_t tail_limit = 4096;
+
+  // worklists / control
+  DevBuf<int> d_dirty_list;
+  DevBuf<uint32_t> d_dirty_stamp;
+  DevBuf<uint32_t> d_trail;
+  Control* d_ctl = nullptr;
+  unsigned trail_len = 0;           // host view of ctl->trail_cnt
+  unsigned epoch = 1;
+  unsigned long long props_total = 0;
+
+  // labels
+  std::vector<LabelRec> labels;
+  DevBuf<int2> d_stack;             // labels.size() x V
+  size_t stack_stride = 0;
+  size_t max_labels = 4096;
+
+  // deferred node prologue
+  bool pending_restore = false;
+  size_t pending_restore_label = 0;
+  bool pending_trail_undo = false;
+  unsigned pending_trail_keep = 0;
+  bool at_fixpoint = false;
+  std::vector<int> host_dirty;      // variables narrowed through pcp_var_update
+  unsigned max_iterations = 1u << 22;
+
+  // pinned staging for small descriptor uploads
+  char* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+
+  Result* d_result() const { return reinterpret_cast<Result*>(d_block); }
+  int2* d_dom() const { return reinterpret_cast<int2*>(d_block + sizeof(Result)); }
+  Result* h_result() const { return reinterpret_cast<Result*>(h_block); }
+  int2* h_dom() const { return reinterpret_cast<int2*>(h_block + sizeof(Result)); }
+  size_t num_props() const { return prop_ref.size(); }
+};
+
+namespace {
+
+void ensure_var_capacity(pcp_engine* e, size_t nvars) {
+  if (nvars > e->block_cap_vars) {
+    size_t ncap = std::max<size_t>(nvars, e->block_cap_vars * 2 + 256);
+    char* q = nullptr;
+    CUDA_CHECK(cudaMalloc(&q, sizeof(Result) + ncap * sizeof(int2)));
+    CUDA_CHECK(cudaMemsetAsync(q, 0, sizeof(Result), e->stream));
+    if (e->d_block) {
+      if (e->V_uploaded)
+        CUDA_CHECK(cudaMemcpyAsync(q + sizeof(Result), e->d_block + sizeof(Result), e->V_uploaded * sizeof(int2),
+                                   cudaMemcpyDeviceToDevice, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      cudaFree(e->d_block);
+    }
+    e->d_block = q;
+    e->block_cap_vars = ncap;
+  }
+  if (nvars > e->h_block_cap_vars) {
+    size_t ncap = std::max<size_t>(nvars, e->h_block_cap_vars * 2 + 256);
+    char* q = nullptr;
+    CUDA_CHECK(cudaMallocHost(&q, sizeof(Result) + ncap * sizeof(int2)));
+    if (e->h_block) {
+      std::memcpy(q, e->h_block, sizeof(Result) + e->h_block_cap_vars * sizeof(int2));
+      cudaFreeHost(e->h_block);
+    } else {
+      std::memset(q, 0, sizeof(Result));
+    }
+    e->h_block = q;
+    e->h_block_cap_vars = ncap;
+  }
+}
+
+void* stage(pcp_engine* e, size_t bytes) {
+  if (bytes > e->h_stage_cap) {
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    size_t ncap = std::max<size_t>(bytes, 1 << 16);
+    CUDA_CHECK(cudaMallocHost(&e->h_stage, ncap));
+    e->h_stage_cap = ncap;
+  }
+  return e->h_stage;
+}
+
+// Upload host range [from, to) of a vector to the device array (pinned staging for small
+// ranges so the copy is truly asynchronous; pageable memcpy for bulk model uploads).
+template <class T>
+void upload_range(pcp_engine* e, DevBuf<T>& dst, const std::vector<T>& src, size_t from, size_t to, size_t& stage_off) {
+  if (to <= from) return;
+  dst.reserve(src.size(), e->stream, true, from);
+  size_t bytes = (to - from) * sizeof(T);
+  if (bytes <= 4096 && stage_off + bytes <= (32u << 10)) {
+    std::memcpy(e->h_stage + stage_off, src.data() + from, bytes);
+    CUDA_CHECK(cudaMemcpyAsync(dst.p + from, e->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, e->stream));
+    stage_off += (bytes + 15) & ~size_t(15);
+  } else {
+    CUDA_CHECK(cudaMemcpyAsync(dst.p + from, src.data() + from, bytes, cudaMemcpyHostToDevice, e->stream));
+  }
+}
+
+void fill_u32(pcp_engine* e, uint32_t* p, uint32_t v, size_t n) {
+  if (!n) return;
+  int blocks = (int)std::min<size_t>((n + 255) / 256, 2048);
+  pcp_fill_u32_kernel<<<blocks, 256, 0, e->stream>>>(p, v, n);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+// Grow a per-propagator bit set / stamp array, zero-filling the new part.
+void reserve_zeroed(pcp_engine* e, DevBuf<uint32_t>& b, size_t words, size_t valid_words) {
+  if (words <= b.cap) return;
+  size_t old_cap = b.cap;
+  b.reserve(words, e->stream, true, std::min(valid_words, old_cap));
+  size_t from = std::min(valid_words, old_cap);
+  fill_u32(e, b.p + from, 0u, b.cap - from);
+}
+
+inline unsigned enc_var28(int var) { return var < 0 ? kConstVar28 : (unsigned)var; }
+
+void check_operand(const pcp_engine* e, pcp_operand op) {
+  if (op.var >= 0) PCP_REQUIRE((size_t)op.var < e->V, "operand variable not registered in the store");
+  else if (op.var <= -2) PCP_REQUIRE((size_t)(-2 - op.var) < e->sums.size(), "unknown sum view");
+  PCP_REQUIRE(op.var < (int)kConstVar28, "variable index too large");
+}
+
+// Sum views with a single term delegate to the term (term/sum.rs:62-64); wider sums have
+// no device lowering yet.
+pcp_operand lower_view(const pcp_engine* e, pcp_operand op) {
+  check_operand(e, op);
+  if (op.var > -2) return op;
+  const auto& s = e->sums[(size_t)(-2 - op.var)];
+  if (s.size() == 1) {
+    pcp_operand t = s[0];
+    t.off += op.off;
+    return t;
+  }
+  PCP_FAIL(PCP_ERR_UNSUPPORTED, "Sum views with more than one term have no device lowering");
+}
+
+void require_distinct_vars(const pcp_operand* ops, int n) {
+  // a propagator subscribing twice to one variable panics in the reference
+  // (reactors/indexed_deps.rs:69-77)
+  for (int i = 0; i < n; ++i)
+    for (int j = i + 1; j < n; ++j)
+      PCP_REQUIRE(ops[i].var < 0 || ops[i].var != ops[j].var, "propagator already subscribed to this variable");
+}
+
+void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
+  pcp_operand ops[6];
+  switch (kind) {
+    case PCP_X_LESS_Y:
+    case PCP_X_NEQ_Y:
+    case PCP_X_EQ_Y: {
+      PCP_REQUIRE(n_ops == 2, "binary propagator takes 2 operands");
+      for (int i = 0; i < 2; ++i) ops[i] = lower_view(e, raw[i]);
+      require_distinct_vars(ops, 2);
+      unsigned k = kind == PCP_X_LESS_Y ? B_LESS : (kind == PCP_X_NEQ_Y ? B_NEQ : B_EQ);
+      HostFamily& f = e->fam[F_BIN];
+      f.desc.push_back(make_int4((int)((k << 28) | enc_var28(ops[0].var)), ops[0].off, ops[1].var, ops[1].off));
+      e->prop_ref.push_back(make_ref(F_BIN, (unsigned)f.n++));
+      break;
+    }
+    case PCP_X_GREATER_Y_PLUS_Z:
+    case PCP_X_LESS_Y_PLUS_Z:
+    case PCP_X_EQ_Y_PLUS_Z: {
+      PCP_REQUIRE(n_ops == 3, "ternary propagator takes 3 operands");
+      for (int i = 0; i < 3; ++i) ops[i] = lower_view(e, raw[i]);
+      require_distinct_vars(ops, 3);
+      unsigned k = kind == PCP_X_GREATER_Y_PLUS_Z ? T_GREATER : (kind == PCP_X_LESS_Y_PLUS_Z ? T_LESS : T_EQ);
+      HostFamily& f = e->fam[F_TER];
+      f.desc.push_back(make_int4((int)((k << 28) | enc_var28(ops[0].var)), ops[0].off, ops[1].var, ops[1].off));
+      f.descB.push_back(make_int2(ops[2].var, ops[2].off));
+      e->prop_ref.push_back(make_ref(F_TER, (unsigned)f.n++));
+      break;
+    }
+    case PCP_DISJ2_X_EQ_Y_PLUS_Z: {
+      PCP_REQUIRE(n_ops == 6, "2-way disjunction of XEqYPlusZ takes 6 operands");
+      for (int i = 0; i < 6; ++i) ops[i] = lower_view(e, raw[i]);
+      require_distinct_vars(ops, 3);
+      require_distinct_vars(ops + 3, 3);
+      HostFamily& f = e->fam[F_DJ];
+      f.desc.push_back(make_int4(ops[0].var, ops[0].off, ops[1].var, ops[1].off));
+      f.desc.push_back(make_int4(ops[2].var, ops[2].off, ops[3].var, ops[3].off));
+      f.desc.push_back(make_int4(ops[4].var, ops[4].off, ops[5].var, ops[5].off));
+      e->prop_ref.push_back(make_ref(F_DJ, (unsigned)f.n++));
+      break;
+    }
+    case PCP_DISTINCT: {
+      PCP_REQUIRE(n_ops >= 1, "Variable array in `Distinct` must be non-empty.");
+      PCP_REQUIRE(n_ops <= 4096, "Distinct over more than 4096 operands is not supported");
+      std::vector<pcp_operand> lo(n_ops);
+      for (int i = 0; i < n_ops; ++i) lo[i] = lower_view(e, raw[i]);
+      {
+        std::vector<int> vs;
+        for (auto& o : lo) if (o.var >= 0) vs.push_back(o.var);
+        std::sort(vs.begin(), vs.end());
+        PCP_REQUIRE(std::adjacent_find(vs.begin(), vs.end()) == vs.end(), "propagator already subscribed to this variable");
+      }
+      for (auto& o : lo) e->h_nary_ops.push_back(make_int2(o.var, o.off));
+      e->h_nary_ptr.push_back((int)e->h_nary_ops.size());
+      e->nary_max_k = std::max(e->nary_max_k, n_ops);
+      e->prop_ref.push_back(make_ref(F_NARY, (unsigned)e->n_nary++));
+      break;
+    }
+    default:
+      PCP_FAIL(PCP_ERR_UNSUPPORTED, "unknown propagator kind");
+  }
+  // binary/ternary/disjunction propagators allocated after a fixpoint land in the tail,
+  // which every launch evaluates; a new n-ary propagator needs a full first sweep
+  if (kind == PCP_DISTINCT) e->at_fixpoint = false;
+}
+
+void truncate_props(pcp_engine* e, const LabelRec& r) {
+  for (int f = 0; f < 3; ++f) {
+    HostFamily& hf = e->fam[f];
+    hf.n = r.n_fam[f];
+    hf.desc.resize(hf.n * hf.width());
+    if (f == F_TER) hf.descB.resize(hf.n);
+    hf.n_static = std::min(hf.n_static, hf.n);
+    hf.uploaded = std::min(hf.uploaded, hf.n);
+    hf.active_set = std::min(hf.active_set, hf.n);
+  }
+  e->n_nary = r.n_fam[F_NARY];
+  e->h_nary_ptr.resize(e->n_nary + 1);
+  e->h_nary_ops.resize(r.n_nary_ops);
+  e->nary_uploaded = std::min(e->nary_uploaded, e->n_nary);
+  e->nary_active_set = std::min(e->nary_active_set, e->n_nary);
+  e->prop_ref.resize(r.n_props);
+}
+
+// Static reactor: CSR var -> refs of the propagators that depend on it, rows grouped by
+// family (so the lanes of a warp expanding a row stay on one code path).
+void build_csr(pcp_engine* e) {
+  const size_t V = e->V;
+  std::vector<int> ptr(V + 1, 0);
+  auto for_each_var = [&](auto&& fn) {
+    {
+      const HostFamily& f = e->fam[F_BIN];
+      for (size_t s = 0; s < f.n; ++s) {
+        const int4& d = f.desc[s];
+        unsigned xv = (unsigned)d.x & kConstVar28;
+        if (xv != kConstVar28) fn((int)xv, make_ref(F_BIN, (unsigned)s));
+        if (d.z >= 0) fn(d.z, make_ref(F_BIN, (unsigned)s));
+      }
+    }
+    {
+      const HostFamily& f = e->fam[F_TER];
+      for (size_t s = 0; s < f.n; ++s) {
+        const int4& d = f.desc[s];
+        unsigned xv = (unsigned)d.x & kConstVar28;
+        if (xv != kConstVar28) fn((int)xv, make_ref(F_TER, (unsigned)s));
+        if (d.z >= 0) fn(d.z, make_ref(F_TER, (unsigned)s));
+        if (f.descB[s].x >= 0) fn(f.descB[s].x, make_ref(F_TER, (unsigned)s));
+      }
+    }
+    {
+      const HostFamily& f = e->fam[F_DJ];
+      for (size_t s = 0; s < f.n; ++s) {
+        int vars[6] = {f.desc[3 * s].x, f.desc[3 * s].z, f.desc[3 * s + 1].x,
+                       f.desc[3 * s + 1].z, f.desc[3 * s + 2].x, f.desc[3 * s + 2].z};
+        std::sort(vars, vars + 6);  // sort + dedup union of the children (disjunction.rs:118-129)
+        for (int i = 0; i < 6; ++i)
+          if (vars[i] >= 0 && (i == 0 || vars[i] != vars[i - 1])) fn(vars[i], make_ref(F_DJ, (unsigned)s));
+      }
+    }
+  };
+  for_each_var([&](int v, unsigned) { ++ptr[v + 1]; });
+  for (size_t v = 0; v < V; ++v) ptr[v + 1] += ptr[v];
+  std::vector<uint32_t> adj((size_t)ptr[V]);
+  std::vector<int> cur(ptr.begin(), ptr.end() - 1);
+  for_each_var([&](int v, unsigned ref) { adj[(size_t)cur[v]++] = ref; });
+  e->d_adj_ptr.reserve(V + 1, e->stream, false);
+  e->d_adj.reserve(std::max<size_t>(adj.size(), 1), e->stream, false);
+  CUDA_CHECK(cudaMemcpyAsync(e->d_adj_ptr.p, ptr.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  if (!adj.empty())
+    CUDA_CHECK(cudaMemcpyAsync(e->d_adj.p, adj.data(), adj.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
+  for (int f = 0; f < 3; ++f) e->fam[f].n_static = e->fam[f].n;
+  e->csr_built = true;
+}
+
+// Bring the device in line with the host-side bookkeeping: upload new variables and
+// descriptors, run the node prologue (restore + new active bits), rebuild the CSR if the
+// tail outgrew its limit.
+void flush(pcp_engine* e) {
+  const size_t V = e->V;
+  size_t stage_off = 0;
+  stage(e, 1 << 16);
+  // --- variables
+  ensure_var_capacity(e, std::max<size_t>(V, 1));
+  if (e->V_uploaded < V) {
+    size_t n = V - e->V_uploaded;
+    CUDA_CHECK(cudaMemcpyAsync(e->d_dom() + e->V_uploaded, e->h_dom_pending.data(), n * sizeof(int2),
+                               cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->h_dom_pending.clear();
+    size_t oldV = e->V_uploaded;
+    e->V_uploaded = V;
+    e->mirror_valid = false;
+    // per-variable worklist storage (3 lists) and stamps
+    e->d_dirty_list.reserve(3 * V, e->stream, false);
+    size_t old_cap = e->d_dirty_stamp.cap;
+    e->d_dirty_stamp.reserve(V, e->stream, true, oldV);
+    if (e->d_dirty_stamp.cap != old_cap) fill_u32(e, e->d_dirty_stamp.p + oldV, 0u, e->d_dirty_stamp.cap - oldV);
+    // the label stack is laid out with stride V: a label taken with fewer variables cannot be
+    // restored after more were allocated (the reference's trail has the same limitation)
+    if (e->stack_stride != V) { e->stack_stride = V; PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); }
+    e->csr_built = false;  // adj_ptr has V+1 entries
+    for (int f = 0; f < 3; ++f) e->fam[f].n_static = 0;
+  }
+  // --- descriptors
+  size_t total = 0;
+  for (int f = 0; f < 3; ++f) {
+    HostFamily& hf = e->fam[f];
+    size_t w = hf.width();
+    upload_range(e, hf.d_desc, hf.desc, hf.uploaded * w, hf.n * w, stage_off);
+    if (f == F_TER) upload_range(e, hf.d_descB, hf.descB, hf.uploaded, hf.n, stage_off);
+    hf.uploaded = hf.n;
+    size_t words = (hf.n + 31) / 32 + 1;
+    reserve_zeroed(e, hf.d_active, words, (hf.active_set + 31) / 32);
+    if (hf.n > hf.d_stamp.cap) {
+      size_t valid = std::min(hf.d_stamp.cap, hf.active_set);
+      hf.d_stamp.reserve(hf.n, e->stream, true, valid);
+      fill_u32(e, hf.d_stamp.p + valid, 0u, hf.d_stamp.cap - valid);
+    }
+    total += hf.n;
+  }
+  if (e->nary_uploaded < e->n_nary) {
+    size_t ops_from = (size_t)e->h_nary_ptr[e->nary_uploaded];
+    upload_range(e, e->d_nary_ops, e->h_nary_ops, ops_from, e->h_nary_ops.size(), stage_off);
+    // ptr entries [nary_uploaded+1, n_nary]; entry 0 on first upload
+    size_t pfrom = e->nary_uploaded == 0 ? 0 : e->nary_uploaded + 1;
+    upload_range(e, e->d_nary_ptr, e->h_nary_ptr, pfrom, e->n_nary + 1, stage_off);
+    e->nary_uploaded = e->n_nary;
+  }
+  reserve_zeroed(e, e->d_nary_active, (e->n_nary + 31) / 32 + 1, (e->nary_active_set + 31) / 32);
+  total += e->n_nary;
+  e->d_trail.reserve(total + 64, e->stream, true, e->trail_len);
+
+  // --- node prologue
+  NodeBegin nb;
+  std::memset(&nb, 0, sizeof(nb));
+  nb.dom = e->d_dom();
+  nb.V = (int)V;
+  nb.ctl = e->d_ctl;
+  nb.trail = e->d_trail.p;
+  if (e->pending_restore) {
+    nb.restore_from = e->d_stack.p + e->pending_restore_label * e->stack_stride;
+    e->mirror_valid = false;
+  }
+  nb.do_trail = e->pending_trail_undo ? 1 : 0;
+  nb.trail_keep = e->pending_trail_keep;
+  for (int f = 0; f < 3; ++f) {
+    nb.active[f] = e->fam[f].d_active.p;
+    nb.new_first[f] = (int)e->fam[f].active_set;
+    nb.new_last[f] = (int)e->fam[f].n;
+    e->fam[f].active_set = e->fam[f].n;
+  }
+  nb.active[F_NARY] = e->d_nary_active.p;
+  nb.new_first[F_NARY] = (int)e->nary_active_set;
+  nb.new_last[F_NARY] = (int)e->n_nary;
+  e->nary_active_set = e->n_nary;
+  pcp_node_begin_kernel<<<1, 1024, 0, e->stream>>>(nb);
+  CUDA_CHECK(cudaGetLastError());
+  if (e->pending_trail_undo) e->trail_len = e->pending_trail_keep;
+  e->pending_restore = false;
+  e->pending_trail_undo = false;
+
+  // --- reactor
+  size_t tail = 0;
+  for (int f = 0; f < 3; ++f) tail += e->fam[f].n - e->fam[f].n_static;
+  if ((!e->csr_built && tail > 0) || tail > e->tail_limit) {
+    build_csr(e);
+    e->at_fixpoint = false;
+  }
+  if (!e->csr_built) {  // no propagators yet: still need a valid adj_ptr
+    e->d_adj_ptr.reserve(V + 1, e->stream, false);
+    e->d_adj.reserve(1, e->stream, false);
+    CUDA_CHECK(cudaMemsetAsync(e->d_adj_ptr.p, 0, (V + 1) * sizeof(int), e->stream));
+  }
+}
+
+size_t nary_smem_bytes(const pcp_engine* e) {
+  if (e->n_nary == 0) return 0;
+  size_t k = (size_t)e->nary_max_k;
+  size_t tab = 4;
+  while (tab < 2 * k) tab <<= 1;
+  return k * 16 + tab * 4;
+}
+
+void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  flush(e);
+  const size_t V = e->V;
+  Params P;
+  std::memset(&P, 0, sizeof(P));
+  P.result = e->d_result();
+  P.dom = e->d_dom();
+  P.V = (int)V;
+  for (int f = 0; f < 3; ++f) {
+    Family& df = f == F_BIN ? P.bin : (f == F_TER ? P.ter : P.dj);
+    HostFamily& hf = e->fam[f];
+    df.desc = hf.d_desc.p;
+    df.descB = hf.d_descB.p;
+    df.active = hf.d_active.p;
+    df.stamp = hf.d_stamp.p;
+    df.n = (int)hf.n;
+    df.n_static = (int)hf.n_static;
+  }
+  P.nary_ptr = e->d_nary_ptr.p;
+  P.nary_ops = e->d_nary_ops.p;
+  P.nary_active = e->d_nary_active.p;
+  P.n_nary = (int)e->n_nary;
+  P.nary_max_k = e->nary_max_k;
+  P.adj_ptr = e->d_adj_ptr.p;
+  P.adj = e->d_adj.p;
+  P.dirty_list = e->d_dirty_list.p;
+  P.dirty_stamp = e->d_dirty_stamp.p;
+  P.trail = e->d_trail.p;
+  P.ctl = e->d_ctl;
+  P.max_iterations = e->max_iterations;
+  const bool incremental = (e->flags & PCP_FLAG_INCREMENTAL) && e->at_fixpoint;
+  P.full_sweep = incremental ? 0 : 1;
+
+  // epoch wrap: stamps are compared for equality with epochs of this launch only
+  if (e->epoch > 0x7f000000u) {
+    for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
+    fill_u32(e, e->d_dirty_stamp.p, 0u, e->d_dirty_stamp.cap);
+    unsigned one = 1;
+    CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->epoch = 1;
+  }
+  if (incremental && !e->host_dirty.empty()) {
+    // seed the worklist of iteration 0 with the variables narrowed by the host
+    size_t n = e->host_dirty.size();
+    // (the first 32 KiB of the staging area may still feed flush()'s async copies)
+    int* st = reinterpret_cast<int*>(static_cast<char*>(stage(e, (32 << 10) + (n + 1) * sizeof(int))) + (32 << 10));
+    std::memcpy(st, e->host_dirty.data(), n * sizeof(int));
+    CUDA_CHECK(cudaMemcpyAsync(e->d_dirty_list.p, st, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    st[n] = (int)n;
+    CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->dirty_cnt[0], st + n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  }
+  e->host_dirty.clear();
+
+  // launch geometry: one CTA per SM, fewer for small stores (cheaper barrier)
+  size_t total = e->n_nary * 4096;
+  for (int f = 0; f < 3; ++f) total += e->fam[f].n;
+  int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 8191) / 8192));
+  size_t nary_bytes = nary_smem_bytes(e);
+  size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
+  bool smem_dom = dom_bytes + nary_bytes + 1024 <= (size_t)e->max_smem_optin && V > 0;
+  PCP_REQUIRE(nary_bytes + 1024 <= (size_t)e->max_smem_optin, "Distinct too wide for shared memory");
+  size_t smem = (smem_dom ? dom_bytes : 0) + nary_bytes;
+  P.smem_dom = smem_dom ? 1 : 0;
+  const void* fn = smem_dom ? (const void*)pcp_fixpoint_kernel<true> : (const void*)pcp_fixpoint_kernel<false>;
+  CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
+  void* args[] = {&P};
+  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
+  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+  // status header (+ domains when small) in one D2H copy
+  const bool eager_dom = V * sizeof(int2) <= (64u << 10);
+  size_t bytes = sizeof(Result) + (eager_dom ? V * sizeof(int2) : 0);
+  CUDA_CHECK(cudaMemcpyAsync(e->h_block, e->d_block, bytes, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  e->mirror_valid = eager_dom;
+
+  const Result& r = *e->h_result();
+  if (r.decision == D_ITER_CAP) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
+  e->trail_len = r.trail_cnt;
+  e->epoch = r.epoch;
+  unsigned long long props = r.propagations - e->props_total;
+  e->props_total = r.propagations;
+  // propagation/store.rs:250-256: False | True (every propagator entailed) | Unknown
+  int st = r.failed ? PCP_FALSE : (r.trail_cnt == e->num_props() ? PCP_TRUE : PCP_UNKNOWN);
+  e->at_fixpoint = !r.failed;
+  *status = st;
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    stats->propagations = props;
+    stats->iterations = r.iterations;
+    stats->active_props = (uint32_t)(e->num_props() - r.trail_cnt);
+    if (e->timing) {
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+      stats->kernel_ms = ms;
+    }
+  }
+}
+
+void fetch_domains(pcp_engine* e) {
+  flush(e);
+  if (e->mirror_valid) return;
+  if (e->V) {
+    CUDA_CHECK(cudaMemcpyAsync(e->h_dom(), e->d_dom(), e->V * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  }
+  e->mirror_valid = true;
+}
+
+template <class F>
+int guarded(pcp_engine* e, F&& f) {
+  try {
+    f();
+    return PCP_OK;
+  } catch (const Error& er) {
+    if (e) e->err = er.msg;
+    return er.code;
+  } catch (const std::bad_alloc&) {
+    if (e) e->err = "host allocation failed";
+    return PCP_ERR_NOMEM;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
+  if (!out) return PCP_ERR_INVALID;
+  *out = nullptr;
+  pcp_engine* e = new pcp_engine();
+  static thread_local std::string create_err;
+  int rc = guarded(e, [&] {
+    e->device = cfg ? cfg->device : 0;
+    e->flags = cfg ? cfg->flags : 0;
+    if (cfg && cfg->max_labels) e->max_labels = cfg->max_labels;
+    if (cfg && cfg->tail_limit) e->tail_limit = cfg->tail_limit;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) PCP_FAIL(PCP_ERR_CUDA, "no CUDA device: the propagation engine has no CPU fallback");
+    PCP_REQUIRE(e->device >= 0 && e->device < count, "device ordinal out of range");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, e->device));
+    if (prop.major < 10) PCP_FAIL(PCP_ERR_CUDA, "device is not sm_100 (Blackwell); the kernels are built for sm_100a only");
+    int coop = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+    if (!coop) PCP_FAIL(PCP_ERR_CUDA, "device does not support cooperative launch");
+    e->num_sms = prop.multiProcessorCount;
+    e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&e->ev0));
+    CUDA_CHECK(cudaEventCreate(&e->ev1));
+    CUDA_CHECK(cudaMalloc(&e->d_ctl, sizeof(Control)));
+    Control c;
+    std::memset(&c, 0, sizeof(c));
+    c.epoch = 1;
+    CUDA_CHECK(cudaMemcpy(e->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
+    e->fam[F_BIN].width_ = 1;
+    e->fam[F_TER].width_ = 1;
+    e->fam[F_DJ].width_ = 3;
+    stage(e, 1 << 16);
+  });
+  if (rc != PCP_OK) {
+    create_err = e->err;
+    std::fprintf(stderr, "pcp_engine_create: %s\n", create_err.c_str());
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return PCP_OK;
+}
+
+void pcp_engine_destroy(pcp_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (int f = 0; f < 3; ++f) {
+    e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
+  }
+  e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_active.free();
+  e->d_adj_ptr.free(); e->d_adj.free();
+  e->d_dirty_list.free(); e->d_dirty_stamp.free(); e->d_trail.free(); e->d_stack.free();
+  if (e->d_ctl) cudaFree(e->d_ctl);
+  if (e->d_block) cudaFree(e->d_block);
+  if (e->h_block) cudaFreeHost(e->h_block);
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+const char* pcp_last_error(const pcp_engine* e) { return e ? e->err.c_str() : "null engine"; }
+
+int pcp_set_timing(pcp_engine* e, int32_t enabled) {
+  if (!e) return PCP_ERR_INVALID;
+  e->timing = enabled != 0;
+  return PCP_OK;
+}
+
+int pcp_vars_alloc(pcp_engine* e, const int32_t* lo, const int32_t* hi, int32_t n, int32_t* first_idx) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(n >= 0 && (n == 0 || (lo && hi)), "bad arguments");
+    for (int i = 0; i < n; ++i) PCP_REQUIRE(lo[i] <= hi[i], "alloc of an empty domain");  // variable/store.rs:136
+    PCP_REQUIRE(e->V + (size_t)n < (size_t)kConstVar28, "too many variables");
+    if (first_idx) *first_idx = (int32_t)e->V;
+    for (int i = 0; i < n; ++i) e->h_dom_pending.push_back(make_int2(lo[i], hi[i]));
+    e->V += (size_t)n;
+    e->at_fixpoint = false;
+  });
+}
+
+int pcp_sum_alloc(pcp_engine* e, const pcp_operand* terms, int32_t n, int32_t* sum_id) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(n >= 1 && terms, "At least one variable in sum.");
+    for (int i = 0; i < n; ++i) { PCP_REQUIRE(terms[i].var >= -1, "nested sums are not supported"); check_operand(e, terms[i]); }
+    e->sums.emplace_back(terms, terms + n);
+    if (sum_id) *sum_id = (int32_t)(e->sums.size() - 1);
+  });
+}
+
+int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops, int64_t n_props, int32_t* first_idx) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(n_props >= 0 && n_ops >= 0 && (n_props == 0 || ops), "bad arguments");
+    PCP_REQUIRE(e->num_props() + (size_t)n_props < (size_t)kSlotMask, "too many propagators");
+    // all-or-nothing: remember the sizes and roll back on a contract violation
+    LabelRec mark;
+    for (int f = 0; f < 3; ++f) mark.n_fam[f] = e->fam[f].n;
+    mark.n_fam[F_NARY] = e->n_nary;
+    mark.n_nary_ops = e->h_nary_ops.size();
+    mark.n_props = e->num_props();
+    int old_max_k = e->nary_max_k;
+    if (first_idx) *first_idx = (int32_t)e->num_props();
+    try {
+      if (kind == PCP_X_LESS_Y || kind == PCP_X_NEQ_Y || kind == PCP_X_EQ_Y) e->fam[F_BIN].desc.reserve(e->fam[F_BIN].desc.size() + (size_t)n_props);
+      e->prop_ref.reserve(e->prop_ref.size() + (size_t)n_props);
+      for (int64_t p = 0; p < n_props; ++p) append_prop(e, kind, ops + p * n_ops, n_ops);
+    } catch (...) {
+      truncate_props(e, mark);
+      e->nary_max_k = old_max_k;
+      throw;
+    }
+  });
+}
+
+int pcp_prop_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops, int32_t* idx) {
+  return pcp_props_alloc(e, kind, ops, n_ops, 1, idx);
+}
+
+int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  if (!e || !status) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    run_fixpoint(e, status, stats);
+  });
+}
+
+int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32_t* hi) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(first >= 0 && n >= 0 && (size_t)first + (size_t)n <= e->V, "Variable not registered in the store.");
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    fetch_domains(e);
+    const int2* d = e->h_dom() + first;
+    for (int i = 0; i < n; ++i) { lo[i] = d[i].x; hi[i] = d[i].y; }
+  });
+}
+
+int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* ok) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(idx >= 0 && (size_t)idx < e->V, "Variable not registered in the store.");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    fetch_domains(e);
+    int2 cur = e->h_dom()[idx];
+    bool empty = lo > hi;
+    // variable/store.rs:153-156: dom must be a subset of the current domain (empty is)
+    PCP_REQUIRE(empty || (lo >= cur.x && hi <= cur.y), "Domain update must be monotonic.");
+    if (empty) { if (ok) *ok = 0; return; }
+    if (lo != cur.x || hi != cur.y) {
+      int2* st = static_cast<int2*>(stage(e, sizeof(int2)));
+      *st = make_int2(lo, hi);
+      CUDA_CHECK(cudaMemcpyAsync(e->d_dom() + idx, st, sizeof(int2), cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      e->h_dom()[idx] = make_int2(lo, hi);
+      e->host_dirty.push_back(idx);
+    }
+    if (ok) *ok = 1;
+  });
+}
+
+int pcp_active_read(pcp_engine* e, int32_t first, int32_t n, uint8_t* out) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(first >= 0 && n >= 0 && (size_t)first + (size_t)n <= e->num_props(), "propagator out of range");
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    flush(e);
+    std::vector<uint32_t> bits[4];
+    for (int f = 0; f < 4; ++f) {
+      size_t cnt = f < 3 ? e->fam[f].n : e->n_nary;
+      const uint32_t* src = f < 3 ? e->fam[f].d_active.p : e->d_nary_active.p;
+      bits[f].resize((cnt + 31) / 32);
+      if (!bits[f].empty())
+        CUDA_CHECK(cudaMemcpyAsync(bits[f].data(), src, bits[f].size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < n; ++i) {
+      uint32_t ref = e->prop_ref[(size_t)first + i];
+      uint32_t slot = ref & kSlotMask;
+      out[i] = (bits[ref >> 29][slot >> 5] >> (slot & 31)) & 1u;
+    }
+  });
+}
+
+int pcp_label(pcp_engine* e, uint64_t* label) {
+  if (!e || !label) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    flush(e);
+    PCP_REQUIRE(e->labels.size() < e->max_labels, "label stack full (pcp_config.max_labels)");
+    size_t idx = e->labels.size();
+    e->d_stack.reserve((idx + 1) * std::max<size_t>(e->stack_stride, 1), e->stream, true, idx * e->stack_stride);
+    if (e->V)
+      CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride, e->d_dom(), e->V * sizeof(int2),
+                                 cudaMemcpyDeviceToDevice, e->stream));
+    LabelRec r;
+    for (int f = 0; f < 3; ++f) r.n_fam[f] = e->fam[f].n;
+    r.n_fam[F_NARY] = e->n_nary;
+    r.n_nary_ops = e->h_nary_ops.size();
+    r.n_props = e->num_props();
+    r.trail_len = e->trail_len;
+    r.at_fixpoint = e->at_fixpoint;
+    e->labels.push_back(r);
+    *label = idx;
+  });
+}
+
+int pcp_restore(pcp_engine* e, uint64_t label) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(label < e->labels.size(), "unknown label (invalidated by an earlier restore?)");
+    const LabelRec r = e->labels[label];
+    e->labels.resize(label + 1);
+    truncate_props(e, r);
+    e->pending_restore = true;
+    e->pending_restore_label = label;
+    e->pending_trail_undo = true;
+    e->pending_trail_keep = r.trail_len;
+    e->at_fixpoint = r.at_fixpoint;
+    e->host_dirty.clear();
+    e->mirror_valid = false;
+  });
+}
+
+int pcp_num_vars(const pcp_engine* e, int32_t* n) {
+  if (!e || !n) return PCP_ERR_INVALID;
+  *n = (int32_t)e->V;
+  return PCP_OK;
+}
+int pcp_num_props(const pcp_engine* e, int32_t* n) {
+  if (!e || !n) return PCP_ERR_INVALID;
+  *n = (int32_t)e->num_props();
+  return PCP_OK;
+}
+
+}  // extern "C"

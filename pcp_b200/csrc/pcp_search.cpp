@@ -1,0 +1,170 @@
+// pcp_search.cpp -- host search driver over the public C ABI.
+//
+// The callers of the hot path (reference src/libpcp/search/): OneSolution / AllSolution
+// (engine/one_solution.rs:92-105, engine/all_solution.rs:41-50) o StopNode
+// (stop_node.rs:54-61) o [BranchAndBound (branch_and_bound.rs:69-94)] o Propagation
+// (propagation.rs:42-55) o Brancher(FirstSmallestVar | InputOrder, MiddleVal | MinVal,
+// BinarySplit | Enumerate) (branching/*.rs).  It touches the engine exclusively through
+// the entry points a Rust host would bind (pcp_restore, pcp_prop_alloc, pcp_consistency,
+// pcp_domains_read, pcp_label) -- one fixpoint launch per node, host buffers on both
+// sides -- so its timings are end-to-end timings of the boundary.
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#include "../../include/pcp_b200.h"
+
+namespace {
+
+struct Branch {
+  uint64_t label;
+  int kind;  // 0: x <= v, 1: x > v (binary_split.rs:46-57); 2: x == v, 3: x != v (enumerate.rs)
+  int32_t var, val;
+};
+
+uint64_t hash_domains(const int32_t* lo, const int32_t* hi, size_t n) {  // FNV-1a over (lo,hi) words
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t w[2] = {(uint32_t)lo[i], (uint32_t)hi[i]};
+    for (int k = 0; k < 2; ++k)
+      for (int b = 0; b < 4; ++b) { h ^= (w[k] >> (8 * b)) & 0xffu; h *= 1099511628211ull; }
+  }
+  return h;
+}
+
+#define TRY(expr) do { int _rc = (expr); if (_rc != PCP_OK) return _rc; } while (0)
+
+struct Driver {
+  pcp_engine* e;
+  const pcp_search_config* cfg;
+  pcp_search_result* res;
+  int32_t *t_status, *t_lo, *t_hi;
+  uint64_t* t_hash;
+  uint64_t t_cap;
+  std::vector<Branch> queue;  // VectorStack: DFS, left child first
+  std::vector<int32_t> lo, hi;
+  bool started = false;
+  uint64_t nodes_explored = 0;
+  int32_t V = 0;
+
+  int apply_alternative(const Branch& b) {
+    pcp_operand x{b.var, 0}, c{PCP_VAR_CONSTANT, b.val}, c1{PCP_VAR_CONSTANT, b.val + 1};
+    pcp_operand ops[2];
+    int kind;
+    switch (b.kind) {
+      case 0: ops[0] = x; ops[1] = c1; kind = PCP_X_LESS_Y; break;   // x_leq_y(x, v) = x < v + 1 (cmp/mod.rs:54-60)
+      case 1: ops[0] = c; ops[1] = x; kind = PCP_X_LESS_Y; break;    // x_greater_y(x, v) = v < x (cmp/mod.rs:40-42)
+      case 2: ops[0] = x; ops[1] = c; kind = PCP_X_EQ_Y; break;
+      default: ops[0] = x; ops[1] = c; kind = PCP_X_NEQ_Y; break;
+    }
+    return pcp_prop_alloc(e, kind, ops, 2, nullptr);
+  }
+
+  // Propagation::enter + Brancher::enter (+ BranchAndBound, StopNode, Monitor/Statistics).
+  // *out: 1 Satisfiable, -1 Unsatisfiable, 0 Unknown (branches pushed), 2 EndOfSearch.
+  int enter_child(int* out) {
+    if (cfg->bb_mode != 0 && res->has_bb_value) {  // branch_and_bound.rs:76-87
+      pcp_operand v{cfg->bb_var, 0}, b{PCP_VAR_CONSTANT, res->bb_value};
+      pcp_operand ops[2];
+      if (cfg->bb_mode == 1) { ops[0] = v; ops[1] = b; } else { ops[0] = b; ops[1] = v; }
+      TRY(pcp_prop_alloc(e, PCP_X_LESS_Y, ops, 2, nullptr));
+    }
+    int32_t k = 0;
+    pcp_stats st;
+    TRY(pcp_consistency(e, &k, &st));  // propagation.rs:49
+    res->propagations += st.propagations;
+    res->iterations += st.iterations;
+    res->kernel_seconds += st.kernel_ms * 1e-3;
+    int status = k;
+    if (k != PCP_FALSE) TRY(pcp_domains_read(e, 0, V, lo.data(), hi.data()));
+    Branch left{}, right{};
+    if (k == PCP_UNKNOWN) {
+      // first_smallest_var.rs:30-39 / input_order.rs; middle_val.rs:25-27 / min_val.rs
+      int32_t var = -1;
+      uint32_t best = 0;
+      for (int32_t i = 0; i < V; ++i) {
+        uint32_t sz = (uint32_t)(hi[i] - lo[i]) + 1u;
+        if (sz > 1 && (var < 0 || (cfg->var_sel == 0 && sz < best))) { var = i; best = sz; if (cfg->var_sel == 1) break; }
+      }
+      if (var < 0) return PCP_ERR_INVALID;  // "Cannot select a variable in a space where all variables are assigned."
+      int32_t val = cfg->val_sel == 0 ? (lo[var] + hi[var]) / 2 : lo[var];
+      uint64_t label = 0;
+      TRY(pcp_label(e, &label));  // Branch::distribute (branch.rs:36-49)
+      int k0 = cfg->distributor == 0 ? 0 : 2;
+      left = Branch{label, k0, var, val};
+      right = Branch{label, k0 + 1, var, val};
+    }
+    uint64_t n = res->num_nodes;
+    if (n < t_cap) {
+      if (t_status) t_status[n] = k;
+      if (t_hash) t_hash[n] = k == PCP_FALSE ? 0 : hash_domains(lo.data(), hi.data(), (size_t)V);
+      if (cfg->trace_domains && t_lo && t_hi && k != PCP_FALSE) {
+        std::memcpy(t_lo + n * (size_t)V, lo.data(), sizeof(int32_t) * (size_t)V);
+        std::memcpy(t_hi + n * (size_t)V, hi.data(), sizeof(int32_t) * (size_t)V);
+      }
+    }
+    if (status == PCP_TRUE && cfg->bb_mode != 0) {  // branch_and_bound.rs:89-92
+      res->has_bb_value = 1;
+      res->bb_value = lo[cfg->bb_var];
+    }
+    ++nodes_explored;  // stop_node.rs:54-61
+    bool stop = cfg->node_limit && nodes_explored >= cfg->node_limit;
+    ++res->num_nodes;  // monitor.rs:61-66 sees the status after StopNode
+    if (stop) status = 2;
+    else if (status == PCP_TRUE) ++res->num_solution;
+    else if (status == PCP_FALSE) ++res->num_failed_node;
+    if (status == PCP_UNKNOWN) {  // one_solution.rs:46-51: reversed push => left first
+      queue.push_back(right);
+      queue.push_back(left);
+    }
+    *out = status;
+    return PCP_OK;
+  }
+
+  // OneSolution::enter (one_solution.rs:92-105)
+  int one_solution(int* out) {
+    if (queue.empty() && started) { *out = 2; return PCP_OK; }
+    int status = -1, child = 0;
+    if (queue.empty() && !started) {
+      started = true;
+      TRY(enter_child(&child));
+      if (child == 1 || child == 2) status = child;
+    }
+    while (status != 2 && status != 1 && !queue.empty()) {
+      Branch b = queue.back();
+      queue.pop_back();
+      TRY(pcp_restore(e, b.label));  // Branch::commit (branch.rs:51-55)
+      TRY(apply_alternative(b));
+      TRY(enter_child(&child));
+      if (child == 1 || child == 2) status = child;
+    }
+    *out = status;
+    return PCP_OK;
+  }
+
+  int run() {
+    TRY(pcp_num_vars(e, &V));
+    lo.assign((size_t)V, 0);
+    hi.assign((size_t)V, 0);
+    int status = 0;
+    TRY(one_solution(&status));
+    if (cfg->all_solutions)  // all_solution.rs:41-50
+      while (status != 2) TRY(one_solution(&status));
+    res->status = status;
+    return PCP_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" int pcp_search_run(pcp_engine* e, const pcp_search_config* cfg, pcp_search_result* res,
+                              int32_t* trace_status, uint64_t* trace_hash, int32_t* trace_lo,
+                              int32_t* trace_hi, uint64_t trace_capacity) {
+  if (!e || !cfg || !res) return PCP_ERR_INVALID;
+  std::memset(res, 0, sizeof(*res));
+  Driver d{e, cfg, res, trace_status, trace_lo, trace_hi, trace_hash, trace_capacity};
+  auto t0 = std::chrono::steady_clock::now();
+  int rc = d.run();
+  res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return rc;
+}
