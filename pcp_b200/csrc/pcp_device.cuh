@@ -443,9 +443,6 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
   unsigned tabsz = 4;
   while (tabsz < 2u * (unsigned)k) tabsz <<= 1;
   const unsigned mask = tabsz - 1;
-  __shared__ int s_flag;  // 1: dirty operand seen / new singleton, 2: failure
-  if (threadIdx.x == 0) s_flag = 0;
-  __syncthreads();
   // stage operands + current domains; is any operand dirty this iteration?
   int any_dirty = 0;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
@@ -495,9 +492,9 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
         if (lo == hi) again = 1;
       }
     }
-    int r = __syncthreads_or(fail ? 2 : again);
-    if (r & 2) { set_failed(c); if (threadIdx.x == 0 && c.count) c.nprop++; return; }
-    if (!r) break;
+    // (__syncthreads_or yields a predicate, not the OR of the operands: two reductions)
+    if (__syncthreads_or(fail)) { set_failed(c); if (threadIdx.x == 0 && c.count) c.nprop++; return; }
+    if (!__syncthreads_or(again)) break;
   }
   // write back narrowed bounds
   long long sum_size = 0;
@@ -518,7 +515,7 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
   // Necessary condition first (pigeonhole): sum of sizes <= span.
   __shared__ long long s_sum;
   __shared__ int s_mn, s_mx;
-  if (threadIdx.x == 0) { s_sum = 0; s_mn = INT32_MAX; s_mx = INT32_MIN; s_flag = 0; }
+  if (threadIdx.x == 0) { s_sum = 0; s_mn = INT32_MAX; s_mx = INT32_MIN; }
   __syncthreads();
   for (int o = 16; o; o >>= 1) {
     sum_size += __shfl_xor_sync(0xffffffffu, sum_size, o);

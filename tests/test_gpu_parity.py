@@ -177,8 +177,10 @@ def test_random_arith_csp_full_size():
     m.load_into(ora)
     ds, st = dev.consistency()
     os_, _ = ora.consistency()
-    assert ds == os_ == 0
+    assert ds == os_ == 1  # bound propagation alone pins every variable to the planted solution
     _assert_same_state(dev, ora)
+    lo, hi = dev.domains()
+    assert (lo == hi).all()
     # idempotence: a second fixpoint changes nothing
     lo0, hi0 = dev.domains()
     ds2, st2 = dev.consistency()
