@@ -155,7 +155,8 @@ typedef struct pcp_search_config {
   int32_t bb_mode;       /* 0 none, 1 minimize, 2 maximize (search/branch_and_bound.rs) */
   int32_t bb_var;
   int32_t trace_domains; /* 1: also copy lo/hi of every non-failed node into the trace */
-  int32_t reserved;
+  int32_t warmup_nodes;  /* the first warmup_nodes nodes are excluded from `seconds`,
+                            `kernel_seconds`, `propagations` and `iterations`         */
 } pcp_search_config;
 
 typedef struct pcp_search_result {
@@ -176,6 +177,20 @@ typedef struct pcp_search_result {
 int pcp_search_run(pcp_engine* e, const pcp_search_config* cfg, pcp_search_result* res,
                    int32_t* trace_status, uint64_t* trace_hash, int32_t* trace_lo,
                    int32_t* trace_hi, uint64_t trace_capacity);
+
+/* The same search as a resumable generator (OneSolution::enter can be called again,
+ * search/engine/one_solution.rs:23): pcp_search_step runs at most `max_nodes` further
+ * nodes (0 = no slice limit) and fills `res` with the cumulative counters;
+ * res->status: 0 slice used up (search still open), 1 Satisfiable (one-solution mode;
+ * step again for the next one), -1 tree exhausted without a further solution,
+ * 2 EndOfSearch.  Between steps the host may exchange an incumbent / stop word with
+ * other ranks.  The trace buffers must outlive the handle. */
+typedef struct pcp_search pcp_search;
+int pcp_search_open(pcp_engine* e, const pcp_search_config* cfg, int32_t* trace_status,
+                    uint64_t* trace_hash, int32_t* trace_lo, int32_t* trace_hi,
+                    uint64_t trace_capacity, pcp_search** out);
+int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res);
+void pcp_search_close(pcp_search* s);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ from pcp_b200._capi import EngineBase, bind, _i32p
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libpcp_oracle.so")
 
-FAITHFUL, TUNED = 0, 1
+FAITHFUL, TUNED, FLAT = 0, 1, 2
 
 
 def build(force: bool = False) -> str:

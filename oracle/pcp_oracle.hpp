@@ -561,6 +561,166 @@ struct AllEqual : Propagator {
 };
 
 // ---------------------------------------------------------------------------
+// FlatProp -- the same propagators without the Box<dyn ..> trees: operands are
+// (var, off) pairs held inline, no heap allocation or view dispatch per call.
+// Semantically identical to the classes above (update order, short-circuit,
+// events); it exists so that the timed CPU baseline is a *tuned* implementation
+// rather than one that pays the reference's allocation pattern
+// (x_neq_y.rs:72,102 bclone()s two views per call).  tests/ check that it
+// produces the same traces as the faithful restatement.
+// ---------------------------------------------------------------------------
+struct FOp { int32_t var, off; };  // var >= 0: Identity+off; var == -1: Constant(off)
+
+struct FlatProp : Propagator {
+  enum Kind : int { LessY = 0, NeqY = 1, EqY = 2, GreaterYPlusZ = 3, LessYPlusZ = 4, EqYPlusZ = 5,
+                    DistinctN = 6, Disj2EqYPlusZ = 7 };
+  int kind;
+  FOp o[6];
+  std::vector<FOp> nary;
+
+  static Interval rd(const VStore& s, FOp a) {
+    return a.var >= 0 ? s.memory[size_t(a.var)].plus(a.off) : Interval::singleton(a.off);
+  }
+  static bool up(VStore& s, FOp a, const Interval& v) {
+    if (a.var >= 0) return s.update(size_t(a.var), v.minus(a.off));
+    return !v.is_empty() && v.contains(a.off);
+  }
+  static void dep(std::vector<Dep>& d, FOp a, FDEvent ev) { if (a.var >= 0) d.emplace_back(size_t(a.var), ev); }
+
+  static SKleene sub_less(const VStore& s, FOp x, FOp y) {
+    Interval a = rd(s, x), b = rd(s, y);
+    if (a.lb >= b.ub) return False;
+    if (a.ub < b.lb) return True;
+    return Unknown;
+  }
+  static SKleene sub_eq(const VStore& s, FOp x, FOp y) {
+    Interval a = rd(s, x), b = rd(s, y);
+    if (a.lb == b.ub && a.ub == b.lb) return True;
+    if (a.is_disjoint(b)) return False;
+    return Unknown;
+  }
+  static bool prop_neq(VStore& s, FOp x, FOp y) {
+    Interval a = rd(s, x), b = rd(s, y);
+    if (a.is_singleton()) return up(s, y, b.difference(a.lb));
+    if (b.is_singleton()) return up(s, x, a.difference(b.lb));
+    return true;
+  }
+  // x (+xs) > y + z  /  x (+xs) < y + z with the Addition(x, +-1) of cmp/mod.rs:62-86 folded in xs
+  static SKleene sub_greater(const VStore& s, FOp x, FOp y, FOp z, int xs) {
+    Interval a = rd(s, x).plus(xs), b = rd(s, y), c = rd(s, z);
+    if (a.ub <= b.lb + c.lb) return False;
+    if (a.lb > b.ub + c.ub) return True;
+    return Unknown;
+  }
+  static SKleene sub_lessyz(const VStore& s, FOp x, FOp y, FOp z, int xs) {
+    Interval a = rd(s, x).plus(xs), b = rd(s, y), c = rd(s, z);
+    if (a.lb >= b.ub + c.ub) return False;
+    if (a.ub < b.lb + c.lb) return True;
+    return Unknown;
+  }
+  static bool prop_greater(VStore& s, FOp x, FOp y, FOp z, int xs) {
+    FOp xx{x.var, x.off + xs};
+    Interval a = rd(s, xx), b = rd(s, y), c = rd(s, z);
+    return up(s, xx, a.strict_shrink_left(b.lb + c.lb)) && up(s, y, b.strict_shrink_right(a.ub - c.lb)) &&
+           up(s, z, c.strict_shrink_right(a.ub - b.lb));
+  }
+  static bool prop_lessyz(VStore& s, FOp x, FOp y, FOp z, int xs) {
+    FOp xx{x.var, x.off + xs};
+    Interval a = rd(s, xx), b = rd(s, y), c = rd(s, z);
+    return up(s, xx, a.strict_shrink_right(b.ub + c.ub)) && up(s, y, b.strict_shrink_left(a.lb - c.ub)) &&
+           up(s, z, c.strict_shrink_left(a.lb - b.ub));
+  }
+  static SKleene sub_eqyz(const VStore& s, const FOp* t) {
+    return k_and(sub_greater(s, t[0], t[1], t[2], 1), sub_lessyz(s, t[0], t[1], t[2], -1));
+  }
+  static bool prop_eqyz(VStore& s, const FOp* t) {
+    return prop_greater(s, t[0], t[1], t[2], 1) && prop_lessyz(s, t[0], t[1], t[2], -1);
+  }
+
+  SKleene is_subsumed(const VStore& s) const override {
+    switch (kind) {
+      case LessY: return sub_less(s, o[0], o[1]);
+      case NeqY: return k_not(sub_eq(s, o[0], o[1]));
+      case EqY: return sub_eq(s, o[0], o[1]);
+      case GreaterYPlusZ: return sub_greater(s, o[0], o[1], o[2], 0);
+      case LessYPlusZ: return sub_lessyz(s, o[0], o[1], o[2], 0);
+      case EqYPlusZ: return sub_eqyz(s, o);
+      case DistinctN: {  // Conjunction::is_subsumed over the pairs (conjunction.rs:77-94)
+        bool all = true;
+        for (size_t i = 0; i + 1 < nary.size(); ++i)
+          for (size_t j = i + 1; j < nary.size(); ++j) {
+            SKleene k = k_not(sub_eq(s, nary[i], nary[j]));
+            if (k == False) return False;
+            if (k == Unknown) all = false;
+          }
+        return all ? True : Unknown;
+      }
+      default: {  // Disjunction::is_subsumed (disjunction.rs:77-94)
+        SKleene a = sub_eqyz(s, o), b = sub_eqyz(s, o + 3);
+        if (a == True || b == True) return True;
+        return (a == False && b == False) ? False : Unknown;
+      }
+    }
+  }
+  bool propagate(VStore& s) override {
+    switch (kind) {
+      case LessY: {
+        Interval a = rd(s, o[0]), b = rd(s, o[1]);
+        return up(s, o[0], a.strict_shrink_right(b.ub)) && up(s, o[1], b.strict_shrink_left(a.lb));
+      }
+      case NeqY: return prop_neq(s, o[0], o[1]);
+      case EqY: {
+        Interval a = rd(s, o[0]), b = rd(s, o[1]);
+        Interval n = a.intersection(b);
+        return up(s, o[0], n) && up(s, o[1], n);
+      }
+      case GreaterYPlusZ: return prop_greater(s, o[0], o[1], o[2], 0);
+      case LessYPlusZ: return prop_lessyz(s, o[0], o[1], o[2], 0);
+      case EqYPlusZ: return prop_eqyz(s, o);
+      case DistinctN:  // Conjunction::propagate over the pairs (conjunction.rs:96-105)
+        for (size_t i = 0; i + 1 < nary.size(); ++i)
+          for (size_t j = i + 1; j < nary.size(); ++j)
+            if (!prop_neq(s, nary[i], nary[j])) return false;
+        return true;
+      default: {  // Disjunction::propagate (disjunction.rs:96-116)
+        SKleene k[2] = {sub_eqyz(s, o), sub_eqyz(s, o + 3)};
+        size_t num_disentailed = 0, unknown_formula = 0;
+        for (size_t i = 0; i < 2; ++i) {
+          if (k[i] == True) return true;
+          if (k[i] == False) ++num_disentailed; else unknown_formula = i;
+        }
+        if (num_disentailed == 1) return prop_eqyz(s, o + 3 * unknown_formula);
+        return num_disentailed != 2;
+      }
+    }
+  }
+  std::vector<Dep> dependencies() const override {
+    std::vector<Dep> d;
+    switch (kind) {
+      case LessY: dep(d, o[0], Bound); dep(d, o[1], Bound); break;
+      case NeqY: case EqY: dep(d, o[0], Inner); dep(d, o[1], Inner); break;
+      case GreaterYPlusZ: case LessYPlusZ: case EqYPlusZ:
+        for (int i = 0; i < 3; ++i) dep(d, o[i], Bound);
+        break;
+      case DistinctN: for (auto& a : nary) dep(d, a, Inner); break;
+      default:
+        for (int i = 0; i < 6; ++i) dep(d, o[i], Bound);
+        d = sorted_dedup(std::move(d));
+    }
+    return d;
+  }
+  Formula bclone() const override { return std::make_unique<FlatProp>(*this); }
+};
+
+inline Formula make_flat(int kind, const FOp* ops, int n) {
+  auto p = std::make_unique<FlatProp>();
+  p->kind = kind;
+  if (kind == FlatProp::DistinctN) p->nary.assign(ops, ops + n);
+  else for (int i = 0; i < n && i < 6; ++i) p->o[i] = ops[i];
+  return p;
+}
+
+// ---------------------------------------------------------------------------
 // propagation/reactors/indexed_deps.rs:23-113
 // ---------------------------------------------------------------------------
 struct IndexedDeps {
@@ -875,7 +1035,20 @@ struct Search {
   uint64_t nodes_explored = 0;  // StopNode counter
   std::function<void(const Space&, int status)> on_node;  // trace hook (called after consistency)
 
+  bool flat = false;  // allocate FlatProp descriptors instead of boxed view trees
+
   void apply_alternative(Space& sp, const Branch& b) {
+    if (flat) {
+      FOp x{int32_t(b.var), 0}, c{-1, b.val}, c1{-1, b.val + 1};
+      FOp leq[2] = {x, c1}, gt[2] = {c, x}, xc[2] = {x, c};
+      switch (b.kind) {
+        case 0: sp.cstore.alloc(make_flat(FlatProp::LessY, leq, 2)); break;
+        case 1: sp.cstore.alloc(make_flat(FlatProp::LessY, gt, 2)); break;
+        case 2: sp.cstore.alloc(make_flat(FlatProp::EqY, xc, 2)); break;
+        default: sp.cstore.alloc(make_flat(FlatProp::NeqY, xc, 2)); break;
+      }
+      return;
+    }
     auto x = [&] { return Var(std::make_unique<Identity>(b.var)); };
     auto v = [&] { return Var(std::make_unique<Constant>(b.val)); };
     switch (b.kind) {
@@ -888,7 +1061,11 @@ struct Search {
 
   // Propagation::enter + Brancher::enter (+ BranchAndBound, StopNode, Monitor).
   NodeStatus enter_child(Space& sp) {
-    if (cfg.bb_mode != BBMode::None && has_bb_value) {  // branch_and_bound.rs:76-87
+    if (cfg.bb_mode != BBMode::None && has_bb_value && flat) {
+      FOp v{int32_t(cfg.bb_var), 0}, b{-1, bb_value};
+      FOp mn[2] = {v, b}, mx[2] = {b, v};
+      sp.cstore.alloc(make_flat(FlatProp::LessY, cfg.bb_mode == BBMode::Minimize ? mn : mx, 2));
+    } else if (cfg.bb_mode != BBMode::None && has_bb_value) {  // branch_and_bound.rs:76-87
       Var var = std::make_unique<Identity>(cfg.bb_var);
       Var bound = std::make_unique<Constant>(bb_value);
       if (cfg.bb_mode == BBMode::Minimize) sp.cstore.alloc(std::make_unique<XLessY>(std::move(var), std::move(bound)));

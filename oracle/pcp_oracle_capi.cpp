@@ -14,6 +14,7 @@ using namespace pcpo;
 
 struct pcpo_engine {
   Space space;
+  bool flat = false;
   std::vector<std::vector<pcp_operand>> sums;
   std::vector<Label> labels;
   std::string err;
@@ -44,6 +45,22 @@ void check_operand(const pcpo_engine* e, pcp_operand op) {
 
 Formula make_prop(const pcpo_engine* e, int kind, const pcp_operand* ops, int n) {
   for (int i = 0; i < n; ++i) check_operand(e, ops[i]);
+  if (e->flat) {  // same kind numbering as enum pcp_prop_kind
+    std::vector<FOp> f;
+    for (int i = 0; i < n; ++i) {
+      pcp_operand op = ops[i];
+      if (op.var <= -2) {  // single-term sums delegate (term/sum.rs:62-64); wider ones need the view tree
+        const auto& terms = e->sums[size_t(-2 - op.var)];
+        PCPO_ASSERT(terms.size() == 1, "flat variant: Sum views with more than one term are not supported");
+        op = pcp_operand{terms[0].var, terms[0].off + op.off};
+      }
+      f.push_back(FOp{op.var, op.off});
+    }
+    static const int arity[8] = {2, 2, 2, 3, 3, 3, -1, 6};
+    PCPO_ASSERT(kind >= 0 && kind < 8, "unknown propagator kind");
+    PCPO_ASSERT(arity[kind] < 0 ? n >= 1 : n == arity[kind], "arity");
+    return make_flat(kind, f.data(), n);
+  }
   auto v = [&](int i) { return make_view(e, ops[i]); };
   switch (kind) {
     case PCP_X_LESS_Y: PCPO_ASSERT(n == 2, "arity"); return std::make_unique<XLessY>(v(0), v(1));
@@ -82,7 +99,9 @@ extern "C" {
 
 int pcpo_engine_create(int variant, pcpo_engine** out) {
   auto* e = new pcpo_engine();
+  // 0 faithful | 1 tuned (static CSR, boxed views) | 2 flat (tuned + inline descriptors)
   e->space.cstore.variant = variant == 0 ? Variant::Faithful : Variant::Tuned;
+  e->flat = variant == 2;
   *out = e;
   return PCP_OK;
 }
@@ -207,6 +226,7 @@ int pcpo_search_run(pcpo_engine* e, const pcp_search_config* cfg, pcp_search_res
                     uint64_t trace_capacity) {
   return guarded(e, [&] {
     Search s;
+    s.flat = e->flat;
     s.cfg.node_limit = cfg->node_limit;
     s.cfg.all_solutions = cfg->all_solutions != 0;
     s.cfg.var_sel = cfg->var_sel;
@@ -216,7 +236,10 @@ int pcpo_search_run(pcpo_engine* e, const pcp_search_config* cfg, pcp_search_res
     s.cfg.bb_var = size_t(cfg->bb_var);
     uint64_t n = 0;
     size_t V = e->space.vstore.size();
+    uint64_t p_warm = e->space.cstore.num_propagations;
+    auto t0 = std::chrono::steady_clock::now();
     s.on_node = [&](const Space& sp, int status) {
+      if (n + 1 == uint64_t(cfg->warmup_nodes)) { t0 = std::chrono::steady_clock::now(); p_warm = e->space.cstore.num_propagations; }
       if (n < trace_capacity) {
         if (trace_status) trace_status[n] = status;
         if (trace_hash) trace_hash[n] = status == int(False) ? 0 : hash_domains(sp.vstore.memory);
@@ -225,8 +248,6 @@ int pcpo_search_run(pcpo_engine* e, const pcp_search_config* cfg, pcp_search_res
       }
       ++n;
     };
-    uint64_t p0 = e->space.cstore.num_propagations;
-    auto t0 = std::chrono::steady_clock::now();
     NodeStatus st = s.run(e->space);
     auto t1 = std::chrono::steady_clock::now();
     std::memset(res, 0, sizeof(*res));
@@ -237,7 +258,7 @@ int pcpo_search_run(pcpo_engine* e, const pcp_search_config* cfg, pcp_search_res
     res->num_solution = s.stats.num_solution;
     res->num_failed_node = s.stats.num_failed_node;
     res->num_prune = s.stats.num_prune;
-    res->propagations = e->space.cstore.num_propagations - p0;
+    res->propagations = e->space.cstore.num_propagations - p_warm;
     res->seconds = std::chrono::duration<double>(t1 - t0).count();
   });
 }

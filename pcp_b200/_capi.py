@@ -44,7 +44,7 @@ class Stats(C.Structure):
 class SearchConfig(C.Structure):
     _fields_ = [("node_limit", C.c_uint64), ("all_solutions", C.c_int32), ("var_sel", C.c_int32),
                 ("val_sel", C.c_int32), ("distributor", C.c_int32), ("bb_mode", C.c_int32),
-                ("bb_var", C.c_int32), ("trace_domains", C.c_int32), ("reserved", C.c_int32)]
+                ("bb_var", C.c_int32), ("trace_domains", C.c_int32), ("warmup_nodes", C.c_int32)]
 
 
 class SearchResult(C.Structure):
@@ -210,9 +210,9 @@ class EngineBase:
     # --- search driver (search/mod.rs:45-52 and friends)
     def search(self, node_limit: int = 0, all_solutions: bool = False, var_sel: int = 0, val_sel: int = 0,
                distributor: int = 0, bb_mode: int = 0, bb_var: int = 0, trace: int = 0,
-               trace_domains: bool = False):
+               trace_domains: bool = False, warmup_nodes: int = 0):
         cfg = SearchConfig(node_limit, int(all_solutions), var_sel, val_sel, distributor, bb_mode, bb_var,
-                           int(trace_domains), 0)
+                           int(trace_domains), warmup_nodes)
         res = SearchResult()
         V = self.num_vars
         t_status = np.zeros(trace, np.int32)

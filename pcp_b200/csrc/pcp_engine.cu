@@ -405,7 +405,7 @@ void build_csr(pcp_engine* e) {
 // Bring the device in line with the host-side bookkeeping: upload new variables and
 // descriptors, run the node prologue (restore + new active bits), rebuild the CSR if the
 // tail outgrew its limit.
-void flush(pcp_engine* e) {
+void flush(pcp_engine* e, bool timed = false) {
   const size_t V = e->V;
   size_t stage_off = 0;
   stage(e, 1 << 16);
@@ -483,6 +483,8 @@ void flush(pcp_engine* e) {
   nb.new_first[F_NARY] = (int)e->nary_active_set;
   nb.new_last[F_NARY] = (int)e->n_nary;
   e->nary_active_set = e->n_nary;
+  // device time of a node = node prologue + fixpoint kernel
+  if (timed && e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   pcp_node_begin_kernel<<<1, 1024, 0, e->stream>>>(nb);
   CUDA_CHECK(cudaGetLastError());
   if (e->pending_trail_undo) e->trail_len = e->pending_trail_keep;
@@ -512,7 +514,7 @@ size_t nary_smem_bytes(const pcp_engine* e) {
 }
 
 void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
-  flush(e);
+  flush(e, true);
   const size_t V = e->V;
   Params P;
   std::memset(&P, 0, sizeof(P));
@@ -577,7 +579,6 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   P.smem_dom = smem_dom ? 1 : 0;
   const void* fn = smem_dom ? (const void*)pcp_fixpoint_kernel<true> : (const void*)pcp_fixpoint_kernel<false>;
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   void* args[] = {&P};
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));

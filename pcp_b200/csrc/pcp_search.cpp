@@ -46,6 +46,7 @@ struct Driver {
   bool started = false;
   uint64_t nodes_explored = 0;
   int32_t V = 0;
+  std::chrono::steady_clock::time_point t_start;
 
   int apply_alternative(const Branch& b) {
     pcp_operand x{b.var, 0}, c{PCP_VAR_CONSTANT, b.val}, c1{PCP_VAR_CONSTANT, b.val + 1};
@@ -69,12 +70,15 @@ struct Driver {
       if (cfg->bb_mode == 1) { ops[0] = v; ops[1] = b; } else { ops[0] = b; ops[1] = v; }
       TRY(pcp_prop_alloc(e, PCP_X_LESS_Y, ops, 2, nullptr));
     }
+    if (res->num_nodes == (uint64_t)cfg->warmup_nodes) t_start = std::chrono::steady_clock::now();
     int32_t k = 0;
     pcp_stats st;
     TRY(pcp_consistency(e, &k, &st));  // propagation.rs:49
-    res->propagations += st.propagations;
-    res->iterations += st.iterations;
-    res->kernel_seconds += st.kernel_ms * 1e-3;
+    if (res->num_nodes >= (uint64_t)cfg->warmup_nodes) {
+      res->propagations += st.propagations;
+      res->iterations += st.iterations;
+      res->kernel_seconds += st.kernel_ms * 1e-3;
+    }
     int status = k;
     if (k != PCP_FALSE) TRY(pcp_domains_read(e, 0, V, lo.data(), hi.data()));
     Branch left{}, right{};
@@ -121,50 +125,95 @@ struct Driver {
     return PCP_OK;
   }
 
-  // OneSolution::enter (one_solution.rs:92-105)
-  int one_solution(int* out) {
-    if (queue.empty() && started) { *out = 2; return PCP_OK; }
-    int status = -1, child = 0;
-    if (queue.empty() && !started) {
-      started = true;
-      TRY(enter_child(&child));
-      if (child == 1 || child == 2) status = child;
-    }
-    while (status != 2 && status != 1 && !queue.empty()) {
-      Branch b = queue.back();
-      queue.pop_back();
-      TRY(pcp_restore(e, b.label));  // Branch::commit (branch.rs:51-55)
-      TRY(apply_alternative(b));
-      TRY(enter_child(&child));
-      if (child == 1 || child == 2) status = child;
-    }
-    *out = status;
-    return PCP_OK;
+  bool stopped = false, exhausted_reported = false;
+  std::chrono::steady_clock::time_point t_mark;
+
+  // OneSolution::enter (one_solution.rs:92-105) / AllSolution::enter (all_solution.rs:41-50),
+  // resumable: runs at most `max_nodes` further nodes.
+  // *out: 0 budget slice used up (search still open), 1 Satisfiable (one-solution mode; call
+  // again for the next solution), -1 Unsatisfiable (tree exhausted, one-solution mode),
+  // 2 EndOfSearch (StopNode limit, or tree exhausted in all-solutions mode).
+  int step(uint64_t max_nodes, int* out) {
+    t_mark = std::chrono::steady_clock::now();
+    t_start = t_mark;
+    int rc = step_inner(max_nodes, out);
+    if (res->num_nodes > (uint64_t)cfg->warmup_nodes)
+      res->seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    res->status = *out;
+    return rc;
   }
 
-  int run() {
-    TRY(pcp_num_vars(e, &V));
-    lo.assign((size_t)V, 0);
-    hi.assign((size_t)V, 0);
-    int status = 0;
-    TRY(one_solution(&status));
-    if (cfg->all_solutions)  // all_solution.rs:41-50
-      while (status != 2) TRY(one_solution(&status));
-    res->status = status;
-    return PCP_OK;
+  int step_inner(uint64_t max_nodes, int* out) {
+    const uint64_t start = res->num_nodes;
+    if (V == 0 && !started) {
+      TRY(pcp_num_vars(e, &V));
+      lo.assign((size_t)V, 0);
+      hi.assign((size_t)V, 0);
+    }
+    if (stopped) { *out = 2; return PCP_OK; }
+    while (true) {
+      if (started && queue.empty()) {  // fully explored (one_solution.rs:66-68)
+        if (cfg->all_solutions || exhausted_reported) *out = 2;
+        else { exhausted_reported = true; *out = -1; }
+        return PCP_OK;
+      }
+      if (res->num_nodes - start >= max_nodes) { *out = 0; return PCP_OK; }
+      int child = 0;
+      if (!started) {
+        started = true;
+      } else {
+        Branch b = queue.back();
+        queue.pop_back();
+        TRY(pcp_restore(e, b.label));  // Branch::commit (branch.rs:51-55)
+        TRY(apply_alternative(b));
+      }
+      TRY(enter_child(&child));
+      if (child == 2) { stopped = true; *out = 2; return PCP_OK; }
+      if (child == 1 && !cfg->all_solutions) { *out = 1; return PCP_OK; }
+    }
   }
 };
 
 }  // namespace
 
-extern "C" int pcp_search_run(pcp_engine* e, const pcp_search_config* cfg, pcp_search_result* res,
-                              int32_t* trace_status, uint64_t* trace_hash, int32_t* trace_lo,
-                              int32_t* trace_hi, uint64_t trace_capacity) {
-  if (!e || !cfg || !res) return PCP_ERR_INVALID;
-  std::memset(res, 0, sizeof(*res));
-  Driver d{e, cfg, res, trace_status, trace_lo, trace_hi, trace_hash, trace_capacity};
-  auto t0 = std::chrono::steady_clock::now();
-  int rc = d.run();
-  res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+struct pcp_search {
+  pcp_search_config cfg;
+  pcp_search_result res;
+  Driver d;
+};
+
+extern "C" {
+
+int pcp_search_open(pcp_engine* e, const pcp_search_config* cfg, int32_t* trace_status, uint64_t* trace_hash,
+                    int32_t* trace_lo, int32_t* trace_hi, uint64_t trace_capacity, pcp_search** out) {
+  if (!e || !cfg || !out) return PCP_ERR_INVALID;
+  pcp_search* s = new pcp_search{*cfg, {}, {}};
+  std::memset(&s->res, 0, sizeof(s->res));
+  s->d = Driver{e, &s->cfg, &s->res, trace_status, trace_lo, trace_hi, trace_hash, trace_capacity};
+  *out = s;
+  return PCP_OK;
+}
+
+int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res) {
+  if (!s) return PCP_ERR_INVALID;
+  int status = 0;
+  int rc = s->d.step(max_nodes ? max_nodes : ~0ull, &status);
+  if (res) *res = s->res;
   return rc;
 }
+
+void pcp_search_close(pcp_search* s) { delete s; }
+
+int pcp_search_run(pcp_engine* e, const pcp_search_config* cfg, pcp_search_result* res, int32_t* trace_status,
+                   uint64_t* trace_hash, int32_t* trace_lo, int32_t* trace_hi, uint64_t trace_capacity) {
+  if (!e || !cfg || !res) return PCP_ERR_INVALID;
+  pcp_search* s = nullptr;
+  int rc = pcp_search_open(e, cfg, trace_status, trace_hash, trace_lo, trace_hi, trace_capacity, &s);
+  if (rc != PCP_OK) return rc;
+  // AllSolution keeps calling its child until EndOfSearch; OneSolution returns at the first solution
+  rc = pcp_search_step(s, 0, res);
+  pcp_search_close(s);
+  return rc;
+}
+
+}  // extern "C"

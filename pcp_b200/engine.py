@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._capi import Config, EngineBase, PcpError, bind
+from ._capi import Config, EngineBase, PcpError, SearchConfig, SearchResult, bind
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcp_b200.so")
@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_vars_alloc",
     "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_consistency", "pcp_domains_read",
     "pcp_var_update", "pcp_active_read", "pcp_label", "pcp_restore", "pcp_num_vars", "pcp_num_props",
-    "pcp_search_run",
+    "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_close",
 ]
 
 _lib = None
@@ -42,6 +42,14 @@ def load_library() -> C.CDLL:
         lib.pcp_engine_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         lib.pcp_set_timing.restype = C.c_int
         lib.pcp_set_timing.argtypes = [C.c_void_p, C.c_int32]
+        i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        lib.pcp_search_open.restype = C.c_int
+        lib.pcp_search_open.argtypes = [C.c_void_p, C.POINTER(SearchConfig), i32p, u64p, i32p, i32p, C.c_uint64,
+                                        C.POINTER(C.c_void_p)]
+        lib.pcp_search_step.restype = C.c_int
+        lib.pcp_search_step.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SearchResult)]
+        lib.pcp_search_close.restype = None
+        lib.pcp_search_close.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 
@@ -65,3 +73,38 @@ class Engine(EngineBase):
 
     def set_timing(self, enabled: bool) -> None:
         self._check(self._lib.pcp_set_timing(self._h, int(enabled)))
+
+    def search_open(self, node_limit: int = 0, all_solutions: bool = False, var_sel: int = 0, val_sel: int = 0,
+                    distributor: int = 0, bb_mode: int = 0, bb_var: int = 0, warmup_nodes: int = 0) -> "SearchHandle":
+        """Resumable search (pcp_search_open/step/close): the host can exchange a stop /
+        incumbent word with other ranks between budget slices."""
+        cfg = SearchConfig(node_limit, int(all_solutions), var_sel, val_sel, distributor, bb_mode, bb_var, 0,
+                           warmup_nodes)
+        return SearchHandle(self, cfg)
+
+
+class SearchHandle:
+    def __init__(self, engine: Engine, cfg: SearchConfig):
+        self._engine = engine
+        self._lib = engine._lib
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        rc = self._lib.pcp_search_open(engine._h, C.byref(cfg), None, None, None, None, 0, C.byref(self._h))
+        engine._check(rc)
+
+    def step(self, max_nodes: int = 0) -> SearchResult:
+        """Run at most `max_nodes` more nodes; `.status` 0 = still open (see pcp_b200.h)."""
+        res = SearchResult()
+        self._engine._check(self._lib.pcp_search_step(self._h, max_nodes, C.byref(res)))
+        return res
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.pcp_search_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

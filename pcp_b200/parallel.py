@@ -1,0 +1,158 @@
+"""Subtree sharding of the search across GPUs / host workers.
+
+One fixpoint is a single global computation and is never split; what shards is the search
+tree: sibling subtrees are independent (a child is `restore(label)` + one branching
+constraint, reference search/branching/branch.rs:51-55).  The root is expanded breadth-first
+into at least `parts` open nodes; a node travels as its decision path
+`[(var, val, alternative)]` and is rebuilt on the owning engine by replaying the path
+(recomputation), so nothing but a few integers crosses ranks.  The only collective on the
+path is a 1 x int32 all-reduce of the "solution found" / incumbent word (NCCL on GPUs,
+gloo in the CPU tests), issued every `sync_every` nodes.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from . import models
+
+Decision = Tuple[int, int, int]  # (var, val, alternative): alternative 0 = x <= val, 1 = x > val
+
+
+def post_decision(engine, d: Decision) -> None:
+    """BinarySplit's alternatives (search/branching/binary_split.rs:46-57)."""
+    var, val, alt = d
+    if alt == 0:
+        engine.prop_alloc(models.X_LESS_Y, [[var, 0], [models.VAR_CONSTANT, val + 1]])  # x <= val
+    else:
+        engine.prop_alloc(models.X_LESS_Y, [[models.VAR_CONSTANT, val], [var, 0]])      # x > val
+
+
+def select_branch(lo: np.ndarray, hi: np.ndarray) -> Tuple[int, int]:
+    """FirstSmallestVar + MiddleVal (first_smallest_var.rs:30-39, middle_val.rs:25-27)."""
+    size = hi.astype(np.int64) - lo.astype(np.int64) + 1
+    cand = np.where(size > 1, size, np.iinfo(np.int64).max)
+    var = int(np.argmin(cand))  # argmin returns the first minimum
+    s = int(lo[var]) + int(hi[var])
+    val = int(s / 2)            # truncating division, like Rust's `/` on i32
+    return var, val
+
+
+def expand_frontier(engine, parts: int, max_expansions: int = 4096) -> List[List[Decision]]:
+    """Breadth-first expansion of the root into >= `parts` open nodes (decision paths).
+
+    `engine` holds the loaded model at its root state.  Deterministic: every rank computes
+    the same frontier and takes its own slice.  The engine is left at the root state."""
+    st, _ = engine.consistency()
+    root = engine.label()
+    if st != 0:
+        engine.restore(root)
+        return [[]]
+    frontier: List[List[Decision]] = [[]]
+    closed: List[List[Decision]] = []
+    n = 0
+    while len(frontier) + len(closed) < parts and frontier and n < max_expansions:
+        path = frontier.pop(0)
+        engine.restore(root)
+        for d in path:
+            post_decision(engine, d)
+        st, _ = engine.consistency()
+        n += 1
+        if st != 0:
+            if st == 1:
+                closed.append(path)  # a solution leaf still counts as a unit of work
+            continue
+        lo, hi = engine.domains()
+        var, val = select_branch(lo, hi)
+        frontier.append(path + [(var, val, 0)])
+        frontier.append(path + [(var, val, 1)])
+    engine.restore(root)
+    return frontier + closed
+
+
+def my_slice(paths: Sequence[List[Decision]], rank: int, world: int) -> List[List[Decision]]:
+    """Static round-robin assignment of frontier nodes to ranks."""
+    return [p for i, p in enumerate(paths) if i % world == rank]
+
+
+def enter_subtree(engine, root_label: int, path: Sequence[Decision]) -> None:
+    """Rebuild a frontier node on this engine: restore the root and replay its decisions."""
+    engine.restore(root_label)
+    for d in path:
+        post_decision(engine, d)
+
+
+class StopFlag:
+    """The one-word collective of the path: max-reduce of a `found` flag (or min/max of an
+    incumbent for BranchAndBound, search/branch_and_bound.rs:76-92) over all ranks."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self._dist = dist if dist.is_available() and dist.is_initialized() else None
+        self._t = torch.zeros(1, dtype=torch.int32, device=device if device is not None else "cpu")
+
+    def exchange(self, local_value: int, op: str = "max") -> int:
+        """All-reduce one int32; returns the global value (identity without a process group)."""
+        self._t.fill_(int(local_value))
+        if self._dist is not None:
+            ops = {"max": self._dist.ReduceOp.MAX, "min": self._dist.ReduceOp.MIN, "sum": self._dist.ReduceOp.SUM}
+            self._dist.all_reduce(self._t, op=ops[op])
+        return int(self._t.item())
+
+
+def sharded_search(engine, rank: int, world: int, node_budget: int, sync_every: int = 64, stop_flag=None,
+                   stop_on_solution: bool = False, warmup_nodes: int = 0, parts_per_rank: int = 4):
+    """Run this rank's share of a sharded DFS.
+
+    Every rank expands the same frontier, takes its round-robin slice and spends `node_budget`
+    nodes on it, subtree after subtree, in rounds of `sync_every` nodes; after each round the
+    stop word is exchanged (every rank executes the same number of rounds, so the collective
+    always matches).  Returns a dict of counters; `seconds` is host wall clock inside the
+    search driver, `kernel_seconds` device time of the fixpoint launches."""
+    paths = expand_frontier(engine, parts=max(world, 1) * parts_per_rank)
+    mine = my_slice(paths, rank, world)
+    root = engine.label()
+    out = {"nodes": 0, "propagations": 0, "iterations": 0, "solutions": 0, "seconds": 0.0, "kernel_seconds": 0.0,
+           "subtrees": 0, "frontier": len(paths), "stopped": False}
+    keys = (("nodes", "num_nodes"), ("propagations", "propagations"), ("iterations", "iterations"),
+            ("solutions", "num_solution"), ("seconds", "seconds"), ("kernel_seconds", "kernel_seconds"))
+    rounds = (node_budget + sync_every - 1) // sync_every
+    handle, prev, idx, found = None, None, 0, 0
+    for _ in range(rounds):
+        round_used = 0
+        while round_used < sync_every and out["nodes"] < node_budget:
+            if handle is None:
+                if idx >= len(mine):
+                    break
+                enter_subtree(engine, root, mine[idx])
+                idx += 1
+                handle = engine.search_open(all_solutions=not stop_on_solution,
+                                            warmup_nodes=warmup_nodes if out["subtrees"] == 0 else 0)
+                prev = {k: 0 for k, _ in keys}
+                out["subtrees"] += 1
+            before = out["nodes"]
+            res = handle.step(min(sync_every - round_used, node_budget - out["nodes"]))
+            for k, attr in keys:
+                cur = getattr(res, attr)
+                out[k] += cur - prev[k]
+                prev[k] = cur
+            round_used += out["nodes"] - before
+            if res.status == 1 and stop_on_solution:
+                found = 1
+            if res.status != 0:
+                handle.close()
+                handle = None
+            if found:
+                break
+        if stop_flag is not None:
+            if stop_flag.exchange(found):
+                out["stopped"] = True
+                break
+        elif found:
+            out["stopped"] = True
+            break
+    if handle is not None:
+        handle.close()
+    return out

@@ -261,7 +261,7 @@ def test_small_tail_limit_rebuilds_csr(tail_limit):
                                    models.nqueens(9, "distinct")], ids=lambda m: m.name)
 def test_incremental_mode_same_fixpoints(model):
     """PCP_FLAG_INCREMENTAL: same per-node domains and statuses, fewer propagations."""
-    limit = 0 if model.num_vars <= 20 else 200
+    limit = 0 if model.name.startswith("nqueens-9") else 250
     rd, ro, _, _ = _compare_search(model, limit, dev_kw={"incremental": True})
     dev_full = _engine()
     model.load_into(dev_full)
