@@ -5,10 +5,13 @@
 // (reference src/libpcp/propagation/store.rs:247-257): one CTA per SM, a device-wide
 // barrier between iterations, quiescence detected by the last CTA to arrive.
 //
+//   prologue      Snapshot::restore + Store::alloc of the few propagators posted since the
+//                 last call (CTA 0), overlapped with the first descriptor loads.
 //   iteration 0   every active propagator is evaluated once (store.rs:144-149 schedules
-//                 all active propagators): a streaming scan over the per-family descriptor
-//                 arrays with 128-bit coalesced loads, domains gathered from a
-//                 shared-memory snapshot (small V) or from L2 (large V).
+//                 all active propagators).  The per-family descriptor arrays are streamed
+//                 from HBM by TMA bulk copies (cp.async.bulk + mbarrier, 4-stage ring in
+//                 shared memory, one producer warp, 31 consumer warps); domains are read
+//                 from a shared-memory snapshot (V <= ~12k) or gathered from L2.
 //   iteration k   only propagators adjacent to variables that changed in iteration k-1
 //                 are re-evaluated (store.rs:191-198 `react`): the dirty variables sit in
 //                 a warp-aggregated worklist, their rows of the static var->propagator
@@ -27,8 +30,18 @@ namespace pcpd {
 
 constexpr int kThreads = 1024;          // one CTA per SM
 constexpr int kWarps = kThreads / 32;
-constexpr int kUnroll = 4;              // descriptor loads in flight per thread
+constexpr int kConsumerWarps = kWarps - 1;  // warp 0 drives the TMA ring
+constexpr int kStages = 4;
+constexpr int kStageBytes = 32768;
+constexpr int kRingBytes = kStages * kStageBytes;
+// propagators per ring stage: multiples of 32 * kConsumerWarps so every consumer warp gets
+// whole 32-propagator groups (aligned with the words of the `active` bit set)
+constexpr int kChunkBin = 1984;         // 1984 * 16 B = 31744 B
+constexpr int kChunkTer = 992;          // 992 * 16 B + 992 * 8 B
+constexpr int kChunkDj = 480;           // 480 * 48 B = 23040 B
+constexpr int kTerPlaneB = 16384;       // offset of the z plane inside a stage
 constexpr unsigned kConstVar28 = 0x0FFFFFFFu;
+constexpr int kMaxInline = 4;
 
 // family tags inside adjacency / trail references (top 3 bits)
 enum Fam : unsigned { F_BIN = 0, F_TER = 1, F_DJ = 2, F_NARY = 3 };
@@ -67,12 +80,19 @@ struct Result {
 static_assert(sizeof(Result) == 64, "Result header is 64 bytes");
 
 struct Family {
-  const int4* desc;     // BIN: 1 int4/prop; TER: int4 (x,y) plane; DJ: 3 int4/prop
-  const int2* descB;    // TER: (z) plane
+  int4* desc;           // BIN: 1 int4/prop; TER: int4 (x,y) plane; DJ: 3 int4/prop
+  int2* descB;          // TER: (z) plane
   uint32_t* active;     // bit set, 1 = active (propagation/store.rs:34)
   uint32_t* stamp;      // epoch of the last worklist evaluation
   int n;                // allocated propagators
   int n_static;         // [0, n_static) are covered by the CSR; [n_static, n) is the tail
+};
+
+struct InlineProp {     // a propagator posted since the last launch, carried in the launch
+  int4 q[3];            // parameters instead of a separate H2D copy
+  unsigned fam;
+  int slot;
+  int pad[2];
 };
 
 struct Params {
@@ -80,7 +100,7 @@ struct Params {
   int2* dom;            // interval per variable: (lo, hi)
   int V;
   int smem_dom;         // 1: domains are staged in shared memory
-  Family bin, ter, dj;
+  Family fam[3];        // BIN, TER, DJ
   const int* nary_ptr;  // CSR of n-ary Distinct operands
   const int2* nary_ops;
   uint32_t* nary_active;
@@ -94,10 +114,22 @@ struct Params {
   Control* ctl;
   int full_sweep;       // 1: schedule every active propagator first (store.rs:144-149)
   unsigned max_iterations;
+  // ---- node prologue (Snapshot::restore + Store::alloc), executed by CTA 0
+  const int2* restore_from;   // label copy of the domains, or nullptr
+  unsigned trail_keep;        // trail length recorded in the label
+  int do_trail;               // 1: re-activate trail entries >= trail_keep (store.rs:319-323)
+  int sync0;                  // 1: the prologue has cross-CTA effects -> barrier before use
+  uint32_t* nary_active_w;    // == nary_active (writable alias for the prologue)
+  int new_first[4], new_last[4];  // slots whose active bit must be set (per family)
+  int n_inline;
+  InlineProp inl[kMaxInline];
+  int seed_dirty;             // incremental launch: dirty_list[0..seed_dirty) seeded by the host
+  // ---- epilogue
+  int2* snapshot_to;          // if not failed: copy of the fixpoint domains (next label slot)
 };
 
 // ---------------------------------------------------------------------------------------
-// memory helpers
+// memory / async helpers
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -110,21 +142,45 @@ __device__ __forceinline__ unsigned lanemask_lt() {
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
 }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+// TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct IV { int lo, hi; };
 
-// Per-thread context of one fixpoint launch.
+// Per-thread context of one fixpoint launch (read-mostly; counters live in registers).
 struct Ctx {
   const Params* P;
   int2* sdom;             // shared-memory snapshot (or nullptr)
   unsigned next_epoch;    // stamp for "dirty in the next iteration"
   int next_buf;           // dirty list written in this iteration
-  unsigned nprop;         // propagations executed by this thread
-  bool count;             // false for redundant (all-CTA) tail evaluations
+  bool local;             // updates go to the shared-memory snapshot only (inline props, non-CTA-0)
+  bool mark_dirty;        // narrowed variables enter the worklist
+  bool bookkeep;          // entailed propagators are deactivated + trailed
 };
 
 // warp-aggregated append to the dirty-variable worklist
-__device__ __forceinline__ void push_dirty(Ctx& c, int v) {
+__device__ __forceinline__ void push_dirty(const Ctx& c, int v) {
   const Params& P = *c.P;
   if (atomicExch(&P.dirty_stamp[v], c.next_epoch) == c.next_epoch) return;  // already queued
   unsigned m = __activemask();
@@ -137,9 +193,9 @@ __device__ __forceinline__ void push_dirty(Ctx& c, int v) {
 }
 
 // warp-aggregated append to the entailment trail + clear of the active bit
-__device__ __forceinline__ void deactivate(Ctx& c, const Family& f, unsigned fam, int slot) {
+__device__ __forceinline__ void deactivate(const Ctx& c, uint32_t* active, unsigned fam, int slot) {
   unsigned bit = 1u << (slot & 31);
-  unsigned old = atomicAnd(&f.active[slot >> 5], ~bit);
+  unsigned old = atomicAnd(&active[slot >> 5], ~bit);
   if (!(old & bit)) return;
   unsigned m = __activemask();
   int leader = __ffs(m) - 1;
@@ -150,7 +206,7 @@ __device__ __forceinline__ void deactivate(Ctx& c, const Family& f, unsigned fam
   c.P->trail[base + __popc(m & lanemask_lt())] = make_ref(fam, (unsigned)slot);
 }
 
-__device__ __forceinline__ void set_failed(Ctx& c) { c.P->ctl->failed = 1; }
+__device__ __forceinline__ void set_failed(const Ctx& c) { c.P->ctl->failed = 1; }
 
 // Domain readers.  `SMEM` reads the CTA's snapshot, otherwise L2 (ld.global.cg).
 template <bool SMEM>
@@ -163,9 +219,13 @@ __device__ __forceinline__ IV rd(const Ctx& c, int var, int off) {
 // Monotone update of one view to [nlo, nhi] (already intersected with `cur`):
 // variable/store.rs:151-166 through term/addition.rs:80-90 / term/constant.rs:43-53.
 // Returns false when the new domain is empty (update -> false).
-__device__ __forceinline__ bool tighten(Ctx& c, int var, int off, IV cur, int nlo, int nhi) {
+__device__ __forceinline__ bool tighten(const Ctx& c, int var, int off, IV cur, int nlo, int nhi) {
   if (nlo > nhi) return false;
   if (var >= 0) {
+    if (c.local) {
+      if (nlo > cur.lo || nhi < cur.hi) c.sdom[var] = make_int2(nlo - off, nhi - off);
+      return true;
+    }
     int2* d = &c.P->dom[var];
     bool ch = false;
     if (nlo > cur.lo) ch |= atomicMax(&d->x, nlo - off) < nlo - off;
@@ -173,7 +233,7 @@ __device__ __forceinline__ bool tighten(Ctx& c, int var, int off, IV cur, int nl
     if (ch) {
       int2 now = ldcg_dom(d);
       if (now.x > now.y) set_failed(c);
-      push_dirty(c, var);
+      if (c.mark_dirty) push_dirty(c, var);
     }
   }
   return true;
@@ -182,13 +242,16 @@ __device__ __forceinline__ bool tighten(Ctx& c, int var, int off, IV cur, int nl
 // Result of evaluating one propagator: propagate + is_subsumed (store.rs:177-183).
 enum Eval : int { E_FAIL = -1, E_UNKNOWN = 0, E_ENTAILED = 1 };
 
+__device__ __forceinline__ int dec_var28(unsigned w0) {
+  unsigned v = w0 & kConstVar28;
+  return v == kConstVar28 ? -1 : (int)v;
+}
+
 // --- binary family: XLessY / XNeqY / XEqY ---------------------------------------------------
 template <bool SMEM>
-__device__ __forceinline__ Eval eval_bin(Ctx& c, int4 d) {
-  unsigned w0 = (unsigned)d.x;
-  unsigned kind = w0 >> 28;
-  int xv = (w0 & kConstVar28) == kConstVar28 ? -1 : (int)(w0 & kConstVar28);
-  int xo = d.y, yv = d.z, yo = d.w;
+__device__ __forceinline__ Eval eval_bin(const Ctx& c, int4 d) {
+  unsigned kind = (unsigned)d.x >> 28;
+  int xv = dec_var28((unsigned)d.x), xo = d.y, yv = d.z, yo = d.w;
   IV x = rd<SMEM>(c, xv, xo), y = rd<SMEM>(c, yv, yo);
   if (kind == B_NEQ) {  // cmp/x_neq_y.rs:82-93 + Interval::difference
     IV nx = x, ny = y;
@@ -214,14 +277,20 @@ __device__ __forceinline__ Eval eval_bin(Ctx& c, int4 d) {
     return lo == hi ? E_ENTAILED : E_UNKNOWN;     // x_eq_y.rs:84-93
   }
 }
+// true when evaluating the propagator would change nothing: no pruning, no failure,
+// not entailed (the common case of a sweep; keeps the hot loop free of calls)
+__device__ __forceinline__ bool bin_is_noop(unsigned kind, IV x, IV y) {
+  if (kind == B_NEQ) return x.lo != x.hi && y.lo != y.hi && !(x.hi < y.lo || y.hi < x.lo);
+  if (kind == B_LESS) return y.hi > x.hi && x.lo < y.lo && x.hi >= y.lo;
+  return x.lo == y.lo && x.hi == y.hi && x.lo < x.hi;
+}
 
 // --- ternary family ------------------------------------------------------------------------
 struct Tri { int xv, xo, yv, yo, zv, zo; };
 
 // XGreaterYPlusZ::propagate on local copies (x_greater_y_plus_z.rs:106-119); `strict`=1 for
 // x > y+z, 0 for x >= y+z (the Addition(x,1) of cmp/mod.rs:73).
-template <bool SMEM>
-__device__ __forceinline__ bool prop_greater(Ctx& c, const Tri& t, IV& x, IV& y, IV& z, int strict) {
+__device__ __forceinline__ bool prop_greater(const Ctx& c, const Tri& t, IV& x, IV& y, IV& z, int strict) {
   int nxlo = max(x.lo, y.lo + z.lo + strict);
   int nyhi = min(y.hi, x.hi - z.lo - strict);
   int nzhi = min(z.hi, x.hi - y.lo - strict);
@@ -232,8 +301,7 @@ __device__ __forceinline__ bool prop_greater(Ctx& c, const Tri& t, IV& x, IV& y,
   return true;
 }
 // XLessYPlusZ::propagate (x_less_y_plus_z.rs:106-120)
-template <bool SMEM>
-__device__ __forceinline__ bool prop_less(Ctx& c, const Tri& t, IV& x, IV& y, IV& z, int strict) {
+__device__ __forceinline__ bool prop_less(const Ctx& c, const Tri& t, IV& x, IV& y, IV& z, int strict) {
   int nxhi = min(x.hi, y.hi + z.hi - strict);
   int nylo = max(y.lo, x.lo - z.hi + strict);
   int nzlo = max(z.lo, x.lo - y.hi + strict);
@@ -259,36 +327,41 @@ __device__ __forceinline__ int sub_eq(IV x, IV y, IV z) {
   return min(sub_greater(x, y, z, 0), sub_less(x, y, z, 0));
 }
 // XEqYPlusZ::propagate = geq then leq re-reading the store (x_eq_y_plus_z.rs:79-81)
-template <bool SMEM>
-__device__ __forceinline__ bool prop_eq(Ctx& c, const Tri& t, IV& x, IV& y, IV& z) {
-  return prop_greater<SMEM>(c, t, x, y, z, 0) && prop_less<SMEM>(c, t, x, y, z, 0);
+__device__ __forceinline__ bool prop_eq(const Ctx& c, const Tri& t, IV& x, IV& y, IV& z) {
+  return prop_greater(c, t, x, y, z, 0) && prop_less(c, t, x, y, z, 0);
 }
 
 template <bool SMEM>
-__device__ __forceinline__ Eval eval_ter(Ctx& c, int4 a, int2 b) {
-  unsigned w0 = (unsigned)a.x;
-  unsigned kind = w0 >> 28;
-  Tri t;
-  t.xv = (w0 & kConstVar28) == kConstVar28 ? -1 : (int)(w0 & kConstVar28);
-  t.xo = a.y; t.yv = a.z; t.yo = a.w; t.zv = b.x; t.zo = b.y;
+__device__ __forceinline__ Eval eval_ter(const Ctx& c, int4 a, int2 b) {
+  unsigned kind = (unsigned)a.x >> 28;
+  Tri t{dec_var28((unsigned)a.x), a.y, a.z, a.w, b.x, b.y};
   IV x = rd<SMEM>(c, t.xv, t.xo), y = rd<SMEM>(c, t.yv, t.yo), z = rd<SMEM>(c, t.zv, t.zo);
   int s;
   if (kind == T_EQ) {
-    if (!prop_eq<SMEM>(c, t, x, y, z)) return E_FAIL;
+    if (!prop_eq(c, t, x, y, z)) return E_FAIL;
     s = sub_eq(x, y, z);
   } else if (kind == T_GREATER) {
-    if (!prop_greater<SMEM>(c, t, x, y, z, 1)) return E_FAIL;
+    if (!prop_greater(c, t, x, y, z, 1)) return E_FAIL;
     s = sub_greater(x, y, z, 1);
   } else {
-    if (!prop_less<SMEM>(c, t, x, y, z, 1)) return E_FAIL;
+    if (!prop_less(c, t, x, y, z, 1)) return E_FAIL;
     s = sub_less(x, y, z, 1);
   }
   return s < 0 ? E_FAIL : (s > 0 ? E_ENTAILED : E_UNKNOWN);
 }
+__device__ __forceinline__ bool ter_is_noop(unsigned kind, IV x, IV y, IV z) {
+  if (kind == T_EQ)
+    return x.lo >= y.lo + z.lo && y.hi <= x.hi - z.lo && z.hi <= x.hi - y.lo &&
+           x.hi <= y.hi + z.hi && y.lo >= x.lo - z.hi && z.lo >= x.lo - y.hi && sub_eq(x, y, z) == 0;
+  if (kind == T_GREATER)
+    return x.lo >= y.lo + z.lo + 1 && y.hi <= x.hi - z.lo - 1 && z.hi <= x.hi - y.lo - 1 &&
+           sub_greater(x, y, z, 1) == 0;
+  return x.hi <= y.hi + z.hi - 1 && y.lo >= x.lo - z.hi + 1 && z.lo >= x.lo - y.hi + 1 && sub_less(x, y, z, 1) == 0;
+}
 
 // --- 2-way disjunction of XEqYPlusZ (logic/disjunction.rs:77-116) ---------------------------
 template <bool SMEM>
-__device__ __forceinline__ Eval eval_dj(Ctx& c, int4 q0, int4 q1, int4 q2) {
+__device__ __forceinline__ Eval eval_dj(const Ctx& c, int4 q0, int4 q1, int4 q2) {
   Tri a{q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
   Tri b{q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
   IV ax = rd<SMEM>(c, a.xv, a.xo), ay = rd<SMEM>(c, a.yv, a.yo), az = rd<SMEM>(c, a.zv, a.zo);
@@ -298,32 +371,57 @@ __device__ __forceinline__ Eval eval_dj(Ctx& c, int4 q0, int4 q1, int4 q2) {
   if (sa < 0 && sb < 0) return E_FAIL;              // disjunction.rs:110-111
   if (sa == 0 && sb == 0) return E_UNKNOWN;         // disjunction.rs:112-114
   if (sa < 0) {                                     // disjunction.rs:108-109
-    if (!prop_eq<SMEM>(c, b, bx, by, bz)) return E_FAIL;
+    if (!prop_eq(c, b, bx, by, bz)) return E_FAIL;
     sb = sub_eq(bx, by, bz);
     return sb < 0 ? E_FAIL : (sb > 0 ? E_ENTAILED : E_UNKNOWN);
   }
-  if (!prop_eq<SMEM>(c, a, ax, ay, az)) return E_FAIL;
+  if (!prop_eq(c, a, ax, ay, az)) return E_FAIL;
   sa = sub_eq(ax, ay, az);
   return sa < 0 ? E_FAIL : (sa > 0 ? E_ENTAILED : E_UNKNOWN);
 }
-
-__device__ __forceinline__ void finish(Ctx& c, Eval r, const Family& f, unsigned fam, int slot) {
-  if (c.count) c.nprop++;
-  if (r == E_FAIL) set_failed(c);
-  else if (r == E_ENTAILED && c.count) deactivate(c, f, fam, slot);  // store.rs:200-207 unlink_prop
+template <bool SMEM>
+__device__ __forceinline__ bool dj_is_noop(const Ctx& c, int4 q0, int4 q1, int4 q2) {
+  IV ax = rd<SMEM>(c, q0.x, q0.y), ay = rd<SMEM>(c, q0.z, q0.w), az = rd<SMEM>(c, q1.x, q1.y);
+  IV bx = rd<SMEM>(c, q1.z, q1.w), by = rd<SMEM>(c, q2.x, q2.y), bz = rd<SMEM>(c, q2.z, q2.w);
+  return sub_eq(ax, ay, az) == 0 && sub_eq(bx, by, bz) == 0;
 }
 
+// The out-of-line slow path: full propagate + is_subsumed of one propagator, with the
+// store bookkeeping of store.rs:166-207 (failure flag, unlink of entailed propagators).
 template <bool SMEM>
-__device__ __forceinline__ void eval_ref(Ctx& c, unsigned fam, int slot) {
-  const Params& P = *c.P;
+__device__ __noinline__ void eval_full(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
+  Eval r;
+  if (fam == F_BIN) r = eval_bin<SMEM>(c, q0);
+  else if (fam == F_TER) r = eval_ter<SMEM>(c, q0, make_int2(q1.x, q1.y));
+  else r = eval_dj<SMEM>(c, q0, q1, q2);
+  if (r == E_FAIL) set_failed(c);
+  else if (r == E_ENTAILED && c.bookkeep) deactivate(c, c.P->fam[fam].active, fam, slot);
+}
+
+// Evaluate a propagator given by reference (worklist expansion, tail): gathers its
+// descriptor from global memory.
+template <bool SMEM>
+__device__ __forceinline__ void eval_ref(const Ctx& c, unsigned fam, int slot) {
+  const Family& f = c.P->fam[fam];
+  int4 q0, q1 = make_int4(0, 0, 0, 0), q2 = q1;
   if (fam == F_BIN) {
-    finish(c, eval_bin<SMEM>(c, __ldg(&P.bin.desc[slot])), P.bin, F_BIN, slot);
+    q0 = __ldg(&f.desc[slot]);
+    unsigned kind = (unsigned)q0.x >> 28;
+    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w);
+    if (bin_is_noop(kind, x, y)) return;
   } else if (fam == F_TER) {
-    finish(c, eval_ter<SMEM>(c, __ldg(&P.ter.desc[slot]), __ldg(&P.ter.descB[slot])), P.ter, F_TER, slot);
+    q0 = __ldg(&f.desc[slot]);
+    int2 b = __ldg(&f.descB[slot]);
+    q1.x = b.x; q1.y = b.y;
+    unsigned kind = (unsigned)q0.x >> 28;
+    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w), z = rd<SMEM>(c, b.x, b.y);
+    if (ter_is_noop(kind, x, y, z)) return;
   } else {
-    const int4* q = &P.dj.desc[3 * (size_t)slot];
-    finish(c, eval_dj<SMEM>(c, __ldg(q), __ldg(q + 1), __ldg(q + 2)), P.dj, F_DJ, slot);
+    const int4* q = &f.desc[3 * (size_t)slot];
+    q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
+    if (dj_is_noop<SMEM>(c, q0, q1, q2)) return;
   }
+  eval_full<SMEM>(c, fam, slot, q0, q1, q2);
 }
 
 __device__ __forceinline__ bool is_active(const Family& f, int slot) {
@@ -331,71 +429,95 @@ __device__ __forceinline__ bool is_active(const Family& f, int slot) {
 }
 
 // ---------------------------------------------------------------------------------------
-// iteration 0: streaming sweep over one family's static range, kUnroll x 32 propagators per
-// warp step (coalesced 128-bit descriptor loads, all issued before the first use).
+// iteration 0: the streaming sweep.  A chunk = up to kChunk* propagators of one family;
+// chunk g belongs to CTA g % gridDim.x.  Warp 0 (one lane) is the producer: it arms the
+// stage's `full` mbarrier with the byte count and issues the TMA bulk copies; the 31
+// consumer warps wait on `full`, evaluate from shared memory and release the stage through
+// the `empty` mbarrier.
 // ---------------------------------------------------------------------------------------
-template <bool SMEM, unsigned FAM>
-__device__ __forceinline__ void sweep_family(Ctx& c, const Family& f) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * kWarps;
-  const int n = f.n_static;
-  constexpr int kChunk = 32 * kUnroll;
-  for (long long base = warp * kChunk; base < n; base += nwarps * kChunk) {
-    uint32_t aw[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      long long p = base + u * 32;
-      aw[u] = p < n ? __ldcg(&f.active[p >> 5]) : 0u;
-    }
-    if (FAM == F_BIN) {
-      int4 d[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        int p = (int)base + u * 32 + lane;
-        if (p < n && ((aw[u] >> lane) & 1u)) d[u] = __ldg(&f.desc[p]);
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        int p = (int)base + u * 32 + lane;
-        if (p < n && ((aw[u] >> lane) & 1u)) finish(c, eval_bin<SMEM>(c, d[u]), f, F_BIN, p);
-      }
-    } else if (FAM == F_TER) {
-      int4 a[kUnroll];
-      int2 b[kUnroll];
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        int p = (int)base + u * 32 + lane;
-        if (p < n && ((aw[u] >> lane) & 1u)) { a[u] = __ldg(&f.desc[p]); b[u] = __ldg(&f.descB[p]); }
-      }
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        int p = (int)base + u * 32 + lane;
-        if (p < n && ((aw[u] >> lane) & 1u)) finish(c, eval_ter<SMEM>(c, a[u], b[u]), f, F_TER, p);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        int p = (int)base + u * 32 + lane;
-        if (p < n && ((aw[u] >> lane) & 1u)) {
-          const int4* q = &f.desc[3 * (size_t)p];
-          finish(c, eval_dj<SMEM>(c, __ldg(q), __ldg(q + 1), __ldg(q + 2)), f, F_DJ, p);
-        }
-      }
-    }
+struct ChunkMap {
+  int nch[3];   // chunks per family
+  int total;
+};
+__device__ __forceinline__ ChunkMap chunk_map(const Params& P) {
+  ChunkMap m;
+  m.nch[0] = (P.fam[0].n_static + kChunkBin - 1) / kChunkBin;
+  m.nch[1] = (P.fam[1].n_static + kChunkTer - 1) / kChunkTer;
+  m.nch[2] = (P.fam[2].n_static + kChunkDj - 1) / kChunkDj;
+  m.total = m.nch[0] + m.nch[1] + m.nch[2];
+  return m;
+}
+struct Chunk { int fam, base, cnt; };
+__device__ __forceinline__ Chunk chunk_of(const Params& P, const ChunkMap& m, int g) {
+  Chunk c;
+  if (g < m.nch[0]) { c.fam = 0; c.base = g * kChunkBin; c.cnt = min(kChunkBin, P.fam[0].n_static - c.base); }
+  else if (g < m.nch[0] + m.nch[1]) { g -= m.nch[0]; c.fam = 1; c.base = g * kChunkTer; c.cnt = min(kChunkTer, P.fam[1].n_static - c.base); }
+  else { g -= m.nch[0] + m.nch[1]; c.fam = 2; c.base = g * kChunkDj; c.cnt = min(kChunkDj, P.fam[2].n_static - c.base); }
+  return c;
+}
+
+__device__ __forceinline__ void producer_issue(const Params& P, const Chunk& ch, char* stage, uint64_t* full) {
+  const Family& f = P.fam[ch.fam];
+  if (ch.fam == F_BIN) {
+    unsigned bytes = (unsigned)ch.cnt * 16u;
+    mbar_expect_tx(full, bytes);
+    bulk_g2s(stage, f.desc + ch.base, bytes, full);
+  } else if (ch.fam == F_TER) {
+    unsigned ba = (unsigned)ch.cnt * 16u, bb = ((unsigned)ch.cnt * 8u + 15u) & ~15u;
+    mbar_expect_tx(full, ba + bb);
+    bulk_g2s(stage, f.desc + ch.base, ba, full);
+    bulk_g2s(stage + kTerPlaneB, f.descB + ch.base, bb, full);
+  } else {
+    unsigned bytes = (unsigned)ch.cnt * 48u;
+    mbar_expect_tx(full, bytes);
+    bulk_g2s(stage, f.desc + 3 * (size_t)ch.base, bytes, full);
   }
 }
 
-// Tail propagators (allocated after the CSR was built, e.g. the branching constraints of
-// search/branching/binary_split.rs:46-57): evaluated every iteration, straight from L2.
-__device__ __forceinline__ void eval_tail(Ctx& c) {
+template <bool SMEM>
+__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, const Chunk& ch, const char* stage) {
   const Params& P = *c.P;
-  for (int p = P.bin.n_static + threadIdx.x; p < P.bin.n; p += blockDim.x)
-    if (is_active(P.bin, p)) eval_ref<false>(c, F_BIN, p);
-  for (int p = P.ter.n_static + threadIdx.x; p < P.ter.n; p += blockDim.x)
-    if (is_active(P.ter, p)) eval_ref<false>(c, F_TER, p);
-  for (int p = P.dj.n_static + threadIdx.x; p < P.dj.n; p += blockDim.x)
-    if (is_active(P.dj, p)) eval_ref<false>(c, F_DJ, p);
+  const int lane = threadIdx.x & 31;
+  const int cw = (threadIdx.x >> 5) - 1;  // consumer warp index 0..30
+  const Family& f = P.fam[ch.fam];
+  unsigned nprop = 0;
+  for (int j0 = cw * 32; j0 < ch.cnt; j0 += kConsumerWarps * 32) {
+    const int j = j0 + lane;
+    const unsigned word = __ldcg(&f.active[(ch.base + j0) >> 5]);
+    if (j >= ch.cnt || !((word >> lane) & 1u)) continue;
+    const int slot = ch.base + j;
+    ++nprop;
+    if (ch.fam == F_BIN) {
+      int4 d = reinterpret_cast<const int4*>(stage)[j];
+      unsigned kind = (unsigned)d.x >> 28;
+      IV x = rd<SMEM>(c, dec_var28((unsigned)d.x), d.y), y = rd<SMEM>(c, d.z, d.w);
+      if (!bin_is_noop(kind, x, y)) eval_full<SMEM>(c, F_BIN, slot, d, d, d);
+    } else if (ch.fam == F_TER) {
+      int4 a = reinterpret_cast<const int4*>(stage)[j];
+      int2 b = reinterpret_cast<const int2*>(stage + kTerPlaneB)[j];
+      unsigned kind = (unsigned)a.x >> 28;
+      IV x = rd<SMEM>(c, dec_var28((unsigned)a.x), a.y), y = rd<SMEM>(c, a.z, a.w), z = rd<SMEM>(c, b.x, b.y);
+      if (!ter_is_noop(kind, x, y, z)) eval_full<SMEM>(c, F_TER, slot, a, make_int4(b.x, b.y, 0, 0), a);
+    } else {
+      const int4* q = reinterpret_cast<const int4*>(stage) + 3 * j;
+      int4 q0 = q[0], q1 = q[1], q2 = q[2];
+      if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full<SMEM>(c, F_DJ, slot, q0, q1, q2);
+    }
+  }
+  return nprop;
+}
+
+// Tail propagators (allocated after the CSR was built, e.g. the branching constraints of
+// search/branching/binary_split.rs:46-57): evaluated every iteration by CTA 0, from L2.
+__device__ __forceinline__ unsigned eval_tail(const Ctx& c) {
+  const Params& P = *c.P;
+  unsigned n = 0;
+  for (unsigned fam = 0; fam < 3; ++fam) {
+    const Family& f = P.fam[fam];
+    for (int p = f.n_static + threadIdx.x; p < f.n; p += blockDim.x)
+      if (is_active(f, p)) { eval_ref<false>(c, fam, p); ++n; }
+  }
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -404,7 +526,7 @@ __device__ __forceinline__ void eval_tail(Ctx& c) {
 // the singleton operands; two equal singletons fail; every other operand advances
 // lo while lo in S and retreats hi while hi in S; an operand that becomes a singleton
 // joins S.  One CTA per propagator: operands staged in shared memory, S is an
-// open-addressing hash set in shared memory, warp ballots decide the rounds.
+// open-addressing hash set in shared memory, block-wide votes decide the rounds.
 // ---------------------------------------------------------------------------------------
 constexpr int kHashEmpty = INT32_MIN;
 
@@ -431,9 +553,12 @@ __device__ __forceinline__ bool hs_contains(const volatile int* tab, unsigned ma
   }
 }
 
-// smem layout for the n-ary stage (after the optional domain snapshot):
+// smem layout of the n-ary stage (aliases the TMA ring, idle by then):
 //   int2 ops[k]; int2 iv[k] (view-space lo/hi); int tab[tabsz];
-__device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_epoch, bool first_iter) {
+// Returns 1 if the propagator was evaluated (thread 0 only), else 0.
+template <bool SMEM>
+__device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* smem_nary, unsigned cur_epoch,
+                                               bool unconditional) {
   const Params& P = *c.P;
   const int b = __ldg(&P.nary_ptr[slot]), e = __ldg(&P.nary_ptr[slot + 1]);
   const int k = e - b;
@@ -443,13 +568,14 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
   unsigned tabsz = 4;
   while (tabsz < 2u * (unsigned)k) tabsz <<= 1;
   const unsigned mask = tabsz - 1;
+  __syncthreads();  // previous users of the staging area are done
   // stage operands + current domains; is any operand dirty this iteration?
   int any_dirty = 0;
   for (int i = threadIdx.x; i < k; i += blockDim.x) {
     int2 op = __ldg(&P.nary_ops[b + i]);
     ops[i] = op;
     if (op.x >= 0) {
-      int2 d = ldcg_dom(&P.dom[op.x]);
+      int2 d = SMEM ? c.sdom[op.x] : ldcg_dom(&P.dom[op.x]);
       iv[i] = make_int2(d.x + op.y, d.y + op.y);
       if (__ldcg(&P.dirty_stamp[op.x]) == cur_epoch) any_dirty = 1;
     } else {
@@ -457,16 +583,14 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
     }
   }
   for (unsigned i = threadIdx.x; i < tabsz; i += blockDim.x) tab[i] = kHashEmpty;
-  if (!first_iter) {
-    if (!__syncthreads_or(any_dirty)) return;  // nothing it depends on changed (distinct.rs:119-126)
+  if (!unconditional) {
+    if (!__syncthreads_or(any_dirty)) return 0;  // nothing it depends on changed (distinct.rs:119-126)
   } else {
     __syncthreads();
   }
-  // rounds: insert new singletons, then prune bounds against S
-  // inserted[i] is tracked in the sign of ops[i].x? keep a separate pass marker: iv.x > iv.y never
-  // happens for live operands, so we mark "inserted" by remembering it in a register per strided i.
-  // (each thread owns indices i = tid, tid+blockDim, ... for the whole evaluation)
-  unsigned inserted_bits = 0;  // bit j: operand tid + j*blockDim already in S (k <= 32*blockDim)
+  // rounds: insert new singletons, then prune bounds against S.  Each thread owns the operands
+  // i = tid, tid + blockDim, ... for the whole evaluation (k <= 32 * blockDim).
+  unsigned inserted_bits = 0;
   while (true) {
     int fail = 0;
     int j = 0;
@@ -477,10 +601,9 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
         if (!hs_insert(tab, mask, d.x)) fail = 1;  // two equal singletons: XNeqY fails
       }
     }
-    if (__syncthreads_or(fail)) { set_failed(c); if (threadIdx.x == 0 && c.count) c.nprop++; return; }
+    if (__syncthreads_or(fail)) { set_failed(c); return 1; }
     int again = 0;
-    j = 0;
-    for (int i = threadIdx.x; i < k; i += blockDim.x, ++j) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
       int2 d = iv[i];
       if (d.x == d.y) continue;
       int lo = d.x, hi = d.y;
@@ -493,7 +616,7 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
       }
     }
     // (__syncthreads_or yields a predicate, not the OR of the operands: two reductions)
-    if (__syncthreads_or(fail)) { set_failed(c); if (threadIdx.x == 0 && c.count) c.nprop++; return; }
+    if (__syncthreads_or(fail)) { set_failed(c); return 1; }
     if (!__syncthreads_or(again)) break;
   }
   // write back narrowed bounds
@@ -542,38 +665,37 @@ __device__ void eval_distinct(Ctx& c, int slot, char* smem_nary, unsigned cur_ep
     }
     entailed = !__syncthreads_or(overlap);
   }
-  if (threadIdx.x == 0 && c.count) {
-    c.nprop++;
-    if (entailed) {
-      unsigned bit = 1u << (slot & 31);
-      unsigned old = atomicAnd(&P.nary_active[slot >> 5], ~bit);
-      if (old & bit) P.trail[atomicAdd(&P.ctl->trail_cnt, 1u)] = make_ref(F_NARY, (unsigned)slot);
-    }
+  if (threadIdx.x == 0 && entailed) {
+    unsigned bit = 1u << (slot & 31);
+    unsigned old = atomicAnd(&P.nary_active[slot >> 5], ~bit);
+    if (old & bit) P.trail[atomicAdd(&P.ctl->trail_cnt, 1u)] = make_ref(F_NARY, (unsigned)slot);
   }
-  __syncthreads();
+  return 1;
 }
 
 // ---------------------------------------------------------------------------------------
 // device-wide barrier; the last CTA to arrive decides whether the fixpoint is reached
 // (the "block-reduce of a changed flag": the reduction operand is the dirty-list length).
+// `decide` = false: plain barrier (after the node prologue).
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned barrier_decide(const Params& P, unsigned& gen, unsigned* s_block_props,
-                                                  int next_buf, unsigned iter) {
+__device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen, unsigned block_props, bool decide,
+                                                 int next_buf, unsigned iter) {
   __shared__ unsigned s_dec;
   __syncthreads();
   if (threadIdx.x == 0) {
     Control* ctl = P.ctl;
-    if (*s_block_props) { atomicAdd(&ctl->propagations, (unsigned long long)*s_block_props); *s_block_props = 0; }
+    if (block_props) atomicAdd(&ctl->propagations, (unsigned long long)block_props);
     __threadfence();
     unsigned arrived = atomicAdd(&ctl->bar_count, 1u);
     if (arrived == gridDim.x - 1) {
-      unsigned dec;
-      int failed = *(volatile int*)&ctl->failed;
-      int nd = *(volatile int*)&ctl->dirty_cnt[next_buf];
-      if (failed) dec = D_FAILED;
-      else if (nd == 0) dec = D_FIXPOINT;
-      else if (iter + 1 >= P.max_iterations) dec = D_ITER_CAP;
-      else dec = D_CONTINUE;
+      unsigned dec = D_CONTINUE;
+      if (decide) {
+        int failed = *(volatile int*)&ctl->failed;
+        int nd = *(volatile int*)&ctl->dirty_cnt[next_buf];
+        if (failed) dec = D_FAILED;
+        else if (nd == 0) dec = D_FIXPOINT;
+        else if (iter + 1 >= P.max_iterations) dec = D_ITER_CAP;
+      }
       ctl->decision[gen & 1u] = dec;
       ctl->bar_count = 0;
       __threadfence();
@@ -591,7 +713,7 @@ __device__ __forceinline__ unsigned barrier_decide(const Params& P, unsigned& ge
 }
 
 template <bool SMEM>
-__device__ __forceinline__ void expand_dirty_rows(Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
+__device__ __forceinline__ unsigned expand_dirty_rows(const Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
   const Params& P = *c.P;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -599,6 +721,7 @@ __device__ __forceinline__ void expand_dirty_rows(Ctx& c, int cur_buf, int n_dir
   const long long S = max(1LL, nwarps / n_dirty);  // segments per row (upper bound)
   const long long items = (long long)n_dirty * S;
   const int* list = P.dirty_list + (size_t)cur_buf * P.V;
+  unsigned nprop = 0;
   for (long long item = warp; item < items; item += nwarps) {
     int e = (int)(item / S);
     long long s = item % S;
@@ -612,77 +735,186 @@ __device__ __forceinline__ void expand_dirty_rows(Ctx& c, int cur_buf, int n_dir
       unsigned ref = __ldg(&P.adj[j]);
       unsigned fam = ref >> 29;
       int slot = (int)(ref & kSlotMask);
-      const Family& f = fam == F_BIN ? P.bin : (fam == F_TER ? P.ter : P.dj);
+      const Family& f = P.fam[fam];
       if (slot >= f.n_static) continue;  // truncated by a restore (store.rs:320)
       if (!is_active(f, slot)) continue;
       if (atomicExch(&f.stamp[slot], cur_epoch) == cur_epoch) continue;  // already scheduled
       eval_ref<SMEM>(c, fam, slot);
+      ++nprop;
     }
   }
+  return nprop;
+}
+
+// Node prologue on CTA 0: Snapshot::restore (domains <- label copy, `active` bits of the
+// trail suffix set again, propagation/store.rs:319-323) and Store::alloc of the propagators
+// posted since the last launch (descriptor + active bit).
+__device__ __forceinline__ void node_prologue(const Params& P) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  if (P.restore_from)
+    for (int v = tid; v < P.V; v += nth) P.dom[v] = P.restore_from[v];
+  if (P.do_trail) {
+    unsigned cnt = *(volatile unsigned*)&P.ctl->trail_cnt;
+    for (unsigned i = P.trail_keep + tid; i < cnt; i += nth) {
+      unsigned ref = P.trail[i];
+      unsigned fam = ref >> 29, slot = ref & kSlotMask;
+      uint32_t* act = fam == F_NARY ? P.nary_active_w : P.fam[fam].active;
+      atomicOr(&act[slot >> 5], 1u << (slot & 31));
+    }
+  }
+  for (int f = 0; f < 4; ++f) {
+    const int first = P.new_first[f], last = P.new_last[f];
+    if (first >= last) continue;
+    uint32_t* act = f == F_NARY ? P.nary_active_w : P.fam[f].active;
+    for (int w = (first >> 5) + tid; w <= ((last - 1) >> 5); w += nth) {
+      int lo = max(first, w * 32) - w * 32, hi = min(last, w * 32 + 32) - w * 32;  // bits [lo, hi)
+      unsigned mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+      atomicOr(&act[w], mask);
+    }
+  }
+  if (tid < P.n_inline) {
+    const InlineProp& ip = P.inl[tid];
+    const Family& f = P.fam[ip.fam];
+    if (ip.fam == F_BIN) f.desc[ip.slot] = ip.q[0];
+    else if (ip.fam == F_TER) { f.desc[ip.slot] = ip.q[0]; f.descB[ip.slot] = make_int2(ip.q[1].x, ip.q[1].y); }
+    else { f.desc[3 * (size_t)ip.slot] = ip.q[0]; f.desc[3 * (size_t)ip.slot + 1] = ip.q[1]; f.desc[3 * (size_t)ip.slot + 2] = ip.q[2]; }
+  }
+  __syncthreads();
+  if (tid == 0 && P.do_trail) P.ctl->trail_cnt = P.trail_keep;
 }
 
 template <bool SMEM>
-__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const Params P) {
-  extern __shared__ __align__(16) char smem[];
-  __shared__ unsigned s_block_props;
-  int2* sdom = SMEM ? reinterpret_cast<int2*>(smem) : nullptr;
-  char* smem_nary = smem + (SMEM ? (size_t)((P.V * 8 + 15) & ~15) : 0);
+__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ unsigned s_block_props, s_gen, s_epoch;
+  // layout: [ring | n-ary staging (aliased)] [domain snapshot]
+  char* ring = smem;
+  int2* sdom = SMEM ? reinterpret_cast<int2*>(smem + kRingBytes) : nullptr;
 
   Control* ctl = P.ctl;
-  unsigned gen = 0;
-  unsigned epoch0 = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ChunkMap cmap = chunk_map(P);
+  const int my_chunks = P.full_sweep && blockIdx.x < cmap.total ? (cmap.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
   if (threadIdx.x == 0) {
     s_block_props = 0;
-    gen = *(volatile unsigned*)&ctl->bar_gen;
-    epoch0 = *(volatile unsigned*)&ctl->epoch;
+    s_gen = *(volatile unsigned*)&ctl->bar_gen;
+    s_epoch = *(volatile unsigned*)&ctl->epoch;
+    for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  {
-    __shared__ unsigned s_gen, s_epoch;
-    if (threadIdx.x == 0) { s_gen = gen; s_epoch = epoch0; }
-    __syncthreads();
-    gen = s_gen;
-    epoch0 = s_epoch;
-  }
+  __syncthreads();
+  unsigned gen = s_gen;
+  const unsigned epoch0 = s_epoch;
+
+  // start streaming descriptors right away: they do not depend on the node prologue
+  if (warp == 0 && lane == 0)
+    for (int i = 0; i < my_chunks && i < kStages; ++i)
+      producer_issue(P, chunk_of(P, cmap, blockIdx.x + i * gridDim.x), ring + i * kStageBytes, &s_full[i]);
+
+  if (blockIdx.x == 0) node_prologue(P);
+  if (P.sync0) grid_barrier(P, gen, 0, false, 0, 0);
 
   Ctx c;
   c.P = &P;
   c.sdom = sdom;
-  c.nprop = 0;
 
   unsigned iter = 0;
   unsigned dec;
-  const int lane = threadIdx.x & 31;
+  unsigned nprop = 0;
   while (true) {
     const int cur_buf = iter % 3, next_buf = (iter + 1) % 3, spare_buf = (iter + 2) % 3;
     const unsigned cur_epoch = epoch0 + iter;
     c.next_epoch = cur_epoch + 1;
     c.next_buf = next_buf;
+    c.local = false;
+    c.mark_dirty = true;
+    c.bookkeep = true;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dirty_cnt[spare_buf] = 0;  // idle this iteration
 
-    // 1. tail propagators: iteration 0 on every CTA (so each snapshot already holds the
-    //    branching decision), afterwards CTA 0 only.  Counted once.
-    if (iter == 0 || blockIdx.x == 0) {
-      c.count = blockIdx.x == 0;
-      eval_tail(c);
-      c.count = true;
-      if (iter == 0) { __threadfence(); __syncthreads(); }
-    }
-
     if (iter == 0) {
+      // Propagators posted since the last launch.  With a full sweep ahead they need not enter
+      // the worklist: every CTA applies them to its own view of the domains first, so the sweep
+      // already sees their effect.
       if (SMEM) {
         for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
         __syncthreads();
-      }
-      if (P.full_sweep) {
-        sweep_family<SMEM, F_BIN>(c, P.bin);
-        sweep_family<SMEM, F_TER>(c, P.ter);
-        sweep_family<SMEM, F_DJ>(c, P.dj);
+        if (threadIdx.x == 0) {
+          c.mark_dirty = !P.full_sweep;
+          if (blockIdx.x == 0) {  // the global store, counted and book-kept once
+            for (int i = 0; i < P.n_inline; ++i) {
+              eval_full<false>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
+              ++nprop;
+            }
+          }
+          c.local = true;
+          c.bookkeep = false;
+          for (int i = 0; i < P.n_inline; ++i)
+            eval_full<true>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
+          c.local = false;
+          c.mark_dirty = true;
+          c.bookkeep = true;
+        }
+        __syncthreads();
+      } else {
+        if (threadIdx.x == 0) {
+          c.mark_dirty = !P.full_sweep;
+          c.bookkeep = blockIdx.x == 0;
+          for (int i = 0; i < P.n_inline; ++i) {
+            eval_full<false>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
+            if (blockIdx.x == 0) ++nprop;
+          }
+          c.mark_dirty = true;
+          c.bookkeep = true;
+          __threadfence();
+        }
+        __syncthreads();
       }
     }
+    // older tail propagators: CTA 0, every iteration (inline ones were just handled)
+    if (blockIdx.x == 0) {
+      unsigned n = 0;
+      for (unsigned fam = 0; fam < 3; ++fam) {
+        const Family& f = P.fam[fam];
+        for (int p = f.n_static + threadIdx.x; p < f.n; p += blockDim.x) {
+          bool inl = false;
+          if (iter == 0)
+            for (int i = 0; i < P.n_inline; ++i) inl |= P.inl[i].fam == fam && P.inl[i].slot == p;
+          if (!inl && is_active(f, p)) { eval_ref<false>(c, fam, p); ++n; }
+        }
+      }
+      nprop += n;
+    }
+
+    if (iter == 0 && my_chunks > 0) {
+      // ---- the streaming sweep over the static descriptor arrays
+      if (warp == 0) {
+        if (lane == 0) {
+          for (int i = kStages; i < my_chunks; ++i) {
+            const int s = i % kStages;
+            mbar_wait(&s_empty[s], ((i / kStages) - 1) & 1);
+            producer_issue(P, chunk_of(P, cmap, blockIdx.x + i * gridDim.x), ring + s * kStageBytes, &s_full[s]);
+          }
+        }
+      } else {
+        for (int i = 0; i < my_chunks; ++i) {
+          const int s = i % kStages;
+          const Chunk ch = chunk_of(P, cmap, blockIdx.x + i * gridDim.x);
+          mbar_wait(&s_full[s], (i / kStages) & 1);
+          nprop += sweep_consume<SMEM>(c, ch, ring + s * kStageBytes);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[s]);
+        }
+      }
+    }
+
     // worklist of variables narrowed in the previous iteration (iteration 0 of an
     // incremental launch: seeded by the host)
     int n_dirty = 0;
-    if (iter > 0 || !P.full_sweep) n_dirty = *(volatile int*)&ctl->dirty_cnt[cur_buf];
+    if (iter > 0) n_dirty = *(volatile int*)&ctl->dirty_cnt[cur_buf];
+    else if (!P.full_sweep) n_dirty = P.seed_dirty;
     if (n_dirty > 0) {
       const int* list = P.dirty_list + (size_t)cur_buf * P.V;
       // refresh the snapshot and catch domains emptied by two concurrent updates
@@ -695,91 +927,60 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const Params 
       }
       if (bad) set_failed(c);
       if (SMEM) __syncthreads();
-      expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
+      nprop += expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
     }
-    // 2. n-ary propagators: one CTA each; re-run when one of their operands is dirty.
+    // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
     if (P.n_nary > 0 && (iter > 0 || P.full_sweep || n_dirty > 0)) {
-      // fold this thread's count first (eval_distinct counts on thread 0)
       for (int s = blockIdx.x; s < P.n_nary; s += gridDim.x) {
         if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-        eval_distinct(c, s, smem_nary, cur_epoch, iter == 0 && P.full_sweep);
+        unsigned ev = eval_distinct<SMEM>(c, s, ring, cur_epoch, iter == 0 && P.full_sweep);
+        if (threadIdx.x == 0) nprop += ev;
       }
     }
 
     // block-level propagation count, then the barrier + decision
-    unsigned np = c.nprop;
-    c.nprop = 0;
-    for (int o = 16; o; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
-    if (lane == 0 && np) atomicAdd(&s_block_props, np);
-    dec = barrier_decide(P, gen, &s_block_props, next_buf, iter);
+    for (int o = 16; o; o >>= 1) nprop += __shfl_xor_sync(0xffffffffu, nprop, o);
+    if (lane == 0 && nprop) atomicAdd(&s_block_props, nprop);
+    nprop = 0;
+    __syncthreads();
+    unsigned bp = 0;
+    if (threadIdx.x == 0) { bp = s_block_props; s_block_props = 0; }
+    dec = grid_barrier(P, gen, bp, true, next_buf, iter);
     ++iter;
     if (dec != D_CONTINUE) break;
   }
 
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    ctl->epoch = epoch0 + iter + 1;
-    ctl->iterations = iter;
-    ctl->last_decision = dec;
-    ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
-    Result r;
-    r.failed = dec == D_FAILED;
-    r.trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
-    r.iterations = iter;
-    r.epoch = epoch0 + iter + 1;
-    r.propagations = *(volatile unsigned long long*)&ctl->propagations;
-    r.decision = dec;
-    *P.result = r;
-  }
-}
-
-// ---------------------------------------------------------------------------------------
-// node prologue: Snapshot::restore (+ Store::alloc of the few propagators posted since),
-// in one launch: domains <- label copy, `active` bits of the trail suffix set again
-// (propagation/store.rs:319-323), active bits of newly allocated tail slots set.
-// ---------------------------------------------------------------------------------------
-struct NodeBegin {
-  int2* dom;
-  const int2* restore_from;  // nullptr: keep the current domains
-  int V;
-  uint32_t* trail;
-  unsigned trail_keep;       // trail length recorded in the label
-  int do_trail;              // 1: undo trail entries >= trail_keep
-  uint32_t* active[4];       // per family (BIN, TER, DJ, NARY)
-  int new_first[4], new_last[4];  // slots whose active bit must be set
-  Control* ctl;
-};
-
-__global__ void __launch_bounds__(1024, 1) pcp_node_begin_kernel(const NodeBegin nb) {
-  const int tid = threadIdx.x, nth = blockDim.x;  // single CTA
-  if (nb.restore_from)
-    for (int v = tid; v < nb.V; v += nth) nb.dom[v] = nb.restore_from[v];
-  if (nb.do_trail) {
-    unsigned cnt = nb.ctl->trail_cnt;
-    for (unsigned i = nb.trail_keep + tid; i < cnt; i += nth) {
-      unsigned ref = nb.trail[i];
-      unsigned slot = ref & kSlotMask;
-      atomicOr(&nb.active[ref >> 29][slot >> 5], 1u << (slot & 31));
+  if (blockIdx.x == 0) {
+    // Branch::distribute takes a label right after an Unknown node (branch.rs:36-49): leave the
+    // copy of the fixpoint domains in the next label slot so that pcp_label is free.
+    if (P.snapshot_to && dec == D_FIXPOINT)
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) P.snapshot_to[v] = ldcg_dom(&P.dom[v]);
+    if (threadIdx.x == 0) {
+      Result r;
+      r.failed = dec == D_FAILED;
+      r.trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
+      r.iterations = iter;
+      r.epoch = epoch0 + iter + 1;
+      r.propagations = *(volatile unsigned long long*)&ctl->propagations;
+      r.decision = dec;
+      *P.result = r;
+      ctl->epoch = epoch0 + iter + 1;
+      ctl->iterations = iter;
+      ctl->last_decision = dec;
+      ctl->failed = 0;  // the next launch starts clean without a prologue barrier
+      ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     }
-  }
-  for (int f = 0; f < 4; ++f) {
-    const int first = nb.new_first[f], last = nb.new_last[f];
-    if (first >= last) continue;
-    for (int w = (first >> 5) + tid; w <= ((last - 1) >> 5); w += nth) {
-      int lo = max(first, w * 32) - w * 32, hi = min(last, w * 32 + 32) - w * 32;  // bits [lo, hi)
-      unsigned mask = (hi == 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-      atomicOr(&nb.active[f][w], mask);
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    nb.ctl->failed = 0;
-    if (nb.do_trail) nb.ctl->trail_cnt = nb.trail_keep;
-    nb.ctl->dirty_cnt[0] = nb.ctl->dirty_cnt[1] = nb.ctl->dirty_cnt[2] = 0;
   }
 }
 
 __global__ void pcp_fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// incremental launches: stamp the host-seeded dirty variables with the epoch of iteration 0
+__global__ void pcp_seed_dirty_kernel(const int* list, int n, uint32_t* dirty_stamp, const Control* ctl) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dirty_stamp[list[i]] = ctl->epoch;
 }
 
 }  // namespace pcpd

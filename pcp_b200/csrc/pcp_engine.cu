@@ -13,6 +13,8 @@
 //                  built once per model; propagators allocated later form a short tail
 //   labels         copy stack of the domain array (variable/memory/copy_memory.rs:141-151)
 //
+// A search node costs one kernel launch and one D2H copy: restore, the posted branching
+// constraint and the label copy all ride inside the fixpoint launch (pcp_device.cuh).
 // There is no CPU path: without a usable CUDA device pcp_engine_create fails.
 #include "../../include/pcp_b200.h"
 
@@ -45,18 +47,21 @@ struct Error {
                std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
   } while (0)
 
-// Growable device array with a host-known logical size.
+constexpr size_t kPad = 64;  // slack elements behind every device array (TMA tails)
+
+// Growable device array.
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
-  void reserve(size_t n, cudaStream_t st, bool keep = true, size_t keep_n = 0) {
+  void reserve(size_t n, cudaStream_t st, size_t keep_n = 0) {
     if (n <= cap) return;
     size_t ncap = std::max<size_t>(n, cap + cap / 2 + 64);
     T* q = nullptr;
-    CUDA_CHECK(cudaMalloc(&q, ncap * sizeof(T)));
+    CUDA_CHECK(cudaMalloc(&q, (ncap + kPad) * sizeof(T)));
+    CUDA_CHECK(cudaMemsetAsync(q + ncap, 0, kPad * sizeof(T), st));
     if (p) {
-      if (keep && keep_n) CUDA_CHECK(cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      if (keep_n) CUDA_CHECK(cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
       CUDA_CHECK(cudaStreamSynchronize(st));
       cudaFree(p);
     }
@@ -76,8 +81,7 @@ struct HostFamily {
   DevBuf<int4> d_desc;
   DevBuf<int2> d_descB;
   DevBuf<uint32_t> d_active, d_stamp;
-  int width() const { return width_; }
-  int width_ = 1;
+  int width = 1;
 };
 
 struct LabelRec {
@@ -86,6 +90,7 @@ struct LabelRec {
   size_t n_props;
   unsigned trail_len;
   bool at_fixpoint;
+  uint64_t dom_version;     // version of the domains captured by this label
 };
 
 }  // namespace
@@ -108,6 +113,7 @@ struct pcp_engine {
   char* h_block = nullptr;          // pinned mirror of d_block
   size_t h_block_cap_vars = 0;
   bool mirror_valid = false;        // h_block domains == device domains
+  uint64_t dom_version = 1;         // bumped whenever the device domains may change
 
   // propagators
   HostFamily fam[3];                // BIN, TER, DJ
@@ -138,9 +144,11 @@ struct pcp_engine {
 
   // labels
   std::vector<LabelRec> labels;
-  DevBuf<int2> d_stack;             // labels.size() x V
+  DevBuf<int2> d_stack;             // label slots, stride = stack_stride
   size_t stack_stride = 0;
   size_t max_labels = 4096;
+  bool snapshot_valid = false;      // slot labels.size() holds the domains of dom_version
+  uint64_t snapshot_version = 0;
 
   // deferred node prologue
   bool pending_restore = false;
@@ -151,7 +159,7 @@ struct pcp_engine {
   std::vector<int> host_dirty;      // variables narrowed through pcp_var_update
   unsigned max_iterations = 1u << 22;
 
-  // pinned staging for small descriptor uploads
+  // pinned staging for small uploads
   char* h_stage = nullptr;
   size_t h_stage_cap = 0;
 
@@ -206,20 +214,13 @@ void* stage(pcp_engine* e, size_t bytes) {
   return e->h_stage;
 }
 
-// Upload host range [from, to) of a vector to the device array (pinned staging for small
-// ranges so the copy is truly asynchronous; pageable memcpy for bulk model uploads).
+// Upload host range [from, to) of a vector to the device array.
 template <class T>
-void upload_range(pcp_engine* e, DevBuf<T>& dst, const std::vector<T>& src, size_t from, size_t to, size_t& stage_off) {
+void upload_range(pcp_engine* e, DevBuf<T>& dst, const std::vector<T>& src, size_t from, size_t to) {
   if (to <= from) return;
-  dst.reserve(src.size(), e->stream, true, from);
-  size_t bytes = (to - from) * sizeof(T);
-  if (bytes <= 4096 && stage_off + bytes <= (32u << 10)) {
-    std::memcpy(e->h_stage + stage_off, src.data() + from, bytes);
-    CUDA_CHECK(cudaMemcpyAsync(dst.p + from, e->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, e->stream));
-    stage_off += (bytes + 15) & ~size_t(15);
-  } else {
-    CUDA_CHECK(cudaMemcpyAsync(dst.p + from, src.data() + from, bytes, cudaMemcpyHostToDevice, e->stream));
-  }
+  dst.reserve(src.size(), e->stream, from);
+  CUDA_CHECK(cudaMemcpyAsync(dst.p + from, src.data() + from, (to - from) * sizeof(T), cudaMemcpyHostToDevice, e->stream));
+  CUDA_CHECK(cudaStreamSynchronize(e->stream));  // pageable source: keep it simple and safe
 }
 
 void fill_u32(pcp_engine* e, uint32_t* p, uint32_t v, size_t n) {
@@ -232,9 +233,8 @@ void fill_u32(pcp_engine* e, uint32_t* p, uint32_t v, size_t n) {
 // Grow a per-propagator bit set / stamp array, zero-filling the new part.
 void reserve_zeroed(pcp_engine* e, DevBuf<uint32_t>& b, size_t words, size_t valid_words) {
   if (words <= b.cap) return;
-  size_t old_cap = b.cap;
-  b.reserve(words, e->stream, true, std::min(valid_words, old_cap));
-  size_t from = std::min(valid_words, old_cap);
+  size_t from = std::min(valid_words, b.cap);
+  b.reserve(words, e->stream, from);
   fill_u32(e, b.p + from, 0u, b.cap - from);
 }
 
@@ -323,21 +323,21 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       e->h_nary_ptr.push_back((int)e->h_nary_ops.size());
       e->nary_max_k = std::max(e->nary_max_k, n_ops);
       e->prop_ref.push_back(make_ref(F_NARY, (unsigned)e->n_nary++));
+      // binary/ternary/disjunction propagators allocated after a fixpoint land in the tail,
+      // which every launch evaluates; a new n-ary propagator needs a full first sweep
+      e->at_fixpoint = false;
       break;
     }
     default:
       PCP_FAIL(PCP_ERR_UNSUPPORTED, "unknown propagator kind");
   }
-  // binary/ternary/disjunction propagators allocated after a fixpoint land in the tail,
-  // which every launch evaluates; a new n-ary propagator needs a full first sweep
-  if (kind == PCP_DISTINCT) e->at_fixpoint = false;
 }
 
 void truncate_props(pcp_engine* e, const LabelRec& r) {
   for (int f = 0; f < 3; ++f) {
     HostFamily& hf = e->fam[f];
     hf.n = r.n_fam[f];
-    hf.desc.resize(hf.n * hf.width());
+    hf.desc.resize(hf.n * hf.width);
     if (f == F_TER) hf.descB.resize(hf.n);
     hf.n_static = std::min(hf.n_static, hf.n);
     hf.uploaded = std::min(hf.uploaded, hf.n);
@@ -392,8 +392,8 @@ void build_csr(pcp_engine* e) {
   std::vector<uint32_t> adj((size_t)ptr[V]);
   std::vector<int> cur(ptr.begin(), ptr.end() - 1);
   for_each_var([&](int v, unsigned ref) { adj[(size_t)cur[v]++] = ref; });
-  e->d_adj_ptr.reserve(V + 1, e->stream, false);
-  e->d_adj.reserve(std::max<size_t>(adj.size(), 1), e->stream, false);
+  e->d_adj_ptr.reserve(V + 1, e->stream);
+  e->d_adj.reserve(std::max<size_t>(adj.size(), 1), e->stream);
   CUDA_CHECK(cudaMemcpyAsync(e->d_adj_ptr.p, ptr.data(), (V + 1) * sizeof(int), cudaMemcpyHostToDevice, e->stream));
   if (!adj.empty())
     CUDA_CHECK(cudaMemcpyAsync(e->d_adj.p, adj.data(), adj.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
@@ -402,13 +402,20 @@ void build_csr(pcp_engine* e) {
   e->csr_built = true;
 }
 
-// Bring the device in line with the host-side bookkeeping: upload new variables and
-// descriptors, run the node prologue (restore + new active bits), rebuild the CSR if the
-// tail outgrew its limit.
-void flush(pcp_engine* e, bool timed = false) {
+size_t nary_smem_bytes(const pcp_engine* e) {
+  if (e->n_nary == 0) return 0;
+  size_t k = (size_t)e->nary_max_k;
+  size_t tab = 4;
+  while (tab < 2 * k) tab <<= 1;
+  return k * 16 + tab * 4;
+}
+
+// Everything except the few "inline" propagators is brought to the device here: new
+// variables, bulk descriptor uploads, buffer growth, CSR (re)build.  Returns the launch
+// parameters with the node prologue filled in; up to kMaxInline freshly posted tail
+// propagators ride in the kernel parameters instead of an H2D copy.
+Params prepare(pcp_engine* e) {
   const size_t V = e->V;
-  size_t stage_off = 0;
-  stage(e, 1 << 16);
   // --- variables
   ensure_var_capacity(e, std::max<size_t>(V, 1));
   if (e->V_uploaded < V) {
@@ -420,109 +427,91 @@ void flush(pcp_engine* e, bool timed = false) {
     size_t oldV = e->V_uploaded;
     e->V_uploaded = V;
     e->mirror_valid = false;
+    ++e->dom_version;
     // per-variable worklist storage (3 lists) and stamps
-    e->d_dirty_list.reserve(3 * V, e->stream, false);
+    e->d_dirty_list.reserve(3 * V, e->stream);
     size_t old_cap = e->d_dirty_stamp.cap;
-    e->d_dirty_stamp.reserve(V, e->stream, true, oldV);
+    e->d_dirty_stamp.reserve(V, e->stream, oldV);
     if (e->d_dirty_stamp.cap != old_cap) fill_u32(e, e->d_dirty_stamp.p + oldV, 0u, e->d_dirty_stamp.cap - oldV);
     // the label stack is laid out with stride V: a label taken with fewer variables cannot be
-    // restored after more were allocated (the reference's trail has the same limitation)
-    if (e->stack_stride != V) { e->stack_stride = V; PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); }
+    // restored after more were allocated
+    if (e->stack_stride != V) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = V; }
     e->csr_built = false;  // adj_ptr has V+1 entries
     for (int f = 0; f < 3; ++f) e->fam[f].n_static = 0;
   }
+  // --- reactor: (re)build when there are propagators outside the CSR beyond the tail limit
+  size_t tail = 0, pending = 0;
+  for (int f = 0; f < 3; ++f) { tail += e->fam[f].n - e->fam[f].n_static; pending += e->fam[f].n - e->fam[f].uploaded; }
+  const bool rebuild = (!e->csr_built && tail > 0) || tail > e->tail_limit;
   // --- descriptors
+  const bool use_inline = !rebuild && pending > 0 && pending <= (size_t)kMaxInline;
   size_t total = 0;
   for (int f = 0; f < 3; ++f) {
     HostFamily& hf = e->fam[f];
-    size_t w = hf.width();
-    upload_range(e, hf.d_desc, hf.desc, hf.uploaded * w, hf.n * w, stage_off);
-    if (f == F_TER) upload_range(e, hf.d_descB, hf.descB, hf.uploaded, hf.n, stage_off);
-    hf.uploaded = hf.n;
-    size_t words = (hf.n + 31) / 32 + 1;
-    reserve_zeroed(e, hf.d_active, words, (hf.active_set + 31) / 32);
+    const size_t w = (size_t)hf.width;
+    if (use_inline) {
+      hf.d_desc.reserve(hf.desc.size(), e->stream, hf.uploaded * w);
+      if (f == F_TER) hf.d_descB.reserve(hf.descB.size(), e->stream, hf.uploaded);
+    } else {
+      upload_range(e, hf.d_desc, hf.desc, hf.uploaded * w, hf.n * w);
+      if (f == F_TER) upload_range(e, hf.d_descB, hf.descB, hf.uploaded, hf.n);
+    }
+    reserve_zeroed(e, hf.d_active, (hf.n + 31) / 32 + 1, (hf.active_set + 31) / 32);
     if (hf.n > hf.d_stamp.cap) {
       size_t valid = std::min(hf.d_stamp.cap, hf.active_set);
-      hf.d_stamp.reserve(hf.n, e->stream, true, valid);
+      hf.d_stamp.reserve(hf.n, e->stream, valid);
       fill_u32(e, hf.d_stamp.p + valid, 0u, hf.d_stamp.cap - valid);
     }
+    if (!hf.d_desc.p) hf.d_desc.reserve(1, e->stream);
+    if (!hf.d_descB.p) hf.d_descB.reserve(1, e->stream);
+    if (!hf.d_stamp.p) { hf.d_stamp.reserve(1, e->stream); fill_u32(e, hf.d_stamp.p, 0u, hf.d_stamp.cap); }
     total += hf.n;
   }
   if (e->nary_uploaded < e->n_nary) {
     size_t ops_from = (size_t)e->h_nary_ptr[e->nary_uploaded];
-    upload_range(e, e->d_nary_ops, e->h_nary_ops, ops_from, e->h_nary_ops.size(), stage_off);
-    // ptr entries [nary_uploaded+1, n_nary]; entry 0 on first upload
+    upload_range(e, e->d_nary_ops, e->h_nary_ops, ops_from, e->h_nary_ops.size());
     size_t pfrom = e->nary_uploaded == 0 ? 0 : e->nary_uploaded + 1;
-    upload_range(e, e->d_nary_ptr, e->h_nary_ptr, pfrom, e->n_nary + 1, stage_off);
+    upload_range(e, e->d_nary_ptr, e->h_nary_ptr, pfrom, e->n_nary + 1);
     e->nary_uploaded = e->n_nary;
   }
   reserve_zeroed(e, e->d_nary_active, (e->n_nary + 31) / 32 + 1, (e->nary_active_set + 31) / 32);
   total += e->n_nary;
-  e->d_trail.reserve(total + 64, e->stream, true, e->trail_len);
+  e->d_trail.reserve(total + 64, e->stream, e->trail_len);
 
-  // --- node prologue
-  NodeBegin nb;
-  std::memset(&nb, 0, sizeof(nb));
-  nb.dom = e->d_dom();
-  nb.V = (int)V;
-  nb.ctl = e->d_ctl;
-  nb.trail = e->d_trail.p;
-  if (e->pending_restore) {
-    nb.restore_from = e->d_stack.p + e->pending_restore_label * e->stack_stride;
-    e->mirror_valid = false;
+  Params P;
+  std::memset(&P, 0, sizeof(P));
+  // --- inline propagators (their descriptors are written by the kernel prologue)
+  if (use_inline) {
+    for (int f = 0; f < 3; ++f) {
+      HostFamily& hf = e->fam[f];
+      for (size_t s = hf.uploaded; s < hf.n; ++s) {
+        InlineProp& ip = P.inl[P.n_inline++];
+        ip.fam = (unsigned)f;
+        ip.slot = (int)s;
+        if (f == F_BIN) ip.q[0] = hf.desc[s];
+        else if (f == F_TER) { ip.q[0] = hf.desc[s]; ip.q[1] = make_int4(hf.descB[s].x, hf.descB[s].y, 0, 0); }
+        else { ip.q[0] = hf.desc[3 * s]; ip.q[1] = hf.desc[3 * s + 1]; ip.q[2] = hf.desc[3 * s + 2]; }
+      }
+    }
   }
-  nb.do_trail = e->pending_trail_undo ? 1 : 0;
-  nb.trail_keep = e->pending_trail_keep;
-  for (int f = 0; f < 3; ++f) {
-    nb.active[f] = e->fam[f].d_active.p;
-    nb.new_first[f] = (int)e->fam[f].active_set;
-    nb.new_last[f] = (int)e->fam[f].n;
-    e->fam[f].active_set = e->fam[f].n;
-  }
-  nb.active[F_NARY] = e->d_nary_active.p;
-  nb.new_first[F_NARY] = (int)e->nary_active_set;
-  nb.new_last[F_NARY] = (int)e->n_nary;
-  e->nary_active_set = e->n_nary;
-  // device time of a node = node prologue + fixpoint kernel
-  if (timed && e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
-  pcp_node_begin_kernel<<<1, 1024, 0, e->stream>>>(nb);
-  CUDA_CHECK(cudaGetLastError());
-  if (e->pending_trail_undo) e->trail_len = e->pending_trail_keep;
-  e->pending_restore = false;
-  e->pending_trail_undo = false;
-
-  // --- reactor
-  size_t tail = 0;
-  for (int f = 0; f < 3; ++f) tail += e->fam[f].n - e->fam[f].n_static;
-  if ((!e->csr_built && tail > 0) || tail > e->tail_limit) {
+  for (int f = 0; f < 3; ++f) e->fam[f].uploaded = e->fam[f].n;
+  if (rebuild) {
     build_csr(e);
     e->at_fixpoint = false;
   }
   if (!e->csr_built) {  // no propagators yet: still need a valid adj_ptr
-    e->d_adj_ptr.reserve(V + 1, e->stream, false);
-    e->d_adj.reserve(1, e->stream, false);
+    e->d_adj_ptr.reserve(V + 1, e->stream);
+    e->d_adj.reserve(1, e->stream);
     CUDA_CHECK(cudaMemsetAsync(e->d_adj_ptr.p, 0, (V + 1) * sizeof(int), e->stream));
   }
-}
 
-size_t nary_smem_bytes(const pcp_engine* e) {
-  if (e->n_nary == 0) return 0;
-  size_t k = (size_t)e->nary_max_k;
-  size_t tab = 4;
-  while (tab < 2 * k) tab <<= 1;
-  return k * 16 + tab * 4;
-}
-
-void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
-  flush(e, true);
-  const size_t V = e->V;
-  Params P;
-  std::memset(&P, 0, sizeof(P));
+  // --- launch parameters
   P.result = e->d_result();
   P.dom = e->d_dom();
   P.V = (int)V;
+  bool sync0 = false;
   for (int f = 0; f < 3; ++f) {
-    Family& df = f == F_BIN ? P.bin : (f == F_TER ? P.ter : P.dj);
+    Family& df = P.fam[f];
     HostFamily& hf = e->fam[f];
     df.desc = hf.d_desc.p;
     df.descB = hf.d_descB.p;
@@ -530,12 +519,21 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     df.stamp = hf.d_stamp.p;
     df.n = (int)hf.n;
     df.n_static = (int)hf.n_static;
+    P.new_first[f] = (int)hf.active_set;
+    P.new_last[f] = (int)hf.n;
+    if (hf.active_set < hf.n && hf.active_set < hf.n_static) sync0 = true;  // bits other CTAs will read
+    hf.active_set = hf.n;
   }
   P.nary_ptr = e->d_nary_ptr.p;
   P.nary_ops = e->d_nary_ops.p;
   P.nary_active = e->d_nary_active.p;
+  P.nary_active_w = e->d_nary_active.p;
   P.n_nary = (int)e->n_nary;
   P.nary_max_k = e->nary_max_k;
+  P.new_first[F_NARY] = (int)e->nary_active_set;
+  P.new_last[F_NARY] = (int)e->n_nary;
+  if (e->nary_active_set < e->n_nary) sync0 = true;
+  e->nary_active_set = e->n_nary;
   P.adj_ptr = e->d_adj_ptr.p;
   P.adj = e->d_adj.p;
   P.dirty_list = e->d_dirty_list.p;
@@ -543,6 +541,45 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   P.trail = e->d_trail.p;
   P.ctl = e->d_ctl;
   P.max_iterations = e->max_iterations;
+  if (e->pending_restore) {
+    P.restore_from = e->d_stack.p + e->pending_restore_label * e->stack_stride;
+    e->mirror_valid = false;
+    ++e->dom_version;
+    sync0 = true;
+  }
+  if (e->pending_trail_undo) {
+    P.do_trail = 1;
+    P.trail_keep = e->pending_trail_keep;
+    if (e->trail_len > e->pending_trail_keep) sync0 = true;  // bits are actually re-set
+    e->trail_len = std::min(e->trail_len, e->pending_trail_keep);
+  }
+  P.sync0 = sync0 ? 1 : 0;
+  e->pending_restore = false;
+  e->pending_trail_undo = false;
+  return P;
+}
+
+bool prologue_pending(const pcp_engine* e) {
+  if (e->V_uploaded < e->V || e->pending_restore || e->pending_trail_undo) return true;
+  for (int f = 0; f < 3; ++f)
+    if (e->fam[f].uploaded < e->fam[f].n || e->fam[f].active_set < e->fam[f].n) return true;
+  return e->nary_uploaded < e->n_nary || e->nary_active_set < e->n_nary;
+}
+
+__global__ void __launch_bounds__(1024, 1) pcp_prologue_kernel(const __grid_constant__ Params P) { node_prologue(P); }
+
+// Bring the device state up to date without running a fixpoint (pcp_domains_read /
+// pcp_label / pcp_active_read right after a restore or an alloc).
+void sync_device_state(pcp_engine* e) {
+  if (!prologue_pending(e)) return;
+  Params P = prepare(e);
+  pcp_prologue_kernel<<<1, 1024, 0, e->stream>>>(P);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  Params P = prepare(e);
+  const size_t V = e->V;
   const bool incremental = (e->flags & PCP_FLAG_INCREMENTAL) && e->at_fixpoint;
   P.full_sweep = incremental ? 0 : 1;
 
@@ -557,31 +594,48 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   }
   if (incremental && !e->host_dirty.empty()) {
     // seed the worklist of iteration 0 with the variables narrowed by the host
+    std::sort(e->host_dirty.begin(), e->host_dirty.end());
+    e->host_dirty.erase(std::unique(e->host_dirty.begin(), e->host_dirty.end()), e->host_dirty.end());
     size_t n = e->host_dirty.size();
-    // (the first 32 KiB of the staging area may still feed flush()'s async copies)
-    int* st = reinterpret_cast<int*>(static_cast<char*>(stage(e, (32 << 10) + (n + 1) * sizeof(int))) + (32 << 10));
+    int* st = static_cast<int*>(stage(e, n * sizeof(int)));
     std::memcpy(st, e->host_dirty.data(), n * sizeof(int));
     CUDA_CHECK(cudaMemcpyAsync(e->d_dirty_list.p, st, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    st[n] = (int)n;
-    CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->dirty_cnt[0], st + n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    pcp_seed_dirty_kernel<<<(int)((n + 255) / 256), 256, 0, e->stream>>>(e->d_dirty_list.p, (int)n, e->d_dirty_stamp.p, e->d_ctl);
+    CUDA_CHECK(cudaGetLastError());
+    P.seed_dirty = (int)n;
   }
   e->host_dirty.clear();
+
+  // label slot for the epilogue snapshot (Branch::distribute labels right after an Unknown node)
+  e->snapshot_valid = false;
+  const bool want_snapshot = V > 0 && V <= 16384 && e->labels.size() < e->max_labels && e->stack_stride == V;
+  if (want_snapshot) {
+    size_t idx = e->labels.size();
+    if ((idx + 1) * e->stack_stride > e->d_stack.cap) {
+      const int2* old = e->d_stack.p;
+      e->d_stack.reserve((idx + 1) * e->stack_stride * 2, e->stream, idx * e->stack_stride);
+      if (P.restore_from) P.restore_from = e->d_stack.p + (P.restore_from - old);
+    }
+    P.snapshot_to = e->d_stack.p + idx * e->stack_stride;
+  }
 
   // launch geometry: one CTA per SM, fewer for small stores (cheaper barrier)
   size_t total = e->n_nary * 4096;
   for (int f = 0; f < 3; ++f) total += e->fam[f].n;
   int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 8191) / 8192));
   size_t nary_bytes = nary_smem_bytes(e);
+  PCP_REQUIRE(nary_bytes <= (size_t)kRingBytes, "Distinct too wide for shared memory");
   size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
-  bool smem_dom = dom_bytes + nary_bytes + 1024 <= (size_t)e->max_smem_optin && V > 0;
-  PCP_REQUIRE(nary_bytes + 1024 <= (size_t)e->max_smem_optin, "Distinct too wide for shared memory");
-  size_t smem = (smem_dom ? dom_bytes : 0) + nary_bytes;
+  bool smem_dom = V > 0 && (size_t)kRingBytes + dom_bytes + 2048 <= (size_t)e->max_smem_optin;
+  size_t smem = (size_t)kRingBytes + (smem_dom ? dom_bytes : 0);
   P.smem_dom = smem_dom ? 1 : 0;
   const void* fn = smem_dom ? (const void*)pcp_fixpoint_kernel<true> : (const void*)pcp_fixpoint_kernel<false>;
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   void* args[] = {&P};
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+  ++e->dom_version;
   // status header (+ domains when small) in one D2H copy
   const bool eager_dom = V * sizeof(int2) <= (64u << 10);
   size_t bytes = sizeof(Result) + (eager_dom ? V * sizeof(int2) : 0);
@@ -598,6 +652,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   // propagation/store.rs:250-256: False | True (every propagator entailed) | Unknown
   int st = r.failed ? PCP_FALSE : (r.trail_cnt == e->num_props() ? PCP_TRUE : PCP_UNKNOWN);
   e->at_fixpoint = !r.failed;
+  if (want_snapshot && !r.failed) { e->snapshot_valid = true; e->snapshot_version = e->dom_version; }
   *status = st;
   if (stats) {
     std::memset(stats, 0, sizeof(*stats));
@@ -613,7 +668,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
 }
 
 void fetch_domains(pcp_engine* e) {
-  flush(e);
+  sync_device_state(e);
   if (e->mirror_valid) return;
   if (e->V) {
     CUDA_CHECK(cudaMemcpyAsync(e->h_dom(), e->d_dom(), e->V * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
@@ -644,7 +699,6 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
   if (!out) return PCP_ERR_INVALID;
   *out = nullptr;
   pcp_engine* e = new pcp_engine();
-  static thread_local std::string create_err;
   int rc = guarded(e, [&] {
     e->device = cfg ? cfg->device : 0;
     e->flags = cfg ? cfg->flags : 0;
@@ -671,14 +725,13 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     std::memset(&c, 0, sizeof(c));
     c.epoch = 1;
     CUDA_CHECK(cudaMemcpy(e->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
-    e->fam[F_BIN].width_ = 1;
-    e->fam[F_TER].width_ = 1;
-    e->fam[F_DJ].width_ = 3;
+    e->fam[F_BIN].width = 1;
+    e->fam[F_TER].width = 1;
+    e->fam[F_DJ].width = 3;
     stage(e, 1 << 16);
   });
   if (rc != PCP_OK) {
-    create_err = e->err;
-    std::fprintf(stderr, "pcp_engine_create: %s\n", create_err.c_str());
+    std::fprintf(stderr, "pcp_engine_create: %s\n", e->err.c_str());
     delete e;
     return rc;
   }
@@ -724,6 +777,7 @@ int pcp_vars_alloc(pcp_engine* e, const int32_t* lo, const int32_t* hi, int32_t 
     for (int i = 0; i < n; ++i) e->h_dom_pending.push_back(make_int2(lo[i], hi[i]));
     e->V += (size_t)n;
     e->at_fixpoint = false;
+    e->snapshot_valid = false;
   });
 }
 
@@ -751,8 +805,11 @@ int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t
     int old_max_k = e->nary_max_k;
     if (first_idx) *first_idx = (int32_t)e->num_props();
     try {
-      if (kind == PCP_X_LESS_Y || kind == PCP_X_NEQ_Y || kind == PCP_X_EQ_Y) e->fam[F_BIN].desc.reserve(e->fam[F_BIN].desc.size() + (size_t)n_props);
-      e->prop_ref.reserve(e->prop_ref.size() + (size_t)n_props);
+      if (n_props > 4096) {  // bulk model upload: one allocation (never for single posts: reserve() is exact)
+        if (kind == PCP_X_LESS_Y || kind == PCP_X_NEQ_Y || kind == PCP_X_EQ_Y)
+          e->fam[F_BIN].desc.reserve(e->fam[F_BIN].desc.size() + (size_t)n_props);
+        e->prop_ref.reserve(e->prop_ref.size() + (size_t)n_props);
+      }
       for (int64_t p = 0; p < n_props; ++p) append_prop(e, kind, ops + p * n_ops, n_ops);
     } catch (...) {
       truncate_props(e, mark);
@@ -779,8 +836,10 @@ int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32
   return guarded(e, [&] {
     PCP_REQUIRE(first >= 0 && n >= 0 && (size_t)first + (size_t)n <= e->V, "Variable not registered in the store.");
     if (n == 0) return;
-    CUDA_CHECK(cudaSetDevice(e->device));
-    fetch_domains(e);
+    if (!e->mirror_valid || prologue_pending(e)) {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      fetch_domains(e);
+    }
     const int2* d = e->h_dom() + first;
     for (int i = 0; i < n; ++i) { lo[i] = d[i].x; hi[i] = d[i].y; }
   });
@@ -804,6 +863,8 @@ int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* 
       CUDA_CHECK(cudaStreamSynchronize(e->stream));
       e->h_dom()[idx] = make_int2(lo, hi);
       e->host_dirty.push_back(idx);
+      ++e->dom_version;
+      e->snapshot_valid = false;
     }
     if (ok) *ok = 1;
   });
@@ -815,7 +876,7 @@ int pcp_active_read(pcp_engine* e, int32_t first, int32_t n, uint8_t* out) {
     PCP_REQUIRE(first >= 0 && n >= 0 && (size_t)first + (size_t)n <= e->num_props(), "propagator out of range");
     if (n == 0) return;
     CUDA_CHECK(cudaSetDevice(e->device));
-    flush(e);
+    sync_device_state(e);
     std::vector<uint32_t> bits[4];
     for (int f = 0; f < 4; ++f) {
       size_t cnt = f < 3 ? e->fam[f].n : e->n_nary;
@@ -836,14 +897,19 @@ int pcp_active_read(pcp_engine* e, int32_t first, int32_t n, uint8_t* out) {
 int pcp_label(pcp_engine* e, uint64_t* label) {
   if (!e || !label) return PCP_ERR_INVALID;
   return guarded(e, [&] {
-    CUDA_CHECK(cudaSetDevice(e->device));
-    flush(e);
     PCP_REQUIRE(e->labels.size() < e->max_labels, "label stack full (pcp_config.max_labels)");
     size_t idx = e->labels.size();
-    e->d_stack.reserve((idx + 1) * std::max<size_t>(e->stack_stride, 1), e->stream, true, idx * e->stack_stride);
-    if (e->V)
-      CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride, e->d_dom(), e->V * sizeof(int2),
-                                 cudaMemcpyDeviceToDevice, e->stream));
+    const bool have = e->snapshot_valid && e->snapshot_version == e->dom_version && !prologue_pending(e);
+    if (!have) {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      sync_device_state(e);
+      if (e->stack_stride != e->V) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = e->V; }
+      e->d_stack.reserve((idx + 1) * std::max<size_t>(e->stack_stride, 1), e->stream, idx * e->stack_stride);
+      if (e->V)
+        CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride, e->d_dom(), e->V * sizeof(int2),
+                                   cudaMemcpyDeviceToDevice, e->stream));
+    }
+    e->snapshot_valid = false;
     LabelRec r;
     for (int f = 0; f < 3; ++f) r.n_fam[f] = e->fam[f].n;
     r.n_fam[F_NARY] = e->n_nary;
@@ -851,6 +917,7 @@ int pcp_label(pcp_engine* e, uint64_t* label) {
     r.n_props = e->num_props();
     r.trail_len = e->trail_len;
     r.at_fixpoint = e->at_fixpoint;
+    r.dom_version = e->dom_version;
     e->labels.push_back(r);
     *label = idx;
   });
@@ -863,13 +930,19 @@ int pcp_restore(pcp_engine* e, uint64_t label) {
     const LabelRec r = e->labels[label];
     e->labels.resize(label + 1);
     truncate_props(e, r);
-    e->pending_restore = true;
-    e->pending_restore_label = label;
+    e->snapshot_valid = false;
+    e->host_dirty.clear();
+    e->at_fixpoint = r.at_fixpoint;
+    // restoring the label that was just taken from the current domains (the left child of
+    // Branch::distribute) needs no copy
+    const bool same_domains = r.dom_version == e->dom_version && !e->pending_restore;
+    if (!same_domains) {
+      e->pending_restore = true;
+      e->pending_restore_label = label;
+      e->mirror_valid = false;
+    }
     e->pending_trail_undo = true;
     e->pending_trail_keep = r.trail_len;
-    e->at_fixpoint = r.at_fixpoint;
-    e->host_dirty.clear();
-    e->mirror_valid = false;
   });
 }
 
