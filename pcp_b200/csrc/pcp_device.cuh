@@ -52,7 +52,8 @@ __host__ __device__ inline unsigned make_ref(unsigned fam, unsigned slot) { retu
 enum BinKind : unsigned { B_LESS = 0, B_NEQ = 1, B_EQ = 2 };
 enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2 };
 
-enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3 };
+enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3, D_SWEEP = 4 };
+constexpr unsigned kDecBits = 3;  // the release word of the barrier = (generation << kDecBits) | decision
 
 struct Control {
   unsigned bar_count;
@@ -126,7 +127,17 @@ struct Params {
   int seed_dirty;             // incremental launch: dirty_list[0..seed_dirty) seeded by the host
   // ---- epilogue
   int2* snapshot_to;          // if not failed: copy of the fixpoint domains (next label slot)
+  // ---- debug: per-CTA phase timestamps (PCP_TRACE=1), 8 slots per CTA
+  unsigned long long* trace;
 };
+
+__device__ __forceinline__ void trace_mark(const Params& P, int slot) {
+  if (P.trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // memory / async helpers
@@ -177,11 +188,13 @@ struct Ctx {
   bool local;             // updates go to the shared-memory snapshot only (inline props, non-CTA-0)
   bool mark_dirty;        // narrowed variables enter the worklist
   bool bookkeep;          // entailed propagators are deactivated + trailed
+  int* flags;             // shared: [0] this CTA queued a dirty variable, [1] saw a failure
 };
 
 // warp-aggregated append to the dirty-variable worklist
 __device__ __forceinline__ void push_dirty(const Ctx& c, int v) {
   const Params& P = *c.P;
+  c.flags[0] = 1;  // (also when another CTA queued it: the list is then non-empty anyway)
   if (atomicExch(&P.dirty_stamp[v], c.next_epoch) == c.next_epoch) return;  // already queued
   unsigned m = __activemask();
   int leader = __ffs(m) - 1;
@@ -206,7 +219,7 @@ __device__ __forceinline__ void deactivate(const Ctx& c, uint32_t* active, unsig
   c.P->trail[base + __popc(m & lanemask_lt())] = make_ref(fam, (unsigned)slot);
 }
 
-__device__ __forceinline__ void set_failed(const Ctx& c) { c.P->ctl->failed = 1; }
+__device__ __forceinline__ void set_failed(const Ctx& c) { c.flags[1] = 1; }
 
 // Domain readers.  `SMEM` reads the CTA's snapshot, otherwise L2 (ld.global.cg).
 template <bool SMEM>
@@ -228,11 +241,13 @@ __device__ __forceinline__ bool tighten(const Ctx& c, int var, int off, IV cur, 
     }
     int2* d = &c.P->dom[var];
     bool ch = false;
-    if (nlo > cur.lo) ch |= atomicMax(&d->x, nlo - off) < nlo - off;
-    if (nhi < cur.hi) ch |= atomicMin(&d->y, nhi - off) > nhi - off;
+    int lo_now = cur.lo - off, hi_now = cur.hi - off;  // best knowledge of the stored bounds
+    if (nlo > cur.lo) { int old = atomicMax(&d->x, nlo - off); ch |= old < nlo - off; lo_now = max(old, nlo - off); }
+    if (nhi < cur.hi) { int old = atomicMin(&d->y, nhi - off); ch |= old > nhi - off; hi_now = min(old, nhi - off); }
     if (ch) {
-      int2 now = ldcg_dom(d);
-      if (now.x > now.y) set_failed(c);
+      // a domain emptied by two concurrent updates that this thread cannot see is caught when
+      // the variable is refreshed from the worklist in the next iteration
+      if (lo_now > hi_now) set_failed(c);
       if (c.mark_dirty) push_dirty(c, var);
     }
   }
@@ -398,30 +413,40 @@ __device__ __noinline__ void eval_full(const Ctx& c, unsigned fam, int slot, int
   else if (r == E_ENTAILED && c.bookkeep) deactivate(c, c.P->fam[fam].active, fam, slot);
 }
 
-// Evaluate a propagator given by reference (worklist expansion, tail): gathers its
-// descriptor from global memory.
-template <bool SMEM>
-__device__ __forceinline__ void eval_ref(const Ctx& c, unsigned fam, int slot) {
-  const Family& f = c.P->fam[fam];
-  int4 q0, q1 = make_int4(0, 0, 0, 0), q2 = q1;
+// Gather one descriptor from global memory (worklist expansion, tail).
+__device__ __forceinline__ void load_desc(const Family& f, unsigned fam, int slot, int4& q0, int4& q1, int4& q2) {
+  q1 = make_int4(0, 0, 0, 0);
+  q2 = q1;
   if (fam == F_BIN) {
     q0 = __ldg(&f.desc[slot]);
-    unsigned kind = (unsigned)q0.x >> 28;
-    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w);
-    if (bin_is_noop(kind, x, y)) return;
   } else if (fam == F_TER) {
     q0 = __ldg(&f.desc[slot]);
     int2 b = __ldg(&f.descB[slot]);
     q1.x = b.x; q1.y = b.y;
-    unsigned kind = (unsigned)q0.x >> 28;
-    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w), z = rd<SMEM>(c, b.x, b.y);
-    if (ter_is_noop(kind, x, y, z)) return;
   } else {
     const int4* q = &f.desc[3 * (size_t)slot];
     q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
+  }
+}
+// Evaluate a gathered propagator: cheap no-op test inline, everything else out of line.
+template <bool SMEM>
+__device__ __forceinline__ void eval_loaded(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
+  if (fam == F_BIN) {
+    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w);
+    if (bin_is_noop((unsigned)q0.x >> 28, x, y)) return;
+  } else if (fam == F_TER) {
+    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w), z = rd<SMEM>(c, q1.x, q1.y);
+    if (ter_is_noop((unsigned)q0.x >> 28, x, y, z)) return;
+  } else {
     if (dj_is_noop<SMEM>(c, q0, q1, q2)) return;
   }
   eval_full<SMEM>(c, fam, slot, q0, q1, q2);
+}
+template <bool SMEM>
+__device__ __forceinline__ void eval_ref(const Ctx& c, unsigned fam, int slot) {
+  int4 q0, q1, q2;
+  load_desc(c.P->fam[fam], fam, slot, q0, q1, q2);
+  eval_loaded<SMEM>(c, fam, slot, q0, q1, q2);
 }
 
 __device__ __forceinline__ bool is_active(const Family& f, int slot) {
@@ -474,16 +499,34 @@ __device__ __forceinline__ void producer_issue(const Params& P, const Chunk& ch,
   }
 }
 
+// The words of the `active` bit set a consumer warp needs for one chunk (at most
+// kGroupsMax groups of 32 propagators); loaded one chunk ahead so that the L2 round trip is
+// off the critical path of the sweep.
+constexpr int kGroupsMax = 2;
+struct ActiveWords { unsigned w[kGroupsMax]; };
+__device__ __forceinline__ ActiveWords load_active_words(const Params& P, const Chunk& ch) {
+  const int cw = (threadIdx.x >> 5) - 1;
+  ActiveWords a;
+#pragma unroll
+  for (int g = 0; g < kGroupsMax; ++g) {
+    const int j0 = cw * 32 + g * kConsumerWarps * 32;
+    a.w[g] = j0 < ch.cnt ? __ldcg(&P.fam[ch.fam].active[(ch.base + j0) >> 5]) : 0u;
+  }
+  return a;
+}
+
 template <bool SMEM>
-__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, const Chunk& ch, const char* stage) {
-  const Params& P = *c.P;
+__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, const Chunk& ch, const char* stage,
+                                                  const ActiveWords& aw) {
   const int lane = threadIdx.x & 31;
   const int cw = (threadIdx.x >> 5) - 1;  // consumer warp index 0..30
-  const Family& f = P.fam[ch.fam];
   unsigned nprop = 0;
-  for (int j0 = cw * 32; j0 < ch.cnt; j0 += kConsumerWarps * 32) {
+#pragma unroll
+  for (int g = 0; g < kGroupsMax; ++g) {
+    const int j0 = cw * 32 + g * kConsumerWarps * 32;
+    if (j0 >= ch.cnt) break;
     const int j = j0 + lane;
-    const unsigned word = __ldcg(&f.active[(ch.base + j0) >> 5]);
+    const unsigned word = aw.w[g];
     if (j >= ch.cnt || !((word >> lane) & 1u)) continue;
     const int slot = ch.base + j;
     ++nprop;
@@ -505,19 +548,6 @@ __device__ __forceinline__ unsigned sweep_consume(const Ctx& c, const Chunk& ch,
     }
   }
   return nprop;
-}
-
-// Tail propagators (allocated after the CSR was built, e.g. the branching constraints of
-// search/branching/binary_split.rs:46-57): evaluated every iteration by CTA 0, from L2.
-__device__ __forceinline__ unsigned eval_tail(const Ctx& c) {
-  const Params& P = *c.P;
-  unsigned n = 0;
-  for (unsigned fam = 0; fam < 3; ++fam) {
-    const Family& f = P.fam[fam];
-    for (int p = f.n_static + threadIdx.x; p < f.n; p += blockDim.x)
-      if (is_active(f, p)) { eval_ref<false>(c, fam, p); ++n; }
-  }
-  return n;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -678,37 +708,47 @@ __device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* sme
 // (the "block-reduce of a changed flag": the reduction operand is the dirty-list length).
 // `decide` = false: plain barrier (after the node prologue).
 // ---------------------------------------------------------------------------------------
+// The arrival word packs three 10-bit counters -- CTAs arrived, CTAs that queued a dirty
+// variable, CTAs that saw a failure -- so one release-atomic per CTA carries everything the
+// decision needs; the release word `bar_gen` = (generation << kDecBits) | decision, so one
+// acquire-load per poll returns both.
 __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen, unsigned block_props, bool decide,
-                                                 int next_buf, unsigned iter) {
+                                                 const int* s_flags, unsigned iter, int next_buf = 0) {
   __shared__ unsigned s_dec;
   __syncthreads();
   if (threadIdx.x == 0) {
     Control* ctl = P.ctl;
     if (block_props) atomicAdd(&ctl->propagations, (unsigned long long)block_props);
-    __threadfence();
-    unsigned arrived = atomicAdd(&ctl->bar_count, 1u);
-    if (arrived == gridDim.x - 1) {
+    unsigned add = 1u + (s_flags[0] ? (1u << 10) : 0u) + (s_flags[1] ? (1u << 20) : 0u);
+    const_cast<int*>(s_flags)[0] = const_cast<int*>(s_flags)[1] = 0;  // nobody sets them inside the barrier
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(&ctl->bar_count), "r"(add) : "memory");
+    unsigned now = old + add;
+    if ((now & 1023u) == gridDim.x) {
       unsigned dec = D_CONTINUE;
       if (decide) {
-        int failed = *(volatile int*)&ctl->failed;
-        int nd = *(volatile int*)&ctl->dirty_cnt[next_buf];
-        if (failed) dec = D_FAILED;
-        else if (nd == 0) dec = D_FIXPOINT;
+        if ((now >> 20) & 1023u) dec = D_FAILED;
+        else if (((now >> 10) & 1023u) == 0) dec = D_FIXPOINT;
         else if (iter + 1 >= P.max_iterations) dec = D_ITER_CAP;
+        else {
+          // many dirty variables: their CSR rows cover most of the store, and a second streaming
+          // sweep is cheaper than gathering the rows
+          int nd = *(volatile int*)&ctl->dirty_cnt[next_buf];
+          if ((long long)nd * 8 >= (long long)P.V) dec = D_SWEEP;
+        }
       }
-      ctl->decision[gen & 1u] = dec;
       ctl->bar_count = 0;
-      __threadfence();
-      atomicAdd(&ctl->bar_gen, 1u);
+      unsigned rel = ((gen + 1u) << kDecBits) | dec;
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->bar_gen), "r"(rel) : "memory");
       s_dec = dec;
     } else {
-      while (ld_acquire_u32(&ctl->bar_gen) == gen) { }
-      s_dec = *(volatile unsigned*)&ctl->decision[gen & 1u];
+      unsigned v;
+      do { v = ld_acquire_u32(&ctl->bar_gen); } while ((v >> kDecBits) == gen);
+      s_dec = v & ((1u << kDecBits) - 1u);
     }
-    __threadfence();
   }
   __syncthreads();
-  gen++;
+  gen = (gen + 1u) & (0xffffffffu >> kDecBits);
   return s_dec;
 }
 
@@ -737,9 +777,13 @@ __device__ __forceinline__ unsigned expand_dirty_rows(const Ctx& c, int cur_buf,
       int slot = (int)(ref & kSlotMask);
       const Family& f = P.fam[fam];
       if (slot >= f.n_static) continue;  // truncated by a restore (store.rs:320)
-      if (!is_active(f, slot)) continue;
+      // the active word and the descriptor are independent loads: both in flight together
+      const unsigned word = __ldcg(&f.active[slot >> 5]);
+      int4 q0, q1, q2;
+      load_desc(f, fam, slot, q0, q1, q2);
+      if (!((word >> (slot & 31)) & 1u)) continue;
       if (atomicExch(&f.stamp[slot], cur_epoch) == cur_epoch) continue;  // already scheduled
-      eval_ref<SMEM>(c, fam, slot);
+      eval_loaded<SMEM>(c, fam, slot, q0, q1, q2);
       ++nprop;
     }
   }
@@ -788,38 +832,61 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   extern __shared__ __align__(128) char smem[];
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   __shared__ unsigned s_block_props, s_gen, s_epoch;
+  __shared__ int s_flags[2];
   // layout: [ring | n-ary staging (aliased)] [domain snapshot]
   char* ring = smem;
   int2* sdom = SMEM ? reinterpret_cast<int2*>(smem + kRingBytes) : nullptr;
 
   Control* ctl = P.ctl;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
+  // by the other CTAs so that nobody waits for it at the barrier
   const ChunkMap cmap = chunk_map(P);
-  const int my_chunks = P.full_sweep && blockIdx.x < cmap.total ? (cmap.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int workers = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
+  const int wid = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+  const int my_chunks = wid >= 0 && wid < cmap.total ? (cmap.total - 1 - wid) / workers + 1 : 0;
+  const int pre_issued = P.full_sweep ? min(my_chunks, kStages) : 0;
+  int pipe_pos = 0;  // chunks this CTA has pushed through the ring so far (all sweeps)
 
   if (threadIdx.x == 0) {
     s_block_props = 0;
-    s_gen = *(volatile unsigned*)&ctl->bar_gen;
-    s_epoch = *(volatile unsigned*)&ctl->epoch;
+    s_flags[0] = s_flags[1] = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // start streaming descriptors right away: they do not depend on the node prologue
+    for (int i = 0; i < pre_issued; ++i)
+      producer_issue(P, chunk_of(P, cmap, wid + i * workers), ring + i * kStageBytes, &s_full[i]);
+  } else if (threadIdx.x == 32) {
+    s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
+    s_epoch = *(volatile unsigned*)&ctl->epoch;
   }
+  // without a restore the domains are already final: snapshot them while the TMA runs
+  if (SMEM && !P.sync0)
+    for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
   __syncthreads();
   unsigned gen = s_gen;
   const unsigned epoch0 = s_epoch;
-
-  // start streaming descriptors right away: they do not depend on the node prologue
-  if (warp == 0 && lane == 0)
-    for (int i = 0; i < my_chunks && i < kStages; ++i)
-      producer_issue(P, chunk_of(P, cmap, blockIdx.x + i * gridDim.x), ring + i * kStageBytes, &s_full[i]);
+  trace_mark(P, 0);
 
   if (blockIdx.x == 0) node_prologue(P);
-  if (P.sync0) grid_barrier(P, gen, 0, false, 0, 0);
+  if (P.sync0) {
+    grid_barrier(P, gen, 0, false, s_flags, 0);
+    if (SMEM) {
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
+      __syncthreads();
+    }
+  }
+  trace_mark(P, 1);
+  ActiveWords aw;
+  aw.w[0] = aw.w[1] = 0u;
+  if (warp > 0 && my_chunks > 0 && P.full_sweep) aw = load_active_words(P, chunk_of(P, cmap, wid));
+  bool sweep_now = P.full_sweep != 0;
 
   Ctx c;
   c.P = &P;
   c.sdom = sdom;
+  c.flags = s_flags;
 
   unsigned iter = 0;
   unsigned dec;
@@ -834,44 +901,30 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
     c.bookkeep = true;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dirty_cnt[spare_buf] = 0;  // idle this iteration
 
-    if (iter == 0) {
+    if (iter == 0 && P.n_inline > 0) {
       // Propagators posted since the last launch.  With a full sweep ahead they need not enter
       // the worklist: every CTA applies them to its own view of the domains first, so the sweep
       // already sees their effect.
-      if (SMEM) {
-        for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          c.mark_dirty = !P.full_sweep;
-          if (blockIdx.x == 0) {  // the global store, counted and book-kept once
-            for (int i = 0; i < P.n_inline; ++i) {
-              eval_full<false>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
-              ++nprop;
-            }
-          }
+      if (threadIdx.x == 0) {
+        c.mark_dirty = !P.full_sweep;
+        if (blockIdx.x == 0 || !SMEM) {  // the global store: counted and book-kept by CTA 0
+          c.bookkeep = blockIdx.x == 0;
+          for (int i = 0; i < P.n_inline; ++i)
+            eval_full<false>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
+          if (blockIdx.x == 0) nprop += P.n_inline;
+          if (!SMEM) __threadfence();
+        }
+        if (SMEM) {
           c.local = true;
           c.bookkeep = false;
           for (int i = 0; i < P.n_inline; ++i)
             eval_full<true>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
-          c.local = false;
-          c.mark_dirty = true;
-          c.bookkeep = true;
         }
-        __syncthreads();
-      } else {
-        if (threadIdx.x == 0) {
-          c.mark_dirty = !P.full_sweep;
-          c.bookkeep = blockIdx.x == 0;
-          for (int i = 0; i < P.n_inline; ++i) {
-            eval_full<false>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
-            if (blockIdx.x == 0) ++nprop;
-          }
-          c.mark_dirty = true;
-          c.bookkeep = true;
-          __threadfence();
-        }
-        __syncthreads();
+        c.local = false;
+        c.mark_dirty = true;
+        c.bookkeep = true;
       }
+      __syncthreads();
     }
     // older tail propagators: CTA 0, every iteration (inline ones were just handled)
     if (blockIdx.x == 0) {
@@ -888,28 +941,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       nprop += n;
     }
 
-    if (iter == 0 && my_chunks > 0) {
-      // ---- the streaming sweep over the static descriptor arrays
-      if (warp == 0) {
-        if (lane == 0) {
-          for (int i = kStages; i < my_chunks; ++i) {
-            const int s = i % kStages;
-            mbar_wait(&s_empty[s], ((i / kStages) - 1) & 1);
-            producer_issue(P, chunk_of(P, cmap, blockIdx.x + i * gridDim.x), ring + s * kStageBytes, &s_full[s]);
-          }
-        }
-      } else {
-        for (int i = 0; i < my_chunks; ++i) {
-          const int s = i % kStages;
-          const Chunk ch = chunk_of(P, cmap, blockIdx.x + i * gridDim.x);
-          mbar_wait(&s_full[s], (i / kStages) & 1);
-          nprop += sweep_consume<SMEM>(c, ch, ring + s * kStageBytes);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[s]);
-        }
-      }
-    }
-
+    if (iter == 0) trace_mark(P, 2);
     // worklist of variables narrowed in the previous iteration (iteration 0 of an
     // incremental launch: seeded by the host)
     int n_dirty = 0;
@@ -927,8 +959,39 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       }
       if (bad) set_failed(c);
       if (SMEM) __syncthreads();
-      nprop += expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
+      if (!sweep_now) nprop += expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
     }
+    if (sweep_now && my_chunks > 0) {
+      // ---- the streaming sweep over the static descriptor arrays (ring positions keep
+      // counting across sweeps so the mbarrier phases stay consistent)
+      if (warp == 0) {
+        if (lane == 0) {
+          // the ring memory doubles as n-ary staging (generic-proxy writes): order them before
+          // the async-proxy writes of the next bulk copies
+          if (iter > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          for (int i = (iter == 0 ? pre_issued : 0); i < my_chunks; ++i) {
+            const int q = pipe_pos + i, s = q % kStages;
+            if (q >= kStages) mbar_wait(&s_empty[s], ((q / kStages) - 1) & 1);
+            producer_issue(P, chunk_of(P, cmap, wid + i * workers), ring + s * kStageBytes, &s_full[s]);
+          }
+        }
+      } else {
+        if (iter > 0) aw = load_active_words(P, chunk_of(P, cmap, wid));
+        for (int i = 0; i < my_chunks; ++i) {
+          const int q = pipe_pos + i, s = q % kStages;
+          const Chunk ch = chunk_of(P, cmap, wid + i * workers);
+          ActiveWords nxt = aw;
+          if (i + 1 < my_chunks) nxt = load_active_words(P, chunk_of(P, cmap, wid + (i + 1) * workers));
+          mbar_wait(&s_full[s], (q / kStages) & 1);
+          nprop += sweep_consume<SMEM>(c, ch, ring + s * kStageBytes, aw);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[s]);
+          aw = nxt;
+        }
+      }
+      pipe_pos += my_chunks;
+    }
+    if (iter == 0 && P.trace) { __syncthreads(); trace_mark(P, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
     if (P.n_nary > 0 && (iter > 0 || P.full_sweep || n_dirty > 0)) {
       for (int s = blockIdx.x; s < P.n_nary; s += gridDim.x) {
@@ -945,11 +1008,15 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
     __syncthreads();
     unsigned bp = 0;
     if (threadIdx.x == 0) { bp = s_block_props; s_block_props = 0; }
-    dec = grid_barrier(P, gen, bp, true, next_buf, iter);
+    if (iter == 0) trace_mark(P, 4);
+    dec = grid_barrier(P, gen, bp, true, s_flags, iter, next_buf);
+    if (iter == 0) trace_mark(P, 5);
     ++iter;
-    if (dec != D_CONTINUE) break;
+    if (dec != D_CONTINUE && dec != D_SWEEP) break;
+    sweep_now = dec == D_SWEEP;
   }
 
+  trace_mark(P, 6);
   if (blockIdx.x == 0) {
     // Branch::distribute takes a label right after an Unknown node (branch.rs:36-49): leave the
     // copy of the fixpoint domains in the next label slot so that pcp_label is free.
@@ -967,7 +1034,6 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       ctl->epoch = epoch0 + iter + 1;
       ctl->iterations = iter;
       ctl->last_decision = dec;
-      ctl->failed = 0;  // the next launch starts clean without a prologue barrier
       ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     }
   }

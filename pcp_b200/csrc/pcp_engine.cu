@@ -159,6 +159,9 @@ struct pcp_engine {
   std::vector<int> host_dirty;      // variables narrowed through pcp_var_update
   unsigned max_iterations = 1u << 22;
 
+  // debug timeline (PCP_TRACE=1)
+  unsigned long long* d_trace = nullptr;
+
   // pinned staging for small uploads
   char* h_stage = nullptr;
   size_t h_stage_cap = 0;
@@ -613,7 +616,9 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     size_t idx = e->labels.size();
     if ((idx + 1) * e->stack_stride > e->d_stack.cap) {
       const int2* old = e->d_stack.p;
-      e->d_stack.reserve((idx + 1) * e->stack_stride * 2, e->stream, idx * e->stack_stride);
+      // grow in big steps: a reallocation costs a cudaMalloc/cudaFree pair on the search path
+      size_t want = std::max<size_t>((idx + 1) * 2, std::min<size_t>(e->max_labels, 256));
+      e->d_stack.reserve(want * e->stack_stride, e->stream, idx * e->stack_stride);
       if (P.restore_from) P.restore_from = e->d_stack.p + (P.restore_from - old);
     }
     P.snapshot_to = e->d_stack.p + idx * e->stack_stride;
@@ -631,6 +636,12 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   P.smem_dom = smem_dom ? 1 : 0;
   const void* fn = smem_dom ? (const void*)pcp_fixpoint_kernel<true> : (const void*)pcp_fixpoint_kernel<false>;
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
+  if (trace_on) {
+    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, 8 * 256 * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, 8 * 256 * sizeof(unsigned long long), e->stream));
+    P.trace = e->d_trace;
+  }
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   void* args[] = {&P};
   CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
@@ -643,6 +654,19 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   CUDA_CHECK(cudaStreamSynchronize(e->stream));
   e->mirror_valid = eager_dom;
 
+  if (trace_on) {
+    std::vector<unsigned long long> t(8 * 256);
+    CUDA_CHECK(cudaMemcpy(t.data(), e->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int b = 0; b < grid; ++b) t0 = std::min(t0, t[b * 8]);
+    std::fprintf(stderr, "[pcp trace] grid=%d sync0=%d iters=%u; per phase: min/avg/max ns since first CTA start\n", grid, P.sync0, e->h_result()->iterations);
+    const char* names[7] = {"start", "after_prologue_sync", "snapshot+inline_done", "sweep_done", "barrier_arrive", "barrier_leave", "exit"};
+    for (int k = 0; k < 7; ++k) {
+      unsigned long long mn = ~0ull, mx = 0, sum = 0;
+      for (int b = 0; b < grid; ++b) { unsigned long long v = t[b * 8 + k] - t0; mn = std::min(mn, v); mx = std::max(mx, v); sum += v; }
+      std::fprintf(stderr, "[pcp trace]   %-22s %8llu %8llu %8llu\n", names[k], mn, sum / grid, mx);
+    }
+  }
   const Result& r = *e->h_result();
   if (r.decision == D_ITER_CAP) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
   e->trail_len = r.trail_cnt;
