@@ -227,3 +227,105 @@ class EngineBase:
         if trace_domains:
             tr["lo"], tr["hi"] = t_lo[:n], t_hi[:n]
         return res, tr
+
+
+class _Counters:
+    """Cumulative search counters with the field names of `SearchResult`."""
+
+    def __init__(self):
+        self.status = 0
+        self.num_nodes = self.num_solution = self.num_failed_node = self.num_prune = 0
+        self.propagations = self.iterations = 0
+        self.seconds = self.kernel_seconds = 0.0
+
+
+class PySearchHandle:
+    """The resumable search of `pcp_search_open/step/close`, node by node over the store
+    surface (restore / prop_alloc / consistency / domains / label).  Any `EngineBase` can use
+    it; the device engine overrides `search_open` with the native driver."""
+
+    def __init__(self, engine: "EngineBase", all_solutions: bool = False, node_limit: int = 0, warmup_nodes: int = 0):
+        self.e = engine
+        self.all_solutions = all_solutions
+        self.node_limit = node_limit
+        self.warmup = warmup_nodes
+        self.stack = []
+        self.started = False
+        self.stopped = False
+        self.exhausted_reported = False
+        self.res = _Counters()
+
+    def _enter_child(self) -> int:
+        import time
+        t0 = time.perf_counter()
+        st, stats = self.e.consistency()
+        r = self.res
+        if r.num_nodes >= self.warmup:
+            r.propagations += int(stats.propagations)
+            r.iterations += int(stats.iterations)
+            r.kernel_seconds += float(stats.kernel_ms) * 1e-3
+        status = st
+        if st == UNKNOWN:
+            lo, hi = self.e.domains()
+            size = hi.astype(np.int64) - lo.astype(np.int64) + 1
+            var = int(np.argmin(np.where(size > 1, size, np.iinfo(np.int64).max)))
+            val = int((int(lo[var]) + int(hi[var])) / 2)
+            label = self.e.label()
+            self.stack.append((label, var, val, 1))
+            self.stack.append((label, var, val, 0))
+        r.num_nodes += 1
+        stop = self.node_limit and r.num_nodes >= self.node_limit
+        if stop:
+            status = 2
+        elif st == TRUE:
+            r.num_solution += 1
+        elif st == FALSE:
+            r.num_failed_node += 1
+        if r.num_nodes > self.warmup:
+            r.seconds += time.perf_counter() - t0
+        return status
+
+    def step(self, max_nodes: int = 0) -> _Counters:
+        r = self.res
+        start = r.num_nodes
+        if self.stopped:
+            r.status = 2
+            return r
+        while True:
+            if self.started and not self.stack:
+                if self.all_solutions or self.exhausted_reported:
+                    r.status = 2
+                else:
+                    self.exhausted_reported = True
+                    r.status = -1
+                return r
+            if max_nodes and r.num_nodes - start >= max_nodes:
+                r.status = 0
+                return r
+            if not self.started:
+                self.started = True
+            else:
+                label, var, val, alt = self.stack.pop()
+                self.e.restore(label)
+                if alt == 0:
+                    self.e.prop_alloc(0, [[var, 0], [-1, val + 1]])  # x <= val (binary_split.rs:46-51)
+                else:
+                    self.e.prop_alloc(0, [[-1, val], [var, 0]])      # x > val  (binary_split.rs:52-57)
+            child = self._enter_child()
+            if child == 2:
+                self.stopped = True
+                r.status = 2
+                return r
+            if child == 1 and not self.all_solutions:
+                r.status = 1
+                return r
+
+    def close(self) -> None:
+        pass
+
+
+def _search_open(self, node_limit: int = 0, all_solutions: bool = False, warmup_nodes: int = 0, **_kw):
+    return PySearchHandle(self, all_solutions=all_solutions, node_limit=node_limit, warmup_nodes=warmup_nodes)
+
+
+EngineBase.search_open = _search_open
