@@ -17,7 +17,8 @@ Numbers on the JSON line (our arm):
   e2e         the same metric through the C ABI with host buffers: the C++ search driver calls
               pcp_restore / pcp_prop_alloc / pcp_consistency / pcp_domains_read / pcp_label per
               node; wall clock, H2D of the posted descriptor and D2H of status + domains inside
-  roofline    algorithmic bytes (32 B per binary propagation) / device time vs the
+  roofline    algorithmic bytes (32 B per binary propagation) / device time of the
+              fixpoint launches (CUDA events, measured live in this run) vs the
               measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the oracle's flat variant, 1 thread, on the same first nodes of the same DFS
 """
@@ -163,13 +164,14 @@ def device_timed_pass(engine, steps, warmup, flush, torch, device):
             props += stats.propagations
             iters += stats.iterations
             ms += stats.kernel_ms
-            launches += 2  # pcp_node_begin_kernel + pcp_fixpoint_kernel
+            launches += 1  # pcp_fixpoint_kernel (restore, posted constraint and label copy ride inside)
         dfs.after_fixpoint(st)
         n += 1
     return {"nodes": max(n - warmup, 0), "propagations": props, "iterations": iters, "ms": ms, "launches": launches}
 
 
 def run_ours(args):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from pcp_b200 import Engine, parallel
@@ -241,7 +243,7 @@ def run_ours(args):
                     ms += stats.kernel_ms
             barrier()
             res[mode] = {"nodes": args.steps, "propagations": props, "iterations": iters, "ms": ms,
-                         "launches": 2 * args.steps}
+                         "launches": args.steps}
             e2.close()
         # e2e: restore + consistency + domains through the ABI, wall clock
         e3 = fresh_engine()
@@ -328,13 +330,13 @@ def run_ours(args):
                      "nodes_per_s": w_nodes / (w_ms * 1e-3) if w_ms > 0 else 0.0, "ms_per_step": w_ms / max(args.steps, 1),
                      "l2": "not flushed (descriptors L2-resident)"},
             "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s",
-                    "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "ms_per_step": 1e3 * e_s / max(e_nodes, 1),
+                    "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "ms_per_step": 1e3 * e_s * world / max(e_nodes, 1),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "path": "C++ search driver -> C ABI (pcp_restore/pcp_prop_alloc/pcp_consistency/pcp_domains_read/pcp_label), L2 not flushed"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pcp_fixpoint_kernel (+ pcp_node_begin_kernel prologue)",
+                         "kernel": "pcp_fixpoint_kernel (node prologue, TMA sweep, worklist iterations, label snapshot)",
                          "algorithmic_bytes_per_propagation": bpp,
                          "warm_frac": ((w["propagations"] * bpp) / (w["ms"] * 1e-3) / 1e9 / peak) if w["ms"] > 0 else None},
             "cpu_baseline": cpu,
