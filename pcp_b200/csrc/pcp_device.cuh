@@ -41,6 +41,7 @@ constexpr int kChunkTer = 992;          // 992 * 16 B + 992 * 8 B
 constexpr int kChunkDj = 480;           // 480 * 48 B = 23040 B
 constexpr int kTerPlaneB = 16384;       // offset of the z plane inside a stage
 constexpr unsigned kConstVar28 = 0x0FFFFFFFu;
+constexpr unsigned kSumBase28 = 0x0F000000u;  // x-operand encodings >= this are sum views / Constant
 constexpr int kMaxInline = 4;
 
 // family tags inside adjacency / trail references (top 3 bits)
@@ -107,6 +108,8 @@ struct Params {
   uint32_t* nary_active;
   int n_nary;
   int nary_max_k;
+  const int* sum_ptr;   // CSR of the Sum views (term/sum.rs): terms are (var, off) operands
+  const int2* sum_terms;
   const int* adj_ptr;   // reactor: var -> propagator refs
   const uint32_t* adj;
   int* dirty_list;      // 3 x V
@@ -177,281 +180,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-struct IV { int lo, hi; };
+}  // namespace pcpd
 
-// Per-thread context of one fixpoint launch (read-mostly; counters live in registers).
-struct Ctx {
-  const Params* P;
-  int2* sdom;             // shared-memory snapshot (or nullptr)
-  unsigned next_epoch;    // stamp for "dirty in the next iteration"
-  int next_buf;           // dirty list written in this iteration
-  bool local;             // updates go to the shared-memory snapshot only (inline props, non-CTA-0)
-  bool mark_dirty;        // narrowed variables enter the worklist
-  bool bookkeep;          // entailed propagators are deactivated + trailed
-  int* flags;             // shared: [0] this CTA queued a dirty variable, [1] saw a failure
-};
+#include "pcp_eval.cuh"
 
-// warp-aggregated append to the dirty-variable worklist
-__device__ __forceinline__ void push_dirty(const Ctx& c, int v) {
-  const Params& P = *c.P;
-  c.flags[0] = 1;  // (also when another CTA queued it: the list is then non-empty anyway)
-  if (atomicExch(&P.dirty_stamp[v], c.next_epoch) == c.next_epoch) return;  // already queued
-  unsigned m = __activemask();
-  int leader = __ffs(m) - 1;
-  int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&P.ctl->dirty_cnt[c.next_buf], __popc(m));
-  base = __shfl_sync(m, base, leader);
-  P.dirty_list[c.next_buf * P.V + base + __popc(m & lanemask_lt())] = v;
-}
-
-// warp-aggregated append to the entailment trail + clear of the active bit
-__device__ __forceinline__ void deactivate(const Ctx& c, uint32_t* active, unsigned fam, int slot) {
-  unsigned bit = 1u << (slot & 31);
-  unsigned old = atomicAnd(&active[slot >> 5], ~bit);
-  if (!(old & bit)) return;
-  unsigned m = __activemask();
-  int leader = __ffs(m) - 1;
-  int lane = threadIdx.x & 31;
-  unsigned base = 0;
-  if (lane == leader) base = atomicAdd(&c.P->ctl->trail_cnt, (unsigned)__popc(m));
-  base = __shfl_sync(m, base, leader);
-  c.P->trail[base + __popc(m & lanemask_lt())] = make_ref(fam, (unsigned)slot);
-}
-
-__device__ __forceinline__ void set_failed(const Ctx& c) { c.flags[1] = 1; }
-
-// Domain readers.  `SMEM` reads the CTA's snapshot, otherwise L2 (ld.global.cg).
-template <bool SMEM>
-__device__ __forceinline__ IV rd(const Ctx& c, int var, int off) {
-  if (var < 0) return IV{off, off};  // Constant (term/constant.rs:55-63)
-  int2 d = SMEM ? c.sdom[var] : ldcg_dom(&c.P->dom[var]);
-  return IV{d.x + off, d.y + off};   // Addition (term/addition.rs:93-101)
-}
-
-// Monotone update of one view to [nlo, nhi] (already intersected with `cur`):
-// variable/store.rs:151-166 through term/addition.rs:80-90 / term/constant.rs:43-53.
-// Returns false when the new domain is empty (update -> false).
-__device__ __forceinline__ bool tighten(const Ctx& c, int var, int off, IV cur, int nlo, int nhi) {
-  if (nlo > nhi) return false;
-  if (var >= 0) {
-    if (c.local) {
-      if (nlo > cur.lo || nhi < cur.hi) c.sdom[var] = make_int2(nlo - off, nhi - off);
-      return true;
-    }
-    int2* d = &c.P->dom[var];
-    bool ch = false;
-    int lo_now = cur.lo - off, hi_now = cur.hi - off;  // best knowledge of the stored bounds
-    if (nlo > cur.lo) { int old = atomicMax(&d->x, nlo - off); ch |= old < nlo - off; lo_now = max(old, nlo - off); }
-    if (nhi < cur.hi) { int old = atomicMin(&d->y, nhi - off); ch |= old > nhi - off; hi_now = min(old, nhi - off); }
-    if (ch) {
-      // a domain emptied by two concurrent updates that this thread cannot see is caught when
-      // the variable is refreshed from the worklist in the next iteration
-      if (lo_now > hi_now) set_failed(c);
-      if (c.mark_dirty) push_dirty(c, var);
-    }
-  }
-  return true;
-}
-
-// Result of evaluating one propagator: propagate + is_subsumed (store.rs:177-183).
-enum Eval : int { E_FAIL = -1, E_UNKNOWN = 0, E_ENTAILED = 1 };
-
-__device__ __forceinline__ int dec_var28(unsigned w0) {
-  unsigned v = w0 & kConstVar28;
-  return v == kConstVar28 ? -1 : (int)v;
-}
-
-// --- binary family: XLessY / XNeqY / XEqY ---------------------------------------------------
-template <bool SMEM>
-__device__ __forceinline__ Eval eval_bin(const Ctx& c, int4 d) {
-  unsigned kind = (unsigned)d.x >> 28;
-  int xv = dec_var28((unsigned)d.x), xo = d.y, yv = d.z, yo = d.w;
-  IV x = rd<SMEM>(c, xv, xo), y = rd<SMEM>(c, yv, yo);
-  if (kind == B_NEQ) {  // cmp/x_neq_y.rs:82-93 + Interval::difference
-    IV nx = x, ny = y;
-    if (x.lo == x.hi) {
-      if (ny.lo == x.lo) ny.lo++; else if (ny.hi == x.lo) ny.hi--;
-    } else if (y.lo == y.hi) {
-      if (nx.lo == y.lo) nx.lo++; else if (nx.hi == y.lo) nx.hi--;
-    }
-    if (!tighten(c, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
-    if (!tighten(c, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
-    // !XEqY::is_subsumed (x_neq_y.rs:71-73, x_eq_y.rs:84-93)
-    return (nx.hi < ny.lo || ny.hi < nx.lo) ? E_ENTAILED : E_UNKNOWN;
-  } else if (kind == B_LESS) {  // cmp/x_less_y.rs:101-108
-    int nxhi = min(x.hi, y.hi - 1);
-    if (!tighten(c, xv, xo, x, x.lo, nxhi)) return E_FAIL;
-    int nylo = max(y.lo, x.lo + 1);
-    if (!tighten(c, yv, yo, y, nylo, y.hi)) return E_FAIL;
-    return nxhi < nylo ? E_ENTAILED : E_UNKNOWN;  // x_less_y.rs:84-91
-  } else {  // B_EQ: cmp/x_eq_y.rs:102-107
-    int lo = max(x.lo, y.lo), hi = min(x.hi, y.hi);
-    if (!tighten(c, xv, xo, x, lo, hi)) return E_FAIL;
-    if (!tighten(c, yv, yo, y, lo, hi)) return E_FAIL;
-    return lo == hi ? E_ENTAILED : E_UNKNOWN;     // x_eq_y.rs:84-93
-  }
-}
-// true when evaluating the propagator would change nothing: no pruning, no failure,
-// not entailed (the common case of a sweep; keeps the hot loop free of calls)
-__device__ __forceinline__ bool bin_is_noop(unsigned kind, IV x, IV y) {
-  if (kind == B_NEQ) return x.lo != x.hi && y.lo != y.hi && !(x.hi < y.lo || y.hi < x.lo);
-  if (kind == B_LESS) return y.hi > x.hi && x.lo < y.lo && x.hi >= y.lo;
-  return x.lo == y.lo && x.hi == y.hi && x.lo < x.hi;
-}
-
-// --- ternary family ------------------------------------------------------------------------
-struct Tri { int xv, xo, yv, yo, zv, zo; };
-
-// XGreaterYPlusZ::propagate on local copies (x_greater_y_plus_z.rs:106-119); `strict`=1 for
-// x > y+z, 0 for x >= y+z (the Addition(x,1) of cmp/mod.rs:73).
-__device__ __forceinline__ bool prop_greater(const Ctx& c, const Tri& t, IV& x, IV& y, IV& z, int strict) {
-  int nxlo = max(x.lo, y.lo + z.lo + strict);
-  int nyhi = min(y.hi, x.hi - z.lo - strict);
-  int nzhi = min(z.hi, x.hi - y.lo - strict);
-  if (!tighten(c, t.xv, t.xo, x, nxlo, x.hi)) return false;
-  if (!tighten(c, t.yv, t.yo, y, y.lo, nyhi)) return false;
-  if (!tighten(c, t.zv, t.zo, z, z.lo, nzhi)) return false;
-  x.lo = nxlo; y.hi = nyhi; z.hi = nzhi;
-  return true;
-}
-// XLessYPlusZ::propagate (x_less_y_plus_z.rs:106-120)
-__device__ __forceinline__ bool prop_less(const Ctx& c, const Tri& t, IV& x, IV& y, IV& z, int strict) {
-  int nxhi = min(x.hi, y.hi + z.hi - strict);
-  int nylo = max(y.lo, x.lo - z.hi + strict);
-  int nzlo = max(z.lo, x.lo - y.hi + strict);
-  if (!tighten(c, t.xv, t.xo, x, x.lo, nxhi)) return false;
-  if (!tighten(c, t.yv, t.yo, y, nylo, y.hi)) return false;
-  if (!tighten(c, t.zv, t.zo, z, nzlo, z.hi)) return false;
-  x.hi = nxhi; y.lo = nylo; z.lo = nzlo;
-  return true;
-}
-// Kleene entailment tests (x_greater_y_plus_z.rs:84-98, x_less_y_plus_z.rs:84-98,
-// x_eq_y_plus_z.rs:56-58)
-__device__ __forceinline__ int sub_greater(IV x, IV y, IV z, int strict) {
-  if (x.hi < y.lo + z.lo + strict) return -1;
-  if (x.lo >= y.hi + z.hi + strict) return 1;
-  return 0;
-}
-__device__ __forceinline__ int sub_less(IV x, IV y, IV z, int strict) {
-  if (x.lo > y.hi + z.hi - strict) return -1;
-  if (x.hi <= y.lo + z.lo - strict) return 1;
-  return 0;
-}
-__device__ __forceinline__ int sub_eq(IV x, IV y, IV z) {
-  return min(sub_greater(x, y, z, 0), sub_less(x, y, z, 0));
-}
-// XEqYPlusZ::propagate = geq then leq re-reading the store (x_eq_y_plus_z.rs:79-81)
-__device__ __forceinline__ bool prop_eq(const Ctx& c, const Tri& t, IV& x, IV& y, IV& z) {
-  return prop_greater(c, t, x, y, z, 0) && prop_less(c, t, x, y, z, 0);
-}
-
-template <bool SMEM>
-__device__ __forceinline__ Eval eval_ter(const Ctx& c, int4 a, int2 b) {
-  unsigned kind = (unsigned)a.x >> 28;
-  Tri t{dec_var28((unsigned)a.x), a.y, a.z, a.w, b.x, b.y};
-  IV x = rd<SMEM>(c, t.xv, t.xo), y = rd<SMEM>(c, t.yv, t.yo), z = rd<SMEM>(c, t.zv, t.zo);
-  int s;
-  if (kind == T_EQ) {
-    if (!prop_eq(c, t, x, y, z)) return E_FAIL;
-    s = sub_eq(x, y, z);
-  } else if (kind == T_GREATER) {
-    if (!prop_greater(c, t, x, y, z, 1)) return E_FAIL;
-    s = sub_greater(x, y, z, 1);
-  } else {
-    if (!prop_less(c, t, x, y, z, 1)) return E_FAIL;
-    s = sub_less(x, y, z, 1);
-  }
-  return s < 0 ? E_FAIL : (s > 0 ? E_ENTAILED : E_UNKNOWN);
-}
-__device__ __forceinline__ bool ter_is_noop(unsigned kind, IV x, IV y, IV z) {
-  if (kind == T_EQ)
-    return x.lo >= y.lo + z.lo && y.hi <= x.hi - z.lo && z.hi <= x.hi - y.lo &&
-           x.hi <= y.hi + z.hi && y.lo >= x.lo - z.hi && z.lo >= x.lo - y.hi && sub_eq(x, y, z) == 0;
-  if (kind == T_GREATER)
-    return x.lo >= y.lo + z.lo + 1 && y.hi <= x.hi - z.lo - 1 && z.hi <= x.hi - y.lo - 1 &&
-           sub_greater(x, y, z, 1) == 0;
-  return x.hi <= y.hi + z.hi - 1 && y.lo >= x.lo - z.hi + 1 && z.lo >= x.lo - y.hi + 1 && sub_less(x, y, z, 1) == 0;
-}
-
-// --- 2-way disjunction of XEqYPlusZ (logic/disjunction.rs:77-116) ---------------------------
-template <bool SMEM>
-__device__ __forceinline__ Eval eval_dj(const Ctx& c, int4 q0, int4 q1, int4 q2) {
-  Tri a{q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
-  Tri b{q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-  IV ax = rd<SMEM>(c, a.xv, a.xo), ay = rd<SMEM>(c, a.yv, a.yo), az = rd<SMEM>(c, a.zv, a.zo);
-  IV bx = rd<SMEM>(c, b.xv, b.xo), by = rd<SMEM>(c, b.yv, b.yo), bz = rd<SMEM>(c, b.zv, b.zo);
-  int sa = sub_eq(ax, ay, az), sb = sub_eq(bx, by, bz);
-  if (sa > 0 || sb > 0) return E_ENTAILED;          // disjunction.rs:102: propagate -> true
-  if (sa < 0 && sb < 0) return E_FAIL;              // disjunction.rs:110-111
-  if (sa == 0 && sb == 0) return E_UNKNOWN;         // disjunction.rs:112-114
-  if (sa < 0) {                                     // disjunction.rs:108-109
-    if (!prop_eq(c, b, bx, by, bz)) return E_FAIL;
-    sb = sub_eq(bx, by, bz);
-    return sb < 0 ? E_FAIL : (sb > 0 ? E_ENTAILED : E_UNKNOWN);
-  }
-  if (!prop_eq(c, a, ax, ay, az)) return E_FAIL;
-  sa = sub_eq(ax, ay, az);
-  return sa < 0 ? E_FAIL : (sa > 0 ? E_ENTAILED : E_UNKNOWN);
-}
-template <bool SMEM>
-__device__ __forceinline__ bool dj_is_noop(const Ctx& c, int4 q0, int4 q1, int4 q2) {
-  IV ax = rd<SMEM>(c, q0.x, q0.y), ay = rd<SMEM>(c, q0.z, q0.w), az = rd<SMEM>(c, q1.x, q1.y);
-  IV bx = rd<SMEM>(c, q1.z, q1.w), by = rd<SMEM>(c, q2.x, q2.y), bz = rd<SMEM>(c, q2.z, q2.w);
-  return sub_eq(ax, ay, az) == 0 && sub_eq(bx, by, bz) == 0;
-}
-
-// The out-of-line slow path: full propagate + is_subsumed of one propagator, with the
-// store bookkeeping of store.rs:166-207 (failure flag, unlink of entailed propagators).
-template <bool SMEM>
-__device__ __noinline__ void eval_full(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
-  Eval r;
-  if (fam == F_BIN) r = eval_bin<SMEM>(c, q0);
-  else if (fam == F_TER) r = eval_ter<SMEM>(c, q0, make_int2(q1.x, q1.y));
-  else r = eval_dj<SMEM>(c, q0, q1, q2);
-  if (r == E_FAIL) set_failed(c);
-  else if (r == E_ENTAILED && c.bookkeep) deactivate(c, c.P->fam[fam].active, fam, slot);
-}
-
-// Gather one descriptor from global memory (worklist expansion, tail).
-__device__ __forceinline__ void load_desc(const Family& f, unsigned fam, int slot, int4& q0, int4& q1, int4& q2) {
-  q1 = make_int4(0, 0, 0, 0);
-  q2 = q1;
-  if (fam == F_BIN) {
-    q0 = __ldg(&f.desc[slot]);
-  } else if (fam == F_TER) {
-    q0 = __ldg(&f.desc[slot]);
-    int2 b = __ldg(&f.descB[slot]);
-    q1.x = b.x; q1.y = b.y;
-  } else {
-    const int4* q = &f.desc[3 * (size_t)slot];
-    q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
-  }
-}
-// Evaluate a gathered propagator: cheap no-op test inline, everything else out of line.
-template <bool SMEM>
-__device__ __forceinline__ void eval_loaded(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
-  if (fam == F_BIN) {
-    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w);
-    if (bin_is_noop((unsigned)q0.x >> 28, x, y)) return;
-  } else if (fam == F_TER) {
-    IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w), z = rd<SMEM>(c, q1.x, q1.y);
-    if (ter_is_noop((unsigned)q0.x >> 28, x, y, z)) return;
-  } else {
-    if (dj_is_noop<SMEM>(c, q0, q1, q2)) return;
-  }
-  eval_full<SMEM>(c, fam, slot, q0, q1, q2);
-}
-template <bool SMEM>
-__device__ __forceinline__ void eval_ref(const Ctx& c, unsigned fam, int slot) {
-  int4 q0, q1, q2;
-  load_desc(c.P->fam[fam], fam, slot, q0, q1, q2);
-  eval_loaded<SMEM>(c, fam, slot, q0, q1, q2);
-}
-
-__device__ __forceinline__ bool is_active(const Family& f, int slot) {
-  return (__ldcg(&f.active[slot >> 5]) >> (slot & 31)) & 1u;
-}
+namespace pcpd {
 
 // ---------------------------------------------------------------------------------------
 // iteration 0: the streaming sweep.  A chunk = up to kChunk* propagators of one family;
@@ -708,6 +441,7 @@ __device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* sme
 // (the "block-reduce of a changed flag": the reduction operand is the dirty-list length).
 // `decide` = false: plain barrier (after the node prologue).
 // ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void node_prologue_finish(const Params& P);
 // The arrival word packs three 10-bit counters -- CTAs arrived, CTAs that queued a dirty
 // variable, CTAs that saw a failure -- so one release-atomic per CTA carries everything the
 // decision needs; the release word `bar_gen` = (generation << kDecBits) | decision, so one
@@ -737,6 +471,7 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
           if ((long long)nd * 8 >= (long long)P.V) dec = D_SWEEP;
         }
       }
+      if (!decide) node_prologue_finish(P);  // prologue barrier: every CTA has read trail_cnt by now
       ctl->bar_count = 0;
       unsigned rel = ((gen + 1u) << kDecBits) | dec;
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->bar_gen), "r"(rel) : "memory");
@@ -790,11 +525,13 @@ __device__ __forceinline__ unsigned expand_dirty_rows(const Ctx& c, int cur_buf,
   return nprop;
 }
 
-// Node prologue on CTA 0: Snapshot::restore (domains <- label copy, `active` bits of the
-// trail suffix set again, propagation/store.rs:319-323) and Store::alloc of the propagators
-// posted since the last launch (descriptor + active bit).
-__device__ __forceinline__ void node_prologue(const Params& P) {
-  const int tid = threadIdx.x, nth = blockDim.x;
+// Node prologue: Snapshot::restore (domains <- label copy, `active` bits of the trail suffix
+// set again, propagation/store.rs:319-323) and Store::alloc of the propagators posted since
+// the last launch (descriptor + active bit).  `tid`/`nth` span CTA 0 when nothing crosses
+// CTAs, or the whole grid when a device barrier follows anyway (a restore over a long trail
+// -- e.g. a store that had become fully entailed -- is then a grid-wide job).  The caller
+// resets `trail_cnt` once every participant has read it (node_prologue_finish).
+__device__ __forceinline__ void node_prologue(const Params& P, int tid, int nth) {
   if (P.restore_from)
     for (int v = tid; v < P.V; v += nth) P.dom[v] = P.restore_from[v];
   if (P.do_trail) {
@@ -823,8 +560,9 @@ __device__ __forceinline__ void node_prologue(const Params& P) {
     else if (ip.fam == F_TER) { f.desc[ip.slot] = ip.q[0]; f.descB[ip.slot] = make_int2(ip.q[1].x, ip.q[1].y); }
     else { f.desc[3 * (size_t)ip.slot] = ip.q[0]; f.desc[3 * (size_t)ip.slot + 1] = ip.q[1]; f.desc[3 * (size_t)ip.slot + 2] = ip.q[2]; }
   }
-  __syncthreads();
-  if (tid == 0 && P.do_trail) P.ctl->trail_cnt = P.trail_keep;
+}
+__device__ __forceinline__ void node_prologue_finish(const Params& P) {
+  if (P.do_trail) P.ctl->trail_cnt = P.trail_keep;
 }
 
 template <bool SMEM>
@@ -869,13 +607,16 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   const unsigned epoch0 = s_epoch;
   trace_mark(P, 0);
 
-  if (blockIdx.x == 0) node_prologue(P);
   if (P.sync0) {
-    grid_barrier(P, gen, 0, false, s_flags, 0);
+    node_prologue(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    grid_barrier(P, gen, 0, false, s_flags, 0);  // its last arriver resets trail_cnt (nobody pushes yet)
     if (SMEM) {
       for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
       __syncthreads();
     }
+  } else if (blockIdx.x == 0) {
+    node_prologue(P, threadIdx.x, blockDim.x);  // CTA-local effects only (posted propagators)
+    __syncthreads();
   }
   trace_mark(P, 1);
   ActiveWords aw;
@@ -950,8 +691,12 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
     if (n_dirty > 0) {
       const int* list = P.dirty_list + (size_t)cur_buf * P.V;
       // refresh the snapshot and catch domains emptied by two concurrent updates
+      // (with a snapshot every CTA needs every dirty variable; without one the check is
+      // shared by the grid)
       int bad = 0;
-      for (int i = threadIdx.x; i < n_dirty; i += blockDim.x) {
+      const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+      const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
+      for (int i = r0; i < n_dirty; i += rs) {
         int v = __ldcg(&list[i]);
         int2 d = ldcg_dom(&P.dom[v]);
         if (SMEM) sdom[v] = d;
@@ -1011,6 +756,13 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
     if (iter == 0) trace_mark(P, 4);
     dec = grid_barrier(P, gen, bp, true, s_flags, iter, next_buf);
     if (iter == 0) trace_mark(P, 5);
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && iter < 32) {  // per-iteration record
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[8 * 256 + iter * 4 + 0] = t;
+      P.trace[8 * 256 + iter * 4 + 1] = (unsigned long long)*(volatile int*)&ctl->dirty_cnt[next_buf];
+      P.trace[8 * 256 + iter * 4 + 2] = dec;
+    }
     ++iter;
     if (dec != D_CONTINUE && dec != D_SWEEP) break;
     sweep_now = dec == D_SWEEP;

@@ -127,6 +127,12 @@ struct pcp_engine {
   std::vector<uint32_t> prop_ref;   // global propagator index -> (family, slot)
   std::vector<std::vector<pcp_operand>> sums;
 
+  std::vector<int> h_sum_ptr{0};
+  std::vector<int2> h_sum_terms;
+  DevBuf<int> d_sum_ptr;
+  DevBuf<int2> d_sum_terms;
+  size_t sums_uploaded = 0;
+
   // reactor CSR
   DevBuf<int> d_adj_ptr;
   DevBuf<uint32_t> d_adj;
@@ -241,16 +247,19 @@ void reserve_zeroed(pcp_engine* e, DevBuf<uint32_t>& b, size_t words, size_t val
   fill_u32(e, b.p + from, 0u, b.cap - from);
 }
 
-inline unsigned enc_var28(int var) { return var < 0 ? kConstVar28 : (unsigned)var; }
+inline unsigned enc_var28(int var) {
+  if (var >= 0) return (unsigned)var;
+  return var == -1 ? kConstVar28 : kSumBase28 + (unsigned)(-2 - var);
+}
 
 void check_operand(const pcp_engine* e, pcp_operand op) {
   if (op.var >= 0) PCP_REQUIRE((size_t)op.var < e->V, "operand variable not registered in the store");
   else if (op.var <= -2) PCP_REQUIRE((size_t)(-2 - op.var) < e->sums.size(), "unknown sum view");
-  PCP_REQUIRE(op.var < (int)kConstVar28, "variable index too large");
+  PCP_REQUIRE(op.var < (int)kSumBase28, "variable index too large");
 }
 
-// Sum views with a single term delegate to the term (term/sum.rs:62-64); wider sums have
-// no device lowering yet.
+// Sum views with a single term delegate to the term (term/sum.rs:62-64); wider sums stay
+// read-only views (var = -2 - sum id) that the device evaluates by a segmented sum.
 pcp_operand lower_view(const pcp_engine* e, pcp_operand op) {
   check_operand(e, op);
   if (op.var > -2) return op;
@@ -260,15 +269,34 @@ pcp_operand lower_view(const pcp_engine* e, pcp_operand op) {
     t.off += op.off;
     return t;
   }
-  PCP_FAIL(PCP_ERR_UNSUPPORTED, "Sum views with more than one term have no device lowering");
+  PCP_REQUIRE((size_t)(-2 - op.var) < (size_t)(kConstVar28 - kSumBase28), "too many sum views");
+  return op;
 }
 
-void require_distinct_vars(const pcp_operand* ops, int n) {
+// The variables a lowered operand depends on (ViewDependencies, term/ops.rs:26-28).
+template <class F>
+void for_each_dep_var(const pcp_engine* e, int var, F&& fn) {
+  if (var >= 0) fn(var);
+  else if (var <= -2)
+    for (const pcp_operand& t : e->sums[(size_t)(-2 - var)])
+      if (t.var >= 0) fn(t.var);
+}
+
+void require_distinct_vars(const pcp_engine* e, const pcp_operand* ops, int n) {
   // a propagator subscribing twice to one variable panics in the reference
   // (reactors/indexed_deps.rs:69-77)
-  for (int i = 0; i < n; ++i)
-    for (int j = i + 1; j < n; ++j)
-      PCP_REQUIRE(ops[i].var < 0 || ops[i].var != ops[j].var, "propagator already subscribed to this variable");
+  bool any_sum = false;
+  for (int i = 0; i < n; ++i) any_sum |= ops[i].var <= -2;
+  if (!any_sum) {  // the bulk-upload path: no allocation
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j)
+        PCP_REQUIRE(ops[i].var < 0 || ops[i].var != ops[j].var, "propagator already subscribed to this variable");
+    return;
+  }
+  std::vector<int> vs;
+  for (int i = 0; i < n; ++i) for_each_dep_var(e, ops[i].var, [&](int v) { vs.push_back(v); });
+  std::sort(vs.begin(), vs.end());
+  PCP_REQUIRE(std::adjacent_find(vs.begin(), vs.end()) == vs.end(), "propagator already subscribed to this variable");
 }
 
 void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
@@ -279,7 +307,7 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
     case PCP_X_EQ_Y: {
       PCP_REQUIRE(n_ops == 2, "binary propagator takes 2 operands");
       for (int i = 0; i < 2; ++i) ops[i] = lower_view(e, raw[i]);
-      require_distinct_vars(ops, 2);
+      require_distinct_vars(e, ops, 2);
       unsigned k = kind == PCP_X_LESS_Y ? B_LESS : (kind == PCP_X_NEQ_Y ? B_NEQ : B_EQ);
       HostFamily& f = e->fam[F_BIN];
       f.desc.push_back(make_int4((int)((k << 28) | enc_var28(ops[0].var)), ops[0].off, ops[1].var, ops[1].off));
@@ -291,7 +319,7 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
     case PCP_X_EQ_Y_PLUS_Z: {
       PCP_REQUIRE(n_ops == 3, "ternary propagator takes 3 operands");
       for (int i = 0; i < 3; ++i) ops[i] = lower_view(e, raw[i]);
-      require_distinct_vars(ops, 3);
+      require_distinct_vars(e, ops, 3);
       unsigned k = kind == PCP_X_GREATER_Y_PLUS_Z ? T_GREATER : (kind == PCP_X_LESS_Y_PLUS_Z ? T_LESS : T_EQ);
       HostFamily& f = e->fam[F_TER];
       f.desc.push_back(make_int4((int)((k << 28) | enc_var28(ops[0].var)), ops[0].off, ops[1].var, ops[1].off));
@@ -302,8 +330,8 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
     case PCP_DISJ2_X_EQ_Y_PLUS_Z: {
       PCP_REQUIRE(n_ops == 6, "2-way disjunction of XEqYPlusZ takes 6 operands");
       for (int i = 0; i < 6; ++i) ops[i] = lower_view(e, raw[i]);
-      require_distinct_vars(ops, 3);
-      require_distinct_vars(ops + 3, 3);
+      require_distinct_vars(e, ops, 3);
+      require_distinct_vars(e, ops + 3, 3);
       HostFamily& f = e->fam[F_DJ];
       f.desc.push_back(make_int4(ops[0].var, ops[0].off, ops[1].var, ops[1].off));
       f.desc.push_back(make_int4(ops[2].var, ops[2].off, ops[3].var, ops[3].off));
@@ -315,7 +343,10 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       PCP_REQUIRE(n_ops >= 1, "Variable array in `Distinct` must be non-empty.");
       PCP_REQUIRE(n_ops <= 4096, "Distinct over more than 4096 operands is not supported");
       std::vector<pcp_operand> lo(n_ops);
-      for (int i = 0; i < n_ops; ++i) lo[i] = lower_view(e, raw[i]);
+      for (int i = 0; i < n_ops; ++i) {
+        lo[i] = lower_view(e, raw[i]);
+        if (lo[i].var <= -2) PCP_FAIL(PCP_ERR_UNSUPPORTED, "Distinct over multi-term Sum views has no device lowering");
+      }
       {
         std::vector<int> vs;
         for (auto& o : lo) if (o.var >= 0) vs.push_back(o.var);
@@ -359,34 +390,41 @@ void truncate_props(pcp_engine* e, const LabelRec& r) {
 void build_csr(pcp_engine* e) {
   const size_t V = e->V;
   std::vector<int> ptr(V + 1, 0);
+  // dependencies of one lowered operand: the variable itself, or every term of a sum view
+  auto dep = [&](int var, unsigned ref, auto&& fn) { for_each_dep_var(e, var, [&](int v) { fn(v, ref); }); };
+  auto x_of = [](const int4& d) {
+    unsigned v = (unsigned)d.x & kConstVar28;
+    return v < kSumBase28 ? (int)v : (v == kConstVar28 ? -1 : -2 - (int)(v - kSumBase28));
+  };
   auto for_each_var = [&](auto&& fn) {
     {
       const HostFamily& f = e->fam[F_BIN];
       for (size_t s = 0; s < f.n; ++s) {
         const int4& d = f.desc[s];
-        unsigned xv = (unsigned)d.x & kConstVar28;
-        if (xv != kConstVar28) fn((int)xv, make_ref(F_BIN, (unsigned)s));
-        if (d.z >= 0) fn(d.z, make_ref(F_BIN, (unsigned)s));
+        dep(x_of(d), make_ref(F_BIN, (unsigned)s), fn);
+        dep(d.z, make_ref(F_BIN, (unsigned)s), fn);
       }
     }
     {
       const HostFamily& f = e->fam[F_TER];
       for (size_t s = 0; s < f.n; ++s) {
         const int4& d = f.desc[s];
-        unsigned xv = (unsigned)d.x & kConstVar28;
-        if (xv != kConstVar28) fn((int)xv, make_ref(F_TER, (unsigned)s));
-        if (d.z >= 0) fn(d.z, make_ref(F_TER, (unsigned)s));
-        if (f.descB[s].x >= 0) fn(f.descB[s].x, make_ref(F_TER, (unsigned)s));
+        dep(x_of(d), make_ref(F_TER, (unsigned)s), fn);
+        dep(d.z, make_ref(F_TER, (unsigned)s), fn);
+        dep(f.descB[s].x, make_ref(F_TER, (unsigned)s), fn);
       }
     }
     {
       const HostFamily& f = e->fam[F_DJ];
+      std::vector<int> vars;
       for (size_t s = 0; s < f.n; ++s) {
-        int vars[6] = {f.desc[3 * s].x, f.desc[3 * s].z, f.desc[3 * s + 1].x,
-                       f.desc[3 * s + 1].z, f.desc[3 * s + 2].x, f.desc[3 * s + 2].z};
-        std::sort(vars, vars + 6);  // sort + dedup union of the children (disjunction.rs:118-129)
-        for (int i = 0; i < 6; ++i)
-          if (vars[i] >= 0 && (i == 0 || vars[i] != vars[i - 1])) fn(vars[i], make_ref(F_DJ, (unsigned)s));
+        const int ops[6] = {f.desc[3 * s].x, f.desc[3 * s].z, f.desc[3 * s + 1].x,
+                            f.desc[3 * s + 1].z, f.desc[3 * s + 2].x, f.desc[3 * s + 2].z};
+        vars.clear();
+        for (int o : ops) for_each_dep_var(e, o, [&](int v) { vars.push_back(v); });
+        std::sort(vars.begin(), vars.end());  // sort + dedup union of the children (disjunction.rs:118-129)
+        vars.erase(std::unique(vars.begin(), vars.end()), vars.end());
+        for (int v : vars) fn(v, make_ref(F_DJ, (unsigned)s));
       }
     }
   };
@@ -479,6 +517,11 @@ Params prepare(pcp_engine* e) {
   }
   reserve_zeroed(e, e->d_nary_active, (e->n_nary + 31) / 32 + 1, (e->nary_active_set + 31) / 32);
   total += e->n_nary;
+  if (e->sums_uploaded < e->sums.size()) {  // Sum views are append-only (not part of a label)
+    upload_range(e, e->d_sum_terms, e->h_sum_terms, (size_t)e->h_sum_ptr[e->sums_uploaded], e->h_sum_terms.size());
+    upload_range(e, e->d_sum_ptr, e->h_sum_ptr, e->sums_uploaded == 0 ? 0 : e->sums_uploaded + 1, e->sums.size() + 1);
+    e->sums_uploaded = e->sums.size();
+  }
   e->d_trail.reserve(total + 64, e->stream, e->trail_len);
 
   Params P;
@@ -537,6 +580,8 @@ Params prepare(pcp_engine* e) {
   P.new_last[F_NARY] = (int)e->n_nary;
   if (e->nary_active_set < e->n_nary) sync0 = true;
   e->nary_active_set = e->n_nary;
+  P.sum_ptr = e->d_sum_ptr.p;
+  P.sum_terms = e->d_sum_terms.p;
   P.adj_ptr = e->d_adj_ptr.p;
   P.adj = e->d_adj.p;
   P.dirty_list = e->d_dirty_list.p;
@@ -569,7 +614,11 @@ bool prologue_pending(const pcp_engine* e) {
   return e->nary_uploaded < e->n_nary || e->nary_active_set < e->n_nary;
 }
 
-__global__ void __launch_bounds__(1024, 1) pcp_prologue_kernel(const __grid_constant__ Params P) { node_prologue(P); }
+__global__ void __launch_bounds__(1024, 1) pcp_prologue_kernel(const __grid_constant__ Params P) {
+  node_prologue(P, threadIdx.x, blockDim.x);  // single CTA
+  __syncthreads();
+  if (threadIdx.x == 0) node_prologue_finish(P);
+}
 
 // Bring the device state up to date without running a fixpoint (pcp_domains_read /
 // pcp_label / pcp_active_read right after a restore or an alloc).
@@ -627,7 +676,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   // launch geometry: one CTA per SM, fewer for small stores (cheaper barrier)
   size_t total = e->n_nary * 4096;
   for (int f = 0; f < 3; ++f) total += e->fam[f].n;
-  int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 8191) / 8192));
+  int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 4095) / 4096));
   size_t nary_bytes = nary_smem_bytes(e);
   PCP_REQUIRE(nary_bytes <= (size_t)kRingBytes, "Distinct too wide for shared memory");
   size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
@@ -638,8 +687,8 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (trace_on) {
-    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, 8 * 256 * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, 8 * 256 * sizeof(unsigned long long), e->stream));
+    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, (8 * 256 + 4 * 32) * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, (8 * 256 + 4 * 32) * sizeof(unsigned long long), e->stream));
     P.trace = e->d_trace;
   }
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
@@ -655,8 +704,15 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   e->mirror_valid = eager_dom;
 
   if (trace_on) {
-    std::vector<unsigned long long> t(8 * 256);
+    std::vector<unsigned long long> t(8 * 256 + 4 * 32);
     CUDA_CHECK(cudaMemcpy(t.data(), e->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    {
+      unsigned long long tb = ~0ull;
+      for (int b = 0; b < grid; ++b) tb = std::min(tb, t[b * 8]);
+      for (unsigned it = 0; it < e->h_result()->iterations && it < 32; ++it)
+        std::fprintf(stderr, "[pcp trace]   iter %2u: barrier left at %8llu ns, dirty=%llu, decision=%llu\n", it,
+                     t[8 * 256 + it * 4] - tb, t[8 * 256 + it * 4 + 1], t[8 * 256 + it * 4 + 2]);
+    }
     unsigned long long t0 = ~0ull;
     for (int b = 0; b < grid; ++b) t0 = std::min(t0, t[b * 8]);
     std::fprintf(stderr, "[pcp trace] grid=%d sync0=%d iters=%u; per phase: min/avg/max ns since first CTA start\n", grid, P.sync0, e->h_result()->iterations);
@@ -771,7 +827,7 @@ void pcp_engine_destroy(pcp_engine* e) {
     e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
   }
   e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_active.free();
-  e->d_adj_ptr.free(); e->d_adj.free();
+  e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
   e->d_dirty_list.free(); e->d_dirty_stamp.free(); e->d_trail.free(); e->d_stack.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
   if (e->d_block) cudaFree(e->d_block);
@@ -811,6 +867,8 @@ int pcp_sum_alloc(pcp_engine* e, const pcp_operand* terms, int32_t n, int32_t* s
     PCP_REQUIRE(n >= 1 && terms, "At least one variable in sum.");
     for (int i = 0; i < n; ++i) { PCP_REQUIRE(terms[i].var >= -1, "nested sums are not supported"); check_operand(e, terms[i]); }
     e->sums.emplace_back(terms, terms + n);
+    for (int i = 0; i < n; ++i) e->h_sum_terms.push_back(make_int2(terms[i].var, terms[i].off));
+    e->h_sum_ptr.push_back((int)e->h_sum_terms.size());
     if (sum_id) *sum_id = (int32_t)(e->sums.size() - 1);
   });
 }

@@ -342,3 +342,71 @@ def test_size_independent_properties_nqueens_1000():
     dev.restore(l0)
     back = dev.domains()
     assert (back[0] == root[0]).all() and (back[1] == root[1]).all()
+
+
+def test_sum_views():
+    """term/sum.rs:56-92: a Sum operand reads [sum lo, sum hi]; with more than one term its
+    update never prunes (overlap test only, can fail); a single-term Sum delegates.  Random
+    stores where cmp propagators take Sum operands, device vs the oracle's view trees."""
+    from pcp_b200 import PcpError
+    rng = np.random.default_rng(99)
+    for trial in range(40):
+        V = int(rng.integers(6, 30))
+        lo = rng.integers(-10, 10, V).astype(np.int32)
+        hi = (lo + rng.integers(0, 12, V)).astype(np.int32)
+        dev, ora = _engine(), _oracle(1)
+        for e in (dev, ora):
+            e.vars_alloc(lo, hi)
+        for _ in range(int(rng.integers(1, 25))):
+            kind = int(rng.integers(0, 6))
+            n_ops = 2 if kind < 3 else 3
+            perm = rng.permutation(V)
+            ops, used = [], 0
+            for j in range(n_ops):
+                if rng.random() < 0.4 and used + 4 <= V:  # a Sum operand over 1..3 fresh variables
+                    k = int(rng.integers(1, 4))
+                    terms = [[int(perm[used + t]), int(rng.integers(-3, 4))] for t in range(k)]
+                    if rng.random() < 0.2:
+                        terms.append([-1, int(rng.integers(-5, 6))])  # constant term
+                    used += k
+                    sid = [e.sum_alloc(terms) for e in (dev, ora)]
+                    assert sid[0] == sid[1]
+                    ops.append([-2 - sid[0], int(rng.integers(-4, 5))])
+                else:
+                    ops.append([int(perm[used]), int(rng.integers(-4, 5))])
+                    used += 1
+            for e in (dev, ora):
+                e.prop_alloc(kind, ops)
+        ds, _ = dev.consistency()
+        os_, _ = ora.consistency()
+        assert ds == os_, trial
+        if ds != -1:
+            _assert_same_state(dev, ora)
+    # a Sum inside Distinct has no device lowering: loud error, not a CPU path
+    dev = _engine()
+    dev.vars_alloc([0, 0, 0], [5, 5, 5])
+    s = dev.sum_alloc([[0, 0], [1, 0]])
+    with pytest.raises(PcpError):
+        dev.prop_alloc(models.DISTINCT, [[-2 - s, 0], [2, 0]])
+    # the same variable directly and inside the sum: double subscription (indexed_deps.rs:69-77)
+    from pcp_b200 import ContractViolation
+    with pytest.raises(ContractViolation):
+        dev.prop_alloc(models.X_LESS_Y, [[0, 0], [-2 - s, 0]])
+
+
+def test_sum_capacity_constraint_search():
+    """A small knapsack-like model with Sum operands through the search driver: per-node parity."""
+    n = 8
+    m = models.Model("sum-capacity", np.zeros(n, np.int32), np.full(n, 3, np.int32))
+    m.sums.append(np.array([[i, 0] for i in range(n)], np.int32))
+    m.sums.append(np.array([[i, 0] for i in range(0, n, 2)], np.int32))
+    m.add(models.X_LESS_Y, [[-2, 0], [-1, 14]])            # sum(x) < 14
+    m.add(models.X_LESS_Y, [[-1, 5], [-2, 0]])             # 5 < sum(x)
+    m.add(models.X_LESS_Y_PLUS_Z, [[-3, 0], [1, 0], [3, 2]])  # sum(x_even) < x1 + x3 + 2
+    ops = np.zeros((n - 1, 2, 2), np.int32)
+    ops[:, 0, 0] = np.arange(n - 1)
+    ops[:, 1, 0] = np.arange(1, n)
+    ops[:, 1, 1] = 1
+    m.add(models.X_LESS_Y, ops)                             # x_i < x_{i+1} + 1
+    rd, _, _, _ = _compare_search(m, 400)
+    assert rd.num_nodes == 71 and rd.num_solution == 3 and rd.num_failed_node == 33
