@@ -182,9 +182,12 @@ template <bool SMEM>
 __device__ __forceinline__ Eval eval_bin(const Ctx& c, int4 d, UpdSet& us) {
   unsigned kind = (unsigned)d.x >> 28;
   int xv = dec_var28((unsigned)d.x), xo = d.y, yv = d.z, yo = d.w;
-  IV x = rd<SMEM>(c, xv, xo), y = rd<SMEM>(c, yv, yo);
+  const IV x = rd<SMEM>(c, xv, xo), y = rd<SMEM>(c, yv, yo);
+  // A multi-term Sum operand is never narrowed (term/sum.rs:62-69): is_subsumed, which the
+  // store evaluates after propagate (store.rs:177-183), re-reads it unchanged.
+  const bool xro = xv <= -2, yro = yv <= -2;
+  IV nx = x, ny = y;
   if (kind == B_NEQ) {  // cmp/x_neq_y.rs:82-93 + Interval::difference
-    IV nx = x, ny = y;
     if (x.lo == x.hi) {
       if (ny.lo == x.lo) ny.lo++; else if (ny.hi == x.lo) ny.hi--;
     } else if (y.lo == y.hi) {
@@ -192,20 +195,27 @@ __device__ __forceinline__ Eval eval_bin(const Ctx& c, int4 d, UpdSet& us) {
     }
     if (!stage(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
     if (!stage(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
-    // !XEqY::is_subsumed (x_neq_y.rs:71-73, x_eq_y.rs:84-93)
-    return (nx.hi < ny.lo || ny.hi < nx.lo) ? E_ENTAILED : E_UNKNOWN;
   } else if (kind == B_LESS) {  // cmp/x_less_y.rs:101-108
-    int nxhi = min(x.hi, y.hi - 1);
-    if (!stage(us, xv, xo, x, x.lo, nxhi)) return E_FAIL;
-    int nylo = max(y.lo, x.lo + 1);
-    if (!stage(us, yv, yo, y, nylo, y.hi)) return E_FAIL;
-    return nxhi < nylo ? E_ENTAILED : E_UNKNOWN;  // x_less_y.rs:84-91
+    nx.hi = min(x.hi, y.hi - 1);
+    if (!stage(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
+    ny.lo = max(y.lo, x.lo + 1);
+    if (!stage(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
   } else {  // B_EQ: cmp/x_eq_y.rs:102-107
-    int lo = max(x.lo, y.lo), hi = min(x.hi, y.hi);
-    if (!stage(us, xv, xo, x, lo, hi)) return E_FAIL;
-    if (!stage(us, yv, yo, y, lo, hi)) return E_FAIL;
-    return lo == hi ? E_ENTAILED : E_UNKNOWN;     // x_eq_y.rs:84-93
+    nx.lo = ny.lo = max(x.lo, y.lo);
+    nx.hi = ny.hi = min(x.hi, y.hi);
+    if (!stage(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
+    if (!stage(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
   }
+  const IV px = xro ? x : nx, py = yro ? y : ny;  // what is_subsumed reads back
+  if (kind == B_LESS) {  // x_less_y.rs:84-91
+    if (px.lo >= py.hi) return E_FAIL;
+    return px.hi < py.lo ? E_ENTAILED : E_UNKNOWN;
+  }
+  // XEqY::is_subsumed (x_eq_y.rs:84-93); XNeqY negates it (x_neq_y.rs:71-73)
+  const bool same_singleton = px.lo == py.hi && px.hi == py.lo;
+  const bool disjoint = px.hi < py.lo || py.hi < px.lo;
+  if (kind == B_NEQ) return same_singleton ? E_FAIL : (disjoint ? E_ENTAILED : E_UNKNOWN);
+  return same_singleton ? E_ENTAILED : (disjoint ? E_FAIL : E_UNKNOWN);
 }
 // true when evaluating the propagator would change nothing: no pruning, no failure,
 // not entailed (the common case of a sweep; keeps the hot loop free of calls)
@@ -252,9 +262,23 @@ __device__ __forceinline__ int sub_less(IV x, IV y, IV z, int strict) {
 __device__ __forceinline__ int sub_eq(IV x, IV y, IV z) {
   return min(sub_greater(x, y, z, 0), sub_less(x, y, z, 0));
 }
+// Operands that are multi-term Sum views are checked (overlap) but never narrowed, so whoever
+// reads them next -- the second half of XEqYPlusZ, is_subsumed -- sees the original interval.
+struct TriRo { bool x, y, z; };
+__device__ __forceinline__ TriRo tri_ro(const Tri& t) { return TriRo{t.xv <= -2, t.yv <= -2, t.zv <= -2}; }
+__device__ __forceinline__ void undo_ro(const TriRo& ro, IV& x, IV& y, IV& z, IV x0, IV y0, IV z0) {
+  if (ro.x) x = x0;
+  if (ro.y) y = y0;
+  if (ro.z) z = z0;
+}
 // XEqYPlusZ::propagate = geq then leq re-reading the store (x_eq_y_plus_z.rs:79-81)
-__device__ __forceinline__ bool prop_eq(IV& x, IV& y, IV& z) {
-  return prop_greater(x, y, z, 0) && prop_less(x, y, z, 0);
+__device__ __forceinline__ bool prop_eq(IV& x, IV& y, IV& z, const TriRo& ro) {
+  const IV x0 = x, y0 = y, z0 = z;
+  if (!prop_greater(x, y, z, 0)) return false;
+  undo_ro(ro, x, y, z, x0, y0, z0);
+  if (!prop_less(x, y, z, 0)) return false;
+  undo_ro(ro, x, y, z, x0, y0, z0);
+  return true;
 }
 __device__ __forceinline__ bool stage_tri(UpdSet& us, const Tri& t, IV x0, IV y0, IV z0, IV x, IV y, IV z) {
   return stage(us, t.xv, t.xo, x0, x.lo, x.hi) && stage(us, t.yv, t.yo, y0, y.lo, y.hi) &&
@@ -267,15 +291,18 @@ __device__ __forceinline__ Eval eval_ter(const Ctx& c, int4 a, int2 b, UpdSet& u
   Tri t{dec_var28((unsigned)a.x), a.y, a.z, a.w, b.x, b.y};
   const IV x0 = rd<SMEM>(c, t.xv, t.xo), y0 = rd<SMEM>(c, t.yv, t.yo), z0 = rd<SMEM>(c, t.zv, t.zo);
   IV x = x0, y = y0, z = z0;
+  const TriRo ro = tri_ro(t);
   int s;
   if (kind == T_EQ) {
-    if (!prop_eq(x, y, z)) return E_FAIL;
+    if (!prop_eq(x, y, z, ro)) return E_FAIL;
     s = sub_eq(x, y, z);
   } else if (kind == T_GREATER) {
     if (!prop_greater(x, y, z, 1)) return E_FAIL;
+    undo_ro(ro, x, y, z, x0, y0, z0);
     s = sub_greater(x, y, z, 1);
   } else {
     if (!prop_less(x, y, z, 1)) return E_FAIL;
+    undo_ro(ro, x, y, z, x0, y0, z0);
     s = sub_less(x, y, z, 1);
   }
   if (!stage_tri(us, t, x0, y0, z0, x, y, z)) return E_FAIL;
@@ -304,12 +331,12 @@ __device__ __forceinline__ Eval eval_dj(const Ctx& c, int4 q0, int4 q1, int4 q2,
   if (sa == 0 && sb == 0) return E_UNKNOWN;         // disjunction.rs:112-114
   if (sa < 0) {                                     // disjunction.rs:108-109
     IV x = bx0, y = by0, z = bz0;
-    if (!prop_eq(x, y, z) || !stage_tri(us, b, bx0, by0, bz0, x, y, z)) return E_FAIL;
+    if (!prop_eq(x, y, z, tri_ro(b)) || !stage_tri(us, b, bx0, by0, bz0, x, y, z)) return E_FAIL;
     sb = sub_eq(x, y, z);
     return sb < 0 ? E_FAIL : (sb > 0 ? E_ENTAILED : E_UNKNOWN);
   }
   IV x = ax0, y = ay0, z = az0;
-  if (!prop_eq(x, y, z) || !stage_tri(us, a, ax0, ay0, az0, x, y, z)) return E_FAIL;
+  if (!prop_eq(x, y, z, tri_ro(a)) || !stage_tri(us, a, ax0, ay0, az0, x, y, z)) return E_FAIL;
   sa = sub_eq(x, y, z);
   return sa < 0 ? E_FAIL : (sa > 0 ? E_ENTAILED : E_UNKNOWN);
 }
