@@ -53,7 +53,11 @@ __host__ __device__ inline unsigned make_ref(unsigned fam, unsigned slot) { retu
 enum BinKind : unsigned { B_LESS = 0, B_NEQ = 1, B_EQ = 2 };
 enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2 };
 
-enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3, D_SWEEP = 4 };
+enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3, D_SWEEP = 4, D_SOLO = 5 };
+constexpr int kSoloMaxDirty = 8;    // a worklist this short is run by CTA 0 alone (solo_iterations)
+constexpr int kSoloCap = 32;        // capacity of the shared-memory worklist
+constexpr int kSoloWords = 384;     // bit set over the variables (snapshot mode: V <= 12288)
+constexpr int kSoloMaxIters = 4096;
 constexpr unsigned kDecBits = 3;  // the release word of the barrier = (generation << kDecBits) | decision
 
 struct Control {
@@ -130,6 +134,7 @@ struct Params {
   int seed_dirty;             // incremental launch: dirty_list[0..seed_dirty) seeded by the host
   // ---- epilogue
   int2* snapshot_to;          // if not failed: copy of the fixpoint domains (next label slot)
+  int solo_ok;                // experimental (PCP_SOLO=1): short cascades run by CTA 0 alone
   // ---- debug: per-CTA phase timestamps (PCP_TRACE=1), 8 slots per CTA
   unsigned long long* trace;
 };
@@ -469,6 +474,8 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
           // sweep is cheaper than gathering the rows
           int nd = *(volatile int*)&ctl->dirty_cnt[next_buf];
           if ((long long)nd * 8 >= (long long)P.V) dec = D_SWEEP;
+          // a short cascade: grid-wide barriers and gathers cost more than the work itself
+          else if (P.solo_ok && P.smem_dom && nd <= kSoloMaxDirty && P.V <= kSoloWords * 32) dec = D_SOLO;
         }
       }
       if (!decide) node_prologue_finish(P);  // prologue barrier: every CTA has read trail_cnt by now
@@ -565,73 +572,269 @@ __device__ __forceinline__ void node_prologue_finish(const Params& P) {
   if (P.do_trail) P.ctl->trail_cnt = P.trail_keep;
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_constant__ Params P) {
-  extern __shared__ __align__(128) char smem[];
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
-  __shared__ unsigned s_block_props, s_gen, s_epoch;
-  __shared__ int s_flags[2];
-  // layout: [ring | n-ary staging (aliased)] [domain snapshot]
-  char* ring = smem;
-  int2* sdom = SMEM ? reinterpret_cast<int2*>(smem + kRingBytes) : nullptr;
+// ---------------------------------------------------------------------------------------
+// Solo mode: a short cascade (<= kSoloMaxDirty dirty variables) is run to its end by CTA 0
+// alone.  The snapshot in shared memory is the authoritative copy of the domains (updates by
+// shared-memory atomics, written through to HBM without waiting), the worklists are a bit set
+// plus a short list in shared memory, iterations are separated by __syncthreads instead of the
+// device barrier, and a propagator adjacent to two dirty variables is evaluated once (from
+// the smaller one) without any stamp traffic.  Everybody else waits at the device barrier.
+// Ends at the fixpoint, at a failure, or when the worklist outgrows the mode; then the next
+// worklist is handed back to the grid through the global dirty list.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool solo_bit(const unsigned* bits, int v) { return v >= 0 && ((bits[v >> 5] >> (v & 31)) & 1u); }
 
-  Control* ctl = P.ctl;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
-  // by the other CTAs so that nobody waits for it at the barrier
-  const ChunkMap cmap = chunk_map(P);
-  const int workers = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
-  const int wid = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
-  const int my_chunks = wid >= 0 && wid < cmap.total ? (cmap.total - 1 - wid) / workers + 1 : 0;
-  const int pre_issued = P.full_sweep ? min(my_chunks, kStages) : 0;
-  int pipe_pos = 0;  // chunks this CTA has pushed through the ring so far (all sweeps)
-
-  if (threadIdx.x == 0) {
-    s_block_props = 0;
-    s_flags[0] = s_flags[1] = 0;
-    for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    // start streaming descriptors right away: they do not depend on the node prologue
-    for (int i = 0; i < pre_issued; ++i)
-      producer_issue(P, chunk_of(P, cmap, wid + i * workers), ring + i * kStageBytes, &s_full[i]);
-  } else if (threadIdx.x == 32) {
-    s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
-    s_epoch = *(volatile unsigned*)&ctl->epoch;
-  }
-  // without a restore the domains are already final: snapshot them while the TMA runs
-  if (SMEM && !P.sync0)
-    for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
-  __syncthreads();
-  unsigned gen = s_gen;
-  const unsigned epoch0 = s_epoch;
-  trace_mark(P, 0);
-
-  if (P.sync0) {
-    node_prologue(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
-    grid_barrier(P, gen, 0, false, s_flags, 0);  // its last arriver resets trail_cnt (nobody pushes yet)
-    if (SMEM) {
-      for (int v = threadIdx.x; v < P.V; v += blockDim.x) sdom[v] = ldcg_dom(&P.dom[v]);
-      __syncthreads();
+// true if `p` will be (was) evaluated from a smaller dirty variable than `v`
+__device__ __forceinline__ bool solo_dup(const Params& P, const unsigned* bits, unsigned fam, int4 q0, int4 q1, int4 q2, int v) {
+  int ops[6];
+  int n;
+  if (fam == F_BIN) { ops[0] = dec_var28((unsigned)q0.x); ops[1] = q0.z; n = 2; }
+  else if (fam == F_TER) { ops[0] = dec_var28((unsigned)q0.x); ops[1] = q0.z; ops[2] = q1.x; n = 3; }
+  else { ops[0] = q0.x; ops[1] = q0.z; ops[2] = q1.x; ops[3] = q1.z; ops[4] = q2.x; ops[5] = q2.z; n = 6; }
+  for (int i = 0; i < n; ++i) {
+    const int u = ops[i];
+    if (u >= 0) { if (u < v && solo_bit(bits, u)) return true; }
+    else if (u <= -2) {  // a sum view: any of its terms
+      const int b = __ldg(&P.sum_ptr[-2 - u]), e = __ldg(&P.sum_ptr[-2 - u + 1]);
+      for (int t = b; t < e; ++t) { const int w = __ldg(&P.sum_terms[t]).x; if (w >= 0 && w < v && solo_bit(bits, w)) return true; }
     }
-  } else if (blockIdx.x == 0) {
-    node_prologue(P, threadIdx.x, blockDim.x);  // CTA-local effects only (posted propagators)
+  }
+  return false;
+}
+
+__device__ __forceinline__ void solo_mark(const Params& P, int slot) {
+  if (P.trace && threadIdx.x == 0 && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[8 * 256 + 4 * 32 + slot] = t;
+  }
+}
+// CTA 0, all threads.  `list`/`n_dirty`: the global worklist of this iteration (already
+// refreshed into the snapshot).  Returns the number of propagator evaluations.
+template <bool SMEM>
+__device__ __noinline__ unsigned solo_iterations(const Params& P, Ctx c, int bin_n, const int* list, int n_dirty,
+                                                 char* smem_nary, unsigned next_epoch, int next_buf) {
+  __shared__ int s_list[2][kSoloCap];
+  __shared__ int s_cnt[2];
+  __shared__ int s_rows[kSoloCap + 1], s_rowbase[kSoloCap], s_rowlen[kSoloCap];
+  __shared__ unsigned s_bits[2][kSoloWords];
+  constexpr int kTailCap = 64;            // active tail propagators, cached for the whole phase
+  __shared__ unsigned s_tail_ref[kTailCap];
+  __shared__ int s_tail_n;
+  const int tid = threadIdx.x;
+  const int words = (P.V + 31) >> 5;
+  solo_mark(P, 0);
+  for (int w = tid; w < 2 * kSoloWords; w += blockDim.x) (&s_bits[0][0])[w] = 0u;
+  if (tid < 2) s_cnt[tid] = 0;
+  if (tid == 0) s_tail_n = 0;
+  __syncthreads();
+  if (tid < n_dirty) { const int v = __ldcg(&list[tid]); s_list[0][tid] = v; atomicOr(&s_bits[0][v >> 5], 1u << (v & 31)); }
+  if (tid == 0) s_cnt[0] = n_dirty;
+  // the active tail propagators (none can appear during the phase; entailed ones just evaluate
+  // as no-ops): collected once
+  for (unsigned fam = 0; fam < 3; ++fam) {
+    const Family& f = P.fam[fam];
+    const int fn = fam == F_BIN ? bin_n : f.n;
+    for (int p = f.n_static + tid; p < fn; p += blockDim.x)
+      if (is_active(f, p)) { int i = atomicAdd(&s_tail_n, 1); if (i < kTailCap) s_tail_ref[i] = make_ref(fam, (unsigned)p); }
+  }
+  __syncthreads();
+  const int tail_n = s_tail_n;
+  solo_mark(P, 1);
+  c.solo = true;
+  c.local = false;
+  c.mark_dirty = true;
+  c.bookkeep = true;
+  c.solo_cap = kSoloCap;
+  unsigned nprop = 0;
+  int cur = 0;
+  for (int it = 0; it < kSoloMaxIters; ++it) {
+    const int n = s_cnt[cur];
+    const unsigned* cur_bits = s_bits[cur];
+    c.solo_next_bits = s_bits[cur ^ 1];
+    c.solo_next_list = s_list[cur ^ 1];
+    c.solo_next_cnt = &s_cnt[cur ^ 1];
+    // rows of the dirty variables (n <= kSoloMaxDirty): bases and lengths in parallel, then a
+    // tiny prefix sum
+    if (tid < n) {
+      const int v = s_list[cur][tid];
+      const int b = __ldg(&P.adj_ptr[v]);
+      s_rowbase[tid] = b;
+      s_rowlen[tid] = __ldg(&P.adj_ptr[v + 1]) - b;
+    }
+    // tail propagators, from the snapshot
+    if (tail_n <= kTailCap) {
+      if (tid < tail_n) { eval_ref<SMEM>(c, s_tail_ref[tid] >> 29, (int)(s_tail_ref[tid] & kSlotMask)); ++nprop; }
+    } else {
+      for (unsigned fam = 0; fam < 3; ++fam) {
+        const Family& f = P.fam[fam];
+        const int fn = fam == F_BIN ? bin_n : f.n;
+        for (int p = f.n_static + tid; p < fn; p += blockDim.x)
+          if (is_active(f, p)) { eval_ref<SMEM>(c, fam, p); ++nprop; }
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0;
+      for (int e = 0; e < n; ++e) { s_rows[e] = acc; acc += s_rowlen[e]; }
+      s_rows[n] = acc;
+    }
+    __syncthreads();
+    const int total = s_rows[n];
+    solo_mark(P, 2 + 3 * it);
+    // the concatenated rows, kBatch entries per thread in flight
+    constexpr int kBatch = 4;
+    for (int base = tid; base < total; base += blockDim.x * kBatch) {
+      unsigned ref[kBatch];
+      int var[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        const int i = base + k * blockDim.x;
+        ref[k] = 0xffffffffu;
+        var[k] = -1;
+        if (i < total) {
+          int e = 0;
+          while (e + 1 < n && s_rows[e + 1] <= i) ++e;
+          var[k] = s_list[cur][e];
+          ref[k] = __ldg(&P.adj[s_rowbase[e] + (i - s_rows[e])]);
+        }
+      }
+      unsigned word[kBatch];
+      int4 q0[kBatch], q1[kBatch], q2[kBatch];
+      bool live[kBatch];
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        live[k] = false;
+        if (ref[k] != 0xffffffffu) {
+          const unsigned fam = ref[k] >> 29;
+          const int slot = (int)(ref[k] & kSlotMask);
+          const Family& f = P.fam[fam];
+          if (slot < f.n_static) {
+            word[k] = __ldcg(&f.active[slot >> 5]);
+            load_desc(f, fam, slot, q0[k], q1[k], q2[k]);
+            live[k] = true;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kBatch; ++k) {
+        if (!live[k]) continue;
+        const unsigned fam = ref[k] >> 29;
+        const int slot = (int)(ref[k] & kSlotMask);
+        if (!((word[k] >> (slot & 31)) & 1u)) continue;
+        if (solo_dup(P, cur_bits, fam, q0[k], q1[k], q2[k], var[k])) continue;
+        eval_loaded<SMEM>(c, fam, slot, q0[k], q1[k], q2[k]);
+        ++nprop;
+      }
+    }
+    solo_mark(P, 3 + 3 * it);
+    // n-ary propagators: all active ones (their operands live in the snapshot)
+    for (int s = 0; s < P.n_nary; ++s) {
+      if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
+      unsigned ev = eval_distinct<SMEM>(c, s, smem_nary, 0u, true);
+      if (tid == 0) nprop += ev;
+    }
+    __syncthreads();
+    const int n_next = s_cnt[cur ^ 1];
+    const bool failed = c.flags[1] != 0;
+    solo_mark(P, 4 + 3 * it);
+    // retire the current worklist
+    if (tid < n && tid < kSoloCap) { const int v = s_list[cur][tid]; atomicAnd(&s_bits[cur][v >> 5], ~(1u << (v & 31))); }
+    __syncthreads();
+    if (tid == 0) s_cnt[cur] = 0;
+    if (failed || n_next == 0) break;
+    if (n_next > kSoloMaxDirty || it + 1 == kSoloMaxIters) {
+      // hand the worklist back to the grid: the bit set is complete even if the list overflowed
+      for (int w = tid; w < words; w += blockDim.x) {
+        unsigned m = s_bits[cur ^ 1][w];
+        while (m) {
+          const int b = __ffs(m) - 1;
+          m &= m - 1;
+          const int v = w * 32 + b;
+          const int idx = atomicAdd(&P.ctl->dirty_cnt[next_buf], 1);
+          P.dirty_list[(size_t)next_buf * P.V + idx] = v;
+          P.dirty_stamp[v] = next_epoch;
+        }
+      }
+      c.flags[0] = 1;
+      break;
+    }
+    cur ^= 1;
     __syncthreads();
   }
-  trace_mark(P, 1);
-  ActiveWords aw;
-  aw.w[0] = aw.w[1] = 0u;
-  if (warp > 0 && my_chunks > 0 && P.full_sweep) aw = load_active_words(P, chunk_of(P, cmap, wid));
-  bool sweep_now = P.full_sweep != 0;
+  __syncthreads();
+  return nprop;
+}
 
+// ---------------------------------------------------------------------------------------
+// Per-CTA state shared by the single-node kernel and the search-burst kernel.
+// ---------------------------------------------------------------------------------------
+struct CtaState {
+  char* ring;
+  int2* sdom;
+  uint64_t* full;
+  uint64_t* empty;
+  unsigned* block_props;
+  int* flags;
+  ChunkMap cmap;
+  int workers, wid, my_chunks;
+  int pipe_pos;      // chunks this CTA has pushed through the ring so far (all sweeps, all nodes)
+  int pre_issued;    // chunks of the coming sweep already issued by the producer
+  unsigned gen;      // barrier generation
+};
+
+__device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* smem, uint64_t* s_full,
+                                         uint64_t* s_empty, unsigned* s_block_props, int* s_flags, bool smem_dom) {
+  st.ring = smem;
+  st.sdom = smem_dom ? reinterpret_cast<int2*>(smem + kRingBytes) : nullptr;
+  st.full = s_full;
+  st.empty = s_empty;
+  st.block_props = s_block_props;
+  st.flags = s_flags;
+  // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
+  // by the other CTAs so that nobody waits for it at the barrier
+  st.cmap = chunk_map(P);
+  st.workers = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
+  st.wid = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+  st.my_chunks = st.wid >= 0 && st.wid < st.cmap.total ? (st.cmap.total - 1 - st.wid) / st.workers + 1 : 0;
+  st.pipe_pos = 0;
+  st.pre_issued = 0;
+}
+
+// Producer: issue the first chunks of the coming sweep (thread 0 only).  Stages that still
+// hold an unconsumed chunk cannot exist here: a sweep is always consumed completely.
+__device__ __forceinline__ void pre_issue(const Params& P, CtaState& st) {
+  // the ring memory doubles as n-ary staging (generic-proxy writes): order them before the
+  // async-proxy writes of the bulk copies
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  int n = min(st.my_chunks, kStages);
+  for (int i = 0; i < n; ++i) {
+    const int q = st.pipe_pos + i, s = q % kStages;
+    if (q >= kStages) mbar_wait(&st.empty[s], ((q / kStages) - 1) & 1);
+    producer_issue(P, chunk_of(P, st.cmap, st.wid + i * st.workers), st.ring + s * kStageBytes, &st.full[s]);
+  }
+}
+
+// One node's fixpoint: iteration 0 (posted propagators, tail, streaming sweep or seeded
+// worklist) and the worklist / re-sweep iterations, each closed by the deciding barrier.
+// Every thread of every CTA calls it with the same arguments; returns the decision, `iters`
+// the number of iterations.  `bin_n` is the end of the binary tail (dynamic during a burst).
+template <bool SMEM>
+__device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st, unsigned epoch0, int bin_n,
+                                                  int n_inline, const InlineProp* inl, bool full_sweep,
+                                                  int seed_dirty, bool pre_issued, unsigned& iters_out) {
+  Control* ctl = P.ctl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Ctx c;
   c.P = &P;
-  c.sdom = sdom;
-  c.flags = s_flags;
-
-  unsigned iter = 0;
-  unsigned dec;
-  unsigned nprop = 0;
+  c.sdom = st.sdom;
+  c.flags = st.flags;
+  ActiveWords aw;
+  aw.w[0] = aw.w[1] = 0u;
+  if (warp > 0 && st.my_chunks > 0 && full_sweep) aw = load_active_words(P, chunk_of(P, st.cmap, st.wid));
+  bool sweep_now = full_sweep, solo_now = false, after_solo = false;
+  c.solo = false;
+  unsigned iter = 0, dec, nprop = 0;
   while (true) {
     const int cur_buf = iter % 3, next_buf = (iter + 1) % 3, spare_buf = (iter + 2) % 3;
     const unsigned cur_epoch = epoch0 + iter;
@@ -641,25 +844,30 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
     c.mark_dirty = true;
     c.bookkeep = true;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dirty_cnt[spare_buf] = 0;  // idle this iteration
+    if (SMEM && after_solo) {
+      // CTA 0 ran a cascade on its own: everybody's snapshot is stale beyond the worklist
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
+      __syncthreads();
+    }
 
-    if (iter == 0 && P.n_inline > 0) {
-      // Propagators posted since the last launch.  With a full sweep ahead they need not enter
+    if (iter == 0 && n_inline > 0) {
+      // Propagators posted since the last node.  With a full sweep ahead they need not enter
       // the worklist: every CTA applies them to its own view of the domains first, so the sweep
       // already sees their effect.
       if (threadIdx.x == 0) {
-        c.mark_dirty = !P.full_sweep;
+        c.mark_dirty = !full_sweep;
         if (blockIdx.x == 0 || !SMEM) {  // the global store: counted and book-kept by CTA 0
           c.bookkeep = blockIdx.x == 0;
-          for (int i = 0; i < P.n_inline; ++i)
-            eval_full<false>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
-          if (blockIdx.x == 0) nprop += P.n_inline;
+          for (int i = 0; i < n_inline; ++i)
+            eval_full<false>(c, inl[i].fam, inl[i].slot, inl[i].q[0], inl[i].q[1], inl[i].q[2]);
+          if (blockIdx.x == 0) nprop += n_inline;
           if (!SMEM) __threadfence();
         }
         if (SMEM) {
           c.local = true;
           c.bookkeep = false;
-          for (int i = 0; i < P.n_inline; ++i)
-            eval_full<true>(c, P.inl[i].fam, P.inl[i].slot, P.inl[i].q[0], P.inl[i].q[1], P.inl[i].q[2]);
+          for (int i = 0; i < n_inline; ++i)
+            eval_full<true>(c, inl[i].fam, inl[i].slot, inl[i].q[0], inl[i].q[1], inl[i].q[2]);
         }
         c.local = false;
         c.mark_dirty = true;
@@ -668,15 +876,16 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       __syncthreads();
     }
     // older tail propagators: CTA 0, every iteration (inline ones were just handled)
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && !solo_now) {
       unsigned n = 0;
       for (unsigned fam = 0; fam < 3; ++fam) {
         const Family& f = P.fam[fam];
-        for (int p = f.n_static + threadIdx.x; p < f.n; p += blockDim.x) {
-          bool inl = false;
+        const int fn = fam == F_BIN ? bin_n : f.n;
+        for (int p = f.n_static + threadIdx.x; p < fn; p += blockDim.x) {
+          bool is_inl = false;
           if (iter == 0)
-            for (int i = 0; i < P.n_inline; ++i) inl |= P.inl[i].fam == fam && P.inl[i].slot == p;
-          if (!inl && is_active(f, p)) { eval_ref<false>(c, fam, p); ++n; }
+            for (int i = 0; i < n_inline; ++i) is_inl |= inl[i].fam == fam && inl[i].slot == p;
+          if (!is_inl && is_active(f, p)) { eval_ref<false>(c, fam, p); ++n; }
         }
       }
       nprop += n;
@@ -687,8 +896,8 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
     // incremental launch: seeded by the host)
     int n_dirty = 0;
     if (iter > 0) n_dirty = *(volatile int*)&ctl->dirty_cnt[cur_buf];
-    else if (!P.full_sweep) n_dirty = P.seed_dirty;
-    if (n_dirty > 0) {
+    else if (!full_sweep) n_dirty = seed_dirty;
+    if (n_dirty > 0 && (!solo_now || blockIdx.x == 0)) {
       const int* list = P.dirty_list + (size_t)cur_buf * P.V;
       // refresh the snapshot and catch domains emptied by two concurrent updates
       // (with a snapshot every CTA needs every dirty variable; without one the check is
@@ -699,62 +908,64 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       for (int i = r0; i < n_dirty; i += rs) {
         int v = __ldcg(&list[i]);
         int2 d = ldcg_dom(&P.dom[v]);
-        if (SMEM) sdom[v] = d;
+        if (SMEM) st.sdom[v] = d;
         bad |= d.x > d.y;
       }
       if (bad) set_failed(c);
       if (SMEM) __syncthreads();
-      if (!sweep_now) nprop += expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
+      if (solo_now) nprop += solo_iterations<SMEM>(P, c, bin_n, list, n_dirty, st.ring, c.next_epoch, next_buf);
+      else if (!sweep_now) nprop += expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
     }
-    if (sweep_now && my_chunks > 0) {
+    if (sweep_now && st.my_chunks > 0) {
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep
       // counting across sweeps so the mbarrier phases stay consistent)
+      const int first = (iter == 0 && pre_issued) ? min(st.my_chunks, kStages) : 0;
       if (warp == 0) {
         if (lane == 0) {
           // the ring memory doubles as n-ary staging (generic-proxy writes): order them before
           // the async-proxy writes of the next bulk copies
-          if (iter > 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          for (int i = (iter == 0 ? pre_issued : 0); i < my_chunks; ++i) {
-            const int q = pipe_pos + i, s = q % kStages;
-            if (q >= kStages) mbar_wait(&s_empty[s], ((q / kStages) - 1) & 1);
-            producer_issue(P, chunk_of(P, cmap, wid + i * workers), ring + s * kStageBytes, &s_full[s]);
+          if (first == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          for (int i = first; i < st.my_chunks; ++i) {
+            const int q = st.pipe_pos + i, s = q % kStages;
+            if (q >= kStages) mbar_wait(&st.empty[s], ((q / kStages) - 1) & 1);
+            producer_issue(P, chunk_of(P, st.cmap, st.wid + i * st.workers), st.ring + s * kStageBytes, &st.full[s]);
           }
         }
       } else {
-        if (iter > 0) aw = load_active_words(P, chunk_of(P, cmap, wid));
-        for (int i = 0; i < my_chunks; ++i) {
-          const int q = pipe_pos + i, s = q % kStages;
-          const Chunk ch = chunk_of(P, cmap, wid + i * workers);
+        if (iter > 0) aw = load_active_words(P, chunk_of(P, st.cmap, st.wid));
+        for (int i = 0; i < st.my_chunks; ++i) {
+          const int q = st.pipe_pos + i, s = q % kStages;
+          const Chunk ch = chunk_of(P, st.cmap, st.wid + i * st.workers);
           ActiveWords nxt = aw;
-          if (i + 1 < my_chunks) nxt = load_active_words(P, chunk_of(P, cmap, wid + (i + 1) * workers));
-          mbar_wait(&s_full[s], (q / kStages) & 1);
-          nprop += sweep_consume<SMEM>(c, ch, ring + s * kStageBytes, aw);
+          if (i + 1 < st.my_chunks) nxt = load_active_words(P, chunk_of(P, st.cmap, st.wid + (i + 1) * st.workers));
+          mbar_wait(&st.full[s], (q / kStages) & 1);
+          nprop += sweep_consume<SMEM>(c, ch, st.ring + s * kStageBytes, aw);
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[s]);
+          if (lane == 0) mbar_arrive(&st.empty[s]);
           aw = nxt;
         }
       }
-      pipe_pos += my_chunks;
+      st.pipe_pos += st.my_chunks;
     }
     if (iter == 0 && P.trace) { __syncthreads(); trace_mark(P, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
-    if (P.n_nary > 0 && (iter > 0 || P.full_sweep || n_dirty > 0)) {
+    if (P.n_nary > 0 && !solo_now && (iter > 0 || full_sweep || n_dirty > 0)) {
       for (int s = blockIdx.x; s < P.n_nary; s += gridDim.x) {
         if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-        unsigned ev = eval_distinct<SMEM>(c, s, ring, cur_epoch, iter == 0 && P.full_sweep);
+        unsigned ev = eval_distinct<SMEM>(c, s, st.ring, cur_epoch, iter == 0 && full_sweep);
         if (threadIdx.x == 0) nprop += ev;
       }
     }
 
     // block-level propagation count, then the barrier + decision
     for (int o = 16; o; o >>= 1) nprop += __shfl_xor_sync(0xffffffffu, nprop, o);
-    if (lane == 0 && nprop) atomicAdd(&s_block_props, nprop);
+    if (lane == 0 && nprop) atomicAdd(st.block_props, nprop);
     nprop = 0;
     __syncthreads();
     unsigned bp = 0;
-    if (threadIdx.x == 0) { bp = s_block_props; s_block_props = 0; }
+    if (threadIdx.x == 0) { bp = *st.block_props; *st.block_props = 0; }
     if (iter == 0) trace_mark(P, 4);
-    dec = grid_barrier(P, gen, bp, true, s_flags, iter, next_buf);
+    dec = grid_barrier(P, st.gen, bp, true, st.flags, iter, next_buf);
     if (iter == 0) trace_mark(P, 5);
     if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && iter < 32) {  // per-iteration record
       unsigned long long t;
@@ -764,9 +975,62 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       P.trace[8 * 256 + iter * 4 + 2] = dec;
     }
     ++iter;
-    if (dec != D_CONTINUE && dec != D_SWEEP) break;
+    if (dec != D_CONTINUE && dec != D_SWEEP && dec != D_SOLO) break;
+    after_solo = solo_now;
     sweep_now = dec == D_SWEEP;
+    solo_now = dec == D_SOLO;
   }
+  iters_out = iter;
+  return dec;
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ unsigned s_block_props, s_gen, s_epoch;
+  __shared__ int s_flags[2];
+  // layout: [ring | n-ary staging (aliased)] [domain snapshot]
+  CtaState st;
+  cta_init(P, st, smem, s_full, s_empty, &s_block_props, s_flags, SMEM);
+  Control* ctl = P.ctl;
+
+  if (threadIdx.x == 0) {
+    s_block_props = 0;
+    s_flags[0] = s_flags[1] = 0;
+    for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // start streaming descriptors right away: they do not depend on the node prologue
+    if (P.full_sweep) pre_issue(P, st);
+  } else if (threadIdx.x == 32) {
+    s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
+    s_epoch = *(volatile unsigned*)&ctl->epoch;
+  }
+  // without a restore the domains are already final: snapshot them while the TMA runs
+  if (SMEM && !P.sync0)
+    for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
+  __syncthreads();
+  st.gen = s_gen;
+  const unsigned epoch0 = s_epoch;
+  trace_mark(P, 0);
+
+  if (P.sync0) {
+    node_prologue(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    grid_barrier(P, st.gen, 0, false, s_flags, 0);  // its last arriver resets trail_cnt (nobody pushes yet)
+    if (SMEM) {
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
+      __syncthreads();
+    }
+  } else if (blockIdx.x == 0) {
+    node_prologue(P, threadIdx.x, blockDim.x);  // CTA-local effects only (posted propagators)
+    __syncthreads();
+  }
+  trace_mark(P, 1);
+
+  unsigned iters = 0;
+  const unsigned dec = fixpoint_node<SMEM>(P, st, epoch0, P.fam[F_BIN].n, P.n_inline, P.inl, P.full_sweep != 0,
+                                           P.seed_dirty, P.full_sweep != 0, iters);
 
   trace_mark(P, 6);
   if (blockIdx.x == 0) {
@@ -778,16 +1042,268 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       Result r;
       r.failed = dec == D_FAILED;
       r.trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
-      r.iterations = iter;
-      r.epoch = epoch0 + iter + 1;
+      r.iterations = iters;
+      r.epoch = epoch0 + iters + 1;
       r.propagations = *(volatile unsigned long long*)&ctl->propagations;
       r.decision = dec;
       *P.result = r;
-      ctl->epoch = epoch0 + iter + 1;
-      ctl->iterations = iter;
+      ctl->epoch = epoch0 + iters + 1;
+      ctl->iterations = iters;
       ctl->last_decision = dec;
       ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Search burst: the callers of the path -- Brancher(FirstSmallestVar,
+// MiddleVal, BinarySplit) under OneSolution/AllSolution/StopNode -- executed on the device
+// between fixpoints, so that a run of DFS nodes costs one launch.  CTA 0 plays the host:
+// after a node's final barrier it derives the status (propagation/store.rs:250-256), selects
+// the branching variable (search/branching/first_smallest_var.rs:30-39: first index among the
+// smallest domains of size > 1) and value (middle_val.rs:25-27), takes the label
+// (branch.rs:36-49: copy of the domains + trail length + number of propagators), pushes the
+// two alternatives (right first, so the left child is explored first,
+// engine/one_solution.rs:46-51), pops the next branch, restores its label (branch.rs:51-55)
+// and posts its constraint (binary_split.rs:46-57) in the tail; the other CTAs wait at a
+// barrier and meanwhile stream the descriptors of the next sweep into shared memory.
+// ---------------------------------------------------------------------------------------
+struct BurstCtl {
+  int cmd;            // 0: run the posted node, 1: stop
+  int root_pending;   // 1: the next node is the root of the search (nothing to pop)
+  int inl_slot;       // slot of the posted branching constraint (-1: none = root)
+  int bin_n;          // end of the binary tail for the posted node
+  int4 inl_desc;
+  int n_branch, n_labels, cur_label, stopped;
+  int status;         // why the burst ended: 0 budget, 1 solution, -1 exhausted, 2 end of search
+  int err;            // 1: label / branch / tail capacity exceeded
+  int last_status;    // status of the last node (-1/0/1)
+  int pad;
+  unsigned long long nodes, solutions, failures, iterations;
+};
+
+struct BurstParams {
+  BurstCtl* bc;
+  int4* branches;          // DFS stack: (label, var, val, alternative)
+  int2* label_meta;        // per label: (bin_n, trail_len)
+  int2* stack;             // label slots (copies of dom[])
+  long long stack_stride;
+  int max_labels, max_branches, bin_cap;
+  int all_solutions;
+  unsigned long long node_budget;   // nodes to run in this launch
+  unsigned long long node_limit;    // StopNode (search/stop_node.rs:54-61), 0 = none
+  long long props_base;             // allocated propagators = props_base + bin_n
+  int* t_status;                    // per-node trace (device buffers), indexed by node number
+  int2* t_dom;
+  unsigned long long t_cap;
+};
+
+// CTA 0, all threads: close the node that just reached its decision.
+__device__ __forceinline__ void burst_after_node(const Params& P, const BurstParams& B, unsigned dec, unsigned iters) {
+  __shared__ unsigned long long s_best[kWarps];
+  BurstCtl* bc = B.bc;
+  Control* ctl = P.ctl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
+  const int bin_n = *(volatile int*)&bc->bin_n;
+  const unsigned long long n = *(volatile unsigned long long*)&bc->nodes;
+  // propagation/store.rs:250-256
+  const int status = dec == D_FAILED ? -1 : ((long long)trail_cnt == B.props_base + bin_n ? 1 : 0);
+  if (n < B.t_cap) {
+    if (tid == 0 && B.t_status) B.t_status[n] = status;
+    if (B.t_dom && status != -1)
+      for (int v = tid; v < P.V; v += blockDim.x) B.t_dom[n * (unsigned long long)P.V + v] = ldcg_dom(&P.dom[v]);
+  }
+  const bool stop = B.node_limit && n + 1 >= B.node_limit;
+  if (status == 0 && !stop) {
+    // FirstSmallestVar: min over (size, index) of the variables with size > 1
+    unsigned long long best = ~0ull;
+    for (int v = tid; v < P.V; v += blockDim.x) {
+      int2 d = ldcg_dom(&P.dom[v]);
+      unsigned size = (unsigned)(d.y - d.x) + 1u;
+      if (size > 1u) best = min(best, ((unsigned long long)size << 32) | (unsigned)v);
+    }
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    best = s_best[0];
+    for (int w = 1; w < kWarps; ++w) best = min(best, s_best[w]);
+    const int var = (int)(best & 0xffffffffu);
+    const int2 d = ldcg_dom(&P.dom[var]);
+    const int val = (d.x + d.y) / 2;  // MiddleVal: truncating division
+    const int slot = *(volatile int*)&bc->n_labels;
+    const int nb = *(volatile int*)&bc->n_branch;
+    if (best == ~0ull || slot >= B.max_labels || nb + 2 > B.max_branches) {
+      if (tid == 0) bc->err = 1;
+    } else {
+      int2* dst = B.stack + (long long)slot * B.stack_stride;
+      for (int v = tid; v < P.V; v += blockDim.x) dst[v] = ldcg_dom(&P.dom[v]);
+      if (tid == 0) {
+        B.label_meta[slot] = make_int2(bin_n, (int)trail_cnt);
+        bc->n_labels = slot + 1;
+        bc->cur_label = slot;
+        B.branches[nb] = make_int4(slot, var, val, 1);      // x > val, explored second
+        B.branches[nb + 1] = make_int4(slot, var, val, 0);  // x <= val, explored first
+        bc->n_branch = nb + 2;
+      }
+    }
+  }
+  if (tid == 0) {
+    bc->nodes = n + 1;
+    bc->iterations += iters;
+    bc->last_status = status;
+    if (stop) bc->stopped = 1;
+    else if (status == 1) bc->solutions += 1;
+    else if (status == -1) bc->failures += 1;
+  }
+  __syncthreads();
+}
+
+// CTA 0, all threads: decide whether the burst goes on; if so pop the next branch, restore its
+// label and post its constraint.  `done` = nodes finished in this launch.
+__device__ __forceinline__ void burst_post_next(const Params& P, const BurstParams& B, unsigned long long done) {
+  __shared__ int4 s_pop;
+  __shared__ int s_run;
+  BurstCtl* bc = B.bc;
+  Control* ctl = P.ctl;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    // a node may end with entries left in its last dirty list (failure): start the next clean
+    ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
+    int run = 0, status = 0;
+    const int nb = bc->n_branch;
+    if (bc->err) status = 2;
+    else if (bc->stopped) status = 2;                                     // StopNode -> EndOfSearch
+    else if (done > 0 && bc->last_status == 1 && !B.all_solutions) status = 1;  // OneSolution returns
+    else if (!bc->root_pending && nb == 0) status = B.all_solutions ? 2 : -1;   // tree exhausted
+    else if (done >= B.node_budget) status = 0;                          // slice used up
+    else run = 1;
+    if (run && !bc->root_pending) { s_pop = B.branches[nb - 1]; bc->n_branch = nb - 1; }
+    s_run = run;
+    if (!run) { bc->status = status; bc->cmd = 1; }
+  }
+  __syncthreads();
+  if (!s_run) return;
+  if (*(volatile int*)&bc->root_pending) {
+    if (tid == 0) { bc->root_pending = 0; bc->inl_slot = -1; bc->cmd = 0; bc->cur_label = -1; }
+    __syncthreads();
+    return;
+  }
+  const int4 br = s_pop;
+  const int L = br.x;
+  const int2 meta = B.label_meta[L];
+  if (*(volatile int*)&bc->cur_label != L) {
+    // Snapshot::restore: domains <- label copy, re-activate the trail suffix (store.rs:319-323)
+    const int2* src = B.stack + (long long)L * B.stack_stride;
+    for (int v = tid; v < P.V; v += blockDim.x) P.dom[v] = src[v];
+    const unsigned cnt = *(volatile unsigned*)&ctl->trail_cnt;
+    for (unsigned i = (unsigned)meta.y + tid; i < cnt; i += blockDim.x) {
+      unsigned ref = P.trail[i];
+      unsigned fam = ref >> 29, slot = ref & kSlotMask;
+      uint32_t* act = fam == F_NARY ? P.nary_active_w : P.fam[fam].active;
+      atomicOr(&act[slot >> 5], 1u << (slot & 31));
+    }
+    __syncthreads();
+    if (tid == 0) ctl->trail_cnt = (unsigned)meta.y;
+  }
+  if (tid == 0) {
+    const int slot = meta.x;  // propagators are truncated to the labelled length (store.rs:320)
+    if (slot >= B.bin_cap) { bc->err = 1; bc->status = 2; bc->cmd = 1; }
+    else {
+      int4 d = br.w == 0 ? make_int4((int)((B_LESS << 28) | (unsigned)br.y), 0, -1, br.z + 1)    // x <= val
+                         : make_int4((int)((B_LESS << 28) | kConstVar28), br.z, br.y, 0);         // val < x
+      P.fam[F_BIN].desc[slot] = d;
+      atomicOr(&P.fam[F_BIN].active[slot >> 5], 1u << (slot & 31));
+      bc->inl_desc = d;
+      bc->inl_slot = slot;
+      bc->bin_n = slot + 1;
+      bc->n_labels = L + 1;
+      bc->cur_label = -1;
+      bc->cmd = 0;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_constant__ Params P,
+                                                                const __grid_constant__ BurstParams B) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ unsigned s_block_props, s_gen, s_epoch;
+  __shared__ int s_flags[2];
+  __shared__ int s_cmd, s_slot, s_bin_n;
+  __shared__ InlineProp s_inl;
+  CtaState st;
+  cta_init(P, st, smem, s_full, s_empty, &s_block_props, s_flags, SMEM);
+  Control* ctl = P.ctl;
+  BurstCtl* bc = B.bc;
+
+  if (threadIdx.x == 0) {
+    s_block_props = 0;
+    s_flags[0] = s_flags[1] = 0;
+    for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    pre_issue(P, st);  // descriptors never depend on the node
+  } else if (threadIdx.x == 32) {
+    s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
+    s_epoch = *(volatile unsigned*)&ctl->epoch;
+  }
+  __syncthreads();
+  st.gen = s_gen;
+  unsigned epoch = s_epoch;
+
+  unsigned long long done = 0;
+  if (blockIdx.x == 0) burst_post_next(P, B, done);
+  while (true) {
+    grid_barrier(P, st.gen, 0, false, s_flags, 0);  // the posted node is visible to every CTA
+    if (threadIdx.x == 0) {
+      s_cmd = *(volatile int*)&bc->cmd;
+      s_slot = *(volatile int*)&bc->inl_slot;
+      s_bin_n = *(volatile int*)&bc->bin_n;
+      if (s_slot >= 0) {
+        s_inl.q[0] = __ldcg(&bc->inl_desc);
+        s_inl.q[1] = s_inl.q[2] = make_int4(0, 0, 0, 0);
+        s_inl.fam = F_BIN;
+        s_inl.slot = s_slot;
+      }
+    }
+    if (SMEM) for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
+    __syncthreads();
+    if (s_cmd != 0) break;
+    unsigned iters = 0;
+    const unsigned dec = fixpoint_node<SMEM>(P, st, epoch, s_bin_n, s_slot >= 0 ? 1 : 0, &s_inl, true, 0, true, iters);
+    epoch += iters + 1;
+    ++done;
+    // the next sweep's descriptors can stream in while CTA 0 does the host's work
+    if (threadIdx.x == 0 && dec != D_ITER_CAP) pre_issue(P, st);
+    if (blockIdx.x == 0) {
+      if (dec == D_ITER_CAP) { if (threadIdx.x == 0) bc->err = 2; __syncthreads(); }
+      else burst_after_node(P, B, dec, iters);
+      burst_post_next(P, B, done);
+    }
+  }
+  // drain the chunks that were pre-issued for a node that will not run in this launch
+  if (threadIdx.x >> 5 > 0 && st.my_chunks > 0) {
+    const int n = min(st.my_chunks, kStages);
+    for (int i = 0; i < n; ++i) {
+      const int q = st.pipe_pos + i, s = q % kStages;
+      mbar_wait(&s_full[s], (q / kStages) & 1);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->epoch = epoch + 1;
+    ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
+    Result r;
+    r.failed = 0;
+    r.trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
+    r.iterations = 0;
+    r.epoch = epoch + 1;
+    r.propagations = *(volatile unsigned long long*)&ctl->propagations;
+    r.decision = 0;
+    *P.result = r;
   }
 }
 

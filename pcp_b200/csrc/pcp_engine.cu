@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "pcp_device.cuh"
+#include "pcp_internal.h"
 
 using namespace pcpd;
 
@@ -164,6 +165,26 @@ struct pcp_engine {
   bool at_fixpoint = false;
   std::vector<int> host_dirty;      // variables narrowed through pcp_var_update
   unsigned max_iterations = 1u << 22;
+
+  // device-resident search bursts (pcp_internal.h)
+  struct Burst {
+    bool open = false;
+    uint64_t root_label = 0;
+    BurstCtl* d_bc = nullptr;
+    DevBuf<int4> d_branches;
+    DevBuf<int2> d_meta;
+    DevBuf<int> d_tstatus;
+    DevBuf<int2> d_tdom;
+    uint64_t trace_cap = 0;
+    bool trace_dom = false;
+    int all_solutions = 0;
+    uint64_t node_limit = 0;
+    int max_labels = 0, bin_cap = 0;
+    long long props_base = 0;
+    unsigned long long props0 = 0;
+    double kernel_seconds = 0;
+    Params P;
+  } burst;
 
   // debug timeline (PCP_TRACE=1)
   unsigned long long* d_trace = nullptr;
@@ -589,6 +610,8 @@ Params prepare(pcp_engine* e) {
   P.trail = e->d_trail.p;
   P.ctl = e->d_ctl;
   P.max_iterations = e->max_iterations;
+  static const bool solo_on = std::getenv("PCP_SOLO") != nullptr;
+  P.solo_ok = solo_on ? 1 : 0;
   if (e->pending_restore) {
     P.restore_from = e->d_stack.p + e->pending_restore_label * e->stack_stride;
     e->mirror_valid = false;
@@ -687,8 +710,8 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (trace_on) {
-    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, (8 * 256 + 4 * 32) * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, (8 * 256 + 4 * 32) * sizeof(unsigned long long), e->stream));
+    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, (8 * 256 + 4 * 32 + 64) * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, (8 * 256 + 4 * 32 + 64) * sizeof(unsigned long long), e->stream));
     P.trace = e->d_trace;
   }
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
@@ -704,11 +727,16 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   e->mirror_valid = eager_dom;
 
   if (trace_on) {
-    std::vector<unsigned long long> t(8 * 256 + 4 * 32);
+    std::vector<unsigned long long> t(8 * 256 + 4 * 32 + 64);
     CUDA_CHECK(cudaMemcpy(t.data(), e->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     {
       unsigned long long tb = ~0ull;
       for (int b = 0; b < grid; ++b) tb = std::min(tb, t[b * 8]);
+      if (t[8 * 256 + 4 * 32]) {
+        std::fprintf(stderr, "[pcp trace]   solo marks (ns since start):");
+        for (int k = 0; k < 64 && t[8 * 256 + 4 * 32 + k]; ++k) std::fprintf(stderr, " %llu", t[8 * 256 + 4 * 32 + k] - tb);
+        std::fprintf(stderr, "\n");
+      }
       for (unsigned it = 0; it < e->h_result()->iterations && it < 32; ++it)
         std::fprintf(stderr, "[pcp trace]   iter %2u: barrier left at %8llu ns, dirty=%llu, decision=%llu\n", it,
                      t[8 * 256 + it * 4] - tb, t[8 * 256 + it * 4 + 1], t[8 * 256 + it * 4 + 2]);
@@ -830,6 +858,8 @@ void pcp_engine_destroy(pcp_engine* e) {
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
   e->d_dirty_list.free(); e->d_dirty_stamp.free(); e->d_trail.free(); e->d_stack.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
+  if (e->burst.d_bc) cudaFree(e->burst.d_bc);
+  e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free();
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1025,6 +1055,222 @@ int pcp_restore(pcp_engine* e, uint64_t label) {
     }
     e->pending_trail_undo = true;
     e->pending_trail_keep = r.trail_len;
+  });
+}
+
+// ---------------------------------------------------------------------------------------
+// device-resident search bursts (private interface, pcp_internal.h)
+// ---------------------------------------------------------------------------------------
+int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, uint64_t trace_capacity) {
+  if (!e || !cfg) return 0;
+  static const bool off = std::getenv("PCP_NO_BURST") != nullptr;
+  if (off) return 0;
+  if (cfg->var_sel != 0 || cfg->val_sel != 0 || cfg->distributor != 0 || cfg->bb_mode != 0) return 0;
+  if (e->V == 0 || e->V > (size_t)(1 << 20)) return 0;
+  if ((e->flags & PCP_FLAG_INCREMENTAL)) return 0;
+  // the device trace keeps full domains for the traced nodes
+  if (trace_capacity * e->V * sizeof(int2) > (size_t)1 << 30) return 0;
+  return 1;
+}
+
+int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node_limit, uint64_t trace_capacity,
+                             int32_t trace_domains) {
+  if (!e) return PCP_ERR_INVALID;
+  int rc = pcp_label(e, &e->burst.root_label);  // flushes everything pending; the root of the search
+  if (rc != PCP_OK) return rc;
+  return guarded(e, [&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    auto& b = e->burst;
+    PCP_REQUIRE(!b.open, "a device search is already open on this engine");
+    const size_t V = e->V;
+    // room for the search: label slots, branching constraints in the binary tail, trail
+    const size_t depth = std::max<size_t>(e->max_labels, 16384);
+    b.max_labels = (int)(e->labels.size() + depth);
+    e->stack_stride = V;
+    e->d_stack.reserve((size_t)b.max_labels * V, e->stream, e->labels.size() * V);
+    HostFamily& hb = e->fam[F_BIN];
+    b.bin_cap = (int)(hb.n + depth);
+    hb.d_desc.reserve((size_t)b.bin_cap, e->stream, hb.n);
+    reserve_zeroed(e, hb.d_active, ((size_t)b.bin_cap + 31) / 32 + 1, (hb.active_set + 31) / 32 + 1);
+    if ((size_t)b.bin_cap > hb.d_stamp.cap) {
+      size_t valid = std::min(hb.d_stamp.cap, hb.n);
+      hb.d_stamp.reserve((size_t)b.bin_cap, e->stream, valid);
+      fill_u32(e, hb.d_stamp.p + valid, 0u, hb.d_stamp.cap - valid);
+    }
+    e->d_trail.reserve(e->num_props() + depth + 64, e->stream, e->trail_len);
+    b.d_branches.reserve(2 * depth + 16, e->stream);
+    b.d_meta.reserve((size_t)b.max_labels, e->stream);
+    b.trace_cap = trace_capacity;
+    b.trace_dom = trace_domains != 0 || trace_capacity > 0;
+    if (trace_capacity) {
+      b.d_tstatus.reserve(trace_capacity, e->stream);
+      if (b.trace_dom) b.d_tdom.reserve(trace_capacity * V, e->stream);
+    }
+    if (!b.d_bc) CUDA_CHECK(cudaMalloc(&b.d_bc, sizeof(BurstCtl)));
+    BurstCtl bc;
+    std::memset(&bc, 0, sizeof(bc));
+    bc.cmd = 1;
+    bc.root_pending = 1;
+    bc.inl_slot = -1;
+    bc.bin_n = (int)hb.n;
+    bc.n_labels = (int)e->labels.size();
+    bc.cur_label = -1;
+    CUDA_CHECK(cudaMemcpyAsync(b.d_bc, &bc, sizeof(bc), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    b.P = prepare(e);  // nothing pending: pure parameter block
+    b.P.full_sweep = 1;
+    b.P.sync0 = 0;
+    b.P.do_trail = 0;
+    b.P.restore_from = nullptr;
+    b.P.n_inline = 0;
+    b.P.snapshot_to = nullptr;
+    b.P.trace = nullptr;
+    b.all_solutions = all_solutions;
+    b.node_limit = node_limit;
+    b.props_base = (long long)e->num_props() - (long long)hb.n;
+    b.props0 = e->props_total;
+    b.kernel_seconds = 0;
+    b.open = true;
+  });
+}
+
+int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result* res) {
+  if (!e || !res) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    auto& b = e->burst;
+    PCP_REQUIRE(b.open, "no device search is open");
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const size_t V = e->V;
+    BurstParams B;
+    std::memset(&B, 0, sizeof(B));
+    B.bc = b.d_bc;
+    B.branches = b.d_branches.p;
+    B.label_meta = b.d_meta.p;
+    B.stack = e->d_stack.p;
+    B.stack_stride = (long long)e->stack_stride;
+    B.max_labels = b.max_labels;
+    B.max_branches = (int)b.d_branches.cap;
+    B.bin_cap = b.bin_cap;
+    B.all_solutions = b.all_solutions;
+    B.node_budget = max_nodes ? max_nodes : ~0ull;
+    B.node_limit = b.node_limit;
+    B.props_base = b.props_base;
+    B.t_status = b.trace_cap ? b.d_tstatus.p : nullptr;
+    B.t_dom = (b.trace_cap && b.trace_dom) ? b.d_tdom.p : nullptr;
+    B.t_cap = b.trace_cap;
+    Params& P = b.P;
+    P.max_iterations = e->max_iterations;
+    if (e->epoch > 0x70000000u) {  // epoch wrap, as in run_fixpoint
+      for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
+      fill_u32(e, e->d_dirty_stamp.p, 0u, e->d_dirty_stamp.cap);
+      unsigned one = 1;
+      CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
+      e->epoch = 1;
+    }
+    size_t total = e->n_nary * 4096;
+    for (int f = 0; f < 3; ++f) total += e->fam[f].n;
+    int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 4095) / 4096));
+    size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
+    bool smem_dom = (size_t)kRingBytes + dom_bytes + 2048 <= (size_t)e->max_smem_optin;
+    size_t smem = (size_t)kRingBytes + (smem_dom ? dom_bytes : 0);
+    P.smem_dom = smem_dom ? 1 : 0;
+    const void* fn = smem_dom ? (const void*)pcp_burst_kernel<true> : (const void*)pcp_burst_kernel<false>;
+    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
+    void* args[] = {&P, &B};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
+    CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+    BurstCtl bc;
+    CUDA_CHECK(cudaMemcpyAsync(&bc, b.d_bc, sizeof(bc), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaMemcpyAsync(e->h_block, e->d_block, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
+    b.kernel_seconds += ms * 1e-3;
+    const Result& r = *e->h_result();
+    e->epoch = r.epoch;
+    e->trail_len = r.trail_cnt;
+    e->props_total = r.propagations;
+    e->mirror_valid = false;
+    e->snapshot_valid = false;
+    e->at_fixpoint = false;
+    ++e->dom_version;
+    if (bc.err == 2) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
+    if (bc.err) PCP_FAIL(PCP_ERR_NOMEM, "device search: label / branch / tail capacity exceeded (pcp_config.max_labels)");
+    res->status = bc.status;
+    res->err = bc.err;
+    res->nodes = bc.nodes;
+    res->solutions = bc.solutions;
+    res->failures = bc.failures;
+    res->iterations = bc.iterations;
+    res->propagations = r.propagations - b.props0;
+    res->kernel_seconds = b.kernel_seconds;
+  });
+}
+
+int pcp_internal_burst_trace(pcp_engine* e, uint64_t first, uint64_t n, int32_t* status, int32_t* lo, int32_t* hi) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    auto& b = e->burst;
+    PCP_REQUIRE(b.open && first + n <= b.trace_cap, "trace range out of bounds");
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const size_t V = e->V;
+    if (status) CUDA_CHECK(cudaMemcpyAsync(status, b.d_tstatus.p + first, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    std::vector<int2> tmp;
+    if (lo && hi && b.trace_dom) {
+      tmp.resize(n * V);
+      CUDA_CHECK(cudaMemcpyAsync(tmp.data(), b.d_tdom.p + first * V, n * V * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < tmp.size(); ++i) { lo[i] = tmp[i].x; hi[i] = tmp[i].y; }
+  });
+}
+
+int pcp_internal_burst_end(pcp_engine* e) {
+  if (!e) return PCP_ERR_INVALID;
+  if (!e->burst.open) return PCP_OK;
+  // Adopt the device's search state, so that the engine is left where the search stopped
+  // (like the space a SearchTreeVisitor hands back): the labels it took, the branching
+  // constraints it posted in the tail, the trail.
+  return guarded(e, [&] {
+    auto& b = e->burst;
+    b.open = false;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    BurstCtl bc;
+    CUDA_CHECK(cudaMemcpy(&bc, b.d_bc, sizeof(bc), cudaMemcpyDeviceToHost));
+    HostFamily& hb = e->fam[F_BIN];
+    const size_t l0 = e->labels.size(), l1 = (size_t)std::max(bc.n_labels, (int)l0);
+    if (l1 > l0) {
+      std::vector<int2> meta(l1 - l0);
+      CUDA_CHECK(cudaMemcpy(meta.data(), b.d_meta.p + l0, meta.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+      for (const int2& m : meta) {
+        LabelRec r;
+        r.n_fam[F_BIN] = (size_t)m.x;
+        r.n_fam[F_TER] = e->fam[F_TER].n;
+        r.n_fam[F_DJ] = e->fam[F_DJ].n;
+        r.n_fam[F_NARY] = e->n_nary;
+        r.n_nary_ops = e->h_nary_ops.size();
+        r.n_props = (size_t)(b.props_base + m.x);
+        r.trail_len = (unsigned)m.y;
+        r.at_fixpoint = true;
+        r.dom_version = 0;  // never "the current domains"
+        e->labels.push_back(r);
+      }
+    }
+    if ((size_t)bc.bin_n > hb.n) {
+      std::vector<int4> tail((size_t)bc.bin_n - hb.n);
+      CUDA_CHECK(cudaMemcpy(tail.data(), hb.d_desc.p + hb.n, tail.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+      for (const int4& d : tail) {
+        hb.desc.push_back(d);
+        e->prop_ref.push_back(make_ref(F_BIN, (unsigned)hb.n++));
+      }
+      hb.uploaded = hb.active_set = hb.n;
+    }
+    ++e->dom_version;
+    e->mirror_valid = false;
+    e->snapshot_valid = false;
+    e->at_fixpoint = false;
   });
 }
 

@@ -24,6 +24,14 @@ struct Ctx {
   bool mark_dirty;        // narrowed variables enter the worklist
   bool bookkeep;          // entailed propagators are deactivated + trailed
   int* flags;             // shared: [0] this CTA queued a dirty variable, [1] saw a failure
+  // solo mode (a short cascade run by CTA 0 alone, see solo_iterations): the snapshot is the
+  // authoritative copy, updated with shared-memory atomics and written through to HBM;
+  // the next worklist is a bit set + short list in shared memory
+  bool solo;
+  unsigned* solo_next_bits;
+  int* solo_next_list;
+  int* solo_next_cnt;
+  int solo_cap;
 };
 
 __device__ __forceinline__ void set_failed(const Ctx& c) { c.flags[1] = 1; }
@@ -104,6 +112,36 @@ __device__ __forceinline__ void apply_updates(const Ctx& c, const UpdSet& us) {
     return;
   }
   const Params& P = *c.P;
+  if (c.solo) {
+    for (int i = 0; i < us.n; ++i) {
+      const Upd& r = us.u[i];
+      const int nl = r.nlo - r.off, nh = r.nhi - r.off;
+      int2* s = &c.sdom[r.var];
+      int2* d = &P.dom[r.var];
+      bool ch = false;
+      int lo_now = r.cur_lo - r.off, hi_now = r.cur_hi - r.off;
+      if (r.nlo > r.cur_lo) {
+        int old = atomicMax(&s->x, nl);     // shared-memory atomic: the authoritative copy
+        if (old < nl) { ch = true; atomicMax(&d->x, nl); }  // write-through, result unused (RED)
+        lo_now = max(old, nl);
+      }
+      if (r.nhi < r.cur_hi) {
+        int old = atomicMin(&s->y, nh);
+        if (old > nh) { ch = true; atomicMin(&d->y, nh); }
+        hi_now = min(old, nh);
+      }
+      if (!ch) continue;
+      // the other bound may have moved under us: re-read the authoritative copy
+      const int now_lo = *(volatile int*)&s->x, now_hi = *(volatile int*)&s->y;
+      if (lo_now > hi_now || now_lo > now_hi) set_failed(c);
+      const unsigned bit = 1u << (r.var & 31);
+      if (!(atomicOr(&c.solo_next_bits[r.var >> 5], bit) & bit)) {
+        int idx = atomicAdd(c.solo_next_cnt, 1);
+        if (idx < c.solo_cap) c.solo_next_list[idx] = r.var;
+      }
+    }
+    return;
+  }
   // 1. all atomics in flight together (plus a plain look at the dirty stamp: a variable that is
   //    already queued for the next iteration needs no exchange)
   int old_lo[3], old_hi[3];

@@ -8,11 +8,13 @@
 // the entry points a Rust host would bind (pcp_restore, pcp_prop_alloc, pcp_consistency,
 // pcp_domains_read, pcp_label) -- one fixpoint launch per node, host buffers on both
 // sides -- so its timings are end-to-end timings of the boundary.
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <vector>
 
 #include "../../include/pcp_b200.h"
+#include "pcp_internal.h"
 
 namespace {
 
@@ -127,6 +129,65 @@ struct Driver {
 
   bool stopped = false, exhausted_reported = false;
   std::chrono::steady_clock::time_point t_mark;
+  // device-resident bursts (the default search configuration): the node loop below runs on the GPU
+  bool burst = false, burst_begun = false;
+  pcp_burst_result br_prev{};
+
+  int copy_burst_trace(uint64_t from, uint64_t to) {
+    if (to > t_cap) to = t_cap;
+    std::vector<int32_t> blo, bhi;
+    for (uint64_t a = from; a < to; a += 256) {
+      uint64_t n = std::min<uint64_t>(256, to - a);
+      int32_t* plo = nullptr;
+      int32_t* phi = nullptr;
+      if (cfg->trace_domains && t_lo && t_hi) { plo = t_lo + a * (size_t)V; phi = t_hi + a * (size_t)V; }
+      else if (t_hash) { blo.resize(n * (size_t)V); bhi.resize(n * (size_t)V); plo = blo.data(); phi = bhi.data(); }
+      std::vector<int32_t> st(n);
+      TRY(pcp_internal_burst_trace(e, a, n, st.data(), plo, phi));
+      for (uint64_t i = 0; i < n; ++i) {
+        if (t_status) t_status[a + i] = st[i];
+        if (t_hash) t_hash[a + i] = st[i] == PCP_FALSE ? 0 : hash_domains(plo + i * (size_t)V, phi + i * (size_t)V, (size_t)V);
+      }
+    }
+    return PCP_OK;
+  }
+
+  int step_burst(uint64_t max_nodes, int* out) {
+    if (!burst_begun) {
+      TRY(pcp_num_vars(e, &V));
+      TRY(pcp_internal_burst_begin(e, cfg->all_solutions, cfg->node_limit, t_cap, cfg->trace_domains));
+      burst_begun = true;
+    }
+    uint64_t remaining = max_nodes;
+    const bool unlimited = max_nodes == ~0ull;
+    while (true) {
+      uint64_t budget = remaining;
+      const uint64_t warm = (uint64_t)cfg->warmup_nodes;
+      const bool timed = res->num_nodes >= warm;
+      if (!timed) budget = std::min<uint64_t>(budget, warm - res->num_nodes);
+      pcp_burst_result br{};
+      auto t0 = std::chrono::steady_clock::now();
+      TRY(pcp_internal_burst_step(e, budget, &br));
+      double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      const uint64_t ran = br.nodes - br_prev.nodes;
+      if (timed) {
+        res->seconds += dt;
+        res->propagations += br.propagations - br_prev.propagations;
+        res->iterations += br.iterations - br_prev.iterations;
+        res->kernel_seconds += br.kernel_seconds - br_prev.kernel_seconds;
+      }
+      if (t_cap && br_prev.nodes < t_cap) TRY(copy_burst_trace(br_prev.nodes, br.nodes));
+      res->num_nodes = br.nodes;
+      res->num_solution = br.solutions;
+      res->num_failed_node = br.failures;
+      br_prev = br;
+      if (br.status != 0) { *out = br.status; if (br.status == 2) stopped = true; return PCP_OK; }
+      if (!unlimited) {
+        remaining -= std::min(remaining, ran);
+        if (remaining == 0) { *out = 0; return PCP_OK; }
+      }
+    }
+  }
 
   // OneSolution::enter (one_solution.rs:92-105) / AllSolution::enter (all_solution.rs:41-50),
   // resumable: runs at most `max_nodes` further nodes.
@@ -134,6 +195,11 @@ struct Driver {
   // again for the next solution), -1 Unsatisfiable (tree exhausted, one-solution mode),
   // 2 EndOfSearch (StopNode limit, or tree exhausted in all-solutions mode).
   int step(uint64_t max_nodes, int* out) {
+    if (burst) {
+      int rc = step_burst(max_nodes, out);
+      res->status = *out;
+      return rc;
+    }
     t_mark = std::chrono::steady_clock::now();
     t_start = t_mark;
     int rc = step_inner(max_nodes, out);
@@ -190,6 +256,7 @@ int pcp_search_open(pcp_engine* e, const pcp_search_config* cfg, int32_t* trace_
   pcp_search* s = new pcp_search{*cfg, {}, {}};
   std::memset(&s->res, 0, sizeof(s->res));
   s->d = Driver{e, &s->cfg, &s->res, trace_status, trace_lo, trace_hi, trace_hash, trace_capacity};
+  s->d.burst = pcp_internal_burst_supported(e, cfg, trace_capacity) != 0;
   *out = s;
   return PCP_OK;
 }
@@ -202,7 +269,11 @@ int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res) {
   return rc;
 }
 
-void pcp_search_close(pcp_search* s) { delete s; }
+void pcp_search_close(pcp_search* s) {
+  if (!s) return;
+  if (s->d.burst_begun) pcp_internal_burst_end(s->d.e);  // the engine goes back to the search root
+  delete s;
+}
 
 int pcp_search_run(pcp_engine* e, const pcp_search_config* cfg, pcp_search_result* res, int32_t* trace_status,
                    uint64_t* trace_hash, int32_t* trace_lo, int32_t* trace_hi, uint64_t trace_capacity) {
