@@ -494,8 +494,56 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
   return s_dec;
 }
 
+// Row-local fixpoint: when the worklist is shorter than the grid, a whole CTA takes one dirty
+// variable v and re-evaluates v's row until v itself stops moving.  On bounds-only domains a
+// variable typically crawls value by value (each XNeqY against an assigned neighbour trims
+// one value off a bound, x_neq_y.rs:82-93): with one device barrier per crawl step a node
+// costs tens of iterations; here the crawl runs inside one iteration, at L1/shared-memory
+// latency (the row's refs and descriptors stay in L1 after the first round, the domains are
+// the CTA's snapshot, kept current by mirroring every update into it).  Still a chaotic
+// iteration of the same propagators: the fixpoint is unchanged.
+constexpr int kLocalRounds = 256;
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_dirty_rows(const Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
+__device__ __forceinline__ unsigned expand_rows_local(Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
+  const Params& P = *c.P;
+  __shared__ int2 s_before;
+  const int* list = P.dirty_list + (size_t)cur_buf * P.V;
+  unsigned nprop = 0;
+  c.mirror = SMEM;
+  for (int e = blockIdx.x; e < n_dirty; e += gridDim.x) {
+    const int v = __ldcg(&list[e]);
+    const int rb = __ldg(&P.adj_ptr[v]), re = __ldg(&P.adj_ptr[v + 1]);
+    for (int round = 0; round < kLocalRounds; ++round) {
+      if (threadIdx.x == 0) s_before = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
+      __syncthreads();
+      for (int j = rb + threadIdx.x; j < re; j += blockDim.x) {
+        unsigned ref = __ldg(&P.adj[j]);
+        unsigned fam = ref >> 29;
+        int slot = (int)(ref & kSlotMask);
+        const Family& f = P.fam[fam];
+        if (slot >= f.n_static) continue;  // truncated by a restore (store.rs:320)
+        const unsigned word = __ldcg(&f.active[slot >> 5]);
+        int4 q0, q1, q2;
+        load_desc(f, fam, slot, q0, q1, q2);
+        if (!((word >> (slot & 31)) & 1u)) continue;
+        // first round: once per iteration across the grid; later rounds belong to this row
+        if (round == 0 && atomicExch(&f.stamp[slot], cur_epoch) == cur_epoch) continue;
+        eval_loaded<SMEM>(c, fam, slot, q0, q1, q2);
+        ++nprop;
+      }
+      __syncthreads();
+      const int2 after = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
+      const bool moved = after.x != s_before.x || after.y != s_before.y;
+      if (!__syncthreads_or(moved) || after.x > after.y) break;
+    }
+  }
+  c.mirror = false;
+  return nprop;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ unsigned expand_dirty_rows(Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
+  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(c, cur_buf, n_dirty, cur_epoch);
   const Params& P = *c.P;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -642,6 +690,7 @@ __device__ __noinline__ unsigned solo_iterations(const Params& P, Ctx c, int bin
   const int tail_n = s_tail_n;
   solo_mark(P, 1);
   c.solo = true;
+  c.mirror = false;
   c.local = false;
   c.mark_dirty = true;
   c.bookkeep = true;
@@ -834,6 +883,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
   if (warp > 0 && st.my_chunks > 0 && full_sweep) aw = load_active_words(P, chunk_of(P, st.cmap, st.wid));
   bool sweep_now = full_sweep, solo_now = false, after_solo = false;
   c.solo = false;
+  c.mirror = false;
   unsigned iter = 0, dec, nprop = 0;
   while (true) {
     const int cur_buf = iter % 3, next_buf = (iter + 1) % 3, spare_buf = (iter + 2) % 3;
@@ -1086,6 +1136,7 @@ struct BurstParams {
   BurstCtl* bc;
   int4* branches;          // DFS stack: (label, var, val, alternative)
   int2* label_meta;        // per label: (bin_n, trail_len)
+  int2* branch_meta;       // the same record next to every branch (one round trip per pop)
   int2* stack;             // label slots (copies of dom[])
   long long stack_stride;
   int max_labels, max_branches, bin_cap;
@@ -1098,107 +1149,146 @@ struct BurstParams {
   unsigned long long t_cap;
 };
 
-// CTA 0, all threads: close the node that just reached its decision.
-__device__ __forceinline__ void burst_after_node(const Params& P, const BurstParams& B, unsigned dec, unsigned iters) {
+// CTA 0's working copy of the search state: lives in shared memory for the whole burst so
+// that the host work between two nodes costs one or two global round trips.
+struct BurstLocal {
+  int n_branch, n_labels, cur_label, bin_n, stopped, root_pending, last_status, err;
+  unsigned long long nodes, solutions, failures, iterations;
+  int4 top;        // the branch pushed last (the left child) and its label record
+  int2 top_meta;
+  int top_valid;
+  int run;         // set by burst_host_step: 1 = a node was posted
+};
+
+__device__ __forceinline__ void burst_load(const BurstCtl* bc, BurstLocal* L) {
+  L->n_branch = bc->n_branch; L->n_labels = bc->n_labels; L->cur_label = bc->cur_label; L->bin_n = bc->bin_n;
+  L->stopped = bc->stopped; L->root_pending = bc->root_pending; L->last_status = bc->last_status; L->err = bc->err;
+  L->nodes = bc->nodes; L->solutions = bc->solutions; L->failures = bc->failures; L->iterations = bc->iterations;
+  L->top_valid = 0;
+  L->run = 0;
+}
+__device__ __forceinline__ void burst_store(BurstCtl* bc, const BurstLocal* L) {
+  bc->n_branch = L->n_branch; bc->n_labels = L->n_labels; bc->cur_label = L->cur_label; bc->bin_n = L->bin_n;
+  bc->stopped = L->stopped; bc->root_pending = L->root_pending; bc->last_status = L->last_status; bc->err = L->err;
+  bc->nodes = L->nodes; bc->solutions = L->solutions; bc->failures = L->failures; bc->iterations = L->iterations;
+}
+
+// CTA 0, all threads: the host's work between two fixpoints.  `have_node`: a node just reached
+// its decision `dec` (false at the start of a launch).  `scratch`: V int2 of shared memory
+// (CTA 0's snapshot area) or nullptr.  Posts the next node through `bc` or stops the burst.
+__device__ __forceinline__ void burst_host_step(const Params& P, const BurstParams& B, BurstLocal* L, int2* scratch,
+                                                bool have_node, unsigned dec, unsigned iters, unsigned long long done) {
   __shared__ unsigned long long s_best[kWarps];
+  __shared__ int4 s_pop;
+  __shared__ int2 s_pop_meta;
   BurstCtl* bc = B.bc;
   Control* ctl = P.ctl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
-  const int bin_n = *(volatile int*)&bc->bin_n;
-  const unsigned long long n = *(volatile unsigned long long*)&bc->nodes;
-  // propagation/store.rs:250-256
-  const int status = dec == D_FAILED ? -1 : ((long long)trail_cnt == B.props_base + bin_n ? 1 : 0);
-  if (n < B.t_cap) {
-    if (tid == 0 && B.t_status) B.t_status[n] = status;
-    if (B.t_dom && status != -1)
-      for (int v = tid; v < P.V; v += blockDim.x) B.t_dom[n * (unsigned long long)P.V + v] = ldcg_dom(&P.dom[v]);
-  }
-  const bool stop = B.node_limit && n + 1 >= B.node_limit;
-  if (status == 0 && !stop) {
-    // FirstSmallestVar: min over (size, index) of the variables with size > 1
+  if (have_node && dec == D_ITER_CAP) { if (tid == 0) L->err = 2; have_node = false; }
+  if (have_node) {
+    // ---- close the node: status, trace, branching, label
+    const unsigned trail_cnt = __ldcg(&ctl->trail_cnt);
+    const int bin_n = L->bin_n;
+    const unsigned long long n = L->nodes;
     unsigned long long best = ~0ull;
-    for (int v = tid; v < P.V; v += blockDim.x) {
+    for (int v = tid; v < P.V; v += blockDim.x) {  // one pass over the final domains
       int2 d = ldcg_dom(&P.dom[v]);
+      if (scratch) scratch[v] = d;
       unsigned size = (unsigned)(d.y - d.x) + 1u;
       if (size > 1u) best = min(best, ((unsigned long long)size << 32) | (unsigned)v);
     }
-    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if (lane == 0) s_best[warp] = best;
-    __syncthreads();
-    best = s_best[0];
-    for (int w = 1; w < kWarps; ++w) best = min(best, s_best[w]);
-    const int var = (int)(best & 0xffffffffu);
-    const int2 d = ldcg_dom(&P.dom[var]);
-    const int val = (d.x + d.y) / 2;  // MiddleVal: truncating division
-    const int slot = *(volatile int*)&bc->n_labels;
-    const int nb = *(volatile int*)&bc->n_branch;
-    if (best == ~0ull || slot >= B.max_labels || nb + 2 > B.max_branches) {
-      if (tid == 0) bc->err = 1;
-    } else {
-      int2* dst = B.stack + (long long)slot * B.stack_stride;
-      for (int v = tid; v < P.V; v += blockDim.x) dst[v] = ldcg_dom(&P.dom[v]);
-      if (tid == 0) {
-        B.label_meta[slot] = make_int2(bin_n, (int)trail_cnt);
-        bc->n_labels = slot + 1;
-        bc->cur_label = slot;
-        B.branches[nb] = make_int4(slot, var, val, 1);      // x > val, explored second
-        B.branches[nb + 1] = make_int4(slot, var, val, 0);  // x <= val, explored first
-        bc->n_branch = nb + 2;
+    // propagation/store.rs:250-256
+    const int status = dec == D_FAILED ? -1 : ((long long)trail_cnt == B.props_base + bin_n ? 1 : 0);
+    const bool stop = B.node_limit && n + 1 >= B.node_limit;
+    if (scratch) __syncthreads();
+    if (n < B.t_cap) {
+      if (tid == 0 && B.t_status) B.t_status[n] = status;
+      if (B.t_dom && status != -1)
+        for (int v = tid; v < P.V; v += blockDim.x)
+          B.t_dom[n * (unsigned long long)P.V + v] = scratch ? scratch[v] : ldcg_dom(&P.dom[v]);
+    }
+    if (status == 0 && !stop) {
+      // FirstSmallestVar: min over (size, index) of the variables with size > 1
+      for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (lane == 0) s_best[warp] = best;
+      __syncthreads();
+      best = s_best[0];
+      for (int w = 1; w < kWarps; ++w) best = min(best, s_best[w]);
+      const int var = (int)(best & 0xffffffffu);
+      const int slot = L->n_labels, nb = L->n_branch;
+      if (best == ~0ull || slot >= B.max_labels || nb + 2 > B.max_branches) {
+        __syncthreads();
+        if (tid == 0) L->err = 1;
+      } else {
+        const int2 d = scratch ? scratch[var] : ldcg_dom(&P.dom[var]);
+        const int val = (d.x + d.y) / 2;  // MiddleVal: truncating division
+        int2* dst = B.stack + (long long)slot * B.stack_stride;
+        for (int v = tid; v < P.V; v += blockDim.x) dst[v] = scratch ? scratch[v] : ldcg_dom(&P.dom[v]);
+        __syncthreads();
+        if (tid == 0) {
+          const int2 meta = make_int2(bin_n, (int)trail_cnt);
+          B.label_meta[slot] = meta;
+          B.branches[nb] = make_int4(slot, var, val, 1);      // x > val, explored second
+          B.branch_meta[nb] = meta;
+          B.branches[nb + 1] = make_int4(slot, var, val, 0);  // x <= val, explored first
+          B.branch_meta[nb + 1] = meta;
+          L->n_labels = slot + 1;
+          L->cur_label = slot;
+          L->n_branch = nb + 2;
+          L->top = make_int4(slot, var, val, 0);
+          L->top_meta = meta;
+          L->top_valid = 1;
+        }
       }
     }
+    if (tid == 0) {
+      L->nodes = n + 1;
+      L->iterations += iters;
+      L->last_status = status;
+      if (stop) L->stopped = 1;
+      else if (status == 1) L->solutions += 1;
+      else if (status == -1) L->failures += 1;
+    }
+    __syncthreads();
   }
-  if (tid == 0) {
-    bc->nodes = n + 1;
-    bc->iterations += iters;
-    bc->last_status = status;
-    if (stop) bc->stopped = 1;
-    else if (status == 1) bc->solutions += 1;
-    else if (status == -1) bc->failures += 1;
-  }
-  __syncthreads();
-}
-
-// CTA 0, all threads: decide whether the burst goes on; if so pop the next branch, restore its
-// label and post its constraint.  `done` = nodes finished in this launch.
-__device__ __forceinline__ void burst_post_next(const Params& P, const BurstParams& B, unsigned long long done) {
-  __shared__ int4 s_pop;
-  __shared__ int s_run;
-  BurstCtl* bc = B.bc;
-  Control* ctl = P.ctl;
-  const int tid = threadIdx.x;
+  // ---- decide whether the burst goes on; pop the next branch
   if (tid == 0) {
     // a node may end with entries left in its last dirty list (failure): start the next clean
     ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     int run = 0, status = 0;
-    const int nb = bc->n_branch;
-    if (bc->err) status = 2;
-    else if (bc->stopped) status = 2;                                     // StopNode -> EndOfSearch
-    else if (done > 0 && bc->last_status == 1 && !B.all_solutions) status = 1;  // OneSolution returns
-    else if (!bc->root_pending && nb == 0) status = B.all_solutions ? 2 : -1;   // tree exhausted
-    else if (done >= B.node_budget) status = 0;                          // slice used up
+    const int nb = L->n_branch;
+    if (L->err) status = 2;
+    else if (L->stopped) status = 2;                                          // StopNode -> EndOfSearch
+    else if (done > 0 && L->last_status == 1 && !B.all_solutions) status = 1; // OneSolution returns
+    else if (!L->root_pending && nb == 0) status = B.all_solutions ? 2 : -1;  // tree exhausted
+    else if (done >= B.node_budget) status = 0;                               // slice used up
     else run = 1;
-    if (run && !bc->root_pending) { s_pop = B.branches[nb - 1]; bc->n_branch = nb - 1; }
-    s_run = run;
+    if (run && !L->root_pending) {
+      if (L->top_valid) { s_pop = L->top; s_pop_meta = L->top_meta; }
+      else { s_pop = __ldcg(&B.branches[nb - 1]); s_pop_meta = __ldcg(&B.branch_meta[nb - 1]); }
+      L->top_valid = 0;
+      L->n_branch = nb - 1;
+    }
+    L->run = run;
     if (!run) { bc->status = status; bc->cmd = 1; }
   }
   __syncthreads();
-  if (!s_run) return;
-  if (*(volatile int*)&bc->root_pending) {
-    if (tid == 0) { bc->root_pending = 0; bc->inl_slot = -1; bc->cmd = 0; bc->cur_label = -1; }
+  if (!L->run) return;
+  if (L->root_pending) {
+    if (tid == 0) { L->root_pending = 0; L->cur_label = -1; bc->inl_slot = -1; bc->bin_n = L->bin_n; bc->cmd = 0; }
     __syncthreads();
     return;
   }
   const int4 br = s_pop;
-  const int L = br.x;
-  const int2 meta = B.label_meta[L];
-  if (*(volatile int*)&bc->cur_label != L) {
+  const int2 meta = s_pop_meta;
+  const int Lb = br.x;
+  if (L->cur_label != Lb) {
     // Snapshot::restore: domains <- label copy, re-activate the trail suffix (store.rs:319-323)
-    const int2* src = B.stack + (long long)L * B.stack_stride;
-    for (int v = tid; v < P.V; v += blockDim.x) P.dom[v] = src[v];
-    const unsigned cnt = *(volatile unsigned*)&ctl->trail_cnt;
+    const int2* src = B.stack + (long long)Lb * B.stack_stride;
+    for (int v = tid; v < P.V; v += blockDim.x) P.dom[v] = __ldcg(&src[v]);
+    const unsigned cnt = __ldcg(&ctl->trail_cnt);
     for (unsigned i = (unsigned)meta.y + tid; i < cnt; i += blockDim.x) {
-      unsigned ref = P.trail[i];
+      unsigned ref = __ldcg(&P.trail[i]);
       unsigned fam = ref >> 29, slot = ref & kSlotMask;
       uint32_t* act = fam == F_NARY ? P.nary_active_w : P.fam[fam].active;
       atomicOr(&act[slot >> 5], 1u << (slot & 31));
@@ -1208,7 +1298,7 @@ __device__ __forceinline__ void burst_post_next(const Params& P, const BurstPara
   }
   if (tid == 0) {
     const int slot = meta.x;  // propagators are truncated to the labelled length (store.rs:320)
-    if (slot >= B.bin_cap) { bc->err = 1; bc->status = 2; bc->cmd = 1; }
+    if (slot >= B.bin_cap) { L->err = 1; bc->status = 2; bc->cmd = 1; L->run = 0; }
     else {
       int4 d = br.w == 0 ? make_int4((int)((B_LESS << 28) | (unsigned)br.y), 0, -1, br.z + 1)    // x <= val
                          : make_int4((int)((B_LESS << 28) | kConstVar28), br.z, br.y, 0);         // val < x
@@ -1217,12 +1307,12 @@ __device__ __forceinline__ void burst_post_next(const Params& P, const BurstPara
       bc->inl_desc = d;
       bc->inl_slot = slot;
       bc->bin_n = slot + 1;
-      bc->n_labels = L + 1;
-      bc->cur_label = -1;
       bc->cmd = 0;
+      L->bin_n = slot + 1;
+      L->n_labels = Lb + 1;
+      L->cur_label = -1;
     }
   }
-  __threadfence();
   __syncthreads();
 }
 
@@ -1235,6 +1325,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   __shared__ int s_flags[2];
   __shared__ int s_cmd, s_slot, s_bin_n;
   __shared__ InlineProp s_inl;
+  __shared__ BurstLocal s_local;
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, &s_block_props, s_flags, SMEM);
   Control* ctl = P.ctl;
@@ -1250,13 +1341,14 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   } else if (threadIdx.x == 32) {
     s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
     s_epoch = *(volatile unsigned*)&ctl->epoch;
+    if (blockIdx.x == 0) burst_load(bc, &s_local);
   }
   __syncthreads();
   st.gen = s_gen;
   unsigned epoch = s_epoch;
 
   unsigned long long done = 0;
-  if (blockIdx.x == 0) burst_post_next(P, B, done);
+  if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, false, 0, 0, done);
   while (true) {
     grid_barrier(P, st.gen, 0, false, s_flags, 0);  // the posted node is visible to every CTA
     if (threadIdx.x == 0) {
@@ -1279,11 +1371,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     ++done;
     // the next sweep's descriptors can stream in while CTA 0 does the host's work
     if (threadIdx.x == 0 && dec != D_ITER_CAP) pre_issue(P, st);
-    if (blockIdx.x == 0) {
-      if (dec == D_ITER_CAP) { if (threadIdx.x == 0) bc->err = 2; __syncthreads(); }
-      else burst_after_node(P, B, dec, iters);
-      burst_post_next(P, B, done);
-    }
+    if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, true, dec, iters, done);
   }
   // drain the chunks that were pre-issued for a node that will not run in this launch
   if (threadIdx.x >> 5 > 0 && st.my_chunks > 0) {
@@ -1294,6 +1382,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
+    burst_store(bc, &s_local);
     ctl->epoch = epoch + 1;
     ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     Result r;

@@ -172,7 +172,7 @@ struct pcp_engine {
     uint64_t root_label = 0;
     BurstCtl* d_bc = nullptr;
     DevBuf<int4> d_branches;
-    DevBuf<int2> d_meta;
+    DevBuf<int2> d_meta, d_bmeta;
     DevBuf<int> d_tstatus;
     DevBuf<int2> d_tdom;
     uint64_t trace_cap = 0;
@@ -859,7 +859,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   e->d_dirty_list.free(); e->d_dirty_stamp.free(); e->d_trail.free(); e->d_stack.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
   if (e->burst.d_bc) cudaFree(e->burst.d_bc);
-  e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free();
+  e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_bmeta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free();
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1099,6 +1099,7 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
     }
     e->d_trail.reserve(e->num_props() + depth + 64, e->stream, e->trail_len);
     b.d_branches.reserve(2 * depth + 16, e->stream);
+    b.d_bmeta.reserve(2 * depth + 16, e->stream);
     b.d_meta.reserve((size_t)b.max_labels, e->stream);
     b.trace_cap = trace_capacity;
     b.trace_dom = trace_domains != 0 || trace_capacity > 0;
@@ -1146,6 +1147,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     B.bc = b.d_bc;
     B.branches = b.d_branches.p;
     B.label_meta = b.d_meta.p;
+    B.branch_meta = b.d_bmeta.p;
     B.stack = e->d_stack.p;
     B.stack_stride = (long long)e->stack_stride;
     B.max_labels = b.max_labels;

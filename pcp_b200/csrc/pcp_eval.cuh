@@ -27,6 +27,7 @@ struct Ctx {
   // solo mode (a short cascade run by CTA 0 alone, see solo_iterations): the snapshot is the
   // authoritative copy, updated with shared-memory atomics and written through to HBM;
   // the next worklist is a bit set + short list in shared memory
+  bool mirror;            // row-local fixpoint: every update is also applied to this CTA's snapshot
   bool solo;
   unsigned* solo_next_bits;
   int* solo_next_list;
@@ -154,6 +155,10 @@ __device__ __forceinline__ void apply_updates(const Ctx& c, const UpdSet& us) {
       old_lo[i] = r.nlo > r.cur_lo ? atomicMax(&d->x, r.nlo - r.off) : r.cur_lo - r.off;
       old_hi[i] = r.nhi < r.cur_hi ? atomicMin(&d->y, r.nhi - r.off) : r.cur_hi - r.off;
       seen[i] = c.mark_dirty ? __ldcg(&P.dirty_stamp[r.var]) : 0u;
+      if (c.mirror) {  // keep the CTA's snapshot current for the next local round
+        if (r.nlo > r.cur_lo) atomicMax(&c.sdom[r.var].x, r.nlo - r.off);
+        if (r.nhi < r.cur_hi) atomicMin(&c.sdom[r.var].y, r.nhi - r.off);
+      }
     }
   }
   // 2. which variables did this thread really narrow?
