@@ -53,11 +53,12 @@ __host__ __device__ inline unsigned make_ref(unsigned fam, unsigned slot) { retu
 enum BinKind : unsigned { B_LESS = 0, B_NEQ = 1, B_EQ = 2 };
 enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2 };
 
-enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3, D_SWEEP = 4, D_SOLO = 5 };
-constexpr int kSoloMaxDirty = 8;    // a worklist this short is run by CTA 0 alone (solo_iterations)
-constexpr int kSoloCap = 32;        // capacity of the shared-memory worklist
-constexpr int kSoloWords = 384;     // bit set over the variables (snapshot mode: V <= 12288)
-constexpr int kSoloMaxIters = 4096;
+enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3 };
+// Worklist iterations: every CTA compacts the dirty bit set into a list that lives in the
+// (idle) TMA ring; the rest of the ring stages the descriptors of a row for the row-local
+// rounds.  A dirty set longer than the list is handled by a streaming sweep instead.
+constexpr int kListCap = 8192;                       // dirty variables (32 KB of the ring)
+constexpr int kRowStageOff = kListCap * 4;           // byte offset of the row staging area
 constexpr unsigned kDecBits = 3;  // the release word of the barrier = (generation << kDecBits) | decision
 
 struct Control {
@@ -67,7 +68,7 @@ struct Control {
   unsigned epoch;        // next unused epoch (stamps < epoch are stale)
   int failed;
   unsigned trail_cnt;    // number of deactivated (entailed) propagators on the trail
-  int dirty_cnt[3];
+  int pad0[3];
   unsigned long long propagations;  // cumulative
   unsigned iterations;   // of the last launch
   unsigned last_decision;
@@ -116,8 +117,8 @@ struct Params {
   const int2* sum_terms;
   const int* adj_ptr;   // reactor: var -> propagator refs
   const uint32_t* adj;
-  int* dirty_list;      // 3 x V
-  uint32_t* dirty_stamp;
+  uint32_t* dirty_bits; // 3 x dirty_words: bit v = variable v was narrowed (triple-buffered across iterations)
+  int dirty_words;
   uint32_t* trail;
   Control* ctl;
   int full_sweep;       // 1: schedule every active propagator first (store.rs:144-149)
@@ -131,10 +132,9 @@ struct Params {
   int new_first[4], new_last[4];  // slots whose active bit must be set (per family)
   int n_inline;
   InlineProp inl[kMaxInline];
-  int seed_dirty;             // incremental launch: dirty_list[0..seed_dirty) seeded by the host
+  int seed_dirty;             // incremental launch: dirty_bits[0] seeded by the host (count, may be 0)
   // ---- epilogue
   int2* snapshot_to;          // if not failed: copy of the fixpoint domains (next label slot)
-  int solo_ok;                // experimental (PCP_SOLO=1): short cascades run by CTA 0 alone
   // ---- debug: per-CTA phase timestamps (PCP_TRACE=1), 8 slots per CTA
   unsigned long long* trace;
 };
@@ -253,36 +253,145 @@ __device__ __forceinline__ ActiveWords load_active_words(const Params& P, const 
   return a;
 }
 
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+  int4 r;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+// Cold paths of the sweep: an operand is a Constant or a Sum view.
 template <bool SMEM>
-__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, const Chunk& ch, const char* stage,
-                                                  const ActiveWords& aw) {
+__device__ __noinline__ void sweep_slow_bin(const Ctx& c, int slot, int4 d) {
+  const IV x = rd<SMEM>(c, dec_var28((unsigned)d.x), d.y), y = rd<SMEM>(c, d.z, d.w);
+  if (!bin_is_noop((unsigned)d.x >> 28, x, y)) eval_full_bin(c, slot, d, x, y);
+}
+template <bool SMEM>
+__device__ __noinline__ void sweep_slow_ter(const Ctx& c, int slot, int4 a, int2 b) {
+  const IV x = rd<SMEM>(c, dec_var28((unsigned)a.x), a.y), y = rd<SMEM>(c, a.z, a.w), z = rd<SMEM>(c, b.x, b.y);
+  if (!ter_is_noop((unsigned)a.x >> 28, x, y, z)) eval_full_ter(c, slot, a, b, x, y, z);
+}
+template <bool SMEM>
+__device__ __forceinline__ int2 rd_plain(uint32_t sdom_s, const int2* dom, int var) {
+  return SMEM ? lds_dom(sdom_s + 8u * (unsigned)var) : ldcg_dom(&dom[var]);
+}
+
+// One chunk, one consumer warp.  The common case -- both (all three) operands are plain
+// variables and the evaluation changes nothing -- is decided inline: descriptor loads first,
+// then all domain reads, then the tests, so that the two groups a warp owns overlap their
+// shared-memory latencies; everything else goes out of line.  Returns the number of
+// evaluations of the whole warp (the same value in every lane).
+template <bool SMEM>
+__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s, const int2* dom, int fam, int base,
+                                                  int cnt, uint32_t stage, const ActiveWords& aw) {
   const int lane = threadIdx.x & 31;
   const int cw = (threadIdx.x >> 5) - 1;  // consumer warp index 0..30
   unsigned nprop = 0;
+  bool on[kGroupsMax];
+  int jj[kGroupsMax];
 #pragma unroll
   for (int g = 0; g < kGroupsMax; ++g) {
     const int j0 = cw * 32 + g * kConsumerWarps * 32;
-    if (j0 >= ch.cnt) break;
-    const int j = j0 + lane;
-    const unsigned word = aw.w[g];
-    if (j >= ch.cnt || !((word >> lane) & 1u)) continue;
-    const int slot = ch.base + j;
-    ++nprop;
-    if (ch.fam == F_BIN) {
-      int4 d = reinterpret_cast<const int4*>(stage)[j];
-      unsigned kind = (unsigned)d.x >> 28;
-      IV x = rd<SMEM>(c, dec_var28((unsigned)d.x), d.y), y = rd<SMEM>(c, d.z, d.w);
-      if (!bin_is_noop(kind, x, y)) eval_full<SMEM>(c, F_BIN, slot, d, d, d);
-    } else if (ch.fam == F_TER) {
-      int4 a = reinterpret_cast<const int4*>(stage)[j];
-      int2 b = reinterpret_cast<const int2*>(stage + kTerPlaneB)[j];
-      unsigned kind = (unsigned)a.x >> 28;
-      IV x = rd<SMEM>(c, dec_var28((unsigned)a.x), a.y), y = rd<SMEM>(c, a.z, a.w), z = rd<SMEM>(c, b.x, b.y);
-      if (!ter_is_noop(kind, x, y, z)) eval_full<SMEM>(c, F_TER, slot, a, make_int4(b.x, b.y, 0, 0), a);
-    } else {
-      const int4* q = reinterpret_cast<const int4*>(stage) + 3 * j;
-      int4 q0 = q[0], q1 = q[1], q2 = q[2];
-      if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full<SMEM>(c, F_DJ, slot, q0, q1, q2);
+    jj[g] = j0 + lane;
+    // aw.w[g] is 0 for a group beyond the chunk; the tail of the last chunk is masked off
+    const unsigned valid = cnt - j0 >= 32 ? 0xffffffffu : (cnt > j0 ? (1u << (cnt - j0)) - 1u : 0u);
+    const unsigned w = aw.w[g] & valid;
+    nprop += __popc(w);
+    on[g] = (w >> lane) & 1u;
+  }
+  if (fam == F_BIN) {
+    int4 d[kGroupsMax];
+    int2 dx[kGroupsMax], dy[kGroupsMax];
+    bool plain[kGroupsMax];
+#pragma unroll
+    for (int g = 0; g < kGroupsMax; ++g) d[g] = on[g] ? lds128(stage + 16u * (unsigned)jj[g]) : make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int g = 0; g < kGroupsMax; ++g) {
+      const unsigned xv = (unsigned)d[g].x & kConstVar28;
+      plain[g] = xv < kSumBase28 && d[g].z >= 0;
+      dx[g] = rd_plain<SMEM>(sdom_s, dom, plain[g] ? (int)xv : 0);
+      dy[g] = rd_plain<SMEM>(sdom_s, dom, plain[g] ? d[g].z : 0);
+    }
+#pragma unroll
+    for (int g = 0; g < kGroupsMax; ++g) {
+      if (!on[g]) continue;
+      if (plain[g]) {
+        const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
+        if (!bin_is_noop((unsigned)d[g].x >> 28, x, y)) eval_full_bin(c, base + jj[g], d[g], x, y);
+      } else {
+        sweep_slow_bin<SMEM>(c, base + jj[g], d[g]);
+      }
+    }
+  } else if (fam == F_TER) {
+#pragma unroll
+    for (int g = 0; g < kGroupsMax; ++g) {
+      if (!on[g]) continue;
+      const int4 a = lds128(stage + 16u * (unsigned)jj[g]);
+      const int2 b = lds_dom(stage + (unsigned)kTerPlaneB + 8u * (unsigned)jj[g]);
+      const unsigned xv = (unsigned)a.x & kConstVar28;
+      if (xv < kSumBase28 && a.z >= 0 && b.x >= 0) {
+        const int2 dx = rd_plain<SMEM>(sdom_s, dom, (int)xv), dy = rd_plain<SMEM>(sdom_s, dom, a.z),
+                   dz = rd_plain<SMEM>(sdom_s, dom, b.x);
+        const IV x{dx.x + a.y, dx.y + a.y}, y{dy.x + a.w, dy.y + a.w}, z{dz.x + b.y, dz.y + b.y};
+        if (!ter_is_noop((unsigned)a.x >> 28, x, y, z)) eval_full_ter(c, base + jj[g], a, b, x, y, z);
+      } else {
+        sweep_slow_ter<SMEM>(c, base + jj[g], a, b);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < kGroupsMax; ++g) {
+      if (!on[g]) continue;
+      const int4 q0 = lds128(stage + 48u * (unsigned)jj[g]), q1 = lds128(stage + 48u * (unsigned)jj[g] + 16u),
+                 q2 = lds128(stage + 48u * (unsigned)jj[g] + 32u);
+      if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full_dj<SMEM>(c, base + jj[g], q0, q1, q2);
+    }
+  }
+  return nprop;
+}
+
+// The streaming sweep of one CTA: warp 0 (one lane) keeps the TMA ring full, the other warps
+// consume.  Out of line, with its own register allocation: this is the hot loop.  `first`:
+// chunks already issued by pre_issue.  Returns the number of evaluations, counted per warp
+// (the same value in every lane: the caller adds it up from lane 0 only).
+struct SweepArgs {
+  char* ring;
+  uint64_t* full;
+  uint64_t* empty;
+  ChunkMap cmap;
+  int wid, workers, my_chunks, pipe_pos, first;
+  int reload_aw;
+};
+template <bool SMEM>
+__device__ __noinline__ unsigned sweep_pass(const Ctx& c, const SweepArgs a, ActiveWords aw) {
+  const Params& P = *c.P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned nprop = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      // the ring memory doubles as worklist / n-ary staging (generic-proxy writes): order them
+      // before the async-proxy writes of the next bulk copies
+      if (a.first == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      for (int i = a.first; i < a.my_chunks; ++i) {
+        const int q = a.pipe_pos + i, s = q % kStages;
+        if (q >= kStages) mbar_wait(&a.empty[s], ((q / kStages) - 1) & 1);
+        producer_issue(P, chunk_of(P, a.cmap, a.wid + i * a.workers), a.ring + s * kStageBytes, &a.full[s]);
+      }
+    }
+  } else {
+    const uint32_t ring_s = smem_u32(a.ring);
+    const uint32_t sdom_s = c.sdom_s;
+    const int2* dom = P.dom;
+    if (a.reload_aw) aw = load_active_words(P, chunk_of(P, a.cmap, a.wid));
+    for (int i = 0; i < a.my_chunks; ++i) {
+      const int q = a.pipe_pos + i, s = q % kStages;
+      const Chunk ch = chunk_of(P, a.cmap, a.wid + i * a.workers);
+      ActiveWords nxt = aw;
+      if (i + 1 < a.my_chunks) nxt = load_active_words(P, chunk_of(P, a.cmap, a.wid + (i + 1) * a.workers));
+      mbar_wait(&a.full[s], (q / kStages) & 1);
+      nprop += sweep_consume<SMEM>(c, sdom_s, dom, ch.fam, ch.base, ch.cnt, ring_s + (unsigned)(s * kStageBytes), aw);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a.empty[s]);
+      aw = nxt;
     }
   }
   return nprop;
@@ -325,7 +434,7 @@ __device__ __forceinline__ bool hs_contains(const volatile int* tab, unsigned ma
 //   int2 ops[k]; int2 iv[k] (view-space lo/hi); int tab[tabsz];
 // Returns 1 if the propagator was evaluated (thread 0 only), else 0.
 template <bool SMEM>
-__device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* smem_nary, unsigned cur_epoch,
+__device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* smem_nary, const uint32_t* cur_bits,
                                                bool unconditional) {
   const Params& P = *c.P;
   const int b = __ldg(&P.nary_ptr[slot]), e = __ldg(&P.nary_ptr[slot + 1]);
@@ -345,7 +454,7 @@ __device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* sme
     if (op.x >= 0) {
       int2 d = SMEM ? c.sdom[op.x] : ldcg_dom(&P.dom[op.x]);
       iv[i] = make_int2(d.x + op.y, d.y + op.y);
-      if (__ldcg(&P.dirty_stamp[op.x]) == cur_epoch) any_dirty = 1;
+      if (!unconditional && ((__ldcg(&cur_bits[op.x >> 5]) >> (op.x & 31)) & 1u)) any_dirty = 1;
     } else {
       iv[i] = make_int2(op.y, op.y);
     }
@@ -443,7 +552,7 @@ __device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* sme
 
 // ---------------------------------------------------------------------------------------
 // device-wide barrier; the last CTA to arrive decides whether the fixpoint is reached
-// (the "block-reduce of a changed flag": the reduction operand is the dirty-list length).
+// (the "block-reduce of a changed flag": every CTA contributes "I narrowed a variable").
 // `decide` = false: plain barrier (after the node prologue).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void node_prologue_finish(const Params& P);
@@ -452,7 +561,7 @@ __device__ __forceinline__ void node_prologue_finish(const Params& P);
 // decision needs; the release word `bar_gen` = (generation << kDecBits) | decision, so one
 // acquire-load per poll returns both.
 __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen, unsigned block_props, bool decide,
-                                                 const int* s_flags, unsigned iter, int next_buf = 0) {
+                                                 const int* s_flags, unsigned iter) {
   __shared__ unsigned s_dec;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -469,14 +578,6 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
         if ((now >> 20) & 1023u) dec = D_FAILED;
         else if (((now >> 10) & 1023u) == 0) dec = D_FIXPOINT;
         else if (iter + 1 >= P.max_iterations) dec = D_ITER_CAP;
-        else {
-          // many dirty variables: their CSR rows cover most of the store, and a second streaming
-          // sweep is cheaper than gathering the rows
-          int nd = *(volatile int*)&ctl->dirty_cnt[next_buf];
-          if ((long long)nd * 8 >= (long long)P.V) dec = D_SWEEP;
-          // a short cascade: grid-wide barriers and gathers cost more than the work itself
-          else if (P.solo_ok && P.smem_dom && nd <= kSoloMaxDirty && P.V <= kSoloWords * 32) dec = D_SOLO;
-        }
       }
       if (!decide) node_prologue_finish(P);  // prologue barrier: every CTA has read trail_cnt by now
       ctl->bar_count = 0;
@@ -494,47 +595,128 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
   return s_dec;
 }
 
+// ---------------------------------------------------------------------------------------
+// The dirty set: one bit per variable, triple-buffered across iterations (written through
+// Ctx::next_bits by apply_updates, read in the next iteration, cleared in the one after).
+// At the start of a worklist iteration every CTA compacts the set into the same list in its
+// own shared memory (the TMA ring is idle then): ascending variable order, so list index e
+// means the same variable everywhere and the rows can be dealt out by index.
+// Returns the number of dirty variables; the list is only written when it fits.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int dirty_compact(const uint32_t* bits, int words, int* list, int cap) {
+  __shared__ int s_warp[kWarps];
+  __shared__ int s_total;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpt = (words + kThreads - 1) / kThreads;  // words per thread (1 for V <= 32768)
+  const int w0 = threadIdx.x * wpt, w1 = min(words, w0 + wpt);
+  const unsigned m0 = w0 < w1 ? __ldcg(&bits[w0]) : 0u;
+  int cnt = __popc(m0);
+  for (int w = w0 + 1; w < w1; ++w) cnt += __popc(__ldcg(&bits[w]));
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int x = s_warp[lane];
+    int xi = x;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+    s_warp[lane] = xi - x;  // exclusive offset of each warp
+    if (lane == 31) s_total = xi;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (total <= cap && cnt > 0) {
+    int pos = s_warp[warp] + incl - cnt;
+    for (int w = w0; w < w1; ++w) {
+      unsigned m = w == w0 ? m0 : __ldcg(&bits[w]);
+      while (m) { const int b = __ffs(m) - 1; m &= m - 1; list[pos++] = w * 32 + b; }
+    }
+  }
+  __syncthreads();
+  return total;
+}
+
 // Row-local fixpoint: when the worklist is shorter than the grid, a whole CTA takes one dirty
 // variable v and re-evaluates v's row until v itself stops moving.  On bounds-only domains a
 // variable typically crawls value by value (each XNeqY against an assigned neighbour trims
 // one value off a bound, x_neq_y.rs:82-93): with one device barrier per crawl step a node
-// costs tens of iterations; here the crawl runs inside one iteration, at L1/shared-memory
-// latency (the row's refs and descriptors stay in L1 after the first round, the domains are
-// the CTA's snapshot, kept current by mirroring every update into it).  Still a chaotic
-// iteration of the same propagators: the fixpoint is unchanged.
-constexpr int kLocalRounds = 256;
+// costs tens of iterations; here the crawl runs inside one iteration.  Round 0 gathers the
+// row from L2 and leaves its active descriptors in shared memory (the idle TMA ring); the
+// later rounds run entirely out of shared memory -- staged descriptors, the CTA's snapshot
+// of the domains (kept current by mirroring every update into it) -- with the updates going
+// to HBM as fire-and-forget reductions.  Still a chaotic iteration of the same propagators:
+// the fixpoint is unchanged.  (A propagator deactivated meanwhile may be evaluated again:
+// an entailed propagator prunes nothing, and `deactivate` trails it only once.)
+constexpr int kLocalRounds = 1024;
+constexpr int kRowCap = 4864;  // staged propagators: 4 B ref + 16 B descriptor word 0 each
+static_assert(kRowStageOff + kRowCap * 20 <= kRingBytes, "row staging area exceeds the ring");
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_rows_local(Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
+__device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring) {
   const Params& P = *c.P;
   __shared__ int2 s_before;
-  const int* list = P.dirty_list + (size_t)cur_buf * P.V;
+  __shared__ int s_nstage, s_moved;
+  unsigned* s_ref = reinterpret_cast<unsigned*>(ring + kRowStageOff);
+  int4* s_q0 = reinterpret_cast<int4*>(ring + kRowStageOff + kRowCap * 4);
+  const int lane = threadIdx.x & 31;
   unsigned nprop = 0;
   c.mirror = SMEM;
   for (int e = blockIdx.x; e < n_dirty; e += gridDim.x) {
-    const int v = __ldcg(&list[e]);
+    const int v = list[e];
     const int rb = __ldg(&P.adj_ptr[v]), re = __ldg(&P.adj_ptr[v + 1]);
-    for (int round = 0; round < kLocalRounds; ++round) {
-      if (threadIdx.x == 0) s_before = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
-      __syncthreads();
-      for (int j = rb + threadIdx.x; j < re; j += blockDim.x) {
-        unsigned ref = __ldg(&P.adj[j]);
-        unsigned fam = ref >> 29;
-        int slot = (int)(ref & kSlotMask);
-        const Family& f = P.fam[fam];
-        if (slot >= f.n_static) continue;  // truncated by a restore (store.rs:320)
-        const unsigned word = __ldcg(&f.active[slot >> 5]);
-        int4 q0, q1, q2;
-        load_desc(f, fam, slot, q0, q1, q2);
-        if (!((word >> (slot & 31)) & 1u)) continue;
-        // first round: once per iteration across the grid; later rounds belong to this row
-        if (round == 0 && atomicExch(&f.stamp[slot], cur_epoch) == cur_epoch) continue;
-        eval_loaded<SMEM>(c, fam, slot, q0, q1, q2);
-        ++nprop;
+    const bool staged = re - rb <= kRowCap;
+    if (threadIdx.x == 0) { s_before = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]); s_nstage = 0; }
+    __syncthreads();
+    for (int round = 0;; ++round) {
+      if (round == 0 || !staged) {
+        for (int j0 = rb; j0 < re; j0 += blockDim.x) {
+          const int j = j0 + threadIdx.x;
+          bool keep = false;
+          unsigned ref = 0, fam = 0;
+          int slot = 0;
+          int4 q0, q1, q2;
+          if (j < re) {
+            ref = __ldg(&P.adj[j]);
+            fam = ref >> 29;
+            slot = (int)(ref & kSlotMask);
+            const Family& f = P.fam[fam];
+            if (slot < f.n_static) {  // else: truncated by a restore (store.rs:320)
+              const unsigned word = __ldcg(&f.active[slot >> 5]);
+              load_desc(f, fam, slot, q0, q1, q2);
+              keep = (word >> (slot & 31)) & 1u;
+            }
+          }
+          if (round == 0 && staged) {
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&s_nstage, __popc(m));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (keep) { const int idx = base + __popc(m & lanemask_lt()); s_ref[idx] = ref; s_q0[idx] = q0; }
+            }
+          }
+          // first round: once per iteration across the grid; later rounds belong to this row
+          if (keep && round == 0 && atomicExch(&P.fam[fam].stamp[slot], cur_epoch) == cur_epoch) keep = false;
+          if (keep) { eval_loaded<SMEM>(c, fam, slot, q0, q1, q2); ++nprop; }
+        }
+      } else {
+        const int n = s_nstage;
+        for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+          const unsigned ref = s_ref[idx];
+          const unsigned fam = ref >> 29;
+          const int slot = (int)(ref & kSlotMask);
+          if (fam == F_BIN) eval_loaded<SMEM>(c, F_BIN, slot, s_q0[idx], make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
+          else eval_ref<SMEM>(c, fam, slot);
+          ++nprop;
+        }
       }
       __syncthreads();
-      const int2 after = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
-      const bool moved = after.x != s_before.x || after.y != s_before.y;
-      if (!__syncthreads_or(moved) || after.x > after.y) break;
+      if (threadIdx.x == 0) {
+        const int2 a = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
+        s_moved = (a.x != s_before.x || a.y != s_before.y) && a.x <= a.y;
+        s_before = a;
+      }
+      __syncthreads();
+      if (!s_moved || round + 1 >= kLocalRounds) break;
     }
   }
   c.mirror = false;
@@ -542,20 +724,19 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, int cur_buf, int n
 }
 
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_dirty_rows(Ctx& c, int cur_buf, int n_dirty, unsigned cur_epoch) {
-  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(c, cur_buf, n_dirty, cur_epoch);
+__device__ __forceinline__ unsigned expand_dirty_rows(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring) {
+  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(c, list, n_dirty, cur_epoch, ring);
   const Params& P = *c.P;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarps;
   const long long S = max(1LL, nwarps / n_dirty);  // segments per row (upper bound)
   const long long items = (long long)n_dirty * S;
-  const int* list = P.dirty_list + (size_t)cur_buf * P.V;
   unsigned nprop = 0;
   for (long long item = warp; item < items; item += nwarps) {
     int e = (int)(item / S);
     long long s = item % S;
-    int v = __ldcg(&list[e]);
+    int v = list[e];
     int rb = __ldg(&P.adj_ptr[v]), re = __ldg(&P.adj_ptr[v + 1]);
     long long len = re - rb;
     long long nseg = min(S, (len + 31) / 32);
@@ -621,201 +802,6 @@ __device__ __forceinline__ void node_prologue_finish(const Params& P) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Solo mode: a short cascade (<= kSoloMaxDirty dirty variables) is run to its end by CTA 0
-// alone.  The snapshot in shared memory is the authoritative copy of the domains (updates by
-// shared-memory atomics, written through to HBM without waiting), the worklists are a bit set
-// plus a short list in shared memory, iterations are separated by __syncthreads instead of the
-// device barrier, and a propagator adjacent to two dirty variables is evaluated once (from
-// the smaller one) without any stamp traffic.  Everybody else waits at the device barrier.
-// Ends at the fixpoint, at a failure, or when the worklist outgrows the mode; then the next
-// worklist is handed back to the grid through the global dirty list.
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ bool solo_bit(const unsigned* bits, int v) { return v >= 0 && ((bits[v >> 5] >> (v & 31)) & 1u); }
-
-// true if `p` will be (was) evaluated from a smaller dirty variable than `v`
-__device__ __forceinline__ bool solo_dup(const Params& P, const unsigned* bits, unsigned fam, int4 q0, int4 q1, int4 q2, int v) {
-  int ops[6];
-  int n;
-  if (fam == F_BIN) { ops[0] = dec_var28((unsigned)q0.x); ops[1] = q0.z; n = 2; }
-  else if (fam == F_TER) { ops[0] = dec_var28((unsigned)q0.x); ops[1] = q0.z; ops[2] = q1.x; n = 3; }
-  else { ops[0] = q0.x; ops[1] = q0.z; ops[2] = q1.x; ops[3] = q1.z; ops[4] = q2.x; ops[5] = q2.z; n = 6; }
-  for (int i = 0; i < n; ++i) {
-    const int u = ops[i];
-    if (u >= 0) { if (u < v && solo_bit(bits, u)) return true; }
-    else if (u <= -2) {  // a sum view: any of its terms
-      const int b = __ldg(&P.sum_ptr[-2 - u]), e = __ldg(&P.sum_ptr[-2 - u + 1]);
-      for (int t = b; t < e; ++t) { const int w = __ldg(&P.sum_terms[t]).x; if (w >= 0 && w < v && solo_bit(bits, w)) return true; }
-    }
-  }
-  return false;
-}
-
-__device__ __forceinline__ void solo_mark(const Params& P, int slot) {
-  if (P.trace && threadIdx.x == 0 && slot < 64) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    P.trace[8 * 256 + 4 * 32 + slot] = t;
-  }
-}
-// CTA 0, all threads.  `list`/`n_dirty`: the global worklist of this iteration (already
-// refreshed into the snapshot).  Returns the number of propagator evaluations.
-template <bool SMEM>
-__device__ __noinline__ unsigned solo_iterations(const Params& P, Ctx c, int bin_n, const int* list, int n_dirty,
-                                                 char* smem_nary, unsigned next_epoch, int next_buf) {
-  __shared__ int s_list[2][kSoloCap];
-  __shared__ int s_cnt[2];
-  __shared__ int s_rows[kSoloCap + 1], s_rowbase[kSoloCap], s_rowlen[kSoloCap];
-  __shared__ unsigned s_bits[2][kSoloWords];
-  constexpr int kTailCap = 64;            // active tail propagators, cached for the whole phase
-  __shared__ unsigned s_tail_ref[kTailCap];
-  __shared__ int s_tail_n;
-  const int tid = threadIdx.x;
-  const int words = (P.V + 31) >> 5;
-  solo_mark(P, 0);
-  for (int w = tid; w < 2 * kSoloWords; w += blockDim.x) (&s_bits[0][0])[w] = 0u;
-  if (tid < 2) s_cnt[tid] = 0;
-  if (tid == 0) s_tail_n = 0;
-  __syncthreads();
-  if (tid < n_dirty) { const int v = __ldcg(&list[tid]); s_list[0][tid] = v; atomicOr(&s_bits[0][v >> 5], 1u << (v & 31)); }
-  if (tid == 0) s_cnt[0] = n_dirty;
-  // the active tail propagators (none can appear during the phase; entailed ones just evaluate
-  // as no-ops): collected once
-  for (unsigned fam = 0; fam < 3; ++fam) {
-    const Family& f = P.fam[fam];
-    const int fn = fam == F_BIN ? bin_n : f.n;
-    for (int p = f.n_static + tid; p < fn; p += blockDim.x)
-      if (is_active(f, p)) { int i = atomicAdd(&s_tail_n, 1); if (i < kTailCap) s_tail_ref[i] = make_ref(fam, (unsigned)p); }
-  }
-  __syncthreads();
-  const int tail_n = s_tail_n;
-  solo_mark(P, 1);
-  c.solo = true;
-  c.mirror = false;
-  c.local = false;
-  c.mark_dirty = true;
-  c.bookkeep = true;
-  c.solo_cap = kSoloCap;
-  unsigned nprop = 0;
-  int cur = 0;
-  for (int it = 0; it < kSoloMaxIters; ++it) {
-    const int n = s_cnt[cur];
-    const unsigned* cur_bits = s_bits[cur];
-    c.solo_next_bits = s_bits[cur ^ 1];
-    c.solo_next_list = s_list[cur ^ 1];
-    c.solo_next_cnt = &s_cnt[cur ^ 1];
-    // rows of the dirty variables (n <= kSoloMaxDirty): bases and lengths in parallel, then a
-    // tiny prefix sum
-    if (tid < n) {
-      const int v = s_list[cur][tid];
-      const int b = __ldg(&P.adj_ptr[v]);
-      s_rowbase[tid] = b;
-      s_rowlen[tid] = __ldg(&P.adj_ptr[v + 1]) - b;
-    }
-    // tail propagators, from the snapshot
-    if (tail_n <= kTailCap) {
-      if (tid < tail_n) { eval_ref<SMEM>(c, s_tail_ref[tid] >> 29, (int)(s_tail_ref[tid] & kSlotMask)); ++nprop; }
-    } else {
-      for (unsigned fam = 0; fam < 3; ++fam) {
-        const Family& f = P.fam[fam];
-        const int fn = fam == F_BIN ? bin_n : f.n;
-        for (int p = f.n_static + tid; p < fn; p += blockDim.x)
-          if (is_active(f, p)) { eval_ref<SMEM>(c, fam, p); ++nprop; }
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int acc = 0;
-      for (int e = 0; e < n; ++e) { s_rows[e] = acc; acc += s_rowlen[e]; }
-      s_rows[n] = acc;
-    }
-    __syncthreads();
-    const int total = s_rows[n];
-    solo_mark(P, 2 + 3 * it);
-    // the concatenated rows, kBatch entries per thread in flight
-    constexpr int kBatch = 4;
-    for (int base = tid; base < total; base += blockDim.x * kBatch) {
-      unsigned ref[kBatch];
-      int var[kBatch];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        const int i = base + k * blockDim.x;
-        ref[k] = 0xffffffffu;
-        var[k] = -1;
-        if (i < total) {
-          int e = 0;
-          while (e + 1 < n && s_rows[e + 1] <= i) ++e;
-          var[k] = s_list[cur][e];
-          ref[k] = __ldg(&P.adj[s_rowbase[e] + (i - s_rows[e])]);
-        }
-      }
-      unsigned word[kBatch];
-      int4 q0[kBatch], q1[kBatch], q2[kBatch];
-      bool live[kBatch];
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        live[k] = false;
-        if (ref[k] != 0xffffffffu) {
-          const unsigned fam = ref[k] >> 29;
-          const int slot = (int)(ref[k] & kSlotMask);
-          const Family& f = P.fam[fam];
-          if (slot < f.n_static) {
-            word[k] = __ldcg(&f.active[slot >> 5]);
-            load_desc(f, fam, slot, q0[k], q1[k], q2[k]);
-            live[k] = true;
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kBatch; ++k) {
-        if (!live[k]) continue;
-        const unsigned fam = ref[k] >> 29;
-        const int slot = (int)(ref[k] & kSlotMask);
-        if (!((word[k] >> (slot & 31)) & 1u)) continue;
-        if (solo_dup(P, cur_bits, fam, q0[k], q1[k], q2[k], var[k])) continue;
-        eval_loaded<SMEM>(c, fam, slot, q0[k], q1[k], q2[k]);
-        ++nprop;
-      }
-    }
-    solo_mark(P, 3 + 3 * it);
-    // n-ary propagators: all active ones (their operands live in the snapshot)
-    for (int s = 0; s < P.n_nary; ++s) {
-      if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-      unsigned ev = eval_distinct<SMEM>(c, s, smem_nary, 0u, true);
-      if (tid == 0) nprop += ev;
-    }
-    __syncthreads();
-    const int n_next = s_cnt[cur ^ 1];
-    const bool failed = c.flags[1] != 0;
-    solo_mark(P, 4 + 3 * it);
-    // retire the current worklist
-    if (tid < n && tid < kSoloCap) { const int v = s_list[cur][tid]; atomicAnd(&s_bits[cur][v >> 5], ~(1u << (v & 31))); }
-    __syncthreads();
-    if (tid == 0) s_cnt[cur] = 0;
-    if (failed || n_next == 0) break;
-    if (n_next > kSoloMaxDirty || it + 1 == kSoloMaxIters) {
-      // hand the worklist back to the grid: the bit set is complete even if the list overflowed
-      for (int w = tid; w < words; w += blockDim.x) {
-        unsigned m = s_bits[cur ^ 1][w];
-        while (m) {
-          const int b = __ffs(m) - 1;
-          m &= m - 1;
-          const int v = w * 32 + b;
-          const int idx = atomicAdd(&P.ctl->dirty_cnt[next_buf], 1);
-          P.dirty_list[(size_t)next_buf * P.V + idx] = v;
-          P.dirty_stamp[v] = next_epoch;
-        }
-      }
-      c.flags[0] = 1;
-      break;
-    }
-    cur ^= 1;
-    __syncthreads();
-  }
-  __syncthreads();
-  return nprop;
-}
-
-// ---------------------------------------------------------------------------------------
 // Per-CTA state shared by the single-node kernel and the search-burst kernel.
 // ---------------------------------------------------------------------------------------
 struct CtaState {
@@ -868,37 +854,38 @@ __device__ __forceinline__ void pre_issue(const Params& P, CtaState& st) {
 // worklist) and the worklist / re-sweep iterations, each closed by the deciding barrier.
 // Every thread of every CTA calls it with the same arguments; returns the decision, `iters`
 // the number of iterations.  `bin_n` is the end of the binary tail (dynamic during a burst).
+// On return the three dirty sets are empty again.
 template <bool SMEM>
 __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st, unsigned epoch0, int bin_n,
                                                   int n_inline, const InlineProp* inl, bool full_sweep,
-                                                  int seed_dirty, bool pre_issued, unsigned& iters_out) {
-  Control* ctl = P.ctl;
+                                                  int seeded, bool pre_issued, unsigned& iters_out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int W = P.dirty_words;
+  int* const list = reinterpret_cast<int*>(st.ring);
   Ctx c;
   c.P = &P;
   c.sdom = st.sdom;
+  c.sdom_s = SMEM ? smem_u32(st.sdom) : 0u;
   c.flags = st.flags;
+  c.mirror = false;
   ActiveWords aw;
   aw.w[0] = aw.w[1] = 0u;
   if (warp > 0 && st.my_chunks > 0 && full_sweep) aw = load_active_words(P, chunk_of(P, st.cmap, st.wid));
-  bool sweep_now = full_sweep, solo_now = false, after_solo = false;
-  c.solo = false;
-  c.mirror = false;
   unsigned iter = 0, dec, nprop = 0;
+  int cur_buf = 0, next_buf = 1;
   while (true) {
-    const int cur_buf = iter % 3, next_buf = (iter + 1) % 3, spare_buf = (iter + 2) % 3;
+    cur_buf = iter % 3;
+    next_buf = (iter + 1) % 3;
+    const int spare_buf = (iter + 2) % 3;
     const unsigned cur_epoch = epoch0 + iter;
-    c.next_epoch = cur_epoch + 1;
-    c.next_buf = next_buf;
+    const uint32_t* cur_bits = P.dirty_bits + (size_t)cur_buf * W;
+    c.next_bits = P.dirty_bits + (size_t)next_buf * W;
     c.local = false;
     c.mark_dirty = true;
     c.bookkeep = true;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->dirty_cnt[spare_buf] = 0;  // idle this iteration
-    if (SMEM && after_solo) {
-      // CTA 0 ran a cascade on its own: everybody's snapshot is stale beyond the worklist
-      for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
-      __syncthreads();
-    }
+    // the spare set was read in the previous iteration and is written in the next one
+    if (iter > 0 && blockIdx.x == 0)
+      for (int w = threadIdx.x; w < W; w += blockDim.x) P.dirty_bits[(size_t)spare_buf * W + w] = 0u;
 
     if (iter == 0 && n_inline > 0) {
       // Propagators posted since the last node.  With a full sweep ahead they need not enter
@@ -926,7 +913,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       __syncthreads();
     }
     // older tail propagators: CTA 0, every iteration (inline ones were just handled)
-    if (blockIdx.x == 0 && !solo_now) {
+    if (blockIdx.x == 0) {
       unsigned n = 0;
       for (unsigned fam = 0; fam < 3; ++fam) {
         const Family& f = P.fam[fam];
@@ -942,67 +929,63 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     }
 
     if (iter == 0) trace_mark(P, 2);
-    // worklist of variables narrowed in the previous iteration (iteration 0 of an
-    // incremental launch: seeded by the host)
+    // ---- the variables narrowed in the previous iteration (iteration 0 of an incremental
+    // launch: seeded by the host).  Every CTA derives the same count, hence the same choice
+    // between expanding their rows and sweeping again.
     int n_dirty = 0;
-    if (iter > 0) n_dirty = *(volatile int*)&ctl->dirty_cnt[cur_buf];
-    else if (!full_sweep) n_dirty = seed_dirty;
-    if (n_dirty > 0 && (!solo_now || blockIdx.x == 0)) {
-      const int* list = P.dirty_list + (size_t)cur_buf * P.V;
-      // refresh the snapshot and catch domains emptied by two concurrent updates
-      // (with a snapshot every CTA needs every dirty variable; without one the check is
-      // shared by the grid)
+    bool sweep_now = iter == 0 && full_sweep, skip = false;
+    if (iter > 0 || (!full_sweep && seeded)) {
+      n_dirty = dirty_compact(cur_bits, W, list, kListCap);
+      // many dirty variables: their CSR rows cover most of the store, and a streaming sweep is
+      // cheaper than gathering the rows
+      if (n_dirty > kListCap || (long long)n_dirty * 8 >= (long long)P.V) sweep_now = true;
+      // refresh the snapshot and catch domains emptied by two concurrent updates (with a
+      // snapshot every CTA needs every dirty variable; without one the check is shared by the
+      // grid)
       int bad = 0;
-      const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
-      const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
-      for (int i = r0; i < n_dirty; i += rs) {
-        int v = __ldcg(&list[i]);
-        int2 d = ldcg_dom(&P.dom[v]);
-        if (SMEM) st.sdom[v] = d;
-        bad |= d.x > d.y;
-      }
-      if (bad) set_failed(c);
-      if (SMEM) __syncthreads();
-      if (solo_now) nprop += solo_iterations<SMEM>(P, c, bin_n, list, n_dirty, st.ring, c.next_epoch, next_buf);
-      else if (!sweep_now) nprop += expand_dirty_rows<SMEM>(c, cur_buf, n_dirty, cur_epoch);
-    }
-    if (sweep_now && st.my_chunks > 0) {
-      // ---- the streaming sweep over the static descriptor arrays (ring positions keep
-      // counting across sweeps so the mbarrier phases stay consistent)
-      const int first = (iter == 0 && pre_issued) ? min(st.my_chunks, kStages) : 0;
-      if (warp == 0) {
-        if (lane == 0) {
-          // the ring memory doubles as n-ary staging (generic-proxy writes): order them before
-          // the async-proxy writes of the next bulk copies
-          if (first == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          for (int i = first; i < st.my_chunks; ++i) {
-            const int q = st.pipe_pos + i, s = q % kStages;
-            if (q >= kStages) mbar_wait(&st.empty[s], ((q / kStages) - 1) & 1);
-            producer_issue(P, chunk_of(P, st.cmap, st.wid + i * st.workers), st.ring + s * kStageBytes, &st.full[s]);
-          }
+      if (sweep_now) {
+        const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+        const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
+        for (int v = r0; v < P.V; v += rs) {  // coalesced re-read of everything beats gathers
+          int2 d = ldcg_dom(&P.dom[v]);
+          if (SMEM) st.sdom[v] = d;
+          bad |= d.x > d.y;
         }
       } else {
-        if (iter > 0) aw = load_active_words(P, chunk_of(P, st.cmap, st.wid));
-        for (int i = 0; i < st.my_chunks; ++i) {
-          const int q = st.pipe_pos + i, s = q % kStages;
-          const Chunk ch = chunk_of(P, st.cmap, st.wid + i * st.workers);
-          ActiveWords nxt = aw;
-          if (i + 1 < st.my_chunks) nxt = load_active_words(P, chunk_of(P, st.cmap, st.wid + (i + 1) * st.workers));
-          mbar_wait(&st.full[s], (q / kStages) & 1);
-          nprop += sweep_consume<SMEM>(c, ch, st.ring + s * kStageBytes, aw);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&st.empty[s]);
-          aw = nxt;
+        const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
+        const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
+        for (int i = r0; i < n_dirty; i += rs) {
+          int v = list[i];
+          int2 d = ldcg_dom(&P.dom[v]);
+          if (SMEM) st.sdom[v] = d;
+          bad |= d.x > d.y;
         }
       }
+      if (__syncthreads_or(bad)) {
+        // failed: with a snapshot every CTA sees it and the iteration's work is skipped
+        if (threadIdx.x == 0) set_failed(c);
+        skip = SMEM;
+      }
+      if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(c, list, n_dirty, cur_epoch, st.ring);
+    }
+    if (sweep_now && !skip && st.my_chunks > 0) {
+      // ---- the streaming sweep over the static descriptor arrays (ring positions keep
+      // counting across sweeps so the mbarrier phases stay consistent).  (`skip` is never set
+      // in iteration 0, so pre-issued chunks are always consumed.)
+      SweepArgs sa;
+      sa.ring = st.ring; sa.full = st.full; sa.empty = st.empty; sa.cmap = st.cmap;
+      sa.wid = st.wid; sa.workers = st.workers; sa.my_chunks = st.my_chunks; sa.pipe_pos = st.pipe_pos;
+      sa.first = (iter == 0 && pre_issued) ? min(st.my_chunks, kStages) : 0;
+      sa.reload_aw = !(iter == 0 && full_sweep);  // iteration 0 of a full sweep prefetched them
+      { const unsigned n = sweep_pass<SMEM>(c, sa, aw); if (lane == 0) nprop += n; }  // counted per warp
       st.pipe_pos += st.my_chunks;
     }
     if (iter == 0 && P.trace) { __syncthreads(); trace_mark(P, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
-    if (P.n_nary > 0 && !solo_now && (iter > 0 || full_sweep || n_dirty > 0)) {
+    if (P.n_nary > 0 && !skip && (iter > 0 || full_sweep || n_dirty > 0)) {
       for (int s = blockIdx.x; s < P.n_nary; s += gridDim.x) {
         if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-        unsigned ev = eval_distinct<SMEM>(c, s, st.ring, cur_epoch, iter == 0 && full_sweep);
+        unsigned ev = eval_distinct<SMEM>(c, s, st.ring, cur_bits, iter == 0 && full_sweep);
         if (threadIdx.x == 0) nprop += ev;
       }
     }
@@ -1015,21 +998,24 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     unsigned bp = 0;
     if (threadIdx.x == 0) { bp = *st.block_props; *st.block_props = 0; }
     if (iter == 0) trace_mark(P, 4);
-    dec = grid_barrier(P, st.gen, bp, true, st.flags, iter, next_buf);
+    dec = grid_barrier(P, st.gen, bp, true, st.flags, iter);
     if (iter == 0) trace_mark(P, 5);
     if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && iter < 32) {  // per-iteration record
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[8 * 256 + iter * 4 + 0] = t;
-      P.trace[8 * 256 + iter * 4 + 1] = (unsigned long long)*(volatile int*)&ctl->dirty_cnt[next_buf];
-      P.trace[8 * 256 + iter * 4 + 2] = dec;
+      P.trace[8 * 256 + iter * 4 + 1] = (unsigned long long)n_dirty;
+      P.trace[8 * 256 + iter * 4 + 2] = dec | (sweep_now ? 8u : 0u);
     }
     ++iter;
-    if (dec != D_CONTINUE && dec != D_SWEEP && dec != D_SOLO) break;
-    after_solo = solo_now;
-    sweep_now = dec == D_SWEEP;
-    solo_now = dec == D_SOLO;
+    if (dec != D_CONTINUE) break;
   }
+  // leave the dirty sets empty: the spare one was cleared during the last iteration
+  if (blockIdx.x == 0)
+    for (int w = threadIdx.x; w < W; w += blockDim.x) {
+      P.dirty_bits[(size_t)cur_buf * W + w] = 0u;
+      P.dirty_bits[(size_t)next_buf * W + w] = 0u;
+    }
   iters_out = iter;
   return dec;
 }
@@ -1100,7 +1086,6 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       ctl->epoch = epoch0 + iters + 1;
       ctl->iterations = iters;
       ctl->last_decision = dec;
-      ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     }
   }
 }
@@ -1253,8 +1238,6 @@ __device__ __forceinline__ void burst_host_step(const Params& P, const BurstPara
   }
   // ---- decide whether the burst goes on; pop the next branch
   if (tid == 0) {
-    // a node may end with entries left in its last dirty list (failure): start the next clean
-    ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     int run = 0, status = 0;
     const int nb = L->n_branch;
     if (L->err) status = 2;
@@ -1384,7 +1367,6 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     burst_store(bc, &s_local);
     ctl->epoch = epoch + 1;
-    ctl->dirty_cnt[0] = ctl->dirty_cnt[1] = ctl->dirty_cnt[2] = 0;
     Result r;
     r.failed = 0;
     r.trail_cnt = *(volatile unsigned*)&ctl->trail_cnt;
@@ -1400,10 +1382,10 @@ __global__ void pcp_fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// incremental launches: stamp the host-seeded dirty variables with the epoch of iteration 0
-__global__ void pcp_seed_dirty_kernel(const int* list, int n, uint32_t* dirty_stamp, const Control* ctl) {
+// incremental launches: the variables narrowed by the host enter the dirty set of iteration 0
+__global__ void pcp_seed_dirty_kernel(const int* list, int n, uint32_t* bits0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dirty_stamp[list[i]] = ctl->epoch;
+  if (i < n) atomicOr(&bits0[list[i] >> 5], 1u << (list[i] & 31));
 }
 
 }  // namespace pcpd

@@ -141,8 +141,9 @@ struct pcp_engine {
   size_t tail_limit = 4096;
 
   // worklists / control
-  DevBuf<int> d_dirty_list;
-  DevBuf<uint32_t> d_dirty_stamp;
+  DevBuf<uint32_t> d_dirty_bits;  // 3 x dirty_words, all zero between launches
+  size_t dirty_words = 0;
+  DevBuf<int> d_seed_list;        // host-narrowed variables of an incremental launch
   DevBuf<uint32_t> d_trail;
   Control* d_ctl = nullptr;
   unsigned trail_len = 0;           // host view of ctl->trail_cnt
@@ -490,11 +491,11 @@ Params prepare(pcp_engine* e) {
     e->V_uploaded = V;
     e->mirror_valid = false;
     ++e->dom_version;
-    // per-variable worklist storage (3 lists) and stamps
-    e->d_dirty_list.reserve(3 * V, e->stream);
-    size_t old_cap = e->d_dirty_stamp.cap;
-    e->d_dirty_stamp.reserve(V, e->stream, oldV);
-    if (e->d_dirty_stamp.cap != old_cap) fill_u32(e, e->d_dirty_stamp.p + oldV, 0u, e->d_dirty_stamp.cap - oldV);
+    // the dirty sets: three bit sets over the variables, empty between launches
+    (void)oldV;
+    e->dirty_words = (V + 31) / 32;
+    e->d_dirty_bits.reserve(3 * e->dirty_words, e->stream);
+    CUDA_CHECK(cudaMemsetAsync(e->d_dirty_bits.p, 0, e->d_dirty_bits.cap * sizeof(uint32_t), e->stream));
     // the label stack is laid out with stride V: a label taken with fewer variables cannot be
     // restored after more were allocated
     if (e->stack_stride != V) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = V; }
@@ -605,13 +606,11 @@ Params prepare(pcp_engine* e) {
   P.sum_terms = e->d_sum_terms.p;
   P.adj_ptr = e->d_adj_ptr.p;
   P.adj = e->d_adj.p;
-  P.dirty_list = e->d_dirty_list.p;
-  P.dirty_stamp = e->d_dirty_stamp.p;
+  P.dirty_bits = e->d_dirty_bits.p;
+  P.dirty_words = (int)e->dirty_words;
   P.trail = e->d_trail.p;
   P.ctl = e->d_ctl;
   P.max_iterations = e->max_iterations;
-  static const bool solo_on = std::getenv("PCP_SOLO") != nullptr;
-  P.solo_ok = solo_on ? 1 : 0;
   if (e->pending_restore) {
     P.restore_from = e->d_stack.p + e->pending_restore_label * e->stack_stride;
     e->mirror_valid = false;
@@ -661,7 +660,6 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   // epoch wrap: stamps are compared for equality with epochs of this launch only
   if (e->epoch > 0x7f000000u) {
     for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
-    fill_u32(e, e->d_dirty_stamp.p, 0u, e->d_dirty_stamp.cap);
     unsigned one = 1;
     CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -674,8 +672,9 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     size_t n = e->host_dirty.size();
     int* st = static_cast<int*>(stage(e, n * sizeof(int)));
     std::memcpy(st, e->host_dirty.data(), n * sizeof(int));
-    CUDA_CHECK(cudaMemcpyAsync(e->d_dirty_list.p, st, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    pcp_seed_dirty_kernel<<<(int)((n + 255) / 256), 256, 0, e->stream>>>(e->d_dirty_list.p, (int)n, e->d_dirty_stamp.p, e->d_ctl);
+    e->d_seed_list.reserve(n, e->stream);
+    CUDA_CHECK(cudaMemcpyAsync(e->d_seed_list.p, st, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    pcp_seed_dirty_kernel<<<(int)((n + 255) / 256), 256, 0, e->stream>>>(e->d_seed_list.p, (int)n, e->d_dirty_bits.p);
     CUDA_CHECK(cudaGetLastError());
     P.seed_dirty = (int)n;
   }
@@ -732,14 +731,10 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     {
       unsigned long long tb = ~0ull;
       for (int b = 0; b < grid; ++b) tb = std::min(tb, t[b * 8]);
-      if (t[8 * 256 + 4 * 32]) {
-        std::fprintf(stderr, "[pcp trace]   solo marks (ns since start):");
-        for (int k = 0; k < 64 && t[8 * 256 + 4 * 32 + k]; ++k) std::fprintf(stderr, " %llu", t[8 * 256 + 4 * 32 + k] - tb);
-        std::fprintf(stderr, "\n");
-      }
       for (unsigned it = 0; it < e->h_result()->iterations && it < 32; ++it)
-        std::fprintf(stderr, "[pcp trace]   iter %2u: barrier left at %8llu ns, dirty=%llu, decision=%llu\n", it,
-                     t[8 * 256 + it * 4] - tb, t[8 * 256 + it * 4 + 1], t[8 * 256 + it * 4 + 2]);
+        std::fprintf(stderr, "[pcp trace]   iter %2u: barrier left at %8llu ns, dirty_in=%llu, decision=%llu%s\n", it,
+                     t[8 * 256 + it * 4] - tb, t[8 * 256 + it * 4 + 1], t[8 * 256 + it * 4 + 2] & 7,
+                     (t[8 * 256 + it * 4 + 2] & 8) ? " (sweep)" : "");
     }
     unsigned long long t0 = ~0ull;
     for (int b = 0; b < grid; ++b) t0 = std::min(t0, t[b * 8]);
@@ -856,7 +851,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   }
   e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_active.free();
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
-  e->d_dirty_list.free(); e->d_dirty_stamp.free(); e->d_trail.free(); e->d_stack.free();
+  e->d_dirty_bits.free(); e->d_seed_list.free(); e->d_trail.free(); e->d_stack.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
   if (e->burst.d_bc) cudaFree(e->burst.d_bc);
   e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_bmeta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free();
@@ -1164,7 +1159,6 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     P.max_iterations = e->max_iterations;
     if (e->epoch > 0x70000000u) {  // epoch wrap, as in run_fixpoint
       for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
-      fill_u32(e, e->d_dirty_stamp.p, 0u, e->d_dirty_stamp.cap);
       unsigned one = 1;
       CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
       e->epoch = 1;

@@ -4,10 +4,9 @@
 // Every propagator is evaluated in two steps: a *pure* step that reads the operand views
 // and computes the narrowed bounds exactly as the reference's `propagate` would (file:line
 // at each function), staging at most one update per operand; and `apply_updates`, which
-// issues all staged atomicMax/atomicMin together (their L2 round trips overlap), then
-// queues the variables that really changed on the dirty worklist with one warp-aggregated
-// reservation.  A cheap inline "would this evaluation change anything?" test keeps the
-// common case of a sweep free of calls.
+// issues the staged updates as fire-and-forget reductions on the bounds and on the dirty
+// bit set.  A cheap inline "would this evaluation change anything?" test keeps the common
+// case of a sweep free of calls.
 #pragma once
 
 namespace pcpd {
@@ -18,21 +17,13 @@ struct IV { int lo, hi; };
 struct Ctx {
   const Params* P;
   int2* sdom;             // shared-memory snapshot (or nullptr)
-  unsigned next_epoch;    // stamp for "dirty in the next iteration"
-  int next_buf;           // dirty list written in this iteration
+  uint32_t sdom_s;        // its shared-space address (hot reads are explicit LDS, not generic loads)
+  uint32_t* next_bits;    // dirty bit set written in this iteration (read in the next one)
   bool local;             // updates go to the shared-memory snapshot only (posted props, per CTA)
   bool mark_dirty;        // narrowed variables enter the worklist
   bool bookkeep;          // entailed propagators are deactivated + trailed
-  int* flags;             // shared: [0] this CTA queued a dirty variable, [1] saw a failure
-  // solo mode (a short cascade run by CTA 0 alone, see solo_iterations): the snapshot is the
-  // authoritative copy, updated with shared-memory atomics and written through to HBM;
-  // the next worklist is a bit set + short list in shared memory
-  bool mirror;            // row-local fixpoint: every update is also applied to this CTA's snapshot
-  bool solo;
-  unsigned* solo_next_bits;
-  int* solo_next_list;
-  int* solo_next_cnt;
-  int solo_cap;
+  bool mirror;            // row-local rounds: every update is also applied to this CTA's snapshot
+  int* flags;             // shared: [0] this CTA narrowed a variable, [1] saw a failure
 };
 
 __device__ __forceinline__ void set_failed(const Ctx& c) { c.flags[1] = 1; }
@@ -53,6 +44,20 @@ __device__ __forceinline__ void deactivate(const Ctx& c, uint32_t* active, unsig
 }
 
 // Domain readers.  `SMEM` reads the CTA's snapshot, otherwise L2 (ld.global.cg).
+// The snapshot is accessed through explicit shared-space instructions: through the generic
+// pointer in Ctx the compiler cannot prove the address space and emits generic loads.
+__device__ __forceinline__ int2 lds_dom(uint32_t addr) {
+  int2 r;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void sts_dom(uint32_t addr, int lo, int hi) {
+  asm volatile("st.shared.v2.s32 [%0], {%1, %2};" ::"r"(addr), "r"(lo), "r"(hi));
+}
+template <bool SMEM>
+__device__ __forceinline__ int2 rd_var(const Ctx& c, int var) {
+  return SMEM ? lds_dom(c.sdom_s + 8u * (unsigned)var) : ldcg_dom(&c.P->dom[var]);
+}
 template <bool SMEM>
 __device__ __noinline__ IV rd_sum(const Ctx& c, int sum_id, int off) {
   // Sum::read (term/sum.rs:71-82): [sum lo_i, sum hi_i] over the terms.  A sum with more than
@@ -64,7 +69,7 @@ __device__ __noinline__ IV rd_sum(const Ctx& c, int sum_id, int off) {
   for (int t = b; t < e; ++t) {
     int2 term = __ldg(&P.sum_terms[t]);
     if (term.x >= 0) {
-      int2 d = SMEM ? c.sdom[term.x] : ldcg_dom(&P.dom[term.x]);
+      int2 d = rd_var<SMEM>(c, term.x);
       lo += d.x + term.y;
       hi += d.y + term.y;
     } else {
@@ -80,7 +85,7 @@ __device__ __forceinline__ IV rd(const Ctx& c, int var, int off) {
     if (var == -1) return IV{off, off};  // Constant (term/constant.rs:55-63)
     return rd_sum<SMEM>(c, -2 - var, off);
   }
-  int2 d = SMEM ? c.sdom[var] : ldcg_dom(&c.P->dom[var]);
+  int2 d = rd_var<SMEM>(c, var);
   return IV{d.x + off, d.y + off};   // Addition (term/addition.rs:93-101)
 }
 
@@ -106,98 +111,31 @@ __device__ __forceinline__ bool stage(UpdSet& us, int var, int off, IV cur, int 
   return true;
 }
 
+// All updates are fire-and-forget reductions (RED.MAX / RED.MIN on the bounds, RED.OR on the
+// dirty bit set): nothing in the evaluation waits for an L2 round trip.  A variable is marked
+// dirty whenever this thread's view says the update narrows it; if a concurrent update had
+// already narrowed it further, that thread marked it too.  A domain emptied by two concurrent
+// updates (lo from one thread, hi from another) is caught when the dirty variables are
+// re-read at the start of the next iteration -- there always is one, flags[0] is set.
 __device__ __forceinline__ void apply_updates(const Ctx& c, const UpdSet& us) {
   if (us.n == 0) return;
-  if (c.local) {
-    for (int i = 0; i < us.n; ++i) c.sdom[us.u[i].var] = make_int2(us.u[i].nlo - us.u[i].off, us.u[i].nhi - us.u[i].off);
-    return;
-  }
   const Params& P = *c.P;
-  if (c.solo) {
-    for (int i = 0; i < us.n; ++i) {
-      const Upd& r = us.u[i];
-      const int nl = r.nlo - r.off, nh = r.nhi - r.off;
-      int2* s = &c.sdom[r.var];
-      int2* d = &P.dom[r.var];
-      bool ch = false;
-      int lo_now = r.cur_lo - r.off, hi_now = r.cur_hi - r.off;
-      if (r.nlo > r.cur_lo) {
-        int old = atomicMax(&s->x, nl);     // shared-memory atomic: the authoritative copy
-        if (old < nl) { ch = true; atomicMax(&d->x, nl); }  // write-through, result unused (RED)
-        lo_now = max(old, nl);
-      }
-      if (r.nhi < r.cur_hi) {
-        int old = atomicMin(&s->y, nh);
-        if (old > nh) { ch = true; atomicMin(&d->y, nh); }
-        hi_now = min(old, nh);
-      }
-      if (!ch) continue;
-      // the other bound may have moved under us: re-read the authoritative copy
-      const int now_lo = *(volatile int*)&s->x, now_hi = *(volatile int*)&s->y;
-      if (lo_now > hi_now || now_lo > now_hi) set_failed(c);
-      const unsigned bit = 1u << (r.var & 31);
-      if (!(atomicOr(&c.solo_next_bits[r.var >> 5], bit) & bit)) {
-        int idx = atomicAdd(c.solo_next_cnt, 1);
-        if (idx < c.solo_cap) c.solo_next_list[idx] = r.var;
-      }
-    }
-    return;
-  }
-  // 1. all atomics in flight together (plus a plain look at the dirty stamp: a variable that is
-  //    already queued for the next iteration needs no exchange)
-  int old_lo[3], old_hi[3];
-  unsigned seen[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    if (i < us.n) {
-      const Upd& r = us.u[i];
-      int2* d = &P.dom[r.var];
-      old_lo[i] = r.nlo > r.cur_lo ? atomicMax(&d->x, r.nlo - r.off) : r.cur_lo - r.off;
-      old_hi[i] = r.nhi < r.cur_hi ? atomicMin(&d->y, r.nhi - r.off) : r.cur_hi - r.off;
-      seen[i] = c.mark_dirty ? __ldcg(&P.dirty_stamp[r.var]) : 0u;
-      if (c.mirror) {  // keep the CTA's snapshot current for the next local round
-        if (r.nlo > r.cur_lo) atomicMax(&c.sdom[r.var].x, r.nlo - r.off);
-        if (r.nhi < r.cur_hi) atomicMin(&c.sdom[r.var].y, r.nhi - r.off);
-      }
+    if (i >= us.n) break;
+    const Upd& r = us.u[i];
+    const int nl = r.nlo - r.off, nh = r.nhi - r.off;
+    if (c.local) { sts_dom(c.sdom_s + 8u * (unsigned)r.var, nl, nh); continue; }
+    int2* d = &P.dom[r.var];
+    if (r.nlo > r.cur_lo) atomicMax(&d->x, nl);
+    if (r.nhi < r.cur_hi) atomicMin(&d->y, nh);
+    if (c.mirror) {  // keep the CTA's snapshot current for the next local round
+      if (r.nlo > r.cur_lo) atomicMax(&c.sdom[r.var].x, nl);
+      if (r.nhi < r.cur_hi) atomicMin(&c.sdom[r.var].y, nh);
     }
+    if (c.mark_dirty) atomicOr(&c.next_bits[r.var >> 5], 1u << (r.var & 31));
   }
-  // 2. which variables did this thread really narrow?
-  bool ch[3] = {false, false, false};
-  bool fail = false;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    if (i < us.n) {
-      const Upd& r = us.u[i];
-      int nl = r.nlo - r.off, nh = r.nhi - r.off;
-      ch[i] = (r.nlo > r.cur_lo && old_lo[i] < nl) || (r.nhi < r.cur_hi && old_hi[i] > nh);
-      // a domain emptied by concurrent updates this thread cannot see is caught when the
-      // variable is refreshed from the worklist in the next iteration
-      fail |= max(old_lo[i], nl) > min(old_hi[i], nh);
-    }
-  }
-  if (fail) set_failed(c);
-  if (!c.mark_dirty) return;
-  // 3. queue them: stamps first (dedup across the grid), then one reservation per warp
-  bool nw[3] = {false, false, false};
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-    if (i < us.n && ch[i] && seen[i] != c.next_epoch)
-      nw[i] = atomicExch(&P.dirty_stamp[us.u[i].var], c.next_epoch) != c.next_epoch;
-  if (ch[0] | ch[1] | ch[2]) c.flags[0] = 1;
-  const unsigned m = __activemask();
-  const unsigned b0 = __ballot_sync(m, nw[0]), b1 = __ballot_sync(m, nw[1]), b2 = __ballot_sync(m, nw[2]);
-  const int total = __popc(b0) + __popc(b1) + __popc(b2);
-  if (total == 0) return;
-  const int leader = __ffs(m) - 1;
-  const int lane = threadIdx.x & 31;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(&P.ctl->dirty_cnt[c.next_buf], total);
-  base = __shfl_sync(m, base, leader);
-  int* list = P.dirty_list + (size_t)c.next_buf * P.V;
-  const unsigned lt = lanemask_lt();
-  if (nw[0]) list[base + __popc(b0 & lt)] = us.u[0].var;
-  if (nw[1]) list[base + __popc(b0) + __popc(b1 & lt)] = us.u[1].var;
-  if (nw[2]) list[base + __popc(b0) + __popc(b1) + __popc(b2 & lt)] = us.u[2].var;
+  if (!c.local && c.mark_dirty) c.flags[0] = 1;
 }
 
 // Single update (n-ary propagators write their operands one by one).
@@ -221,11 +159,10 @@ __device__ __forceinline__ int dec_var28(unsigned w0) {
 }
 
 // --- binary family: XLessY / XNeqY / XEqY ---------------------------------------------------
-template <bool SMEM>
-__device__ __forceinline__ Eval eval_bin(const Ctx& c, int4 d, UpdSet& us) {
+// `x`, `y`: the operand views as read by the caller (each propagate reads its views once).
+__device__ __forceinline__ Eval eval_bin(int4 d, IV x, IV y, UpdSet& us) {
   unsigned kind = (unsigned)d.x >> 28;
   int xv = dec_var28((unsigned)d.x), xo = d.y, yv = d.z, yo = d.w;
-  const IV x = rd<SMEM>(c, xv, xo), y = rd<SMEM>(c, yv, yo);
   // A multi-term Sum operand is never narrowed (term/sum.rs:62-69): is_subsumed, which the
   // store evaluates after propagate (store.rs:177-183), re-reads it unchanged.
   const bool xro = xv <= -2, yro = yv <= -2;
@@ -328,11 +265,9 @@ __device__ __forceinline__ bool stage_tri(UpdSet& us, const Tri& t, IV x0, IV y0
          stage(us, t.zv, t.zo, z0, z.lo, z.hi);
 }
 
-template <bool SMEM>
-__device__ __forceinline__ Eval eval_ter(const Ctx& c, int4 a, int2 b, UpdSet& us) {
+__device__ __forceinline__ Eval eval_ter(int4 a, int2 b, IV x0, IV y0, IV z0, UpdSet& us) {
   unsigned kind = (unsigned)a.x >> 28;
   Tri t{dec_var28((unsigned)a.x), a.y, a.z, a.w, b.x, b.y};
-  const IV x0 = rd<SMEM>(c, t.xv, t.xo), y0 = rd<SMEM>(c, t.yv, t.yo), z0 = rd<SMEM>(c, t.zv, t.zo);
   IV x = x0, y = y0, z = z0;
   const TriRo ro = tri_ro(t);
   int s;
@@ -390,20 +325,41 @@ __device__ __forceinline__ bool dj_is_noop(const Ctx& c, int4 q0, int4 q1, int4 
   return sub_eq(ax, ay, az) == 0 && sub_eq(bx, by, bz) == 0;
 }
 
-// The out-of-line slow path: full propagate + is_subsumed of one propagator, with the
+// The out-of-line slow paths: full propagate + is_subsumed of one propagator, with the
 // store bookkeeping of store.rs:166-207 (failure flag, unlink of entailed propagators).
 // A failed propagate applies nothing (the node is discarded anyway).
-template <bool SMEM>
-__device__ __noinline__ void eval_full(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
-  UpdSet us;
-  us.n = 0;
-  Eval r;
-  if (fam == F_BIN) r = eval_bin<SMEM>(c, q0, us);
-  else if (fam == F_TER) r = eval_ter<SMEM>(c, q0, make_int2(q1.x, q1.y), us);
-  else r = eval_dj<SMEM>(c, q0, q1, q2, us);
+__device__ __forceinline__ void finish_eval(const Ctx& c, Eval r, const UpdSet& us, unsigned fam, int slot) {
   if (r == E_FAIL) { set_failed(c); return; }
   apply_updates(c, us);
   if (r == E_ENTAILED && c.bookkeep) deactivate(c, c.P->fam[fam].active, fam, slot);
+}
+__device__ __noinline__ void eval_full_bin(const Ctx& c, int slot, int4 d, IV x, IV y) {
+  UpdSet us;
+  us.n = 0;
+  finish_eval(c, eval_bin(d, x, y, us), us, F_BIN, slot);
+}
+__device__ __noinline__ void eval_full_ter(const Ctx& c, int slot, int4 a, int2 b, IV x, IV y, IV z) {
+  UpdSet us;
+  us.n = 0;
+  finish_eval(c, eval_ter(a, b, x, y, z, us), us, F_TER, slot);
+}
+template <bool SMEM>
+__device__ __noinline__ void eval_full_dj(const Ctx& c, int slot, int4 q0, int4 q1, int4 q2) {
+  UpdSet us;
+  us.n = 0;
+  finish_eval(c, eval_dj<SMEM>(c, q0, q1, q2, us), us, F_DJ, slot);
+}
+// Any family, operands read here (posted propagators, tail).
+template <bool SMEM>
+__device__ __forceinline__ void eval_full(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
+  if (fam == F_BIN) {
+    eval_full_bin(c, slot, q0, rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), rd<SMEM>(c, q0.z, q0.w));
+  } else if (fam == F_TER) {
+    eval_full_ter(c, slot, q0, make_int2(q1.x, q1.y), rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), rd<SMEM>(c, q0.z, q0.w),
+                  rd<SMEM>(c, q1.x, q1.y));
+  } else {
+    eval_full_dj<SMEM>(c, slot, q0, q1, q2);
+  }
 }
 
 // Gather one descriptor from global memory (worklist expansion, tail).
@@ -426,14 +382,13 @@ template <bool SMEM>
 __device__ __forceinline__ void eval_loaded(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
   if (fam == F_BIN) {
     IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w);
-    if (bin_is_noop((unsigned)q0.x >> 28, x, y)) return;
+    if (!bin_is_noop((unsigned)q0.x >> 28, x, y)) eval_full_bin(c, slot, q0, x, y);
   } else if (fam == F_TER) {
     IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w), z = rd<SMEM>(c, q1.x, q1.y);
-    if (ter_is_noop((unsigned)q0.x >> 28, x, y, z)) return;
+    if (!ter_is_noop((unsigned)q0.x >> 28, x, y, z)) eval_full_ter(c, slot, q0, make_int2(q1.x, q1.y), x, y, z);
   } else {
-    if (dj_is_noop<SMEM>(c, q0, q1, q2)) return;
+    if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full_dj<SMEM>(c, slot, q0, q1, q2);
   }
-  eval_full<SMEM>(c, fam, slot, q0, q1, q2);
 }
 template <bool SMEM>
 __device__ __forceinline__ void eval_ref(const Ctx& c, unsigned fam, int slot) {

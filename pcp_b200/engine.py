@@ -12,7 +12,8 @@ import os
 from ._capi import Config, EngineBase, PcpError, SearchConfig, SearchResult, bind
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcp_b200.so")
+# PCP_B200_LIB: development override (kernel variants built side by side for A/B timing)
+LIB_PATH = os.environ.get("PCP_B200_LIB") or os.path.join(_HERE, "libpcp_b200.so")
 
 FLAG_INCREMENTAL = 1
 
