@@ -202,6 +202,7 @@ struct ChunkMap {
   int nch[3];   // chunks per family
   int total;
 };
+__device__ __forceinline__ constexpr int chunk_props(int fam) { return fam == 0 ? kChunkBin : (fam == 1 ? kChunkTer : kChunkDj); }
 __device__ __forceinline__ ChunkMap chunk_map(const Params& P) {
   ChunkMap m;
   m.nch[0] = (P.fam[0].n_static + kChunkBin - 1) / kChunkBin;
@@ -210,30 +211,59 @@ __device__ __forceinline__ ChunkMap chunk_map(const Params& P) {
   m.total = m.nch[0] + m.nch[1] + m.nch[2];
   return m;
 }
-struct Chunk { int fam, base, cnt; };
-__device__ __forceinline__ Chunk chunk_of(const Params& P, const ChunkMap& m, int g) {
-  Chunk c;
-  if (g < m.nch[0]) { c.fam = 0; c.base = g * kChunkBin; c.cnt = min(kChunkBin, P.fam[0].n_static - c.base); }
-  else if (g < m.nch[0] + m.nch[1]) { g -= m.nch[0]; c.fam = 1; c.base = g * kChunkTer; c.cnt = min(kChunkTer, P.fam[1].n_static - c.base); }
-  else { g -= m.nch[0] + m.nch[1]; c.fam = 2; c.base = g * kChunkDj; c.cnt = min(kChunkDj, P.fam[2].n_static - c.base); }
-  return c;
+
+// mbarrier / bulk-copy helpers on shared-space addresses (the hot loop keeps no generic pointers)
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void* src, unsigned bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void producer_issue(const Params& P, const Chunk& ch, char* stage, uint64_t* full) {
-  const Family& f = P.fam[ch.fam];
-  if (ch.fam == F_BIN) {
-    unsigned bytes = (unsigned)ch.cnt * 16u;
-    mbar_expect_tx(full, bytes);
-    bulk_g2s(stage, f.desc + ch.base, bytes, full);
-  } else if (ch.fam == F_TER) {
-    unsigned ba = (unsigned)ch.cnt * 16u, bb = ((unsigned)ch.cnt * 8u + 15u) & ~15u;
-    mbar_expect_tx(full, ba + bb);
-    bulk_g2s(stage, f.desc + ch.base, ba, full);
-    bulk_g2s(stage + kTerPlaneB, f.descB + ch.base, bb, full);
+// One family's share of the sweep for this CTA: chunks g0, g0 + workers, ... (cnt of them),
+// ring positions pipe_pos, pipe_pos + 1, ...  Everything the loop needs travels by value: a
+// dereference of the kernel parameters from an out-of-line function is a generic load.
+struct FamSweep {
+  const int4* desc;
+  const int2* descB;
+  const uint32_t* active;
+  const int2* dom;
+  int n;                 // propagators covered (n_static)
+  int g0, workers, cnt;
+  int pipe_pos, first;   // `first` chunks were already issued (pre_issue)
+  uint32_t ring_s, full_s, empty_s, sdom_s;
+  int have_aw;           // the caller prefetched the active words of the first chunk
+};
+
+template <int FAM>
+__device__ __forceinline__ void producer_issue(const FamSweep& a, int g, uint32_t stage, uint32_t full) {
+  const int base = g * chunk_props(FAM);
+  const int cnt = min(chunk_props(FAM), a.n - base);
+  if (FAM == F_BIN) {
+    unsigned bytes = (unsigned)cnt * 16u;
+    mbar_expect_tx_s(full, bytes);
+    bulk_g2s_s(stage, a.desc + base, bytes, full);
+  } else if (FAM == F_TER) {
+    unsigned ba = (unsigned)cnt * 16u, bb = ((unsigned)cnt * 8u + 15u) & ~15u;
+    mbar_expect_tx_s(full, ba + bb);
+    bulk_g2s_s(stage, a.desc + base, ba, full);
+    bulk_g2s_s(stage + kTerPlaneB, a.descB + base, bb, full);
   } else {
-    unsigned bytes = (unsigned)ch.cnt * 48u;
-    mbar_expect_tx(full, bytes);
-    bulk_g2s(stage, f.desc + 3 * (size_t)ch.base, bytes, full);
+    unsigned bytes = (unsigned)cnt * 48u;
+    mbar_expect_tx_s(full, bytes);
+    bulk_g2s_s(stage, a.desc + 3 * (size_t)base, bytes, full);
   }
 }
 
@@ -242,13 +272,13 @@ __device__ __forceinline__ void producer_issue(const Params& P, const Chunk& ch,
 // off the critical path of the sweep.
 constexpr int kGroupsMax = 2;
 struct ActiveWords { unsigned w[kGroupsMax]; };
-__device__ __forceinline__ ActiveWords load_active_words(const Params& P, const Chunk& ch) {
+__device__ __forceinline__ ActiveWords load_active_words(const uint32_t* active, int base, int cnt) {
   const int cw = (threadIdx.x >> 5) - 1;
   ActiveWords a;
 #pragma unroll
   for (int g = 0; g < kGroupsMax; ++g) {
     const int j0 = cw * 32 + g * kConsumerWarps * 32;
-    a.w[g] = j0 < ch.cnt ? __ldcg(&P.fam[ch.fam].active[(ch.base + j0) >> 5]) : 0u;
+    a.w[g] = j0 < cnt ? __ldcg(&active[(base + j0) >> 5]) : 0u;
   }
   return a;
 }
@@ -280,9 +310,9 @@ __device__ __forceinline__ int2 rd_plain(uint32_t sdom_s, const int2* dom, int v
 // then all domain reads, then the tests, so that the two groups a warp owns overlap their
 // shared-memory latencies; everything else goes out of line.  Returns the number of
 // evaluations of the whole warp (the same value in every lane).
-template <bool SMEM>
-__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s, const int2* dom, int fam, int base,
-                                                  int cnt, uint32_t stage, const ActiveWords& aw) {
+template <bool SMEM, int FAM>
+__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s, const int2* dom, int base, int cnt,
+                                                  uint32_t stage, const ActiveWords& aw) {
   const int lane = threadIdx.x & 31;
   const int cw = (threadIdx.x >> 5) - 1;  // consumer warp index 0..30
   unsigned nprop = 0;
@@ -298,7 +328,7 @@ __device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s,
     nprop += __popc(w);
     on[g] = (w >> lane) & 1u;
   }
-  if (fam == F_BIN) {
+  if (FAM == F_BIN) {
     int4 d[kGroupsMax];
     int2 dx[kGroupsMax], dy[kGroupsMax];
     bool plain[kGroupsMax];
@@ -321,7 +351,7 @@ __device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s,
         sweep_slow_bin<SMEM>(c, base + jj[g], d[g]);
       }
     }
-  } else if (fam == F_TER) {
+  } else if (FAM == F_TER) {
 #pragma unroll
     for (int g = 0; g < kGroupsMax; ++g) {
       if (!on[g]) continue;
@@ -349,49 +379,38 @@ __device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s,
   return nprop;
 }
 
-// The streaming sweep of one CTA: warp 0 (one lane) keeps the TMA ring full, the other warps
-// consume.  Out of line, with its own register allocation: this is the hot loop.  `first`:
-// chunks already issued by pre_issue.  Returns the number of evaluations, counted per warp
-// (the same value in every lane: the caller adds it up from lane 0 only).
-struct SweepArgs {
-  char* ring;
-  uint64_t* full;
-  uint64_t* empty;
-  ChunkMap cmap;
-  int wid, workers, my_chunks, pipe_pos, first;
-  int reload_aw;
-};
-template <bool SMEM>
-__device__ __noinline__ unsigned sweep_pass(const Ctx& c, const SweepArgs a, ActiveWords aw) {
-  const Params& P = *c.P;
+// The streaming sweep of one CTA over one family: warp 0 (one lane) keeps the TMA ring full,
+// the other warps consume.  Out of line, with its own register allocation: this is the hot
+// loop.  Returns the number of evaluations, counted per warp (the same value in every lane:
+// the caller adds it up from lane 0 only).
+template <bool SMEM, int FAM>
+__device__ __noinline__ unsigned sweep_family(const Ctx& c, const FamSweep a, ActiveWords aw) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kChunk = chunk_props(FAM);
   unsigned nprop = 0;
   if (warp == 0) {
     if (lane == 0) {
-      // the ring memory doubles as worklist / n-ary staging (generic-proxy writes): order them
-      // before the async-proxy writes of the next bulk copies
-      if (a.first == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      for (int i = a.first; i < a.my_chunks; ++i) {
+      for (int i = a.first; i < a.cnt; ++i) {
         const int q = a.pipe_pos + i, s = q % kStages;
-        if (q >= kStages) mbar_wait(&a.empty[s], ((q / kStages) - 1) & 1);
-        producer_issue(P, chunk_of(P, a.cmap, a.wid + i * a.workers), a.ring + s * kStageBytes, &a.full[s]);
+        if (q >= kStages) mbar_wait_s(a.empty_s + 8u * s, ((q / kStages) - 1) & 1);
+        producer_issue<FAM>(a, a.g0 + i * a.workers, a.ring_s + (unsigned)(s * kStageBytes), a.full_s + 8u * s);
       }
     }
   } else {
-    const uint32_t ring_s = smem_u32(a.ring);
-    const uint32_t sdom_s = c.sdom_s;
-    const int2* dom = P.dom;
-    if (a.reload_aw) aw = load_active_words(P, chunk_of(P, a.cmap, a.wid));
-    for (int i = 0; i < a.my_chunks; ++i) {
+    int base = a.g0 * kChunk;
+    if (!a.have_aw) aw = load_active_words(a.active, base, min(kChunk, a.n - base));
+    for (int i = 0; i < a.cnt; ++i) {
       const int q = a.pipe_pos + i, s = q % kStages;
-      const Chunk ch = chunk_of(P, a.cmap, a.wid + i * a.workers);
+      const int cnt = min(kChunk, a.n - base);
+      const int nbase = base + a.workers * kChunk;
       ActiveWords nxt = aw;
-      if (i + 1 < a.my_chunks) nxt = load_active_words(P, chunk_of(P, a.cmap, a.wid + (i + 1) * a.workers));
-      mbar_wait(&a.full[s], (q / kStages) & 1);
-      nprop += sweep_consume<SMEM>(c, sdom_s, dom, ch.fam, ch.base, ch.cnt, ring_s + (unsigned)(s * kStageBytes), aw);
+      if (i + 1 < a.cnt) nxt = load_active_words(a.active, nbase, min(kChunk, a.n - nbase));
+      mbar_wait_s(a.full_s + 8u * s, (q / kStages) & 1);
+      nprop += sweep_consume<SMEM, FAM>(c, a.sdom_s, a.dom, base, cnt, a.ring_s + (unsigned)(s * kStageBytes), aw);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a.empty[s]);
+      if (lane == 0) mbar_arrive_s(a.empty_s + 8u * s);
       aw = nxt;
+      base = nbase;
     }
   }
   return nprop;
@@ -811,12 +830,33 @@ struct CtaState {
   uint64_t* empty;
   unsigned* block_props;
   int* flags;
-  ChunkMap cmap;
+  // this CTA's share of a sweep: chunk G of the concatenated families belongs to worker
+  // G % workers; per family the first chunk index, and the number of chunks
   int workers, wid, my_chunks;
+  int fam_g0[3], fam_cnt[3];
   int pipe_pos;      // chunks this CTA has pushed through the ring so far (all sweeps, all nodes)
-  int pre_issued;    // chunks of the coming sweep already issued by the producer
   unsigned gen;      // barrier generation
 };
+
+__device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& st, int fam, int seq_off, int pre) {
+  FamSweep a;
+  a.desc = P.fam[fam].desc;
+  a.descB = P.fam[fam].descB;
+  a.active = P.fam[fam].active;
+  a.dom = P.dom;
+  a.n = P.fam[fam].n_static;
+  a.g0 = st.fam_g0[fam];
+  a.workers = st.workers;
+  a.cnt = st.fam_cnt[fam];
+  a.pipe_pos = st.pipe_pos + seq_off;
+  a.first = max(0, min(a.cnt, pre - seq_off));
+  a.ring_s = smem_u32(st.ring);
+  a.full_s = smem_u32(st.full);
+  a.empty_s = smem_u32(st.empty);
+  a.sdom_s = st.sdom ? smem_u32(st.sdom) : 0u;
+  a.have_aw = 0;
+  return a;
+}
 
 __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* smem, uint64_t* s_full,
                                          uint64_t* s_empty, unsigned* s_block_props, int* s_flags, bool smem_dom) {
@@ -828,25 +868,46 @@ __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* sm
   st.flags = s_flags;
   // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
   // by the other CTAs so that nobody waits for it at the barrier
-  st.cmap = chunk_map(P);
+  const ChunkMap m = chunk_map(P);
   st.workers = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
   st.wid = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
-  st.my_chunks = st.wid >= 0 && st.wid < st.cmap.total ? (st.cmap.total - 1 - st.wid) / st.workers + 1 : 0;
+  st.my_chunks = 0;
+  int off = 0;
+  for (int f = 0; f < 3; ++f) {
+    // my chunks of family f: G = wid + i * workers with off <= G < off + nch[f]
+    int i_lo = 0, i_hi = 0;
+    if (st.wid >= 0) {
+      i_lo = off > st.wid ? (off - st.wid + st.workers - 1) / st.workers : 0;
+      const int end = off + m.nch[f];
+      i_hi = end > st.wid ? (end - st.wid + st.workers - 1) / st.workers : 0;
+    }
+    st.fam_cnt[f] = max(0, i_hi - i_lo);
+    st.fam_g0[f] = st.wid + i_lo * st.workers - off;
+    st.my_chunks += st.fam_cnt[f];
+    off += m.nch[f];
+  }
   st.pipe_pos = 0;
-  st.pre_issued = 0;
 }
 
 // Producer: issue the first chunks of the coming sweep (thread 0 only).  Stages that still
 // hold an unconsumed chunk cannot exist here: a sweep is always consumed completely.
 __device__ __forceinline__ void pre_issue(const Params& P, CtaState& st) {
-  // the ring memory doubles as n-ary staging (generic-proxy writes): order them before the
-  // async-proxy writes of the bulk copies
+  // the ring memory doubles as worklist / n-ary staging (generic-proxy writes): order them
+  // before the async-proxy writes of the bulk copies
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  int n = min(st.my_chunks, kStages);
-  for (int i = 0; i < n; ++i) {
-    const int q = st.pipe_pos + i, s = q % kStages;
-    if (q >= kStages) mbar_wait(&st.empty[s], ((q / kStages) - 1) & 1);
-    producer_issue(P, chunk_of(P, st.cmap, st.wid + i * st.workers), st.ring + s * kStageBytes, &st.full[s]);
+  const int n = min(st.my_chunks, kStages);
+  int seq = 0;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    FamSweep a = fam_sweep(P, st, f, seq, 0);
+    for (int i = 0; i < a.cnt && seq + i < n; ++i) {
+      const int q = a.pipe_pos + i, s = q % kStages;
+      if (q >= kStages) mbar_wait_s(a.empty_s + 8u * s, ((q / kStages) - 1) & 1);
+      if (f == 0) producer_issue<0>(a, a.g0 + i * a.workers, a.ring_s + (unsigned)(s * kStageBytes), a.full_s + 8u * s);
+      else if (f == 1) producer_issue<1>(a, a.g0 + i * a.workers, a.ring_s + (unsigned)(s * kStageBytes), a.full_s + 8u * s);
+      else producer_issue<2>(a, a.g0 + i * a.workers, a.ring_s + (unsigned)(s * kStageBytes), a.full_s + 8u * s);
+    }
+    seq += a.cnt;
   }
 }
 
@@ -870,7 +931,12 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
   c.mirror = false;
   ActiveWords aw;
   aw.w[0] = aw.w[1] = 0u;
-  if (warp > 0 && st.my_chunks > 0 && full_sweep) aw = load_active_words(P, chunk_of(P, st.cmap, st.wid));
+  // the active words of this CTA's first chunk: prefetched while the prologue settles
+  const int fam_first = st.fam_cnt[0] > 0 ? 0 : (st.fam_cnt[1] > 0 ? 1 : 2);
+  if (warp > 0 && st.my_chunks > 0 && full_sweep) {
+    const int base = st.fam_g0[fam_first] * chunk_props(fam_first);
+    aw = load_active_words(P.fam[fam_first].active, base, min(chunk_props(fam_first), P.fam[fam_first].n_static - base));
+  }
   unsigned iter = 0, dec, nprop = 0;
   int cur_buf = 0, next_buf = 1;
   while (true) {
@@ -972,12 +1038,32 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep
       // counting across sweeps so the mbarrier phases stay consistent).  (`skip` is never set
       // in iteration 0, so pre-issued chunks are always consumed.)
-      SweepArgs sa;
-      sa.ring = st.ring; sa.full = st.full; sa.empty = st.empty; sa.cmap = st.cmap;
-      sa.wid = st.wid; sa.workers = st.workers; sa.my_chunks = st.my_chunks; sa.pipe_pos = st.pipe_pos;
-      sa.first = (iter == 0 && pre_issued) ? min(st.my_chunks, kStages) : 0;
-      sa.reload_aw = !(iter == 0 && full_sweep);  // iteration 0 of a full sweep prefetched them
-      { const unsigned n = sweep_pass<SMEM>(c, sa, aw); if (lane == 0) nprop += n; }  // counted per warp
+      const int pre = (iter == 0 && pre_issued) ? min(st.my_chunks, kStages) : 0;
+      // the ring memory doubles as worklist / n-ary staging (generic-proxy writes): order them
+      // before the async-proxy writes of the next bulk copies
+      if (threadIdx.x == 0 && pre == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const bool have_aw = iter == 0 && full_sweep;  // prefetched above
+      unsigned n = 0;
+      int seq = 0;
+      if (st.fam_cnt[0] > 0) {
+        FamSweep a = fam_sweep(P, st, 0, seq, pre);
+        a.have_aw = have_aw && fam_first == 0;
+        n += sweep_family<SMEM, 0>(c, a, aw);
+        seq += a.cnt;
+      }
+      if (st.fam_cnt[1] > 0) {
+        FamSweep a = fam_sweep(P, st, 1, seq, pre);
+        a.have_aw = have_aw && fam_first == 1;
+        n += sweep_family<SMEM, 1>(c, a, aw);
+        seq += a.cnt;
+      }
+      if (st.fam_cnt[2] > 0) {
+        FamSweep a = fam_sweep(P, st, 2, seq, pre);
+        a.have_aw = have_aw && fam_first == 2;
+        n += sweep_family<SMEM, 2>(c, a, aw);
+        seq += a.cnt;
+      }
+      if (lane == 0) nprop += n;  // counted per warp
       st.pipe_pos += st.my_chunks;
     }
     if (iter == 0 && P.trace) { __syncthreads(); trace_mark(P, 3); }
