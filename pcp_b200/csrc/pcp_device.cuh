@@ -28,17 +28,19 @@
 
 namespace pcpd {
 
-constexpr int kThreads = 1024;          // one CTA per SM
+constexpr int kThreads = 512;           // one CTA per SM, 128 registers per thread
 constexpr int kWarps = kThreads / 32;
 constexpr int kConsumerWarps = kWarps - 1;  // warp 0 drives the TMA ring
 constexpr int kStages = 4;
 constexpr int kStageBytes = 32768;
 constexpr int kRingBytes = kStages * kStageBytes;
-// propagators per ring stage: multiples of 32 * kConsumerWarps so every consumer warp gets
-// whole 32-propagator groups (aligned with the words of the `active` bit set)
-constexpr int kChunkBin = 1984;         // 1984 * 16 B = 31744 B
-constexpr int kChunkTer = 992;          // 992 * 16 B + 992 * 8 B
+// propagators per ring stage: every consumer warp gets kGroupsBin / kGroupsTer whole groups of
+// 32 consecutive propagators (= words of the `active` bit set) of each chunk
+constexpr int kGroupsBin = 4, kGroupsTer = 2;
+constexpr int kChunkBin = kConsumerWarps * 32 * kGroupsBin;  // 1920 * 16 B = 30720 B
+constexpr int kChunkTer = kConsumerWarps * 32 * kGroupsTer;  // 960 * 16 B + 960 * 8 B
 constexpr int kChunkDj = 480;           // 480 * 48 B = 23040 B
+static_assert(kChunkBin * 16 <= kStageBytes && kChunkTer * 16 <= 16384 && kChunkTer * 8 <= kStageBytes - 16384, "stage too small");
 constexpr int kTerPlaneB = 16384;       // offset of the z plane inside a stage
 constexpr unsigned kConstVar28 = 0x0FFFFFFFu;
 constexpr unsigned kSumBase28 = 0x0F000000u;  // x-operand encodings >= this are sum views / Constant
@@ -82,7 +84,8 @@ struct Result {
   unsigned epoch;
   unsigned long long propagations;
   unsigned decision;
-  unsigned pad[9];
+  unsigned gen;          // barrier generation after the launch
+  unsigned pad[8];
 };
 static_assert(sizeof(Result) == 64, "Result header is 64 bytes");
 
@@ -93,6 +96,8 @@ struct Family {
   uint32_t* stamp;      // epoch of the last worklist evaluation
   int n;                // allocated propagators
   int n_static;         // [0, n_static) are covered by the CSR; [n_static, n) is the tail
+  int all_plain;        // 1: no descriptor in [0, n_static) has a Constant or Sum operand
+  int kind_mask;        // bit k: a descriptor of kind k was allocated (over-approximation after restores)
 };
 
 struct InlineProp {     // a propagator posted since the last launch, carried in the launch
@@ -123,6 +128,8 @@ struct Params {
   Control* ctl;
   int full_sweep;       // 1: schedule every active propagator first (store.rs:144-149)
   unsigned max_iterations;
+  unsigned gen0;        // generation of the device-wide barrier at launch (Result::gen of the last launch)
+  unsigned epoch0;      // first unused stamp epoch (Result::epoch of the last launch)
   // ---- node prologue (Snapshot::restore + Store::alloc), executed by CTA 0
   const int2* restore_from;   // label copy of the domains, or nullptr
   unsigned trail_keep;        // trail length recorded in the label
@@ -267,36 +274,25 @@ __device__ __forceinline__ void producer_issue(const FamSweep& a, int g, uint32_
   }
 }
 
-// The words of the `active` bit set a consumer warp needs for one chunk (at most
-// kGroupsMax groups of 32 propagators); loaded one chunk ahead so that the L2 round trip is
-// off the critical path of the sweep.
-constexpr int kGroupsMax = 2;
-struct ActiveWords { unsigned w[kGroupsMax]; };
-__device__ __forceinline__ ActiveWords load_active_words(const uint32_t* active, int base, int cnt) {
-  const int cw = (threadIdx.x >> 5) - 1;
-  ActiveWords a;
-#pragma unroll
-  for (int g = 0; g < kGroupsMax; ++g) {
-    const int j0 = cw * 32 + g * kConsumerWarps * 32;
-    a.w[g] = j0 < cnt ? __ldcg(&active[(base + j0) >> 5]) : 0u;
-  }
-  return a;
-}
-
 __device__ __forceinline__ int4 lds128(uint32_t addr) {
   int4 r;
   asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
 
-// Cold paths of the sweep: an operand is a Constant or a Sum view.
+// Cold path of the sweep: the propagator prunes, fails, is entailed, or has a Constant / Sum
+// operand.  The descriptor is re-read from the ring stage (still owned by this warp), so the
+// call carries three registers and the hot loop keeps nothing alive for it.
 template <bool SMEM>
-__device__ __noinline__ void sweep_slow_bin(const Ctx& c, int slot, int4 d) {
+__device__ __noinline__ void sweep_slow_bin(const Ctx& c, int slot, uint32_t desc_s) {
+  const int4 d = lds128(desc_s);
   const IV x = rd<SMEM>(c, dec_var28((unsigned)d.x), d.y), y = rd<SMEM>(c, d.z, d.w);
   if (!bin_is_noop((unsigned)d.x >> 28, x, y)) eval_full_bin(c, slot, d, x, y);
 }
 template <bool SMEM>
-__device__ __noinline__ void sweep_slow_ter(const Ctx& c, int slot, int4 a, int2 b) {
+__device__ __noinline__ void sweep_slow_ter(const Ctx& c, int slot, uint32_t a_s, uint32_t b_s) {
+  const int4 a = lds128(a_s);
+  const int2 b = lds_dom(b_s);
   const IV x = rd<SMEM>(c, dec_var28((unsigned)a.x), a.y), y = rd<SMEM>(c, a.z, a.w), z = rd<SMEM>(c, b.x, b.y);
   if (!ter_is_noop((unsigned)a.x >> 28, x, y, z)) eval_full_ter(c, slot, a, b, x, y, z);
 }
@@ -305,113 +301,237 @@ __device__ __forceinline__ int2 rd_plain(uint32_t sdom_s, const int2* dom, int v
   return SMEM ? lds_dom(sdom_s + 8u * (unsigned)var) : ldcg_dom(&dom[var]);
 }
 
-// One chunk, one consumer warp.  The common case -- both (all three) operands are plain
-// variables and the evaluation changes nothing -- is decided inline: descriptor loads first,
-// then all domain reads, then the tests, so that the two groups a warp owns overlap their
-// shared-memory latencies; everything else goes out of line.  Returns the number of
-// evaluations of the whole warp (the same value in every lane).
-template <bool SMEM, int FAM>
-__device__ __forceinline__ unsigned sweep_consume(const Ctx& c, uint32_t sdom_s, const int2* dom, int base, int cnt,
-                                                  uint32_t stage, const ActiveWords& aw) {
-  const int lane = threadIdx.x & 31;
-  const int cw = (threadIdx.x >> 5) - 1;  // consumer warp index 0..30
-  unsigned nprop = 0;
-  bool on[kGroupsMax];
-  int jj[kGroupsMax];
-#pragma unroll
-  for (int g = 0; g < kGroupsMax; ++g) {
-    const int j0 = cw * 32 + g * kConsumerWarps * 32;
-    jj[g] = j0 + lane;
-    // aw.w[g] is 0 for a group beyond the chunk; the tail of the last chunk is masked off
-    const unsigned valid = cnt - j0 >= 32 ? 0xffffffffu : (cnt > j0 ? (1u << (cnt - j0)) - 1u : 0u);
-    const unsigned w = aw.w[g] & valid;
-    nprop += __popc(w);
-    on[g] = (w >> lane) & 1u;
+// The words of the `active` bit set a consumer warp needs for one chunk: its descriptors are
+// consecutive and start at a multiple of their count, so the words are one aligned vector
+// load; loaded one chunk ahead so that the L2 round trip is off the critical path of the sweep.
+struct ActiveWords { unsigned w[4]; };
+template <int G>
+__device__ __forceinline__ ActiveWords load_active(const uint32_t* active, int base, int n) {
+  ActiveWords a;
+  a.w[0] = a.w[1] = a.w[2] = a.w[3] = 0u;
+  if (base < n) {
+    if (G == 4) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(active + (base >> 5)));
+      a.w[0] = v.x; a.w[1] = v.y; a.w[2] = v.z; a.w[3] = v.w;
+    } else {
+      const uint2 v = __ldcg(reinterpret_cast<const uint2*>(active + (base >> 5)));
+      a.w[0] = v.x; a.w[1] = v.y;
+    }
   }
-  if (FAM == F_BIN) {
-    int4 d[kGroupsMax];
-    int2 dx[kGroupsMax], dy[kGroupsMax];
-    bool plain[kGroupsMax];
+  return a;
+}
+// bits [0, rem) of a 32-propagator group that starts `rem` descriptors before the end
+__device__ __forceinline__ unsigned tail_mask(int rem) {
+  return rem >= 32 ? 0xffffffffu : (rem > 0 ? (1u << rem) - 1u : 0u);
+}
+
+// Producer side of a family sweep: one lane keeps the TMA ring full.
+template <int FAM>
+__device__ __forceinline__ void sweep_produce(const FamSweep& a) {
+  for (int i = a.first; i < a.cnt; ++i) {
+    const int q = a.pipe_pos + i, s = q % kStages;
+    if (q >= kStages) mbar_wait_s(a.empty_s + 8u * s, ((q / kStages) - 1) & 1);
+    producer_issue<FAM>(a, a.g0 + i * a.workers, a.ring_s + (unsigned)(s * kStageBytes), a.full_s + 8u * s);
+  }
+}
+
+// Ring position of a consumer warp, carried across the chunks of a family sweep (no division
+// or re-derivation per chunk): stage index, phase parity of its `full` barrier, and the
+// shared-space addresses that go with them.
+struct RingPos {
+  unsigned s, ph;
+  uint32_t stage, full, empty;
+};
+__device__ __forceinline__ RingPos ring_pos(const FamSweep& a) {
+  RingPos r;
+  r.s = (unsigned)a.pipe_pos % kStages;
+  r.ph = ((unsigned)a.pipe_pos / kStages) & 1u;
+  r.stage = a.ring_s + r.s * (unsigned)kStageBytes;
+  r.full = a.full_s + 8u * r.s;
+  r.empty = a.empty_s + 8u * r.s;
+  return r;
+}
+__device__ __forceinline__ void ring_advance(RingPos& r) {
+  ++r.s; r.stage += (unsigned)kStageBytes; r.full += 8u; r.empty += 8u;
+  if (r.s == (unsigned)kStages) {
+    r.s = 0u; r.ph ^= 1u; r.stage -= (unsigned)kRingBytes; r.full -= 8u * kStages; r.empty -= 8u * kStages;
+  }
+}
+
+// The streaming sweep of one CTA over the binary family (XLessY / XNeqY / XEqY): warp 0 (one
+// lane) keeps the ring full, every other warp owns 128 consecutive descriptors of each chunk
+// (kGroupsBin groups of 32 = four words of the `active` set).  Hot loop: the descriptor loads
+// of all groups first, then the eight domain reads, then the tests; whatever is not a no-op
+// goes out of line with three registers.  NEQ_PLAIN: every static descriptor of the family
+// is an XNeqY over plain variables (host-side flags Family::all_plain / kind_mask) -- the
+// n-queens and pairwise-distinct stores -- so neither the kind nor the operand encoding is
+// inspected.  Returns the number of evaluations of the warp (the same value in every lane).
+template <bool SMEM, bool NEQ_PLAIN>
+__device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, ActiveWords aw) {
+  constexpr int G = kGroupsBin;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (lane == 0) sweep_produce<F_BIN>(a);
+    return 0u;
+  }
+  const unsigned lane_bit = 1u << lane;
+  const uint32_t lane_off = (uint32_t)((warp - 1) * (32 * G) + lane) * 16u;
+  const int stride = a.workers * kChunkBin;
+  int base = a.g0 * kChunkBin + (warp - 1) * (32 * G);  // this warp's first descriptor of the chunk
+  if (!a.have_aw) aw = load_active<G>(a.active, base, a.n);
+  RingPos r = ring_pos(a);
+  unsigned nprop = 0;
+  for (int i = 0; i < a.cnt; ++i) {
+    const int nbase = base + stride;
+    ActiveWords nxt;
+    nxt.w[0] = nxt.w[1] = nxt.w[2] = nxt.w[3] = 0u;
+    if (i + 1 < a.cnt) nxt = load_active<G>(a.active, nbase, a.n);
+    const int rem = a.n - base;
+    if (rem < 32 * G) {  // last chunk of the family
 #pragma unroll
-    for (int g = 0; g < kGroupsMax; ++g) d[g] = on[g] ? lds128(stage + 16u * (unsigned)jj[g]) : make_int4(0, 0, 0, 0);
+      for (int g = 0; g < G; ++g) aw.w[g] &= tail_mask(rem - 32 * g);
+    }
+    const uint32_t d_s = r.stage + lane_off;
+    mbar_wait_s(r.full, r.ph);
+    int4 d[G];
+    int2 dx[G], dy[G];
+    bool on[G], plain[G], need[G];
 #pragma unroll
-    for (int g = 0; g < kGroupsMax; ++g) {
+    for (int g = 0; g < G; ++g) {
+      nprop += __popc(aw.w[g]);
+      on[g] = (aw.w[g] & lane_bit) != 0u;
+      d[g] = make_int4(0, 0, 0, 0);
+      if (on[g]) d[g] = lds128(d_s + 512u * g);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
       const unsigned xv = (unsigned)d[g].x & kConstVar28;
-      plain[g] = xv < kSumBase28 && d[g].z >= 0;
-      dx[g] = rd_plain<SMEM>(sdom_s, dom, plain[g] ? (int)xv : 0);
-      dy[g] = rd_plain<SMEM>(sdom_s, dom, plain[g] ? d[g].z : 0);
+      plain[g] = NEQ_PLAIN || (xv < kSumBase28 && d[g].z >= 0);
+      dx[g] = rd_plain<SMEM>(a.sdom_s, a.dom, plain[g] ? (int)xv : 0);
+      dy[g] = rd_plain<SMEM>(a.sdom_s, a.dom, plain[g] ? d[g].z : 0);
     }
+    bool any = false;
 #pragma unroll
-    for (int g = 0; g < kGroupsMax; ++g) {
-      if (!on[g]) continue;
-      if (plain[g]) {
-        const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
-        if (!bin_is_noop((unsigned)d[g].x >> 28, x, y)) eval_full_bin(c, base + jj[g], d[g], x, y);
-      } else {
-        sweep_slow_bin<SMEM>(c, base + jj[g], d[g]);
-      }
+    for (int g = 0; g < G; ++g) {
+      const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
+      need[g] = on[g] && !(plain[g] && bin_is_noop(NEQ_PLAIN ? (unsigned)B_NEQ : (unsigned)d[g].x >> 28, x, y));
+      any |= need[g];
     }
-  } else if (FAM == F_TER) {
+    if (any) {
 #pragma unroll
-    for (int g = 0; g < kGroupsMax; ++g) {
-      if (!on[g]) continue;
-      const int4 a = lds128(stage + 16u * (unsigned)jj[g]);
-      const int2 b = lds_dom(stage + (unsigned)kTerPlaneB + 8u * (unsigned)jj[g]);
-      const unsigned xv = (unsigned)a.x & kConstVar28;
-      if (xv < kSumBase28 && a.z >= 0 && b.x >= 0) {
-        const int2 dx = rd_plain<SMEM>(sdom_s, dom, (int)xv), dy = rd_plain<SMEM>(sdom_s, dom, a.z),
-                   dz = rd_plain<SMEM>(sdom_s, dom, b.x);
-        const IV x{dx.x + a.y, dx.y + a.y}, y{dy.x + a.w, dy.y + a.w}, z{dz.x + b.y, dz.y + b.y};
-        if (!ter_is_noop((unsigned)a.x >> 28, x, y, z)) eval_full_ter(c, base + jj[g], a, b, x, y, z);
-      } else {
-        sweep_slow_ter<SMEM>(c, base + jj[g], a, b);
-      }
+      for (int g = 0; g < G; ++g)
+        if (need[g]) sweep_slow_bin<SMEM>(c, base + 32 * g + lane, d_s + 512u * g);
     }
-  } else {
-#pragma unroll
-    for (int g = 0; g < kGroupsMax; ++g) {
-      if (!on[g]) continue;
-      const int4 q0 = lds128(stage + 48u * (unsigned)jj[g]), q1 = lds128(stage + 48u * (unsigned)jj[g] + 16u),
-                 q2 = lds128(stage + 48u * (unsigned)jj[g] + 32u);
-      if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full_dj<SMEM>(c, base + jj[g], q0, q1, q2);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_s(r.empty);
+    ring_advance(r);
+    aw = nxt;
+    base = nbase;
   }
   return nprop;
 }
 
-// The streaming sweep of one CTA over one family: warp 0 (one lane) keeps the TMA ring full,
-// the other warps consume.  Out of line, with its own register allocation: this is the hot
-// loop.  Returns the number of evaluations, counted per warp (the same value in every lane:
-// the caller adds it up from lane 0 only).
-template <bool SMEM, int FAM>
-__device__ __noinline__ unsigned sweep_family(const Ctx& c, const FamSweep a, ActiveWords aw) {
+// The same for the ternary family (XGreaterYPlusZ / XLessYPlusZ / XEqYPlusZ): kGroupsTer
+// groups per warp and chunk, the (x, y) plane and the z plane of the stage read separately.
+// EQ_PLAIN: every static descriptor is an XEqYPlusZ over plain variables.
+template <bool SMEM, bool EQ_PLAIN>
+__device__ __noinline__ unsigned sweep_ter(const Ctx& c, const FamSweep a, ActiveWords aw) {
+  constexpr int G = kGroupsTer;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int kChunk = chunk_props(FAM);
-  unsigned nprop = 0;
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = a.first; i < a.cnt; ++i) {
-        const int q = a.pipe_pos + i, s = q % kStages;
-        if (q >= kStages) mbar_wait_s(a.empty_s + 8u * s, ((q / kStages) - 1) & 1);
-        producer_issue<FAM>(a, a.g0 + i * a.workers, a.ring_s + (unsigned)(s * kStageBytes), a.full_s + 8u * s);
+    if (lane == 0) sweep_produce<F_TER>(a);
+    return 0u;
+  }
+  const unsigned lane_bit = 1u << lane;
+  const uint32_t lane_j = (uint32_t)((warp - 1) * (32 * G) + lane);
+  const int stride = a.workers * kChunkTer;
+  int base = a.g0 * kChunkTer + (warp - 1) * (32 * G);
+  if (!a.have_aw) aw = load_active<G>(a.active, base, a.n);
+  RingPos r = ring_pos(a);
+  unsigned nprop = 0;
+  for (int i = 0; i < a.cnt; ++i) {
+    const int nbase = base + stride;
+    ActiveWords nxt;
+    nxt.w[0] = nxt.w[1] = nxt.w[2] = nxt.w[3] = 0u;
+    if (i + 1 < a.cnt) nxt = load_active<G>(a.active, nbase, a.n);
+    const int rem = a.n - base;
+    if (rem < 32 * G) {
+#pragma unroll
+      for (int g = 0; g < G; ++g) aw.w[g] &= tail_mask(rem - 32 * g);
+    }
+    const uint32_t a_s = r.stage + 16u * lane_j, b_s = r.stage + (unsigned)kTerPlaneB + 8u * lane_j;
+    mbar_wait_s(r.full, r.ph);
+    int4 d[G];
+    int2 e[G], dx[G], dy[G], dz[G];
+    bool on[G], plain[G], need[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      nprop += __popc(aw.w[g]);
+      on[g] = (aw.w[g] & lane_bit) != 0u;
+      d[g] = make_int4(0, 0, 0, 0);
+      e[g] = make_int2(0, 0);
+      if (on[g]) { d[g] = lds128(a_s + 512u * g); e[g] = lds_dom(b_s + 256u * g); }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const unsigned xv = (unsigned)d[g].x & kConstVar28;
+      plain[g] = EQ_PLAIN || (xv < kSumBase28 && d[g].z >= 0 && e[g].x >= 0);
+      dx[g] = rd_plain<SMEM>(a.sdom_s, a.dom, plain[g] ? (int)xv : 0);
+      dy[g] = rd_plain<SMEM>(a.sdom_s, a.dom, plain[g] ? d[g].z : 0);
+      dz[g] = rd_plain<SMEM>(a.sdom_s, a.dom, plain[g] ? e[g].x : 0);
+    }
+    bool any = false;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w},
+               z{dz[g].x + e[g].y, dz[g].y + e[g].y};
+      need[g] = on[g] && !(plain[g] && ter_is_noop(EQ_PLAIN ? (unsigned)T_EQ : (unsigned)d[g].x >> 28, x, y, z));
+      any |= need[g];
+    }
+    if (any) {
+#pragma unroll
+      for (int g = 0; g < G; ++g)
+        if (need[g]) sweep_slow_ter<SMEM>(c, base + 32 * g + lane, a_s + 512u * g, b_s + 256u * g);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_s(r.empty);
+    ring_advance(r);
+    aw = nxt;
+    base = nbase;
+  }
+  return nprop;
+}
+
+// The disjunction family (logic/disjunction.rs) is small wherever it occurs: one generic loop.
+template <bool SMEM>
+__device__ __noinline__ unsigned sweep_dj(const Ctx& c, const FamSweep a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (lane == 0) sweep_produce<F_DJ>(a);
+    return 0u;
+  }
+  const int cw = warp - 1;
+  unsigned nprop = 0;
+  int base = a.g0 * kChunkDj;
+  for (int i = 0; i < a.cnt; ++i) {
+    const int q = a.pipe_pos + i, s = q % kStages;
+    const int cnt = min(kChunkDj, a.n - base);
+    const uint32_t stage = a.ring_s + (unsigned)(s * kStageBytes);
+    mbar_wait_s(a.full_s + 8u * s, (q / kStages) & 1);
+    for (int j0 = cw * 32; j0 < cnt; j0 += kConsumerWarps * 32) {
+      const int j = j0 + lane;
+      const unsigned word = __ldcg(&a.active[(base + j0) >> 5]);  // base, j0 are multiples of 32
+      const bool on = j < cnt && ((word >> lane) & 1u);
+      nprop += __popc(__ballot_sync(0xffffffffu, on));
+      if (on) {
+        const int4 q0 = lds128(stage + 48u * (unsigned)j), q1 = lds128(stage + 48u * (unsigned)j + 16u),
+                   q2 = lds128(stage + 48u * (unsigned)j + 32u);
+        if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full_dj<SMEM>(c, base + j, q0, q1, q2);
       }
     }
-  } else {
-    int base = a.g0 * kChunk;
-    if (!a.have_aw) aw = load_active_words(a.active, base, min(kChunk, a.n - base));
-    for (int i = 0; i < a.cnt; ++i) {
-      const int q = a.pipe_pos + i, s = q % kStages;
-      const int cnt = min(kChunk, a.n - base);
-      const int nbase = base + a.workers * kChunk;
-      ActiveWords nxt = aw;
-      if (i + 1 < a.cnt) nxt = load_active_words(a.active, nbase, min(kChunk, a.n - nbase));
-      mbar_wait_s(a.full_s + 8u * s, (q / kStages) & 1);
-      nprop += sweep_consume<SMEM, FAM>(c, a.sdom_s, a.dom, base, cnt, a.ring_s + (unsigned)(s * kStageBytes), aw);
-      __syncwarp();
-      if (lane == 0) mbar_arrive_s(a.empty_s + 8u * s);
-      aw = nxt;
-      base = nbase;
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_s(a.empty_s + 8u * s);
+    base += a.workers * kChunkDj;
   }
   return nprop;
 }
@@ -636,10 +756,10 @@ __device__ __forceinline__ int dirty_compact(const uint32_t* bits, int words, in
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
   if (warp == 0) {
-    const int x = s_warp[lane];
+    const int x = lane < kWarps ? s_warp[lane] : 0;
     int xi = x;
     for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
-    s_warp[lane] = xi - x;  // exclusive offset of each warp
+    if (lane < kWarps) s_warp[lane] = xi - x;  // exclusive offset of each warp
     if (lane == 31) s_total = xi;
   }
   __syncthreads();
@@ -828,7 +948,6 @@ struct CtaState {
   int2* sdom;
   uint64_t* full;
   uint64_t* empty;
-  unsigned* block_props;
   int* flags;
   // this CTA's share of a sweep: chunk G of the concatenated families belongs to worker
   // G % workers; per family the first chunk index, and the number of chunks
@@ -859,12 +978,11 @@ __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& s
 }
 
 __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* smem, uint64_t* s_full,
-                                         uint64_t* s_empty, unsigned* s_block_props, int* s_flags, bool smem_dom) {
+                                         uint64_t* s_empty, int* s_flags, bool smem_dom) {
   st.ring = smem;
   st.sdom = smem_dom ? reinterpret_cast<int2*>(smem + kRingBytes) : nullptr;
   st.full = s_full;
   st.empty = s_empty;
-  st.block_props = s_block_props;
   st.flags = s_flags;
   // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
   // by the other CTAs so that nobody waits for it at the barrier
@@ -920,6 +1038,7 @@ template <bool SMEM>
 __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st, unsigned epoch0, int bin_n,
                                                   int n_inline, const InlineProp* inl, bool full_sweep,
                                                   int seeded, bool pre_issued, unsigned& iters_out) {
+  __shared__ unsigned s_wprops[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = P.dirty_words;
   int* const list = reinterpret_cast<int*>(st.ring);
@@ -930,12 +1049,14 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
   c.flags = st.flags;
   c.mirror = false;
   ActiveWords aw;
-  aw.w[0] = aw.w[1] = 0u;
+  aw.w[0] = aw.w[1] = aw.w[2] = aw.w[3] = 0u;
   // the active words of this CTA's first chunk: prefetched while the prologue settles
   const int fam_first = st.fam_cnt[0] > 0 ? 0 : (st.fam_cnt[1] > 0 ? 1 : 2);
-  if (warp > 0 && st.my_chunks > 0 && full_sweep) {
-    const int base = st.fam_g0[fam_first] * chunk_props(fam_first);
-    aw = load_active_words(P.fam[fam_first].active, base, min(chunk_props(fam_first), P.fam[fam_first].n_static - base));
+  if (warp > 0 && st.my_chunks > 0 && full_sweep && fam_first < 2) {
+    if (fam_first == 0)
+      aw = load_active<kGroupsBin>(P.fam[0].active, st.fam_g0[0] * kChunkBin + (warp - 1) * 32 * kGroupsBin, P.fam[0].n_static);
+    else
+      aw = load_active<kGroupsTer>(P.fam[1].active, st.fam_g0[1] * kChunkTer + (warp - 1) * 32 * kGroupsTer, P.fam[1].n_static);
   }
   unsigned iter = 0, dec, nprop = 0;
   int cur_buf = 0, next_buf = 1;
@@ -1048,19 +1169,20 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       if (st.fam_cnt[0] > 0) {
         FamSweep a = fam_sweep(P, st, 0, seq, pre);
         a.have_aw = have_aw && fam_first == 0;
-        n += sweep_family<SMEM, 0>(c, a, aw);
+        const bool lean = P.fam[0].all_plain && P.fam[0].kind_mask == (1 << B_NEQ);
+        n += lean ? sweep_bin<SMEM, true>(c, a, aw) : sweep_bin<SMEM, false>(c, a, aw);
         seq += a.cnt;
       }
       if (st.fam_cnt[1] > 0) {
         FamSweep a = fam_sweep(P, st, 1, seq, pre);
         a.have_aw = have_aw && fam_first == 1;
-        n += sweep_family<SMEM, 1>(c, a, aw);
+        const bool lean = P.fam[1].all_plain && P.fam[1].kind_mask == (1 << T_EQ);
+        n += lean ? sweep_ter<SMEM, true>(c, a, aw) : sweep_ter<SMEM, false>(c, a, aw);
         seq += a.cnt;
       }
       if (st.fam_cnt[2] > 0) {
         FamSweep a = fam_sweep(P, st, 2, seq, pre);
-        a.have_aw = have_aw && fam_first == 2;
-        n += sweep_family<SMEM, 2>(c, a, aw);
+        n += sweep_dj<SMEM>(c, a);
         seq += a.cnt;
       }
       if (lane == 0) nprop += n;  // counted per warp
@@ -1076,13 +1198,17 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       }
     }
 
-    // block-level propagation count, then the barrier + decision
+    // block-level propagation count (per-warp partial sums in shared memory, no atomics),
+    // then the barrier + decision
     for (int o = 16; o; o >>= 1) nprop += __shfl_xor_sync(0xffffffffu, nprop, o);
-    if (lane == 0 && nprop) atomicAdd(st.block_props, nprop);
+    if (lane == 0) s_wprops[warp] = nprop;
     nprop = 0;
     __syncthreads();
     unsigned bp = 0;
-    if (threadIdx.x == 0) { bp = *st.block_props; *st.block_props = 0; }
+    if (warp == 0) {
+      bp = lane < kWarps ? s_wprops[lane] : 0u;
+      for (int o = 16; o; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
+    }
     if (iter == 0) trace_mark(P, 4);
     dec = grid_barrier(P, st.gen, bp, true, st.flags, iter);
     if (iter == 0) trace_mark(P, 5);
@@ -1110,31 +1236,28 @@ template <bool SMEM>
 __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_constant__ Params P) {
   extern __shared__ __align__(128) char smem[];
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
-  __shared__ unsigned s_block_props, s_gen, s_epoch;
   __shared__ int s_flags[2];
   // layout: [ring | n-ary staging (aliased)] [domain snapshot]
   CtaState st;
-  cta_init(P, st, smem, s_full, s_empty, &s_block_props, s_flags, SMEM);
+  cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   Control* ctl = P.ctl;
 
   if (threadIdx.x == 0) {
-    s_block_props = 0;
     s_flags[0] = s_flags[1] = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     // start streaming descriptors right away: they do not depend on the node prologue
     if (P.full_sweep) pre_issue(P, st);
-  } else if (threadIdx.x == 32) {
-    s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
-    s_epoch = *(volatile unsigned*)&ctl->epoch;
   }
   // without a restore the domains are already final: snapshot them while the TMA runs
   if (SMEM && !P.sync0)
     for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
   __syncthreads();
-  st.gen = s_gen;
-  const unsigned epoch0 = s_epoch;
+  // barrier generation and epoch travel in the launch parameters (the host tracks both from
+  // the result header): no dependent global load before the first useful one
+  st.gen = P.gen0;
+  const unsigned epoch0 = P.epoch0;
   trace_mark(P, 0);
 
   if (P.sync0) {
@@ -1168,6 +1291,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       r.epoch = epoch0 + iters + 1;
       r.propagations = *(volatile unsigned long long*)&ctl->propagations;
       r.decision = dec;
+      r.gen = st.gen;
       *P.result = r;
       ctl->epoch = epoch0 + iters + 1;
       ctl->iterations = iters;
@@ -1390,31 +1514,27 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
                                                                 const __grid_constant__ BurstParams B) {
   extern __shared__ __align__(128) char smem[];
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
-  __shared__ unsigned s_block_props, s_gen, s_epoch;
   __shared__ int s_flags[2];
   __shared__ int s_cmd, s_slot, s_bin_n;
   __shared__ InlineProp s_inl;
   __shared__ BurstLocal s_local;
   CtaState st;
-  cta_init(P, st, smem, s_full, s_empty, &s_block_props, s_flags, SMEM);
+  cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   Control* ctl = P.ctl;
   BurstCtl* bc = B.bc;
 
   if (threadIdx.x == 0) {
-    s_block_props = 0;
     s_flags[0] = s_flags[1] = 0;
     for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     pre_issue(P, st);  // descriptors never depend on the node
   } else if (threadIdx.x == 32) {
-    s_gen = *(volatile unsigned*)&ctl->bar_gen >> kDecBits;
-    s_epoch = *(volatile unsigned*)&ctl->epoch;
     if (blockIdx.x == 0) burst_load(bc, &s_local);
   }
   __syncthreads();
-  st.gen = s_gen;
-  unsigned epoch = s_epoch;
+  st.gen = P.gen0;
+  unsigned epoch = P.epoch0;
 
   unsigned long long done = 0;
   if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, false, 0, 0, done);
@@ -1460,6 +1580,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     r.epoch = epoch + 1;
     r.propagations = *(volatile unsigned long long*)&ctl->propagations;
     r.decision = 0;
+    r.gen = st.gen;
     *P.result = r;
   }
 }

@@ -79,6 +79,8 @@ struct HostFamily {
   size_t n_static = 0;      // covered by the CSR
   size_t uploaded = 0;      // descriptors [0, uploaded) are on the device
   size_t active_set = 0;    // active bits [0, active_set) are initialised on the device
+  size_t first_nonplain = SIZE_MAX;  // first descriptor with a Constant / Sum operand (lean sweep variant)
+  int kind_mask = 0;                 // kinds ever allocated in this family
   DevBuf<int4> d_desc;
   DevBuf<int2> d_descB;
   DevBuf<uint32_t> d_active, d_stamp;
@@ -148,6 +150,7 @@ struct pcp_engine {
   Control* d_ctl = nullptr;
   unsigned trail_len = 0;           // host view of ctl->trail_cnt
   unsigned epoch = 1;
+  unsigned bar_gen = 0;             // generation of the device-wide barrier (Result::gen of the last launch)
   unsigned long long props_total = 0;
 
   // labels
@@ -332,6 +335,8 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       require_distinct_vars(e, ops, 2);
       unsigned k = kind == PCP_X_LESS_Y ? B_LESS : (kind == PCP_X_NEQ_Y ? B_NEQ : B_EQ);
       HostFamily& f = e->fam[F_BIN];
+      if (ops[0].var < 0 || ops[1].var < 0) f.first_nonplain = std::min(f.first_nonplain, f.n);
+      f.kind_mask |= 1 << k;
       f.desc.push_back(make_int4((int)((k << 28) | enc_var28(ops[0].var)), ops[0].off, ops[1].var, ops[1].off));
       e->prop_ref.push_back(make_ref(F_BIN, (unsigned)f.n++));
       break;
@@ -344,6 +349,8 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       require_distinct_vars(e, ops, 3);
       unsigned k = kind == PCP_X_GREATER_Y_PLUS_Z ? T_GREATER : (kind == PCP_X_LESS_Y_PLUS_Z ? T_LESS : T_EQ);
       HostFamily& f = e->fam[F_TER];
+      if (ops[0].var < 0 || ops[1].var < 0 || ops[2].var < 0) f.first_nonplain = std::min(f.first_nonplain, f.n);
+      f.kind_mask |= 1 << k;
       f.desc.push_back(make_int4((int)((k << 28) | enc_var28(ops[0].var)), ops[0].off, ops[1].var, ops[1].off));
       f.descB.push_back(make_int2(ops[2].var, ops[2].off));
       e->prop_ref.push_back(make_ref(F_TER, (unsigned)f.n++));
@@ -398,6 +405,7 @@ void truncate_props(pcp_engine* e, const LabelRec& r) {
     hf.n_static = std::min(hf.n_static, hf.n);
     hf.uploaded = std::min(hf.uploaded, hf.n);
     hf.active_set = std::min(hf.active_set, hf.n);
+    if (hf.first_nonplain >= hf.n) hf.first_nonplain = SIZE_MAX;
   }
   e->n_nary = r.n_fam[F_NARY];
   e->h_nary_ptr.resize(e->n_nary + 1);
@@ -587,6 +595,8 @@ Params prepare(pcp_engine* e) {
     df.stamp = hf.d_stamp.p;
     df.n = (int)hf.n;
     df.n_static = (int)hf.n_static;
+    df.all_plain = hf.first_nonplain >= hf.n_static ? 1 : 0;
+    df.kind_mask = hf.kind_mask;
     P.new_first[f] = (int)hf.active_set;
     P.new_last[f] = (int)hf.n;
     if (hf.active_set < hf.n && hf.active_set < hf.n_static) sync0 = true;  // bits other CTAs will read
@@ -611,6 +621,8 @@ Params prepare(pcp_engine* e) {
   P.trail = e->d_trail.p;
   P.ctl = e->d_ctl;
   P.max_iterations = e->max_iterations;
+  P.gen0 = e->bar_gen;
+  P.epoch0 = e->epoch;
   if (e->pending_restore) {
     P.restore_from = e->d_stack.p + e->pending_restore_label * e->stack_stride;
     e->mirror_valid = false;
@@ -651,6 +663,16 @@ void sync_device_state(pcp_engine* e) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+// The persistent kernels need every CTA co-resident (they meet at a device-wide barrier):
+// grid <= number of SMs at one CTA per SM.  A cooperative launch makes the driver check
+// that; PCP_LAUNCH=plain uses an ordinary launch (same grid; valid while the engine has the
+// device to itself) -- kept as a measurement switch.
+void launch_persistent(const void* fn, int grid, void** args, size_t smem, cudaStream_t stream) {
+  static const bool plain = [] { const char* v = std::getenv("PCP_LAUNCH"); return v && std::strcmp(v, "plain") == 0; }();
+  if (plain) CUDA_CHECK(cudaLaunchKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
+  else CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
+}
+
 void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   Params P = prepare(e);
   const size_t V = e->V;
@@ -660,10 +682,8 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   // epoch wrap: stamps are compared for equality with epochs of this launch only
   if (e->epoch > 0x7f000000u) {
     for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
-    unsigned one = 1;
-    CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->epoch = 1;
+    P.epoch0 = 1;
   }
   if (incremental && !e->host_dirty.empty()) {
     // seed the worklist of iteration 0 with the variables narrowed by the host
@@ -715,7 +735,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   }
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   void* args[] = {&P};
-  CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
+  launch_persistent(fn, grid, args, smem, e->stream);
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
   ++e->dom_version;
   // status header (+ domains when small) in one D2H copy
@@ -750,6 +770,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   if (r.decision == D_ITER_CAP) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
   e->trail_len = r.trail_cnt;
   e->epoch = r.epoch;
+  e->bar_gen = r.gen;
   unsigned long long props = r.propagations - e->props_total;
   e->props_total = r.propagations;
   // propagation/store.rs:250-256: False | True (every propagator entailed) | Unknown
@@ -1159,10 +1180,10 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     P.max_iterations = e->max_iterations;
     if (e->epoch > 0x70000000u) {  // epoch wrap, as in run_fixpoint
       for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
-      unsigned one = 1;
-      CUDA_CHECK(cudaMemcpyAsync(&e->d_ctl->epoch, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
       e->epoch = 1;
     }
+    P.gen0 = e->bar_gen;
+    P.epoch0 = e->epoch;
     size_t total = e->n_nary * 4096;
     for (int f = 0; f < 3; ++f) total += e->fam[f].n;
     int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 4095) / 4096));
@@ -1174,7 +1195,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
     void* args[] = {&P, &B};
-    CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, e->stream));
+    launch_persistent(fn, grid, args, smem, e->stream);
     CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
     BurstCtl bc;
     CUDA_CHECK(cudaMemcpyAsync(&bc, b.d_bc, sizeof(bc), cudaMemcpyDeviceToHost, e->stream));
@@ -1185,6 +1206,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     b.kernel_seconds += ms * 1e-3;
     const Result& r = *e->h_result();
     e->epoch = r.epoch;
+    e->bar_gen = r.gen;
     e->trail_len = r.trail_cnt;
     e->props_total = r.propagations;
     e->mirror_valid = false;

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu.log
+timeout 300 python scratch/t9.py 2>&1 | tail -8
+PCP_LAUNCH=plain timeout 300 python scratch/t9.py c2 2>&1 | tail -3
+PCP_TRACE=1 PCP_NO_BURST=1 timeout 200 python scratch/t10.py > gpurun_out/trace_v6.log 2>&1; echo "trace rc=$?"
