@@ -100,6 +100,10 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out);
 void pcp_engine_destroy(pcp_engine* e);
 const char* pcp_last_error(const pcp_engine* e);
 int pcp_set_timing(pcp_engine* e, int32_t enabled);
+/* The CUDA stream (cudaStream_t, returned as an opaque pointer) every launch and copy of this
+ * engine is issued on: lets a caller order its own device work -- e.g. a benchmark's L2
+ * flush -- directly before a fixpoint without a host synchronisation in between. */
+int pcp_stream(pcp_engine* e, void** stream);
 
 /* VStore::alloc (variable/store.rs:135-140): n new variables with domains
  * [lo[i], hi[i]]; an empty domain is a contract violation (store.rs:136). */

@@ -252,6 +252,9 @@ struct FamSweep {
   int pipe_pos, first;   // `first` chunks were already issued (pre_issue)
   uint32_t ring_s, full_s, empty_s, sdom_s;
   int have_aw;           // the caller prefetched the active words of the first chunk
+  int2* dom_w;           // the store itself (updates)
+  uint32_t* next_bits;   // dirty set written in this iteration
+  uint32_t flags_s;      // shared-space address of the CTA's {narrowed, failed} flags
 };
 
 template <int FAM>
@@ -358,6 +361,60 @@ __device__ __forceinline__ void ring_advance(RingPos& r) {
   }
 }
 
+// XEqYPlusZ over plain variables that prunes (the common case of the first sweeps of an
+// arithmetic store): propagate + is_subsumed inline, exactly eval_ter's T_EQ branch followed
+// by finish_eval -- geq half, then leq half on the narrowed values (x_eq_y_plus_z.rs:79-81),
+// Kleene entailment on the result, nothing applied on failure -- with the updates issued as
+// fire-and-forget reductions straight from registers.  Entailment (rare) stays out of line.
+__device__ __forceinline__ bool sweep_upd(const FamSweep& a, int var, int off, IV o, IV n) {
+  const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
+  if (lo) atomicMax(&a.dom_w[var].x, n.lo - off);
+  if (hi) atomicMin(&a.dom_w[var].y, n.hi - off);
+  if (lo || hi) atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
+  return lo || hi;
+}
+__device__ __noinline__ void sweep_deactivate_ter(const Ctx& c, int slot) {
+  deactivate(c, c.P->fam[F_TER].active, F_TER, slot);
+}
+__device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
+  IV x = x0, y = y0, z = z0;
+  const bool ok = prop_greater(x, y, z, 0) && prop_less(x, y, z, 0);
+  const int s = ok ? sub_eq(x, y, z) : -1;
+  if (s < 0) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s + 4u), "r"(1) : "memory");  // flags[1]: failure
+    return;
+  }
+  bool ch = sweep_upd(a, (int)((unsigned)d.x & kConstVar28), d.y, x0, x);
+  ch |= sweep_upd(a, d.z, d.w, y0, y);
+  ch |= sweep_upd(a, e.x, e.y, z0, z);
+  if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s), "r"(1) : "memory");  // flags[0]: narrowed
+  if (s > 0) sweep_deactivate_ter(c, slot);
+}
+
+// XNeqY over plain variables that is not a no-op: eval_bin's B_NEQ branch + finish_eval inline
+// (x_neq_y.rs:82-93 on Interval: a singleton side trims the matching bound of the other side;
+// is_subsumed = not XEqY, x_neq_y.rs:71-73).
+__device__ __noinline__ void sweep_deactivate_bin(const Ctx& c, int slot) {
+  deactivate(c, c.P->fam[F_BIN].active, F_BIN, slot);
+}
+__device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, IV x, IV y) {
+  IV nx = x, ny = y;
+  if (x.lo == x.hi) {
+    if (ny.lo == x.lo) ny.lo++; else if (ny.hi == x.lo) ny.hi--;
+  } else if (y.lo == y.hi) {
+    if (nx.lo == y.lo) nx.lo++; else if (nx.hi == y.lo) nx.hi--;
+  }
+  const bool fail = ny.lo > ny.hi || nx.lo > nx.hi || (nx.lo == ny.hi && nx.hi == ny.lo);
+  if (fail) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s + 4u), "r"(1) : "memory");
+    return;
+  }
+  bool ch = sweep_upd(a, d.z, d.w, y, ny);
+  ch |= sweep_upd(a, (int)((unsigned)d.x & kConstVar28), d.y, x, nx);
+  if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s), "r"(1) : "memory");
+  if (nx.hi < ny.lo || ny.hi < nx.lo) sweep_deactivate_bin(c, slot);
+}
+
 // The streaming sweep of one CTA over the binary family (XLessY / XNeqY / XEqY): warp 0 (one
 // lane) keeps the ring full, every other warp owns 128 consecutive descriptors of each chunk
 // (kGroupsBin groups of 32 = four words of the `active` set).  Hot loop: the descriptor loads
@@ -419,8 +476,15 @@ __device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, Activ
     }
     if (any) {
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-        if (need[g]) sweep_slow_bin<SMEM>(c, base + 32 * g + lane, d_s + 512u * g);
+      for (int g = 0; g < G; ++g) {
+        if (!need[g]) continue;
+        if (NEQ_PLAIN) {
+          const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
+          sweep_neq_update(c, a, base + 32 * g + lane, d[g], x, y);
+        } else {
+          sweep_slow_bin<SMEM>(c, base + 32 * g + lane, d_s + 512u * g);
+        }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_s(r.empty);
@@ -490,8 +554,16 @@ __device__ __noinline__ unsigned sweep_ter(const Ctx& c, const FamSweep a, Activ
     }
     if (any) {
 #pragma unroll
-      for (int g = 0; g < G; ++g)
-        if (need[g]) sweep_slow_ter<SMEM>(c, base + 32 * g + lane, a_s + 512u * g, b_s + 256u * g);
+      for (int g = 0; g < G; ++g) {
+        if (!need[g]) continue;
+        if (EQ_PLAIN) {
+          const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w},
+                   z{dz[g].x + e[g].y, dz[g].y + e[g].y};
+          sweep_ter_eq_update(c, a, base + 32 * g + lane, d[g], e[g], x, y, z);
+        } else {
+          sweep_slow_ter<SMEM>(c, base + 32 * g + lane, a_s + 512u * g, b_s + 256u * g);
+        }
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive_s(r.empty);
@@ -974,6 +1046,9 @@ __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& s
   a.empty_s = smem_u32(st.empty);
   a.sdom_s = st.sdom ? smem_u32(st.sdom) : 0u;
   a.have_aw = 0;
+  a.dom_w = P.dom;
+  a.next_bits = nullptr;  // set per iteration by the caller
+  a.flags_s = smem_u32(st.flags);
   return a;
 }
 
@@ -1168,6 +1243,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       int seq = 0;
       if (st.fam_cnt[0] > 0) {
         FamSweep a = fam_sweep(P, st, 0, seq, pre);
+        a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 0;
         const bool lean = P.fam[0].all_plain && P.fam[0].kind_mask == (1 << B_NEQ);
         n += lean ? sweep_bin<SMEM, true>(c, a, aw) : sweep_bin<SMEM, false>(c, a, aw);
@@ -1175,6 +1251,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       }
       if (st.fam_cnt[1] > 0) {
         FamSweep a = fam_sweep(P, st, 1, seq, pre);
+        a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 1;
         const bool lean = P.fam[1].all_plain && P.fam[1].kind_mask == (1 << T_EQ);
         n += lean ? sweep_ter<SMEM, true>(c, a, aw) : sweep_ter<SMEM, false>(c, a, aw);

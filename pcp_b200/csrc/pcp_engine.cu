@@ -893,6 +893,12 @@ int pcp_set_timing(pcp_engine* e, int32_t enabled) {
   return PCP_OK;
 }
 
+int pcp_stream(pcp_engine* e, void** stream) {
+  if (!e || !stream) return PCP_ERR_INVALID;
+  *stream = (void*)e->stream;
+  return PCP_OK;
+}
+
 int pcp_vars_alloc(pcp_engine* e, const int32_t* lo, const int32_t* hi, int32_t n, int32_t* first_idx) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {

@@ -19,7 +19,7 @@ FLAG_INCREMENTAL = 1
 
 # every symbol include/pcp_b200.h declares
 ABI_SYMBOLS = [
-    "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_vars_alloc",
+    "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_stream", "pcp_vars_alloc",
     "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_consistency", "pcp_domains_read",
     "pcp_var_update", "pcp_active_read", "pcp_label", "pcp_restore", "pcp_num_vars", "pcp_num_props",
     "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_close",
@@ -43,6 +43,8 @@ def load_library() -> C.CDLL:
         lib.pcp_engine_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         lib.pcp_set_timing.restype = C.c_int
         lib.pcp_set_timing.argtypes = [C.c_void_p, C.c_int32]
+        lib.pcp_stream.restype = C.c_int
+        lib.pcp_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
         lib.pcp_search_open.restype = C.c_int
         lib.pcp_search_open.argtypes = [C.c_void_p, C.POINTER(SearchConfig), i32p, u64p, i32p, i32p, C.c_uint64,
@@ -74,6 +76,12 @@ class Engine(EngineBase):
 
     def set_timing(self, enabled: bool) -> None:
         self._check(self._lib.pcp_set_timing(self._h, int(enabled)))
+
+    def cuda_stream(self) -> int:
+        """The engine's cudaStream_t as an integer (torch.cuda.ExternalStream(ptr) wraps it)."""
+        p = C.c_void_p()
+        self._check(self._lib.pcp_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
 
     def search_open(self, node_limit: int = 0, all_solutions: bool = False, var_sel: int = 0, val_sel: int = 0,
                     distributor: int = 0, bb_mode: int = 0, bb_var: int = 0, warmup_nodes: int = 0) -> "SearchHandle":
