@@ -861,11 +861,67 @@ __device__ __forceinline__ int dirty_compact(const uint32_t* bits, int words, in
 constexpr int kLocalRounds = 1024;
 constexpr int kRowCap = 4864;  // staged propagators: 4 B ref + 16 B descriptor word 0 each
 static_assert(kRowStageOff + kRowCap * 20 <= kRingBytes, "row staging area exceeds the ring");
+constexpr int kRowBatch = 8;   // row entries a thread keeps in flight in round 0
+constexpr int kJumpBits = 1024;  // window of the crawl shortcut, per bound
+
+// The crawl shortcut.  v's row tells which neighbours are assigned: every XNeqY(v, u) over
+// plain operands with u a singleton forbids exactly one value of v, and the fixpoint of those
+// propagators alone moves lo to the first value >= lo that no assigned neighbour forbids (hi
+// symmetrically) -- the composition of the single steps x_neq_y.rs:82-93 would take one by
+// one.  While a round evaluates the row, the forbidden values near each bound of v (as it
+// stood at the start of the round) are collected in two bit windows in shared memory; after
+// the round the bounds jump in one update, and the next round evaluates the row again
+// (entailment, failure, the neighbours of a newly assigned v).  Neighbours are read from this
+// CTA's snapshot: a stale (wider) view only delays a step to a later iteration.
+struct CrawlWin { unsigned bm[2][kJumpBits / 32]; };
+__device__ __forceinline__ void crawl_note(const Ctx& c, CrawlWin* w, int v, int2 d, int4 q) {
+  const unsigned xv = (unsigned)q.x & kConstVar28;
+  if (((unsigned)q.x >> 28) != B_NEQ || xv >= kSumBase28 || q.z < 0) return;
+  // X = dom[xv] + q.y must differ from Y = dom[q.z] + q.w
+  const bool v_is_x = (int)xv == v;
+  const int2 du = c.sdom[v_is_x ? q.z : (int)xv];
+  if (du.x != du.y) return;
+  const int f = v_is_x ? du.x + q.w - q.y : du.x + q.y - q.w;  // the value of v this neighbour forbids
+  if (f >= d.x && f - d.x < kJumpBits) atomicOr(&w->bm[0][(f - d.x) >> 5], 1u << ((f - d.x) & 31));
+  if (f <= d.y && d.y - f < kJumpBits) atomicOr(&w->bm[1][(d.y - f) >> 5], 1u << ((d.y - f) & 31));
+}
+// After the round (every thread of the CTA): move the bounds of v past the forbidden values.
+// `d` is the domain the windows are anchored at.  Returns false when every value of the
+// domain is forbidden (the reference ends with two equal singletons: failure).
+__device__ __forceinline__ bool crawl_jump(Ctx& c, CrawlWin* w, int v, int2 d) {
+  __shared__ int2 s_steps;
+  const Params& P = *c.P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp < 2) {  // warp 0: steps lo takes upwards; warp 1: steps hi takes downwards
+    const unsigned word = w->bm[warp][lane];
+    const unsigned open = __ballot_sync(0xffffffffu, word != 0xffffffffu);
+    int steps = kJumpBits;
+    if (open) {
+      const int l = __ffs(open) - 1;
+      const unsigned wl = __shfl_sync(0xffffffffu, word, l);
+      steps = l * 32 + __ffs(~wl) - 1;
+    }
+    if (lane == 0) { if (warp == 0) s_steps.x = steps; else s_steps.y = steps; }
+  }
+  __syncthreads();
+  const int up = s_steps.x, down = s_steps.y;
+  if ((long long)up + down >= (long long)d.y - d.x + 1) return false;
+  if (threadIdx.x == 0 && (up || down)) {
+    const int nlo = d.x + up, nhi = d.y - down;
+    if (up) { atomicMax(&P.dom[v].x, nlo); c.sdom[v].x = max(c.sdom[v].x, nlo); }
+    if (down) { atomicMin(&P.dom[v].y, nhi); c.sdom[v].y = min(c.sdom[v].y, nhi); }
+    atomicOr(&c.next_bits[v >> 5], 1u << (v & 31));
+    c.flags[0] = 1;
+  }
+  return true;
+}
+
 template <bool SMEM>
 __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring) {
   const Params& P = *c.P;
   __shared__ int2 s_before;
   __shared__ int s_nstage, s_moved;
+  __shared__ CrawlWin s_win;
   unsigned* s_ref = reinterpret_cast<unsigned*>(ring + kRowStageOff);
   int4* s_q0 = reinterpret_cast<int4*>(ring + kRowStageOff + kRowCap * 4);
   const int lane = threadIdx.x & 31;
@@ -878,36 +934,57 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
     if (threadIdx.x == 0) { s_before = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]); s_nstage = 0; }
     __syncthreads();
     for (int round = 0;; ++round) {
+      const int2 d0 = s_before;                   // v at the start of the round
+      const bool crawl = SMEM && d0.x < d0.y;     // an unassigned v can crawl
+      if (crawl && threadIdx.x < 2 * (kJumpBits / 32)) (&s_win.bm[0][0])[threadIdx.x] = 0u;
+      if (crawl) __syncthreads();
       if (round == 0 || !staged) {
-        for (int j0 = rb; j0 < re; j0 += blockDim.x) {
-          const int j = j0 + threadIdx.x;
-          bool keep = false;
-          unsigned ref = 0, fam = 0;
-          int slot = 0;
-          int4 q0, q1, q2;
-          if (j < re) {
-            ref = __ldg(&P.adj[j]);
-            fam = ref >> 29;
-            slot = (int)(ref & kSlotMask);
+        // the row is gathered from L2 in batches: all references of a batch first, then their
+        // active words and descriptors, then the evaluations -- two round trips per batch
+        // instead of two per entry
+        for (int j0 = rb; j0 < re; j0 += blockDim.x * kRowBatch) {
+          unsigned ref[kRowBatch], word[kRowBatch];
+          int4 q0[kRowBatch];
+#pragma unroll
+          for (int u = 0; u < kRowBatch; ++u) {
+            const int j = j0 + u * (int)blockDim.x + (int)threadIdx.x;
+            ref[u] = j < re ? __ldg(&P.adj[j]) : 0xffffffffu;
+          }
+#pragma unroll
+          for (int u = 0; u < kRowBatch; ++u) {
+            word[u] = 0u;
+            q0[u] = make_int4(0, 0, 0, 0);
+            if (ref[u] == 0xffffffffu) continue;
+            const unsigned fam = ref[u] >> 29;
+            const int slot = (int)(ref[u] & kSlotMask);
             const Family& f = P.fam[fam];
-            if (slot < f.n_static) {  // else: truncated by a restore (store.rs:320)
-              const unsigned word = __ldcg(&f.active[slot >> 5]);
-              load_desc(f, fam, slot, q0, q1, q2);
-              keep = (word >> (slot & 31)) & 1u;
+            if (slot >= f.n_static) { ref[u] = 0xffffffffu; continue; }  // truncated by a restore (store.rs:320)
+            word[u] = __ldcg(&f.active[slot >> 5]);
+            q0[u] = __ldg(&f.desc[fam == F_DJ ? 3 * (size_t)slot : (size_t)slot]);
+          }
+#pragma unroll
+          for (int u = 0; u < kRowBatch; ++u) {
+            const unsigned fam = ref[u] >> 29;
+            const int slot = (int)(ref[u] & kSlotMask);
+            bool keep = ref[u] != 0xffffffffu && ((word[u] >> (slot & 31)) & 1u);
+            if (round == 0 && staged) {
+              const unsigned m = __ballot_sync(0xffffffffu, keep);
+              if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nstage, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) { const int idx = base + __popc(m & lanemask_lt()); s_ref[idx] = ref[u]; s_q0[idx] = q0[u]; }
+              }
+            }
+            if (keep && crawl && fam == F_BIN) crawl_note(c, &s_win, v, d0, q0[u]);
+            // first round: once per iteration across the grid; later rounds belong to this row
+            if (keep && round == 0 && atomicExch(&P.fam[fam].stamp[slot], cur_epoch) == cur_epoch) keep = false;
+            if (keep) {
+              if (fam == F_BIN) eval_loaded<SMEM>(c, F_BIN, slot, q0[u], make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
+              else eval_ref<SMEM>(c, fam, slot);
+              ++nprop;
             }
           }
-          if (round == 0 && staged) {
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (m) {
-              int base = 0;
-              if (lane == 0) base = atomicAdd(&s_nstage, __popc(m));
-              base = __shfl_sync(0xffffffffu, base, 0);
-              if (keep) { const int idx = base + __popc(m & lanemask_lt()); s_ref[idx] = ref; s_q0[idx] = q0; }
-            }
-          }
-          // first round: once per iteration across the grid; later rounds belong to this row
-          if (keep && round == 0 && atomicExch(&P.fam[fam].stamp[slot], cur_epoch) == cur_epoch) keep = false;
-          if (keep) { eval_loaded<SMEM>(c, fam, slot, q0, q1, q2); ++nprop; }
         }
       } else {
         const int n = s_nstage;
@@ -915,12 +992,24 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
           const unsigned ref = s_ref[idx];
           const unsigned fam = ref >> 29;
           const int slot = (int)(ref & kSlotMask);
-          if (fam == F_BIN) eval_loaded<SMEM>(c, F_BIN, slot, s_q0[idx], make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
-          else eval_ref<SMEM>(c, fam, slot);
+          if (fam == F_BIN) {
+            const int4 q = s_q0[idx];
+            if (crawl) crawl_note(c, &s_win, v, d0, q);
+            eval_loaded<SMEM>(c, F_BIN, slot, q, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
+          } else {
+            eval_ref<SMEM>(c, fam, slot);
+          }
           ++nprop;
         }
       }
       __syncthreads();
+      if (crawl) {
+        if (!crawl_jump(c, &s_win, v, d0)) {  // uniform across the CTA
+          if (threadIdx.x == 0) set_failed(c);
+          break;
+        }
+        __syncthreads();
+      }
       if (threadIdx.x == 0) {
         const int2 a = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
         s_moved = (a.x != s_before.x || a.y != s_before.y) && a.x <= a.y;
