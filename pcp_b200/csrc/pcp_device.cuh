@@ -977,8 +977,9 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
               }
             }
             if (keep && crawl && fam == F_BIN) crawl_note(c, &s_win, v, d0, q0[u]);
-            // first round: once per iteration across the grid; later rounds belong to this row
-            if (keep && round == 0 && atomicExch(&P.fam[fam].stamp[slot], cur_epoch) == cur_epoch) keep = false;
+            // (no epoch stamp here: a propagator shared by two dirty rows may run twice in an
+            // iteration, which changes nothing but the count, and the stamp would cost this
+            // row a further L2 round trip)
             if (keep) {
               if (fam == F_BIN) eval_loaded<SMEM>(c, F_BIN, slot, q0[u], make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
               else eval_ref<SMEM>(c, fam, slot);
