@@ -97,7 +97,7 @@ struct Family {
   int n;                // allocated propagators
   int n_static;         // [0, n_static) are covered by the CSR; [n_static, n) is the tail
   int all_plain;        // 1: no descriptor in [0, n_static) has a Constant or Sum operand
-  int kind_mask;        // bit k: a descriptor of kind k was allocated (over-approximation after restores)
+  int kind_mask;        // bit k: a descriptor of kind k may sit in [0, n_static) (over-approximation after restores)
 };
 
 struct InlineProp {     // a propagator posted since the last launch, carried in the launch
@@ -146,11 +146,20 @@ struct Params {
   unsigned long long* trace;
 };
 
+constexpr int kTraceIter1 = 8 * 256 + 4 * 32 + 64;  // second mark region: phases of iteration 1
+constexpr int kTraceWords = kTraceIter1 + 8 * 256;
 __device__ __forceinline__ void trace_mark(const Params& P, int slot) {
   if (P.trace && threadIdx.x == 0) {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
     P.trace[blockIdx.x * 8 + slot] = t;
+  }
+}
+__device__ __forceinline__ void trace_mark1(const Params& P, unsigned iter, int slot) {
+  if (P.trace && iter == 1 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
+    P.trace[kTraceIter1 + blockIdx.x * 8 + slot] = t;
   }
 }
 
@@ -255,7 +264,51 @@ struct FamSweep {
   int2* dom_w;           // the store itself (updates)
   uint32_t* next_bits;   // dirty set written in this iteration
   uint32_t flags_s;      // shared-space address of the CTA's {narrowed, failed} flags
+  uint32_t tbuf_s;       // shared-space address of the CTA's TrailBuf (entailed propagators of this sweep)
+  uint32_t* active_w;    // the family's `active` bit set (writable)
+  uint32_t* trail;       // the entailment trail and its length (overflow path of the buffer)
+  unsigned* trail_cnt;
 };
+
+// Propagators found entailed during a sweep: their active bit is cleared with a fire-and-
+// forget reduction (a static propagator is evaluated by exactly one thread per sweep, so
+// nobody needs the old bit) and their references are collected in shared memory; the CTA
+// appends them to the trail (Store::unlink_prop, propagation/store.rs:200-207) with one
+// reservation before the iteration's barrier.  The order inside one node's trail segment is
+// immaterial: a restore re-activates the whole suffix (store.rs:319-323).
+constexpr int kTrailBuf = 4088;
+struct TrailBuf { unsigned n; unsigned pad; unsigned ref[kTrailBuf]; };
+__device__ __forceinline__ void sweep_deactivate(const FamSweep& a, unsigned fam, int slot) {
+  atomicAnd(&a.active_w[slot >> 5], ~(1u << (slot & 31)));
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(a.tbuf_s), "r"(__popc(m)) : "memory");
+  base = __shfl_sync(m, base, leader);
+  const unsigned pos = base + __popc(m & lanemask_lt());
+  const unsigned ref = make_ref(fam, (unsigned)slot);
+  if (pos < (unsigned)kTrailBuf) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.tbuf_s + 8u + 4u * pos), "r"(ref) : "memory");
+  } else {  // buffer full: straight to the trail, one reservation per warp
+    const unsigned mo = __activemask();
+    const int lo = __ffs(mo) - 1;
+    unsigned gb = 0;
+    if (lane == lo) gb = atomicAdd(a.trail_cnt, (unsigned)__popc(mo));
+    gb = __shfl_sync(mo, gb, lo);
+    a.trail[gb + __popc(mo & lanemask_lt())] = ref;
+  }
+}
+// Every thread of the CTA, before the iteration's barrier.
+__device__ __forceinline__ void trail_flush(const Params& P, TrailBuf* tb) {
+  __shared__ unsigned s_base;
+  const unsigned n = min(tb->n, (unsigned)kTrailBuf);  // (uniform: read after a barrier)
+  if (n == 0) return;
+  if (threadIdx.x == 0) s_base = atomicAdd(&P.ctl->trail_cnt, n);
+  __syncthreads();
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) P.trail[s_base + i] = tb->ref[i];
+  __syncthreads();
+  if (threadIdx.x == 0) tb->n = 0u;
+}
 
 template <int FAM>
 __device__ __forceinline__ void producer_issue(const FamSweep& a, int g, uint32_t stage, uint32_t full) {
@@ -373,9 +426,6 @@ __device__ __forceinline__ bool sweep_upd(const FamSweep& a, int var, int off, I
   if (lo || hi) atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
   return lo || hi;
 }
-__device__ __noinline__ void sweep_deactivate_ter(const Ctx& c, int slot) {
-  deactivate(c, c.P->fam[F_TER].active, F_TER, slot);
-}
 __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
   IV x = x0, y = y0, z = z0;
   const bool ok = prop_greater(x, y, z, 0) && prop_less(x, y, z, 0);
@@ -388,15 +438,12 @@ __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep
   ch |= sweep_upd(a, d.z, d.w, y0, y);
   ch |= sweep_upd(a, e.x, e.y, z0, z);
   if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s), "r"(1) : "memory");  // flags[0]: narrowed
-  if (s > 0) sweep_deactivate_ter(c, slot);
+  if (s > 0) sweep_deactivate(a, F_TER, slot);
 }
 
 // XNeqY over plain variables that is not a no-op: eval_bin's B_NEQ branch + finish_eval inline
 // (x_neq_y.rs:82-93 on Interval: a singleton side trims the matching bound of the other side;
 // is_subsumed = not XEqY, x_neq_y.rs:71-73).
-__device__ __noinline__ void sweep_deactivate_bin(const Ctx& c, int slot) {
-  deactivate(c, c.P->fam[F_BIN].active, F_BIN, slot);
-}
 __device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, IV x, IV y) {
   IV nx = x, ny = y;
   if (x.lo == x.hi) {
@@ -412,7 +459,7 @@ __device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a
   bool ch = sweep_upd(a, d.z, d.w, y, ny);
   ch |= sweep_upd(a, (int)((unsigned)d.x & kConstVar28), d.y, x, nx);
   if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s), "r"(1) : "memory");
-  if (nx.hi < ny.lo || ny.hi < nx.lo) sweep_deactivate_bin(c, slot);
+  if (nx.hi < ny.lo || ny.hi < nx.lo) sweep_deactivate(a, F_BIN, slot);
 }
 
 // The streaming sweep of one CTA over the binary family (XLessY / XNeqY / XEqY): warp 0 (one
@@ -424,7 +471,9 @@ __device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a
 // n-queens and pairwise-distinct stores -- so neither the kind nor the operand encoding is
 // inspected.  Returns the number of evaluations of the warp (the same value in every lane).
 template <bool SMEM, bool NEQ_PLAIN>
-__device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, ActiveWords aw) {
+__device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, uint4 aw4) {
+  ActiveWords aw;
+  aw.w[0] = aw4.x; aw.w[1] = aw4.y; aw.w[2] = aw4.z; aw.w[3] = aw4.w;
   constexpr int G = kGroupsBin;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -499,7 +548,9 @@ __device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, Activ
 // groups per warp and chunk, the (x, y) plane and the z plane of the stage read separately.
 // EQ_PLAIN: every static descriptor is an XEqYPlusZ over plain variables.
 template <bool SMEM, bool EQ_PLAIN>
-__device__ __noinline__ unsigned sweep_ter(const Ctx& c, const FamSweep a, ActiveWords aw) {
+__device__ __noinline__ unsigned sweep_ter(const Ctx& c, const FamSweep a, uint4 aw4) {
+  ActiveWords aw;
+  aw.w[0] = aw4.x; aw.w[1] = aw4.y; aw.w[2] = aw4.z; aw.w[3] = aw4.w;
   constexpr int G = kGroupsTer;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -926,7 +977,7 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
   int4* s_q0 = reinterpret_cast<int4*>(ring + kRowStageOff + kRowCap * 4);
   const int lane = threadIdx.x & 31;
   unsigned nprop = 0;
-  c.mirror = SMEM;
+  if (threadIdx.x == 0) c.mirror = SMEM;  // (ordered by the barrier that opens every row)
   for (int e = blockIdx.x; e < n_dirty; e += gridDim.x) {
     const int v = list[e];
     const int rb = __ldg(&P.adj_ptr[v]), re = __ldg(&P.adj_ptr[v + 1]);
@@ -1020,7 +1071,7 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
       if (!s_moved || round + 1 >= kLocalRounds) break;
     }
   }
-  c.mirror = false;
+  if (threadIdx.x == 0) c.mirror = false;
   return nprop;
 }
 
@@ -1111,6 +1162,7 @@ struct CtaState {
   uint64_t* full;
   uint64_t* empty;
   int* flags;
+  TrailBuf* tbuf;
   // this CTA's share of a sweep: chunk G of the concatenated families belongs to worker
   // G % workers; per family the first chunk index, and the number of chunks
   int workers, wid, my_chunks;
@@ -1139,6 +1191,10 @@ __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& s
   a.dom_w = P.dom;
   a.next_bits = nullptr;  // set per iteration by the caller
   a.flags_s = smem_u32(st.flags);
+  a.tbuf_s = smem_u32(st.tbuf);
+  a.active_w = P.fam[fam].active;
+  a.trail = P.trail;
+  a.trail_cnt = &P.ctl->trail_cnt;
   return a;
 }
 
@@ -1207,12 +1263,22 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = P.dirty_words;
   int* const list = reinterpret_cast<int*>(st.ring);
-  Ctx c;
-  c.P = &P;
-  c.sdom = st.sdom;
-  c.sdom_s = SMEM ? smem_u32(st.sdom) : 0u;
-  c.flags = st.flags;
-  c.mirror = false;
+  // The evaluation context is uniform across the CTA and lives in shared memory: as a local
+  // variable handed to the out-of-line evaluators by reference it sat in local memory, and
+  // every reload of one of its fields could miss L1 (the CTA's shared memory leaves little
+  // of it) and cost an L2 round trip on the critical path.  Thread 0 writes, a barrier orders.
+  __shared__ Ctx s_ctx;
+  __shared__ TrailBuf s_tbuf;
+  Ctx& c = s_ctx;
+  st.tbuf = &s_tbuf;
+  if (threadIdx.x == 0) {
+    s_tbuf.n = 0u;
+    c.P = &P;
+    c.sdom = st.sdom;
+    c.sdom_s = SMEM ? smem_u32(st.sdom) : 0u;
+    c.flags = st.flags;
+    c.mirror = false;
+  }
   ActiveWords aw;
   aw.w[0] = aw.w[1] = aw.w[2] = aw.w[3] = 0u;
   // the active words of this CTA's first chunk: prefetched while the prologue settles
@@ -1231,10 +1297,13 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     const int spare_buf = (iter + 2) % 3;
     const unsigned cur_epoch = epoch0 + iter;
     const uint32_t* cur_bits = P.dirty_bits + (size_t)cur_buf * W;
-    c.next_bits = P.dirty_bits + (size_t)next_buf * W;
-    c.local = false;
-    c.mark_dirty = true;
-    c.bookkeep = true;
+    if (threadIdx.x == 0) {
+      c.next_bits = P.dirty_bits + (size_t)next_buf * W;
+      c.local = false;
+      c.mark_dirty = true;
+      c.bookkeep = true;
+    }
+    __syncthreads();
     // the spare set was read in the previous iteration and is written in the next one
     if (iter > 0 && blockIdx.x == 0)
       for (int w = threadIdx.x; w < W; w += blockDim.x) P.dirty_bits[(size_t)spare_buf * W + w] = 0u;
@@ -1288,6 +1357,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     bool sweep_now = iter == 0 && full_sweep, skip = false;
     if (iter > 0 || (!full_sweep && seeded)) {
       n_dirty = dirty_compact(cur_bits, W, list, kListCap);
+      trace_mark1(P, iter, 1);
       // many dirty variables: their CSR rows cover most of the store, and a streaming sweep is
       // cheaper than gathering the rows
       if (n_dirty > kListCap || (long long)n_dirty * 8 >= (long long)P.V) sweep_now = true;
@@ -1318,6 +1388,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         if (threadIdx.x == 0) set_failed(c);
         skip = SMEM;
       }
+      trace_mark1(P, iter, 2);
       if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(c, list, n_dirty, cur_epoch, st.ring);
     }
     if (sweep_now && !skip && st.my_chunks > 0) {
@@ -1329,6 +1400,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       // before the async-proxy writes of the next bulk copies
       if (threadIdx.x == 0 && pre == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       const bool have_aw = iter == 0 && full_sweep;  // prefetched above
+      const uint4 aw4 = make_uint4(aw.w[0], aw.w[1], aw.w[2], aw.w[3]);
       unsigned n = 0;
       int seq = 0;
       if (st.fam_cnt[0] > 0) {
@@ -1336,7 +1408,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 0;
         const bool lean = P.fam[0].all_plain && P.fam[0].kind_mask == (1 << B_NEQ);
-        n += lean ? sweep_bin<SMEM, true>(c, a, aw) : sweep_bin<SMEM, false>(c, a, aw);
+        n += lean ? sweep_bin<SMEM, true>(c, a, aw4) : sweep_bin<SMEM, false>(c, a, aw4);
         seq += a.cnt;
       }
       if (st.fam_cnt[1] > 0) {
@@ -1344,7 +1416,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 1;
         const bool lean = P.fam[1].all_plain && P.fam[1].kind_mask == (1 << T_EQ);
-        n += lean ? sweep_ter<SMEM, true>(c, a, aw) : sweep_ter<SMEM, false>(c, a, aw);
+        n += lean ? sweep_ter<SMEM, true>(c, a, aw4) : sweep_ter<SMEM, false>(c, a, aw4);
         seq += a.cnt;
       }
       if (st.fam_cnt[2] > 0) {
@@ -1355,7 +1427,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       if (lane == 0) nprop += n;  // counted per warp
       st.pipe_pos += st.my_chunks;
     }
-    if (iter == 0 && P.trace) { __syncthreads(); trace_mark(P, 3); }
+    if (iter <= 1 && P.trace) { __syncthreads(); if (iter == 0) trace_mark(P, 3); else trace_mark1(P, iter, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
     if (P.n_nary > 0 && !skip && (iter > 0 || full_sweep || n_dirty > 0)) {
       for (int s = blockIdx.x; s < P.n_nary; s += gridDim.x) {
@@ -1371,14 +1443,17 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     if (lane == 0) s_wprops[warp] = nprop;
     nprop = 0;
     __syncthreads();
+    trail_flush(P, &s_tbuf);  // the propagators this CTA's sweep found entailed
     unsigned bp = 0;
     if (warp == 0) {
       bp = lane < kWarps ? s_wprops[lane] : 0u;
       for (int o = 16; o; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
     }
     if (iter == 0) trace_mark(P, 4);
+    trace_mark1(P, iter, 4);
     dec = grid_barrier(P, st.gen, bp, true, st.flags, iter);
     if (iter == 0) trace_mark(P, 5);
+    trace_mark1(P, iter, 5);
     if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && iter < 32) {  // per-iteration record
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -81,6 +81,7 @@ struct HostFamily {
   size_t active_set = 0;    // active bits [0, active_set) are initialised on the device
   size_t first_nonplain = SIZE_MAX;  // first descriptor with a Constant / Sum operand (lean sweep variant)
   int kind_mask = 0;                 // kinds ever allocated in this family
+  int static_kind_mask = 0;          // ... among the descriptors covered by the CSR (over-approximation)
   DevBuf<int4> d_desc;
   DevBuf<int2> d_descB;
   DevBuf<uint32_t> d_active, d_stamp;
@@ -469,7 +470,7 @@ void build_csr(pcp_engine* e) {
   if (!adj.empty())
     CUDA_CHECK(cudaMemcpyAsync(e->d_adj.p, adj.data(), adj.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   CUDA_CHECK(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
-  for (int f = 0; f < 3; ++f) e->fam[f].n_static = e->fam[f].n;
+  for (int f = 0; f < 3; ++f) { e->fam[f].n_static = e->fam[f].n; e->fam[f].static_kind_mask = e->fam[f].kind_mask; }
   e->csr_built = true;
 }
 
@@ -596,7 +597,7 @@ Params prepare(pcp_engine* e) {
     df.n = (int)hf.n;
     df.n_static = (int)hf.n_static;
     df.all_plain = hf.first_nonplain >= hf.n_static ? 1 : 0;
-    df.kind_mask = hf.kind_mask;
+    df.kind_mask = hf.static_kind_mask;
     P.new_first[f] = (int)hf.active_set;
     P.new_last[f] = (int)hf.n;
     if (hf.active_set < hf.n && hf.active_set < hf.n_static) sync0 = true;  // bits other CTAs will read
@@ -729,8 +730,8 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (trace_on) {
-    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, (8 * 256 + 4 * 32 + 64) * sizeof(unsigned long long)));
-    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, (8 * 256 + 4 * 32 + 64) * sizeof(unsigned long long), e->stream));
+    if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, kTraceWords * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, kTraceWords * sizeof(unsigned long long), e->stream));
     P.trace = e->d_trace;
   }
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
@@ -746,7 +747,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   e->mirror_valid = eager_dom;
 
   if (trace_on) {
-    std::vector<unsigned long long> t(8 * 256 + 4 * 32 + 64);
+    std::vector<unsigned long long> t(kTraceWords);
     CUDA_CHECK(cudaMemcpy(t.data(), e->d_trace, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     {
       unsigned long long tb = ~0ull;
@@ -764,6 +765,30 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
       unsigned long long mn = ~0ull, mx = 0, sum = 0;
       for (int b = 0; b < grid; ++b) { unsigned long long v = t[b * 8 + k] - t0; mn = std::min(mn, v); mx = std::max(mx, v); sum += v; }
       std::fprintf(stderr, "[pcp trace]   %-22s %8llu %8llu %8llu\n", names[k], mn, sum / grid, mx);
+    }
+    {  // the stragglers of iteration 0: CTAs by time of their last sweep chunk
+      std::vector<std::pair<unsigned long long, int>> by;
+      for (int b = 0; b < grid; ++b) by.push_back({t[b * 8 + 3] - t0, b});
+      std::sort(by.begin(), by.end());
+      std::fprintf(stderr, "[pcp trace]   sweep_done by CTA: fastest");
+      for (int i = 0; i < 4 && i < grid; ++i) std::fprintf(stderr, " %d:%llu", by[i].second, by[i].first);
+      std::fprintf(stderr, "  median %llu  slowest", by[grid / 2].first);
+      for (int i = std::max(0, grid - 8); i < grid; ++i) std::fprintf(stderr, " %d:%llu(start %llu)", by[i].second, by[i].first, t[by[i].second * 8] - t0);
+      std::fprintf(stderr, "\n");
+    }
+    if (e->h_result()->iterations > 1) {
+      const char* n1[6] = {"it1 start", "it1 compacted", "it1 refreshed", "it1 rows/sweep done", "it1 barrier_arrive", "it1 barrier_leave"};
+      for (int k = 0; k < 6; ++k) {
+        unsigned long long mn = ~0ull, mx = 0, sum = 0;
+        int cnt = 0;
+        for (int b = 0; b < grid; ++b) {
+          unsigned long long raw = t[kTraceIter1 + b * 8 + k];
+          if (!raw) continue;
+          unsigned long long v = raw - t0; mn = std::min(mn, v); mx = std::max(mx, v); sum += v; ++cnt;
+        }
+        if (cnt) std::fprintf(stderr, "[pcp trace]   %-22s %8llu %8llu %8llu  (%d CTAs)  cta0 %llu\n", n1[k], mn, sum / cnt, mx, cnt,
+                              t[kTraceIter1 + k] ? t[kTraceIter1 + k] - t0 : 0ull);
+      }
     }
   }
   const Result& r = *e->h_result();

@@ -94,18 +94,21 @@ __device__ __forceinline__ IV rd(const Ctx& c, int var, int off) {
 // term/constant.rs:43-53.  All bounds are in view space.
 // ---------------------------------------------------------------------------------------
 struct Upd { int var, off, cur_lo, cur_hi, nlo, nhi; };
-struct UpdSet {
+struct UpdSet {   // slot 0 = x, 1 = y, 2 = z: constant indices only, so the set lives in registers
   Upd u[3];
-  int n;
+  bool on[3];
 };
+__device__ __forceinline__ void upd_clear(UpdSet& us) { us.on[0] = us.on[1] = us.on[2] = false; }
 
 // Stage "view <- [nlo, nhi]" (already intersected with `cur`).  Returns false when the new
 // domain is empty (the reference's update -> false); a Constant is never written but fails
 // when it falls outside (nlo > nhi covers it because cur is the singleton).
+template <int I>
 __device__ __forceinline__ bool stage(UpdSet& us, int var, int off, IV cur, int nlo, int nhi) {
   if (nlo > nhi) return false;
   if (var >= 0 && (nlo > cur.lo || nhi < cur.hi)) {
-    Upd& r = us.u[us.n++];
+    Upd& r = us.u[I];
+    us.on[I] = true;
     r.var = var; r.off = off; r.cur_lo = cur.lo; r.cur_hi = cur.hi; r.nlo = nlo; r.nhi = nhi;
   }
   return true;
@@ -118,11 +121,11 @@ __device__ __forceinline__ bool stage(UpdSet& us, int var, int off, IV cur, int 
 // updates (lo from one thread, hi from another) is caught when the dirty variables are
 // re-read at the start of the next iteration -- there always is one, flags[0] is set.
 __device__ __forceinline__ void apply_updates(const Ctx& c, const UpdSet& us) {
-  if (us.n == 0) return;
+  if (!(us.on[0] || us.on[1] || us.on[2])) return;
   const Params& P = *c.P;
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    if (i >= us.n) break;
+    if (!us.on[i]) continue;
     const Upd& r = us.u[i];
     const int nl = r.nlo - r.off, nh = r.nhi - r.off;
     if (c.local) { sts_dom(c.sdom_s + 8u * (unsigned)r.var, nl, nh); continue; }
@@ -141,8 +144,8 @@ __device__ __forceinline__ void apply_updates(const Ctx& c, const UpdSet& us) {
 // Single update (n-ary propagators write their operands one by one).
 __device__ __forceinline__ bool tighten(const Ctx& c, int var, int off, IV cur, int nlo, int nhi) {
   UpdSet us;
-  us.n = 0;
-  if (!stage(us, var, off, cur, nlo, nhi)) return false;
+  upd_clear(us);
+  if (!stage<0>(us, var, off, cur, nlo, nhi)) return false;
   apply_updates(c, us);
   return true;
 }
@@ -173,18 +176,18 @@ __device__ __forceinline__ Eval eval_bin(int4 d, IV x, IV y, UpdSet& us) {
     } else if (y.lo == y.hi) {
       if (nx.lo == y.lo) nx.lo++; else if (nx.hi == y.lo) nx.hi--;
     }
-    if (!stage(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
-    if (!stage(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
+    if (!stage<1>(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
+    if (!stage<0>(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
   } else if (kind == B_LESS) {  // cmp/x_less_y.rs:101-108
     nx.hi = min(x.hi, y.hi - 1);
-    if (!stage(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
+    if (!stage<0>(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
     ny.lo = max(y.lo, x.lo + 1);
-    if (!stage(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
+    if (!stage<1>(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
   } else {  // B_EQ: cmp/x_eq_y.rs:102-107
     nx.lo = ny.lo = max(x.lo, y.lo);
     nx.hi = ny.hi = min(x.hi, y.hi);
-    if (!stage(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
-    if (!stage(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
+    if (!stage<0>(us, xv, xo, x, nx.lo, nx.hi)) return E_FAIL;
+    if (!stage<1>(us, yv, yo, y, ny.lo, ny.hi)) return E_FAIL;
   }
   const IV px = xro ? x : nx, py = yro ? y : ny;  // what is_subsumed reads back
   if (kind == B_LESS) {  // x_less_y.rs:84-91
@@ -261,8 +264,8 @@ __device__ __forceinline__ bool prop_eq(IV& x, IV& y, IV& z, const TriRo& ro) {
   return true;
 }
 __device__ __forceinline__ bool stage_tri(UpdSet& us, const Tri& t, IV x0, IV y0, IV z0, IV x, IV y, IV z) {
-  return stage(us, t.xv, t.xo, x0, x.lo, x.hi) && stage(us, t.yv, t.yo, y0, y.lo, y.hi) &&
-         stage(us, t.zv, t.zo, z0, z.lo, z.hi);
+  return stage<0>(us, t.xv, t.xo, x0, x.lo, x.hi) && stage<1>(us, t.yv, t.yo, y0, y.lo, y.hi) &&
+         stage<2>(us, t.zv, t.zo, z0, z.lo, z.hi);
 }
 
 __device__ __forceinline__ Eval eval_ter(int4 a, int2 b, IV x0, IV y0, IV z0, UpdSet& us) {
@@ -335,18 +338,18 @@ __device__ __forceinline__ void finish_eval(const Ctx& c, Eval r, const UpdSet& 
 }
 __device__ __noinline__ void eval_full_bin(const Ctx& c, int slot, int4 d, IV x, IV y) {
   UpdSet us;
-  us.n = 0;
+  upd_clear(us);
   finish_eval(c, eval_bin(d, x, y, us), us, F_BIN, slot);
 }
 __device__ __noinline__ void eval_full_ter(const Ctx& c, int slot, int4 a, int2 b, IV x, IV y, IV z) {
   UpdSet us;
-  us.n = 0;
+  upd_clear(us);
   finish_eval(c, eval_ter(a, b, x, y, z, us), us, F_TER, slot);
 }
 template <bool SMEM>
 __device__ __noinline__ void eval_full_dj(const Ctx& c, int slot, int4 q0, int4 q1, int4 q2) {
   UpdSet us;
-  us.n = 0;
+  upd_clear(us);
   finish_eval(c, eval_dj<SMEM>(c, q0, q1, q2, us), us, F_DJ, slot);
 }
 // Any family, operands read here (posted propagators, tail).
