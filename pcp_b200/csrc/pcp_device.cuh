@@ -147,7 +147,8 @@ struct Params {
 };
 
 constexpr int kTraceIter1 = 8 * 256 + 4 * 32 + 64;  // second mark region: phases of iteration 1
-constexpr int kTraceWords = kTraceIter1 + 8 * 256;
+constexpr int kTraceSeq = kTraceIter1 + 8 * 256;   // CTA 0, iteration 1: (id, time) sequence inside the row-local rounds
+constexpr int kTraceWords = kTraceSeq + 2 + 2 * 64;
 __device__ __forceinline__ void trace_mark(const Params& P, int slot) {
   if (P.trace && threadIdx.x == 0) {
     unsigned long long t;
@@ -155,7 +156,16 @@ __device__ __forceinline__ void trace_mark(const Params& P, int slot) {
     P.trace[blockIdx.x * 8 + slot] = t;
   }
 }
+__device__ __forceinline__ void trace_seq(const Params& P, unsigned id, unsigned dep = 0u) {
+  if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && P.trace[kTraceSeq + 1] == 1ull) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer; // %1" : "=l"(t) : "r"(dep) : "memory");  // `dep`: wait for that register
+    const unsigned long long n = P.trace[kTraceSeq];
+    if (n < 64) { P.trace[kTraceSeq + 2 + 2 * n] = id; P.trace[kTraceSeq + 3 + 2 * n] = t; P.trace[kTraceSeq] = n + 1; }
+  }
+}
 __device__ __forceinline__ void trace_mark1(const Params& P, unsigned iter, int slot) {
+  if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && slot == 0) P.trace[kTraceSeq + 1] = iter == 1 ? 1ull : 0ull;
   if (P.trace && iter == 1 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory");
@@ -910,8 +920,8 @@ __device__ __forceinline__ int dirty_compact(const uint32_t* bits, int words, in
 // the fixpoint is unchanged.  (A propagator deactivated meanwhile may be evaluated again:
 // an entailed propagator prunes nothing, and `deactivate` trails it only once.)
 constexpr int kLocalRounds = 1024;
-constexpr int kRowCap = 4864;  // staged propagators: 4 B ref + 16 B descriptor word 0 each
-static_assert(kRowStageOff + kRowCap * 20 <= kRingBytes, "row staging area exceeds the ring");
+constexpr int kRowCap = 4096;  // staged propagators: 4 B ref + 16 B descriptor word 0 + 4 B unlink slot each
+static_assert(kRowStageOff + kRowCap * 24 <= kRingBytes, "row staging area exceeds the ring");
 constexpr int kRowBatch = 8;   // row entries a thread keeps in flight in round 0
 constexpr int kJumpBits = 1024;  // window of the crawl shortcut, per bound
 
@@ -967,14 +977,78 @@ __device__ __forceinline__ bool crawl_jump(Ctx& c, CrawlWin* w, int v, int2 d) {
   return true;
 }
 
+// Row-local evaluation of an XNeqY over plain variables against the CTA's snapshot: eval_bin's
+// B_NEQ branch + finish_eval inline (x_neq_y.rs:82-93, is_subsumed x_neq_y.rs:71-73), every
+// narrowing applied to the store (reductions) and mirrored into the snapshot.  Returns true
+// when the propagator is entailed: the caller clears its active bit -- with the old bit
+// returned, because a propagator shared by two dirty rows can be found entailed twice -- for
+// a whole batch at once, so that the round trips of those atomics overlap.
+__device__ __forceinline__ bool row_upd(const Ctx& c, int var, int off, IV o, IV n) {
+  const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
+  if (lo) { atomicMax(&c.P->dom[var].x, n.lo - off); atomicMax(&c.sdom[var].x, n.lo - off); }
+  if (hi) { atomicMin(&c.P->dom[var].y, n.hi - off); atomicMin(&c.sdom[var].y, n.hi - off); }
+  if (lo || hi) atomicOr(&c.next_bits[var >> 5], 1u << (var & 31));
+  return lo || hi;
+}
+__device__ __forceinline__ bool row_eval_neq(const Ctx& c, int4 q) {
+  const int xv = (int)((unsigned)q.x & kConstVar28);
+  const int2 dx = c.sdom[xv], dy = c.sdom[q.z];
+  const IV x{dx.x + q.y, dx.y + q.y}, y{dy.x + q.w, dy.y + q.w};
+  if (bin_is_noop(B_NEQ, x, y)) return false;
+  IV nx = x, ny = y;
+  if (x.lo == x.hi) {
+    if (ny.lo == x.lo) ny.lo++; else if (ny.hi == x.lo) ny.hi--;
+  } else if (y.lo == y.hi) {
+    if (nx.lo == y.lo) nx.lo++; else if (nx.hi == y.lo) nx.hi--;
+  }
+  if (ny.lo > ny.hi || nx.lo > nx.hi || (nx.lo == ny.hi && nx.hi == ny.lo)) { set_failed(c); return false; }
+  bool ch = row_upd(c, q.z, q.w, y, ny);
+  ch |= row_upd(c, xv, q.y, x, nx);
+  if (ch) c.flags[0] = 1;
+  return nx.hi < ny.lo || ny.hi < nx.lo;
+}
+__device__ __forceinline__ bool is_plain_neq(int4 q) {
+  return ((unsigned)q.x >> 28) == B_NEQ && ((unsigned)q.x & kConstVar28) < kSumBase28 && q.z >= 0;
+}
+// Append references to the CTA's TrailBuf (warp-aggregated; overflow goes straight to the trail).
+__device__ __forceinline__ void tbuf_push(const Params& P, TrailBuf* tb, unsigned ref) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(&tb->n, (unsigned)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  const unsigned pos = base + __popc(m & lanemask_lt());
+  if (pos < (unsigned)kTrailBuf) tb->ref[pos] = ref;
+  else P.trail[atomicAdd(&P.ctl->trail_cnt, 1u)] = ref;
+}
+
+// One row entry evaluated against the CTA's snapshot (rolled loops only: this code exists once
+// per kernel and stays warm in the instruction cache across rounds).  Returns true when the
+// inline XNeqY path found the propagator entailed (the caller unlinks it).
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring) {
+__device__ __forceinline__ bool row_eval_entry(Ctx& c, unsigned ref, int4 q) {
+  const unsigned fam = ref >> 29;
+  const int slot = (int)(ref & kSlotMask);
+  if (fam == F_BIN) {
+    if (SMEM && is_plain_neq(q)) return row_eval_neq(c, q);
+    eval_loaded<SMEM>(c, F_BIN, slot, q, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
+  } else {
+    eval_ref<SMEM>(c, fam, slot);
+  }
+  return false;
+}
+
+template <bool SMEM>
+__device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
   const Params& P = *c.P;
   __shared__ int2 s_before;
-  __shared__ int s_nstage, s_moved;
+  __shared__ int s_nstage, s_nunlink, s_moved;
   __shared__ CrawlWin s_win;
+  // staging area (the idle TMA ring behind the dirty list): references, descriptor word 0, and
+  // the entries a round found entailed
   unsigned* s_ref = reinterpret_cast<unsigned*>(ring + kRowStageOff);
   int4* s_q0 = reinterpret_cast<int4*>(ring + kRowStageOff + kRowCap * 4);
+  unsigned* s_unlink = reinterpret_cast<unsigned*>(ring + kRowStageOff + kRowCap * 20);
   const int lane = threadIdx.x & 31;
   unsigned nprop = 0;
   if (threadIdx.x == 0) c.mirror = SMEM;  // (ordered by the barrier that opens every row)
@@ -982,17 +1056,18 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
     const int v = list[e];
     const int rb = __ldg(&P.adj_ptr[v]), re = __ldg(&P.adj_ptr[v + 1]);
     const bool staged = re - rb <= kRowCap;
-    if (threadIdx.x == 0) { s_before = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]); s_nstage = 0; }
+    if (threadIdx.x == 0) { s_before = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]); s_nstage = 0; s_nunlink = 0; }
     __syncthreads();
+    trace_seq(P, 100);
     for (int round = 0;; ++round) {
       const int2 d0 = s_before;                   // v at the start of the round
       const bool crawl = SMEM && d0.x < d0.y;     // an unassigned v can crawl
       if (crawl && threadIdx.x < 2 * (kJumpBits / 32)) (&s_win.bm[0][0])[threadIdx.x] = 0u;
-      if (crawl) __syncthreads();
-      if (round == 0 || !staged) {
-        // the row is gathered from L2 in batches: all references of a batch first, then their
-        // active words and descriptors, then the evaluations -- two round trips per batch
-        // instead of two per entry
+      if (round == 0 && staged) {
+        // Round 0 of a row that fits the staging area: gather it from L2 in batches -- all
+        // references of a batch first, then their active words and descriptors: two round
+        // trips per batch instead of two per entry -- and leave the active entries in shared
+        // memory; the evaluation loop below is the one every later round runs as well.
         for (int j0 = rb; j0 < re; j0 += blockDim.x * kRowBatch) {
           unsigned ref[kRowBatch], word[kRowBatch];
           int4 q0[kRowBatch];
@@ -1009,52 +1084,87 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
             const unsigned fam = ref[u] >> 29;
             const int slot = (int)(ref[u] & kSlotMask);
             const Family& f = P.fam[fam];
-            if (slot >= f.n_static) { ref[u] = 0xffffffffu; continue; }  // truncated by a restore (store.rs:320)
-            word[u] = __ldcg(&f.active[slot >> 5]);
+            if (slot >= f.n_static) continue;  // truncated by a restore (store.rs:320)
+            word[u] = (__ldcg(&f.active[slot >> 5]) >> (slot & 31)) & 1u;
             q0[u] = __ldg(&f.desc[fam == F_DJ ? 3 * (size_t)slot : (size_t)slot]);
           }
 #pragma unroll
           for (int u = 0; u < kRowBatch; ++u) {
-            const unsigned fam = ref[u] >> 29;
-            const int slot = (int)(ref[u] & kSlotMask);
-            bool keep = ref[u] != 0xffffffffu && ((word[u] >> (slot & 31)) & 1u);
-            if (round == 0 && staged) {
-              const unsigned m = __ballot_sync(0xffffffffu, keep);
-              if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nstage, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (keep) { const int idx = base + __popc(m & lanemask_lt()); s_ref[idx] = ref[u]; s_q0[idx] = q0[u]; }
-              }
-            }
-            if (keep && crawl && fam == F_BIN) crawl_note(c, &s_win, v, d0, q0[u]);
-            // (no epoch stamp here: a propagator shared by two dirty rows may run twice in an
-            // iteration, which changes nothing but the count, and the stamp would cost this
-            // row a further L2 round trip)
-            if (keep) {
-              if (fam == F_BIN) eval_loaded<SMEM>(c, F_BIN, slot, q0[u], make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
-              else eval_ref<SMEM>(c, fam, slot);
-              ++nprop;
+            const bool keep = word[u] != 0u;
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+              int base = 0;
+              if (lane == 0) base = atomicAdd(&s_nstage, __popc(m));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (keep) { const int idx = base + __popc(m & lanemask_lt()); s_ref[idx] = ref[u]; s_q0[idx] = q0[u]; }
             }
           }
         }
-      } else {
+      }
+      __syncthreads();
+      trace_seq(P, 150 + round);
+      if (staged) {
         const int n = s_nstage;
+#pragma unroll 1
         for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
           const unsigned ref = s_ref[idx];
+          if (ref == 0xffffffffu) continue;  // found entailed in an earlier round
+          const int4 q = s_q0[idx];
+          if (crawl && (ref >> 29) == F_BIN) crawl_note(c, &s_win, v, d0, q);
+          // (no epoch stamp: a propagator shared by two dirty rows may run twice in an
+          // iteration, which changes nothing but the count)
+          if (row_eval_entry<SMEM>(c, ref, q)) {
+            s_ref[idx] = 0xffffffffu;
+            s_unlink[atomicAdd(&s_nunlink, 1)] = ref;
+          }
+          ++nprop;
+        }
+      } else {
+        // a row longer than the staging area: gathered again in every round
+#pragma unroll 1
+        for (int j = rb + (int)threadIdx.x; j < re; j += (int)blockDim.x) {
+          const unsigned ref = __ldg(&P.adj[j]);
           const unsigned fam = ref >> 29;
           const int slot = (int)(ref & kSlotMask);
-          if (fam == F_BIN) {
-            const int4 q = s_q0[idx];
-            if (crawl) crawl_note(c, &s_win, v, d0, q);
-            eval_loaded<SMEM>(c, F_BIN, slot, q, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
-          } else {
-            eval_ref<SMEM>(c, fam, slot);
+          const Family& f = P.fam[fam];
+          if (slot >= f.n_static) continue;
+          const unsigned word = __ldcg(&f.active[slot >> 5]);
+          const int4 q = __ldg(&f.desc[fam == F_DJ ? 3 * (size_t)slot : (size_t)slot]);
+          if (!((word >> (slot & 31)) & 1u)) continue;
+          if (crawl && fam == F_BIN) crawl_note(c, &s_win, v, d0, q);
+          if (row_eval_entry<SMEM>(c, ref, q)) {
+            const unsigned bit = 1u << (slot & 31);
+            if (atomicAnd(&P.fam[F_BIN].active[slot >> 5], ~bit) & bit) tbuf_push(P, tb, ref);
           }
           ++nprop;
         }
       }
       __syncthreads();
+      trace_seq(P, 200 + round);
+      if (staged && s_nunlink > 0) {
+        // unlink what this round found entailed (store.rs:200-207).  The old bit comes back
+        // (a propagator shared by two dirty rows can be found entailed by both); four
+        // independent atomics per thread and trip keep their round trips overlapped.
+        const int n = s_nunlink;
+        for (int i0 = threadIdx.x; i0 < n; i0 += blockDim.x * 4) {
+          unsigned r4[4], old[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            r4[u] = i < n ? s_unlink[i] : 0xffffffffu;
+            old[u] = 0u;
+            if (r4[u] != 0xffffffffu) {
+              const int slot = (int)(r4[u] & kSlotMask);
+              old[u] = atomicAnd(&P.fam[F_BIN].active[slot >> 5], ~(1u << (slot & 31))) & (1u << (slot & 31));
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (old[u]) tbuf_push(P, tb, r4[u]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_nunlink = 0;
+      }
       if (crawl) {
         if (!crawl_jump(c, &s_win, v, d0)) {  // uniform across the CTA
           if (threadIdx.x == 0) set_failed(c);
@@ -1068,6 +1178,7 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
         s_before = a;
       }
       __syncthreads();
+      trace_seq(P, 300 + round);
       if (!s_moved || round + 1 >= kLocalRounds) break;
     }
   }
@@ -1076,8 +1187,8 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
 }
 
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_dirty_rows(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring) {
-  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(c, list, n_dirty, cur_epoch, ring);
+__device__ __forceinline__ unsigned expand_dirty_rows(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
+  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(c, list, n_dirty, cur_epoch, ring, tb);
   const Params& P = *c.P;
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
@@ -1304,6 +1415,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       c.bookkeep = true;
     }
     __syncthreads();
+    trace_mark1(P, iter, 0);
     // the spare set was read in the previous iteration and is written in the next one
     if (iter > 0 && blockIdx.x == 0)
       for (int w = threadIdx.x; w < W; w += blockDim.x) P.dirty_bits[(size_t)spare_buf * W + w] = 0u;
@@ -1389,7 +1501,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         skip = SMEM;
       }
       trace_mark1(P, iter, 2);
-      if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(c, list, n_dirty, cur_epoch, st.ring);
+      if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
     }
     if (sweep_now && !skip && st.my_chunks > 0) {
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep

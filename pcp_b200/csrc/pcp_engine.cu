@@ -776,6 +776,12 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
       for (int i = std::max(0, grid - 8); i < grid; ++i) std::fprintf(stderr, " %d:%llu(start %llu)", by[i].second, by[i].first, t[by[i].second * 8] - t0);
       std::fprintf(stderr, "\n");
     }
+    if (e->h_result()->iterations > 1 && t[kTraceSeq] > 0) {
+      std::fprintf(stderr, "[pcp trace]   cta0 row-local sequence (id:ns since first CTA start):");
+      for (unsigned long long i = 0; i < t[kTraceSeq] && i < 64; ++i)
+        std::fprintf(stderr, " %llu:%llu", t[kTraceSeq + 2 + 2 * i], t[kTraceSeq + 3 + 2 * i] - t0);
+      std::fprintf(stderr, "\n");
+    }
     if (e->h_result()->iterations > 1) {
       const char* n1[6] = {"it1 start", "it1 compacted", "it1 refreshed", "it1 rows/sweep done", "it1 barrier_arrive", "it1 barrier_leave"};
       for (int k = 0; k < 6; ++k) {
