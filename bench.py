@@ -217,8 +217,8 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     V = model.num_vars
 
-    def fresh_engine():
-        e = Engine(device=local_rank, timing=True, max_labels=1 << 16)
+    def fresh_engine(host_search=False):
+        e = Engine(device=local_rank, timing=True, max_labels=1 << 16, host_search=host_search)
         model.load_into(e)
         return e
 
@@ -267,6 +267,7 @@ def run_ours(args):
         torch.cuda.synchronize(device)
         e2e_s = time.perf_counter() - t0
         e2e = {"propagations": props_e2e, "seconds": e2e_s, "nodes": args.steps}
+        e2e_dev = None
         h2d, d2h = 0, 64 + 8 * V
     else:
         res = {}
@@ -281,19 +282,26 @@ def run_ours(args):
             res[mode] = device_timed_pass(e, args.steps, args.warmup, mode == "flush", torch, device)
             barrier()
             e.close()
-        # e2e through the C++ driver over the C ABI
-        e = fresh_engine()
-        stop = parallel.StopFlag(device) if world > 1 else None
-        barrier()
-        if world > 1:
-            out = parallel.sharded_search(e, rank, world, node_budget=args.warmup + args.steps, sync_every=64,
-                                          stop_flag=stop, warmup_nodes=args.warmup, parts_per_rank=1)
-            e2e = {"propagations": out["propagations"], "seconds": out["seconds"], "nodes": out["nodes"] - args.warmup}
-        else:
-            r, _ = e.search(node_limit=args.warmup + args.steps, all_solutions=True, warmup_nodes=args.warmup)
-            e2e = {"propagations": int(r.propagations), "seconds": float(r.seconds), "nodes": int(r.num_nodes) - args.warmup}
-        barrier()
-        e.close()
+        # e2e through the C++ driver over the C ABI, twice: the host-driven node loop (what a
+        # libpcp host does: one launch, one posted descriptor in, status + domains out per node)
+        # is the `e2e` key; the device-resident search (same C entry point, branching on the
+        # GPU, results copied back when the search stops) is reported beside it
+        def e2e_pass(host_search):
+            e = fresh_engine(host_search=host_search)
+            stop = parallel.StopFlag(device) if world > 1 else None
+            barrier()
+            if world > 1:
+                out = parallel.sharded_search(e, rank, world, node_budget=args.warmup + args.steps, sync_every=64,
+                                              stop_flag=stop, warmup_nodes=args.warmup, parts_per_rank=1)
+                res_ = {"propagations": out["propagations"], "seconds": out["seconds"], "nodes": out["nodes"] - args.warmup}
+            else:
+                r, _ = e.search(node_limit=args.warmup + args.steps, all_solutions=True, warmup_nodes=args.warmup)
+                res_ = {"propagations": int(r.propagations), "seconds": float(r.seconds), "nodes": int(r.num_nodes) - args.warmup}
+            barrier()
+            e.close()
+            return res_
+        e2e = e2e_pass(True)
+        e2e_dev = e2e_pass(False)
         h2d, d2h = 16, 64 + 8 * V  # one posted descriptor in, result header + domains out
 
     clocks = sampler.stop() if sampler else None
@@ -306,6 +314,9 @@ def run_ours(args):
     w = res["warm"]
     w_props, w_nodes, w_ms = reduce_sum(w["propagations"]), reduce_sum(w["nodes"]), reduce_max(w["ms"])
     e_props, e_nodes, e_s = reduce_sum(e2e["propagations"]), reduce_sum(e2e["nodes"]), reduce_max(e2e["seconds"])
+    if e2e_dev is not None:
+        d_props, d_nodes, d_s = (reduce_sum(e2e_dev["propagations"]), reduce_sum(e2e_dev["nodes"]),
+                                 reduce_max(e2e_dev["seconds"]))
     launches = int(reduce_sum(f["launches"]))
 
     if rank == 0:
@@ -338,7 +349,16 @@ def run_ours(args):
             "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s",
                     "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "ms_per_step": 1e3 * e_s * world / max(e_nodes, 1),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "path": "C++ search driver -> C ABI (pcp_restore/pcp_prop_alloc/pcp_consistency/pcp_domains_read/pcp_label), L2 not flushed"},
+                    "path": ("restore + pcp_consistency + pcp_domains_read per step through the C ABI (ctypes), L2 not flushed"
+                             if single_fixpoint else
+                             "host-driven node loop: C++ search driver -> C ABI (pcp_restore / pcp_prop_alloc / "
+                             "pcp_consistency / pcp_domains_read / pcp_label per node), wall clock, L2 not flushed")},
+            "e2e_device_search": (None if e2e_dev is None else {
+                "value": d_props / d_s if d_s > 0 else 0.0, "unit": "propagations/s",
+                "nodes_per_s": d_nodes / d_s if d_s > 0 else 0.0, "ms_per_step": 1e3 * d_s * world / max(d_nodes, 1),
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "path": "pcp_search_run with the device-resident DFS (pcp_burst_kernel): branching, label/restore and "
+                        "the fixpoints in one launch per budget slice; counters copied back when it stops"}),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,

@@ -77,6 +77,11 @@ enum pcp_prop_kind {
                                    engine can prove the restored state was a fixpoint
                                    (same domains/status; fewer propagations than
                                    store.rs:144-149)                                  */
+#define PCP_FLAG_HOST_SEARCH 2u /* pcp_search_* drive every node from the host through the
+                                   store surface (restore / prop_alloc / consistency /
+                                   domains_read / label, one launch and one D2H copy per
+                                   node) -- the loop a libpcp host runs -- instead of the
+                                   device-resident search                             */
 typedef struct pcp_config {
   int32_t device;      /* CUDA device ordinal                                        */
   uint32_t flags;      /* PCP_FLAG_*                                                 */

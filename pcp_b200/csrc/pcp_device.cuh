@@ -85,7 +85,8 @@ struct Result {
   unsigned long long propagations;
   unsigned decision;
   unsigned gen;          // barrier generation after the launch
-  unsigned pad[8];
+  unsigned seq;          // host copy only: launch sequence number, written last (the host polls it)
+  unsigned pad[7];
 };
 static_assert(sizeof(Result) == 64, "Result header is 64 bytes");
 
@@ -142,6 +143,9 @@ struct Params {
   int seed_dirty;             // incremental launch: dirty_bits[0] seeded by the host (count, may be 0)
   // ---- epilogue
   int2* snapshot_to;          // if not failed: copy of the fixpoint domains (next label slot)
+  Result* host_result;        // mapped pinned host memory: result header (+ domains behind it when
+  int host_dom;               //   host_dom = 1), stored by the kernel itself and published through
+  unsigned host_seq;          //   Result::seq, so the host polls instead of copying + synchronising
   // ---- debug: per-CTA phase timestamps (PCP_TRACE=1), 8 slots per CTA
   unsigned long long* trace;
 };
@@ -1635,8 +1639,17 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   if (blockIdx.x == 0) {
     // Branch::distribute takes a label right after an Unknown node (branch.rs:36-49): leave the
     // copy of the fixpoint domains in the next label slot so that pcp_label is free.
+    // (the last iteration of a fixpoint narrowed nothing anywhere, so this CTA's snapshot --
+    // refreshed at the start of that iteration -- is the store: no reload)
     if (P.snapshot_to && dec == D_FIXPOINT)
-      for (int v = threadIdx.x; v < P.V; v += blockDim.x) P.snapshot_to[v] = ldcg_dom(&P.dom[v]);
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) P.snapshot_to[v] = SMEM ? st.sdom[v] : ldcg_dom(&P.dom[v]);
+    if (P.host_result && P.host_dom) {  // the domains go straight to the host's mirror
+      int2* hd = reinterpret_cast<int2*>(P.host_result + 1);
+      const bool from_snapshot = SMEM && dec == D_FIXPOINT;
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) hd[v] = from_snapshot ? st.sdom[v] : ldcg_dom(&P.dom[v]);
+      __threadfence_system();
+    }
+    if (P.host_result) __syncthreads();
     if (threadIdx.x == 0) {
       Result r;
       r.failed = dec == D_FAILED;
@@ -1646,10 +1659,18 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       r.propagations = *(volatile unsigned long long*)&ctl->propagations;
       r.decision = dec;
       r.gen = st.gen;
+      r.seq = 0u;
       *P.result = r;
       ctl->epoch = epoch0 + iters + 1;
       ctl->iterations = iters;
       ctl->last_decision = dec;
+      if (P.host_result) {
+        Result* h = P.host_result;
+        h->failed = r.failed; h->trail_cnt = r.trail_cnt; h->iterations = r.iterations; h->epoch = r.epoch;
+        h->propagations = r.propagations; h->decision = r.decision; h->gen = r.gen;
+        __threadfence_system();
+        *(volatile unsigned*)&h->seq = P.host_seq;
+      }
     }
   }
 }
@@ -1740,9 +1761,12 @@ __device__ __forceinline__ void burst_host_step(const Params& P, const BurstPara
     const int bin_n = L->bin_n;
     const unsigned long long n = L->nodes;
     unsigned long long best = ~0ull;
-    for (int v = tid; v < P.V; v += blockDim.x) {  // one pass over the final domains
-      int2 d = ldcg_dom(&P.dom[v]);
-      if (scratch) scratch[v] = d;
+    // one pass over the final domains; at a fixpoint CTA 0's snapshot (`scratch`) already is
+    // the store -- the last iteration narrowed nothing -- so nothing is reloaded
+    const bool from_snapshot = scratch != nullptr && dec == D_FIXPOINT;
+    for (int v = tid; v < P.V; v += blockDim.x) {
+      int2 d = from_snapshot ? scratch[v] : ldcg_dom(&P.dom[v]);
+      if (scratch && !from_snapshot) scratch[v] = d;
       unsigned size = (unsigned)(d.y - d.x) + 1u;
       if (size > 1u) best = min(best, ((unsigned long long)size << 32) | (unsigned)v);
     }

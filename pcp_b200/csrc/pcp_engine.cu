@@ -19,6 +19,7 @@
 #include "../../include/pcp_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -107,6 +108,7 @@ struct pcp_engine {
   bool timing = false;
   int num_sms = 0;
   int max_smem_optin = 0;
+  size_t static_smem = 0;           // largest static shared memory of the persistent kernels
   std::string err;
 
   // variables
@@ -114,7 +116,9 @@ struct pcp_engine {
   size_t V = 0, V_uploaded = 0;
   char* d_block = nullptr;          // [Result | dom ...]
   size_t block_cap_vars = 0;
-  char* h_block = nullptr;          // pinned mirror of d_block
+  char* h_block = nullptr;          // pinned mirror of d_block (mapped: the fixpoint kernel stores into it)
+  char* h_block_dev = nullptr;      // its device-side address
+  unsigned host_seq = 0;            // sequence number of the last zero-copy result
   size_t h_block_cap_vars = 0;
   bool mirror_valid = false;        // h_block domains == device domains
   uint64_t dom_version = 1;         // bumped whenever the device domains may change
@@ -226,7 +230,7 @@ void ensure_var_capacity(pcp_engine* e, size_t nvars) {
   if (nvars > e->h_block_cap_vars) {
     size_t ncap = std::max<size_t>(nvars, e->h_block_cap_vars * 2 + 256);
     char* q = nullptr;
-    CUDA_CHECK(cudaMallocHost(&q, sizeof(Result) + ncap * sizeof(int2)));
+    CUDA_CHECK(cudaHostAlloc(&q, sizeof(Result) + ncap * sizeof(int2), cudaHostAllocMapped));
     if (e->h_block) {
       std::memcpy(q, e->h_block, sizeof(Result) + e->h_block_cap_vars * sizeof(int2));
       cudaFreeHost(e->h_block);
@@ -235,6 +239,9 @@ void ensure_var_capacity(pcp_engine* e, size_t nvars) {
     }
     e->h_block = q;
     e->h_block_cap_vars = ncap;
+    void* dp = nullptr;
+    CUDA_CHECK(cudaHostGetDevicePointer(&dp, q, 0));
+    e->h_block_dev = static_cast<char*>(dp);
   }
 }
 
@@ -674,8 +681,22 @@ void launch_persistent(const void* fn, int grid, void** args, size_t smem, cudaS
   else CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
 }
 
+struct HostProf {
+  double prepare = 0, launch = 0, wait = 0, total = 0;
+  unsigned long long n = 0;
+  ~HostProf() {
+    if (n && std::getenv("PCP_HOSTPROF"))
+      std::fprintf(stderr, "[pcp hostprof] %llu fixpoint calls: prepare %.2f us, launch API %.2f us, wait %.2f us, total %.2f us per call\n",
+                   n, 1e6 * prepare / n, 1e6 * launch / n, 1e6 * wait / n, 1e6 * total / n);
+  }
+};
+static HostProf g_hostprof;
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  const double hp0 = now_s();
   Params P = prepare(e);
+  const double hp1 = now_s();
   const size_t V = e->V;
   const bool incremental = (e->flags & PCP_FLAG_INCREMENTAL) && e->at_fixpoint;
   P.full_sweep = incremental ? 0 : 1;
@@ -723,28 +744,63 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   size_t nary_bytes = nary_smem_bytes(e);
   PCP_REQUIRE(nary_bytes <= (size_t)kRingBytes, "Distinct too wide for shared memory");
   size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
-  bool smem_dom = V > 0 && (size_t)kRingBytes + dom_bytes + 2048 <= (size_t)e->max_smem_optin;
+  bool smem_dom = V > 0 && (size_t)kRingBytes + dom_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin;
   size_t smem = (size_t)kRingBytes + (smem_dom ? dom_bytes : 0);
   P.smem_dom = smem_dom ? 1 : 0;
   const void* fn = smem_dom ? (const void*)pcp_fixpoint_kernel<true> : (const void*)pcp_fixpoint_kernel<false>;
-  CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
   static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (trace_on) {
     if (!e->d_trace) CUDA_CHECK(cudaMalloc(&e->d_trace, kTraceWords * sizeof(unsigned long long)));
     CUDA_CHECK(cudaMemsetAsync(e->d_trace, 0, kTraceWords * sizeof(unsigned long long), e->stream));
     P.trace = e->d_trace;
   }
+  // The result header (+ the domains when small) comes back without a copy or a stream
+  // synchronisation: the kernel's epilogue stores them into the mapped pinned mirror and
+  // publishes a sequence number last; the host polls that word.  (Timed or traced launches
+  // synchronise anyway.)
+  const bool eager_dom = V * sizeof(int2) <= (64u << 10);
+  const bool zero_copy = !trace_on && !e->timing && e->h_block_dev != nullptr;
+  if (zero_copy) {
+    P.host_result = reinterpret_cast<Result*>(e->h_block_dev);
+    P.host_dom = eager_dom ? 1 : 0;
+    P.host_seq = ++e->host_seq ? e->host_seq : ++e->host_seq;  // never 0
+  }
+  const double hp2 = now_s();
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   void* args[] = {&P};
   launch_persistent(fn, grid, args, smem, e->stream);
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+  const double hp3 = now_s();
   ++e->dom_version;
-  // status header (+ domains when small) in one D2H copy
-  const bool eager_dom = V * sizeof(int2) <= (64u << 10);
-  size_t bytes = sizeof(Result) + (eager_dom ? V * sizeof(int2) : 0);
-  CUDA_CHECK(cudaMemcpyAsync(e->h_block, e->d_block, bytes, cudaMemcpyDeviceToHost, e->stream));
-  CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  if (zero_copy) {
+    volatile unsigned* seq = &e->h_result()->seq;
+    for (unsigned long long spins = 1; *seq != P.host_seq; ++spins) {
+      if ((spins & 0xfffffull) == 0) {  // every ~1M polls: has the launch died?
+        cudaError_t q = cudaStreamQuery(e->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) CUDA_CHECK(q);
+        if (q == cudaSuccess && *seq != P.host_seq) PCP_FAIL(PCP_ERR_CUDA, "fixpoint kernel finished without publishing its result");
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  } else {
+    // status header (+ domains when small) in one D2H copy
+    size_t bytes = sizeof(Result) + (eager_dom ? V * sizeof(int2) : 0);
+    CUDA_CHECK(cudaMemcpyAsync(e->h_block, e->d_block, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+  }
   e->mirror_valid = eager_dom;
+  {
+    const double hp4 = now_s();
+    static unsigned long long skip = 0;
+    if (++skip > 10) {  // (the first calls build the CSR and upload the store)
+      g_hostprof.prepare += hp1 - hp0; g_hostprof.launch += hp3 - hp2; g_hostprof.wait += hp4 - hp3; g_hostprof.total += hp4 - hp0;
+      ++g_hostprof.n;
+    }
+  }
 
   if (trace_on) {
     std::vector<unsigned long long> t(kTraceWords);
@@ -872,6 +928,21 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     if (!coop) PCP_FAIL(PCP_ERR_CUDA, "device does not support cooperative launch");
     e->num_sms = prop.multiProcessorCount;
     e->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    {
+      // dynamic shared memory every persistent kernel may use = the opt-in maximum minus its own
+      // static part; configured once (an engine never lowers what another engine relies on)
+      const void* fns[4] = {(const void*)pcp_fixpoint_kernel<false>, (const void*)pcp_fixpoint_kernel<true>,
+                            (const void*)pcp_burst_kernel<false>, (const void*)pcp_burst_kernel<true>};
+      size_t max_static = 0;
+      for (const void* fn : fns) {
+        cudaFuncAttributes fa;
+        CUDA_CHECK(cudaFuncGetAttributes(&fa, fn));
+        max_static = std::max(max_static, fa.sharedSizeBytes);
+        CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)((size_t)e->max_smem_optin - fa.sharedSizeBytes)));
+      }
+      e->static_smem = max_static;
+    }
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreate(&e->ev0));
     CUDA_CHECK(cudaEventCreate(&e->ev1));
@@ -1120,7 +1191,7 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
   if (off) return 0;
   if (cfg->var_sel != 0 || cfg->val_sel != 0 || cfg->distributor != 0 || cfg->bb_mode != 0) return 0;
   if (e->V == 0 || e->V > (size_t)(1 << 20)) return 0;
-  if ((e->flags & PCP_FLAG_INCREMENTAL)) return 0;
+  if ((e->flags & (PCP_FLAG_INCREMENTAL | PCP_FLAG_HOST_SEARCH))) return 0;
   // the device trace keeps full domains for the traced nodes
   if (trace_capacity * e->V * sizeof(int2) > (size_t)1 << 30) return 0;
   return 1;
@@ -1225,11 +1296,10 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     for (int f = 0; f < 3; ++f) total += e->fam[f].n;
     int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 4095) / 4096));
     size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
-    bool smem_dom = (size_t)kRingBytes + dom_bytes + 2048 <= (size_t)e->max_smem_optin;
+    bool smem_dom = (size_t)kRingBytes + dom_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin;
     size_t smem = (size_t)kRingBytes + (smem_dom ? dom_bytes : 0);
     P.smem_dom = smem_dom ? 1 : 0;
     const void* fn = smem_dom ? (const void*)pcp_burst_kernel<true> : (const void*)pcp_burst_kernel<false>;
-    CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
     void* args[] = {&P, &B};
     launch_persistent(fn, grid, args, smem, e->stream);

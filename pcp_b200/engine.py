@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PCP_B200_LIB") or os.path.join(_HERE, "libpcp_b200.so")
 
 FLAG_INCREMENTAL = 1
+FLAG_HOST_SEARCH = 2
 
 # every symbol include/pcp_b200.h declares
 ABI_SYMBOLS = [
@@ -63,9 +64,10 @@ class Engine(EngineBase):
     _prefix = "pcp_"
 
     def __init__(self, device: int = 0, incremental: bool = False, max_labels: int = 0, tail_limit: int = 0,
-                 timing: bool = False):
+                 timing: bool = False, host_search: bool = False):
         self._lib = load_library()
-        cfg = Config(device, FLAG_INCREMENTAL if incremental else 0, max_labels, tail_limit)
+        flags = (FLAG_INCREMENTAL if incremental else 0) | (FLAG_HOST_SEARCH if host_search else 0)
+        cfg = Config(device, flags, max_labels, tail_limit)
         h = C.c_void_p()
         rc = self._lib.pcp_engine_create(C.byref(cfg), C.byref(h))
         if rc != 0:

@@ -101,8 +101,22 @@ def test_long_chain_many_iterations():
     assert dev2.consistency()[0] == -1
 
 
-def _compare_search(model, node_limit, dev_kw=None, all_solutions=True, **skw):
-    dev, ora = _engine(**(dev_kw or {})), _oracle()
+@pytest.mark.parametrize("n", [10300, 10700, 13000])
+def test_snapshot_capacity_boundary(n):
+    """Stores just below / above the size whose domains still fit the CTA's shared-memory
+    snapshot next to the TMA ring (both kernel variants, same results): a loose x_i < x_{i+1}
+    chain over n variables (two propagation waves) and 40 search nodes on it."""
+    m = models.chained_lt(n, 0, n + 5)
+    dev, ora = _engine(), _oracle(2)
+    m.load_into(dev)
+    m.load_into(ora)
+    assert dev.consistency()[0] == ora.consistency()[0] == 0
+    _assert_same_state(dev, ora)
+    _compare_search(m, 40, oracle_variant=2)
+
+
+def _compare_search(model, node_limit, dev_kw=None, all_solutions=True, oracle_variant=1, **skw):
+    dev, ora = _engine(**(dev_kw or {})), _oracle(oracle_variant)
     model.load_into(dev)
     model.load_into(ora)
     rd, td = dev.search(node_limit=node_limit, all_solutions=all_solutions, trace=node_limit or 100000,
@@ -140,6 +154,47 @@ def test_nqueens_1000_node_budget():
     rd, ro, dev, ora = _compare_search(models.nqueens(1000), 40)
     assert rd.propagations >= 40 * 1_498_500 * 0  # counts differ by schedule; just present
     _assert_same_state(dev, ora, check_active=True)
+
+
+def test_nqueens_deep_crawl():
+    """Deep DFS nodes on bounds-only domains: variables crawl across runs of assigned values
+    (x_neq_y.rs:82-93 one step at a time in the reference; the device jumps) -- 1500 nodes of
+    N=300 and 150 nodes of N=1000, per-node bit-exact incl. failed-node statuses."""
+    _compare_search(models.nqueens(300), 1000, oracle_variant=2)   # 2 = the oracle's flat variant (same results, faster)
+    _compare_search(models.nqueens(1000), 120, oracle_variant=2)
+
+
+@pytest.mark.parametrize("n,nodes", [(60, 400), (250, 150)])
+def test_host_driven_dfs_matches_oracle(n, nodes):
+    """The node loop driven from the host through the store surface alone (restore, post the
+    BinarySplit constraint, consistency, read domains, label) -- the path a libpcp host takes
+    (search/branching/branch.rs:36-55) -- instead of the device-resident search."""
+    from pcp_b200 import parallel
+    dev, ora = _engine(), _oracle()
+    m = models.nqueens(n)
+    m.load_into(dev)
+    m.load_into(ora)
+    stack = []
+    for k in range(nodes):
+        if k:
+            if not stack:
+                break
+            (dl, ol), d = stack.pop()
+            dev.restore(dl)
+            ora.restore(ol)
+            parallel.post_decision(dev, d)
+            parallel.post_decision(ora, d)
+        ds, os_ = dev.consistency()[0], ora.consistency()[0]
+        assert ds == os_, k
+        if ds == -1:
+            continue
+        _assert_same_state(dev, ora)
+        if ds == 0:
+            lo, hi = dev.domains()
+            var, val = parallel.select_branch(lo, hi)
+            labels = (dev.label(), ora.label())
+            stack.append((labels, (var, val, 1)))
+            stack.append((labels, (var, val, 0)))
 
 
 @pytest.mark.parametrize("n", [5, 8, 12, 30])
