@@ -437,7 +437,14 @@ __device__ __forceinline__ bool sweep_upd(const FamSweep& a, int var, int off, I
   const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
   if (lo) atomicMax(&a.dom_w[var].x, n.lo - off);
   if (hi) atomicMin(&a.dom_w[var].y, n.hi - off);
-  if (lo || hi) atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
+  if (lo || hi) {
+    // A variable is typically narrowed by several propagators of a sweep: look before marking.
+    // The look may be served by L1: within an iteration the bits of this set only go 0 -> 1
+    // (a stale 0 costs one redundant reduction), and the acquire of the iteration's barrier
+    // has invalidated whatever an earlier use of the buffer left there.
+    const unsigned bit = 1u << (var & 31);
+    if (!(__ldca(&a.next_bits[var >> 5]) & bit)) atomicOr(&a.next_bits[var >> 5], bit);
+  }
   return lo || hi;
 }
 __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
@@ -1546,7 +1553,9 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     if (iter <= 1 && P.trace) { __syncthreads(); if (iter == 0) trace_mark(P, 3); else trace_mark1(P, iter, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
     if (P.n_nary > 0 && !skip && (iter > 0 || full_sweep || n_dirty > 0)) {
-      for (int s = blockIdx.x; s < P.n_nary; s += gridDim.x) {
+      // dealt from the last CTA backwards: CTA 0 (prologue, posted and tail propagators) is
+      // the last to get one
+      for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
         if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
         unsigned ev = eval_distinct<SMEM>(c, s, st.ring, cur_bits, iter == 0 && full_sweep);
         if (threadIdx.x == 0) nprop += ev;
@@ -1846,7 +1855,10 @@ __device__ __forceinline__ void burst_host_step(const Params& P, const BurstPara
   __syncthreads();
   if (!L->run) return;
   if (L->root_pending) {
-    if (tid == 0) { L->root_pending = 0; L->cur_label = -1; bc->inl_slot = -1; bc->bin_n = L->bin_n; bc->cmd = 0; }
+    if (tid == 0) {
+      L->root_pending = 0; L->cur_label = -1; bc->inl_slot = -1; bc->bin_n = L->bin_n; bc->cmd = 0;
+      bc->n_labels = L->n_labels; bc->n_branch = L->n_branch; bc->nodes = L->nodes;  // the other CTAs' mirrors
+    }
     __syncthreads();
     return;
   }
@@ -1882,6 +1894,7 @@ __device__ __forceinline__ void burst_host_step(const Params& P, const BurstPara
       L->bin_n = slot + 1;
       L->n_labels = Lb + 1;
       L->cur_label = -1;
+      bc->n_labels = L->n_labels; bc->n_branch = L->n_branch; bc->nodes = L->nodes;  // the other CTAs' mirrors
     }
   }
   __syncthreads();
@@ -1914,31 +1927,96 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   st.gen = P.gen0;
   unsigned epoch = P.epoch0;
 
+  // Every CTA mirrors the few scalars of the search state that decide whether the next step is
+  // a plain descent to the left child (refreshed from `bc` at every device barrier below).
+  __shared__ int s_mlabels, s_mbranch, s_mbin;
+  __shared__ unsigned long long s_mnodes, s_sel[kWarps];
+  __shared__ unsigned s_tc;
   unsigned long long done = 0;
   if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, false, 0, 0, done);
+  bool fast = false;  // uniform across the grid
   while (true) {
-    grid_barrier(P, st.gen, 0, false, s_flags, 0);  // the posted node is visible to every CTA
-    if (threadIdx.x == 0) {
-      s_cmd = *(volatile int*)&bc->cmd;
-      s_slot = *(volatile int*)&bc->inl_slot;
-      s_bin_n = *(volatile int*)&bc->bin_n;
-      if (s_slot >= 0) {
-        s_inl.q[0] = __ldcg(&bc->inl_desc);
-        s_inl.q[1] = s_inl.q[2] = make_int4(0, 0, 0, 0);
-        s_inl.fam = F_BIN;
-        s_inl.slot = s_slot;
+    if (!fast) {
+      grid_barrier(P, st.gen, 0, false, s_flags, 0);  // the posted node is visible to every CTA
+      if (threadIdx.x == 0) {
+        s_cmd = *(volatile int*)&bc->cmd;
+        s_slot = *(volatile int*)&bc->inl_slot;
+        s_bin_n = *(volatile int*)&bc->bin_n;
+        s_mlabels = *(volatile int*)&bc->n_labels;
+        s_mbranch = *(volatile int*)&bc->n_branch;
+        s_mnodes = *(volatile unsigned long long*)&bc->nodes;
+        s_mbin = s_bin_n;
+        if (s_slot >= 0) {
+          s_inl.q[0] = __ldcg(&bc->inl_desc);
+          s_inl.q[1] = s_inl.q[2] = make_int4(0, 0, 0, 0);
+          s_inl.fam = F_BIN;
+          s_inl.slot = s_slot;
+        }
       }
+      if (SMEM) for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
+      __syncthreads();
+      if (s_cmd != 0) break;
     }
-    if (SMEM) for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
-    __syncthreads();
-    if (s_cmd != 0) break;
     unsigned iters = 0;
     const unsigned dec = fixpoint_node<SMEM>(P, st, epoch, s_bin_n, s_slot >= 0 ? 1 : 0, &s_inl, true, 0, true, iters);
     epoch += iters + 1;
     ++done;
     // the next sweep's descriptors can stream in while CTA 0 does the host's work
     if (threadIdx.x == 0 && dec != D_ITER_CAP) pre_issue(P, st);
+
+    // Fast descent.  At a fixpoint every CTA's snapshot is the store (the last iteration narrowed
+    // nothing), so every CTA can derive what CTA 0 is about to do: if the node is Unknown and
+    // neither a limit nor a capacity stops the search, the next node is its left child --
+    // FirstSmallestVar / MiddleVal on the snapshot, x <= val posted in the next tail slot
+    // (binary_split.rs:46-57, explored first: one_solution.rs:46-51).  Then nobody waits for
+    // CTA 0: the others apply the constraint to their snapshots and start the next sweep while
+    // CTA 0 does the bookkeeping of burst_host_step (trace, label, branch records, descriptor).
+    fast = false;
+    unsigned long long best = ~0ull;
+    if (SMEM && dec == D_FIXPOINT) {
+      if (threadIdx.x == 0) s_tc = __ldcg(&ctl->trail_cnt);
+      for (int v = threadIdx.x; v < P.V; v += blockDim.x) {
+        const int2 d = st.sdom[v];
+        const unsigned size = (unsigned)(d.y - d.x) + 1u;
+        if (size > 1u) best = min(best, ((unsigned long long)size << 32) | (unsigned)v);
+      }
+      for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if ((threadIdx.x & 31) == 0) s_sel[threadIdx.x >> 5] = best;
+      __syncthreads();
+      best = s_sel[0];
+      for (int w = 1; w < kWarps; ++w) best = min(best, s_sel[w]);
+      const bool unknown = (long long)s_tc != B.props_base + s_mbin;
+      const bool stop = B.node_limit && s_mnodes + 1 >= B.node_limit;
+      fast = unknown && best != ~0ull && !stop && done < B.node_budget && s_mlabels < B.max_labels &&
+             s_mbranch + 2 <= B.max_branches && s_mbin < B.bin_cap;
+    }
     if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, true, dec, iters, done);
+    if (fast) {
+      __syncthreads();  // everybody has read the mirrors (and CTA 0 is done with its snapshot)
+      if (threadIdx.x == 0) {
+        const int var = (int)(best & 0xffffffffu);
+        const int2 d = st.sdom[var];
+        const int val = (d.x + d.y) / 2;  // MiddleVal: truncating division
+        s_inl.q[0] = make_int4((int)((B_LESS << 28) | (unsigned)var), 0, -1, val + 1);  // x <= val
+        if (blockIdx.x == 0) {  // what the bookkeeper posted must be what everybody derived
+          const int4 posted = __ldcg(&bc->inl_desc);
+          const int4 mine = s_inl.q[0];
+          if (!s_local.run || *(volatile int*)&bc->inl_slot != s_mbin || posted.x != mine.x || posted.y != mine.y ||
+              posted.z != mine.z || posted.w != mine.w)
+            s_local.err = 3;
+        }
+        s_inl.q[1] = s_inl.q[2] = make_int4(0, 0, 0, 0);
+        s_inl.fam = F_BIN;
+        s_inl.slot = s_mbin;
+        s_slot = s_mbin;
+        s_bin_n = s_mbin + 1;
+        s_mbin += 1;
+        s_mlabels += 1;
+        s_mbranch += 1;
+        s_mnodes += 1;
+      }
+      __syncthreads();
+    }
   }
   // drain the chunks that were pre-issued for a node that will not run in this launch
   if (threadIdx.x >> 5 > 0 && st.my_chunks > 0) {

@@ -1321,6 +1321,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     e->at_fixpoint = false;
     ++e->dom_version;
     if (bc.err == 2) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
+    if (bc.err == 3) PCP_FAIL(PCP_ERR_CUDA, "device search: the bookkeeping CTA and the grid derived different branching decisions");
     if (bc.err) PCP_FAIL(PCP_ERR_NOMEM, "device search: label / branch / tail capacity exceeded (pcp_config.max_labels)");
     res->status = bc.status;
     res->err = bc.err;
