@@ -437,14 +437,9 @@ __device__ __forceinline__ bool sweep_upd(const FamSweep& a, int var, int off, I
   const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
   if (lo) atomicMax(&a.dom_w[var].x, n.lo - off);
   if (hi) atomicMin(&a.dom_w[var].y, n.hi - off);
-  if (lo || hi) {
-    // A variable is typically narrowed by several propagators of a sweep: look before marking.
-    // The look may be served by L1: within an iteration the bits of this set only go 0 -> 1
-    // (a stale 0 costs one redundant reduction), and the acquire of the iteration's barrier
-    // has invalidated whatever an earlier use of the buffer left there.
-    const unsigned bit = 1u << (var & 31);
-    if (!(__ldca(&a.next_bits[var >> 5]) & bit)) atomicOr(&a.next_bits[var >> 5], bit);
-  }
+  // (fire-and-forget: looking the bit up first was measured slower -- the look is a dependent
+  // load on the update path, the reduction is not)
+  if (lo || hi) atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
   return lo || hi;
 }
 __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
@@ -717,9 +712,8 @@ __device__ __forceinline__ bool hs_contains(const volatile int* tab, unsigned ma
 //   int2 ops[k]; int2 iv[k] (view-space lo/hi); int tab[tabsz];
 // Returns 1 if the propagator was evaluated (thread 0 only), else 0.
 template <bool SMEM>
-__device__ __noinline__ unsigned eval_distinct(const Ctx& c, int slot, char* smem_nary, const uint32_t* cur_bits,
-                                               bool unconditional) {
-  const Params& P = *c.P;
+__device__ __forceinline__ unsigned eval_distinct(const Params& P, const Ctx& c, int slot, char* smem_nary, const uint32_t* cur_bits,
+                                                  bool unconditional) {
   const int b = __ldg(&P.nary_ptr[slot]), e = __ldg(&P.nary_ptr[slot + 1]);
   const int k = e - b;
   int2* ops = reinterpret_cast<int2*>(smem_nary);
@@ -960,9 +954,8 @@ __device__ __forceinline__ void crawl_note(const Ctx& c, CrawlWin* w, int v, int
 // After the round (every thread of the CTA): move the bounds of v past the forbidden values.
 // `d` is the domain the windows are anchored at.  Returns false when every value of the
 // domain is forbidden (the reference ends with two equal singletons: failure).
-__device__ __forceinline__ bool crawl_jump(Ctx& c, CrawlWin* w, int v, int2 d) {
+__device__ __forceinline__ bool crawl_jump(const Params& P, Ctx& c, CrawlWin* w, int v, int2 d) {
   __shared__ int2 s_steps;
-  const Params& P = *c.P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (warp < 2) {  // warp 0: steps lo takes upwards; warp 1: steps hi takes downwards
     const unsigned word = w->bm[warp][lane];
@@ -994,14 +987,14 @@ __device__ __forceinline__ bool crawl_jump(Ctx& c, CrawlWin* w, int v, int2 d) {
 // when the propagator is entailed: the caller clears its active bit -- with the old bit
 // returned, because a propagator shared by two dirty rows can be found entailed twice -- for
 // a whole batch at once, so that the round trips of those atomics overlap.
-__device__ __forceinline__ bool row_upd(const Ctx& c, int var, int off, IV o, IV n) {
+__device__ __forceinline__ bool row_upd(const Params& P, const Ctx& c, int var, int off, IV o, IV n) {
   const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
-  if (lo) { atomicMax(&c.P->dom[var].x, n.lo - off); atomicMax(&c.sdom[var].x, n.lo - off); }
-  if (hi) { atomicMin(&c.P->dom[var].y, n.hi - off); atomicMin(&c.sdom[var].y, n.hi - off); }
+  if (lo) { atomicMax(&P.dom[var].x, n.lo - off); atomicMax(&c.sdom[var].x, n.lo - off); }
+  if (hi) { atomicMin(&P.dom[var].y, n.hi - off); atomicMin(&c.sdom[var].y, n.hi - off); }
   if (lo || hi) atomicOr(&c.next_bits[var >> 5], 1u << (var & 31));
   return lo || hi;
 }
-__device__ __forceinline__ bool row_eval_neq(const Ctx& c, int4 q) {
+__device__ __forceinline__ bool row_eval_neq(const Params& P, const Ctx& c, int4 q) {
   const int xv = (int)((unsigned)q.x & kConstVar28);
   const int2 dx = c.sdom[xv], dy = c.sdom[q.z];
   const IV x{dx.x + q.y, dx.y + q.y}, y{dy.x + q.w, dy.y + q.w};
@@ -1013,8 +1006,8 @@ __device__ __forceinline__ bool row_eval_neq(const Ctx& c, int4 q) {
     if (nx.lo == y.lo) nx.lo++; else if (nx.hi == y.lo) nx.hi--;
   }
   if (ny.lo > ny.hi || nx.lo > nx.hi || (nx.lo == ny.hi && nx.hi == ny.lo)) { set_failed(c); return false; }
-  bool ch = row_upd(c, q.z, q.w, y, ny);
-  ch |= row_upd(c, xv, q.y, x, nx);
+  bool ch = row_upd(P, c, q.z, q.w, y, ny);
+  ch |= row_upd(P, c, xv, q.y, x, nx);
   if (ch) c.flags[0] = 1;
   return nx.hi < ny.lo || ny.hi < nx.lo;
 }
@@ -1037,11 +1030,11 @@ __device__ __forceinline__ void tbuf_push(const Params& P, TrailBuf* tb, unsigne
 // per kernel and stays warm in the instruction cache across rounds).  Returns true when the
 // inline XNeqY path found the propagator entailed (the caller unlinks it).
 template <bool SMEM>
-__device__ __forceinline__ bool row_eval_entry(Ctx& c, unsigned ref, int4 q) {
+__device__ __forceinline__ bool row_eval_entry(const Params& P, Ctx& c, unsigned ref, int4 q) {
   const unsigned fam = ref >> 29;
   const int slot = (int)(ref & kSlotMask);
   if (fam == F_BIN) {
-    if (SMEM && is_plain_neq(q)) return row_eval_neq(c, q);
+    if (SMEM && is_plain_neq(q)) return row_eval_neq(P, c, q);
     eval_loaded<SMEM>(c, F_BIN, slot, q, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
   } else {
     eval_ref<SMEM>(c, fam, slot);
@@ -1050,8 +1043,7 @@ __device__ __forceinline__ bool row_eval_entry(Ctx& c, unsigned ref, int4 q) {
 }
 
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
-  const Params& P = *c.P;
+__device__ __forceinline__ unsigned expand_rows_local(const Params& P, Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
   __shared__ int2 s_before;
   __shared__ int s_nstage, s_nunlink, s_moved;
   __shared__ CrawlWin s_win;
@@ -1124,7 +1116,7 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
           if (crawl && (ref >> 29) == F_BIN) crawl_note(c, &s_win, v, d0, q);
           // (no epoch stamp: a propagator shared by two dirty rows may run twice in an
           // iteration, which changes nothing but the count)
-          if (row_eval_entry<SMEM>(c, ref, q)) {
+          if (row_eval_entry<SMEM>(P, c, ref, q)) {
             s_ref[idx] = 0xffffffffu;
             s_unlink[atomicAdd(&s_nunlink, 1)] = ref;
           }
@@ -1143,7 +1135,7 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
           const int4 q = __ldg(&f.desc[fam == F_DJ ? 3 * (size_t)slot : (size_t)slot]);
           if (!((word >> (slot & 31)) & 1u)) continue;
           if (crawl && fam == F_BIN) crawl_note(c, &s_win, v, d0, q);
-          if (row_eval_entry<SMEM>(c, ref, q)) {
+          if (row_eval_entry<SMEM>(P, c, ref, q)) {
             const unsigned bit = 1u << (slot & 31);
             if (atomicAnd(&P.fam[F_BIN].active[slot >> 5], ~bit) & bit) tbuf_push(P, tb, ref);
           }
@@ -1177,7 +1169,7 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
         if (threadIdx.x == 0) s_nunlink = 0;
       }
       if (crawl) {
-        if (!crawl_jump(c, &s_win, v, d0)) {  // uniform across the CTA
+        if (!crawl_jump(P, c, &s_win, v, d0)) {  // uniform across the CTA
           if (threadIdx.x == 0) set_failed(c);
           break;
         }
@@ -1198,9 +1190,8 @@ __device__ __forceinline__ unsigned expand_rows_local(Ctx& c, const int* list, i
 }
 
 template <bool SMEM>
-__device__ __forceinline__ unsigned expand_dirty_rows(Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
-  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(c, list, n_dirty, cur_epoch, ring, tb);
-  const Params& P = *c.P;
+__device__ __forceinline__ unsigned expand_dirty_rows(const Params& P, Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
+  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(P, c, list, n_dirty, cur_epoch, ring, tb);
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * kWarps;
@@ -1512,7 +1503,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         skip = SMEM;
       }
       trace_mark1(P, iter, 2);
-      if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
+      if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(P, c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
     }
     if (sweep_now && !skip && st.my_chunks > 0) {
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep
@@ -1557,7 +1548,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       // the last to get one
       for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
         if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-        unsigned ev = eval_distinct<SMEM>(c, s, st.ring, cur_bits, iter == 0 && full_sweep);
+        unsigned ev = eval_distinct<SMEM>(P, c, s, st.ring, cur_bits, iter == 0 && full_sweep);
         if (threadIdx.x == 0) nprop += ev;
       }
     }

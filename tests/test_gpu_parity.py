@@ -465,3 +465,37 @@ def test_sum_capacity_constraint_search():
     m.add(models.X_LESS_Y, ops)                             # x_i < x_{i+1} + 1
     rd, _, _, _ = _compare_search(m, 400)
     assert rd.num_nodes == 71 and rd.num_solution == 3 and rd.num_failed_node == 33
+
+
+@pytest.mark.parametrize("slice_nodes", [1, 5, 64])
+def test_resumable_search_slices_match_one_shot(slice_nodes):
+    """pcp_search_open/step/close in budget slices (the multi-GPU driver's pattern: the device
+    search stops and resumes at arbitrary nodes, mixing barrier steps and fast descents) visits
+    the same tree as one pcp_search_run: node, failure and solution counts (n-queens N=8: 92
+    solutions, all_solution.rs:67-74)."""
+    m = models.nqueens(8)
+    one = _engine()
+    m.load_into(one)
+    r1, _ = one.search(all_solutions=True)
+    dev = _engine()
+    m.load_into(dev)
+    h = dev.search_open(all_solutions=True)
+    res = None
+    for _ in range(100000):
+        res = h.step(slice_nodes)
+        if res.status != 0:
+            break
+    h.close()
+    assert res is not None and res.status == r1.status == 2
+    assert (res.num_nodes, res.num_solution, res.num_failed_node) == (r1.num_nodes, r1.num_solution, r1.num_failed_node)
+    assert res.num_solution == 92
+
+
+def test_sharded_search_single_rank_covers_the_tree():
+    """pcp_b200.parallel on the device engine (world = 1): the frontier's subtrees together hold
+    every solution of n-queens N=7 (40, all_solution.rs:67-74)."""
+    from pcp_b200 import parallel
+    dev = _engine()
+    models.nqueens(7).load_into(dev)
+    out = parallel.sharded_search(dev, 0, 1, node_budget=10**6, sync_every=50, parts_per_rank=6)
+    assert out["solutions"] == 40 and out["subtrees"] == out["frontier"] >= 6
