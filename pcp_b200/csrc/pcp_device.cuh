@@ -39,6 +39,8 @@ constexpr int kRingBytes = kStages * kStageBytes;
 constexpr int kGroupsBin = 4, kGroupsTer = 2;
 constexpr int kChunkBin = kConsumerWarps * 32 * kGroupsBin;  // 1920 * 16 B = 30720 B
 constexpr int kChunkTer = kConsumerWarps * 32 * kGroupsTer;  // 960 * 16 B + 960 * 8 B
+constexpr int kGroupsBinC = 8;           // compact 8-byte binary descriptors (Family::cdesc): twice the groups per stage
+constexpr int kChunkBinC = kConsumerWarps * 32 * kGroupsBinC;  // 3840 * 8 B = 30720 B
 constexpr int kChunkDj = 480;           // 480 * 48 B = 23040 B
 static_assert(kChunkBin * 16 <= kStageBytes && kChunkTer * 16 <= 16384 && kChunkTer * 8 <= kStageBytes - 16384, "stage too small");
 constexpr int kTerPlaneB = 16384;       // offset of the z plane inside a stage
@@ -99,6 +101,8 @@ struct Family {
   int n_static;         // [0, n_static) are covered by the CSR; [n_static, n) is the tail
   int all_plain;        // 1: no descriptor in [0, n_static) has a Constant or Sum operand
   int kind_mask;        // bit k: a descriptor of kind k may sit in [0, n_static) (over-approximation after restores)
+  const uint2* cdesc;   // BIN: 8-byte copies {xvar | yvar << 16, (u16)xoff | yoff << 16} of [0, n_static) when all of
+                        // them are XNeqY over plain variables with 16-bit ids / offsets, else nullptr
 };
 
 struct InlineProp {     // a propagator posted since the last launch, carried in the launch
@@ -235,7 +239,8 @@ struct ChunkMap {
 __device__ __forceinline__ constexpr int chunk_props(int fam) { return fam == 0 ? kChunkBin : (fam == 1 ? kChunkTer : kChunkDj); }
 __device__ __forceinline__ ChunkMap chunk_map(const Params& P) {
   ChunkMap m;
-  m.nch[0] = (P.fam[0].n_static + kChunkBin - 1) / kChunkBin;
+  const int cb = P.fam[0].cdesc ? kChunkBinC : kChunkBin;
+  m.nch[0] = (P.fam[0].n_static + cb - 1) / cb;
   m.nch[1] = (P.fam[1].n_static + kChunkTer - 1) / kChunkTer;
   m.nch[2] = (P.fam[2].n_static + kChunkDj - 1) / kChunkDj;
   m.total = m.nch[0] + m.nch[1] + m.nch[2];
@@ -268,6 +273,7 @@ __device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void* src, unsign
 struct FamSweep {
   const int4* desc;
   const int2* descB;
+  const uint2* cdesc;    // compact binary stream (or nullptr)
   const uint32_t* active;
   const int2* dom;
   int n;                 // propagators covered (n_static)
@@ -326,6 +332,13 @@ __device__ __forceinline__ void trail_flush(const Params& P, TrailBuf* tb) {
 
 template <int FAM>
 __device__ __forceinline__ void producer_issue(const FamSweep& a, int g, uint32_t stage, uint32_t full) {
+  if (FAM == F_BIN && a.cdesc) {  // compact stream: 8 B per descriptor, twice the descriptors per stage
+    const int cbase = g * kChunkBinC;
+    const unsigned bytes = ((unsigned)min(kChunkBinC, a.n - cbase) * 8u + 15u) & ~15u;
+    mbar_expect_tx_s(full, bytes);
+    bulk_g2s_s(stage, a.cdesc + cbase, bytes, full);
+    return;
+  }
   const int base = g * chunk_props(FAM);
   const int cnt = min(chunk_props(FAM), a.n - base);
   if (FAM == F_BIN) {
@@ -375,6 +388,19 @@ __device__ __forceinline__ int2 rd_plain(uint32_t sdom_s, const int2* dom, int v
 // consecutive and start at a multiple of their count, so the words are one aligned vector
 // load; loaded one chunk ahead so that the L2 round trip is off the critical path of the sweep.
 struct ActiveWords { unsigned w[4]; };
+struct ActiveWords8 { unsigned w[8]; };
+__device__ __forceinline__ ActiveWords8 load_active8(const uint32_t* active, int base, int n) {
+  ActiveWords8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.w[i] = 0u;
+  if (base < n) {
+    const uint4* p = reinterpret_cast<const uint4*>(active + (base >> 5));
+    const uint4 v0 = __ldcg(p), v1 = __ldcg(p + 1);
+    a.w[0] = v0.x; a.w[1] = v0.y; a.w[2] = v0.z; a.w[3] = v0.w;
+    a.w[4] = v1.x; a.w[5] = v1.y; a.w[6] = v1.z; a.w[7] = v1.w;
+  }
+  return a;
+}
 template <int G>
 __device__ __forceinline__ ActiveWords load_active(const uint32_t* active, int base, int n) {
   ActiveWords a;
@@ -555,6 +581,86 @@ __device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, uint4
     if (lane == 0) mbar_arrive_s(r.empty);
     ring_advance(r);
     aw = nxt;
+    base = nbase;
+  }
+  return nprop;
+}
+
+// The lean binary sweep over the compact stream (Family::cdesc): every static descriptor is an
+// XNeqY over plain variables and fits 8 bytes, so a 32 KB stage holds 3840 of them and every
+// consumer warp owns 256 consecutive ones (eight groups = eight words of the `active` set) per
+// chunk -- half the bytes from HBM / L2 per propagation and half the per-chunk overhead.
+template <bool SMEM>
+__device__ __noinline__ unsigned sweep_bin_compact(const Ctx& c, const FamSweep a, uint4 aw4a, uint4 aw4b) {
+  constexpr int G = kGroupsBinC;
+  ActiveWords8 aw;
+  aw.w[0] = aw4a.x; aw.w[1] = aw4a.y; aw.w[2] = aw4a.z; aw.w[3] = aw4a.w;
+  aw.w[4] = aw4b.x; aw.w[5] = aw4b.y; aw.w[6] = aw4b.z; aw.w[7] = aw4b.w;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    if (lane == 0) sweep_produce<F_BIN>(a);
+    return 0u;
+  }
+  const unsigned lane_bit = 1u << lane;
+  const uint32_t lane_off = (uint32_t)((warp - 1) * (32 * G) + lane) * 8u;
+  const int stride = a.workers * kChunkBinC;
+  int base = a.g0 * kChunkBinC + (warp - 1) * (32 * G);  // this warp's first descriptor of the chunk
+  if (!a.have_aw) aw = load_active8(a.active, base, a.n);
+  RingPos r = ring_pos(a);
+  unsigned nprop = 0;
+  for (int i = 0; i < a.cnt; ++i) {
+    const int nbase = base + stride;
+    ActiveWords8 nxt;
+#pragma unroll
+    for (int g = 0; g < G; ++g) nxt.w[g] = 0u;
+    if (i + 1 < a.cnt) nxt = load_active8(a.active, nbase, a.n);
+    const int rem = a.n - base;
+    if (rem < 32 * G) {  // last chunk of the family
+#pragma unroll
+      for (int g = 0; g < G; ++g) aw.w[g] &= tail_mask(rem - 32 * g);
+    }
+    const uint32_t d_s = r.stage + lane_off;
+    mbar_wait_s(r.full, r.ph);
+#pragma unroll
+    for (int g = 0; g < G; ++g) nprop += __popc(aw.w[g]);
+    // two half-batches of four groups: the register budget of the 16-byte loop, half its
+    // per-chunk overhead
+#pragma unroll
+    for (int h = 0; h < G; h += 4) {
+      int2 d[4], dx[4], dy[4];
+      unsigned need = 0u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        d[g] = make_int2(0, 0);
+        if (aw.w[h + g] & lane_bit) d[g] = lds_dom(d_s + 256u * (h + g));
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        dx[g] = rd_plain<SMEM>(a.sdom_s, a.dom, (int)((unsigned)d[g].x & 0xffffu));
+        dy[g] = rd_plain<SMEM>(a.sdom_s, a.dom, (int)((unsigned)d[g].x >> 16));
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int xo = (int)(short)((unsigned)d[g].y & 0xffffu), yo = d[g].y >> 16;
+        const IV x{dx[g].x + xo, dx[g].y + xo}, y{dy[g].x + yo, dy[g].y + yo};
+        if ((aw.w[h + g] & lane_bit) && !bin_is_noop(B_NEQ, x, y)) need |= 1u << g;
+      }
+      if (need) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (!((need >> g) & 1u)) continue;
+          const int xo = (int)(short)((unsigned)d[g].y & 0xffffu), yo = d[g].y >> 16;
+          const IV x{dx[g].x + xo, dx[g].y + xo}, y{dy[g].x + yo, dy[g].y + yo};
+          const int4 full = make_int4((int)((B_NEQ << 28) | ((unsigned)d[g].x & 0xffffu)), xo, (int)((unsigned)d[g].x >> 16), yo);
+          sweep_neq_update(c, a, base + 32 * (h + g) + lane, full, x, y);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_s(r.empty);
+    ring_advance(r);
+#pragma unroll
+    for (int g = 0; g < G; ++g) aw.w[g] = nxt.w[g];
     base = nbase;
   }
   return nprop;
@@ -1288,6 +1394,7 @@ __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& s
   FamSweep a;
   a.desc = P.fam[fam].desc;
   a.descB = P.fam[fam].descB;
+  a.cdesc = fam == F_BIN ? P.fam[fam].cdesc : nullptr;
   a.active = P.fam[fam].active;
   a.dom = P.dom;
   a.n = P.fam[fam].n_static;
@@ -1394,13 +1501,23 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
   }
   ActiveWords aw;
   aw.w[0] = aw.w[1] = aw.w[2] = aw.w[3] = 0u;
+  uint4 awc0 = make_uint4(0u, 0u, 0u, 0u), awc1 = awc0;  // compact binary stream: eight words
+  const bool compact = P.fam[0].cdesc != nullptr;
   // the active words of this CTA's first chunk: prefetched while the prologue settles
   const int fam_first = st.fam_cnt[0] > 0 ? 0 : (st.fam_cnt[1] > 0 ? 1 : 2);
   if (warp > 0 && st.my_chunks > 0 && full_sweep && fam_first < 2) {
-    if (fam_first == 0)
+    if (fam_first == 0 && compact) {
+      const int base = st.fam_g0[0] * kChunkBinC + (warp - 1) * 32 * kGroupsBinC;
+      if (base < P.fam[0].n_static) {
+        const uint4* p = reinterpret_cast<const uint4*>(P.fam[0].active + (base >> 5));
+        awc0 = __ldcg(p);
+        awc1 = __ldcg(p + 1);
+      }
+    } else if (fam_first == 0) {
       aw = load_active<kGroupsBin>(P.fam[0].active, st.fam_g0[0] * kChunkBin + (warp - 1) * 32 * kGroupsBin, P.fam[0].n_static);
-    else
+    } else {
       aw = load_active<kGroupsTer>(P.fam[1].active, st.fam_g0[1] * kChunkTer + (warp - 1) * 32 * kGroupsTer, P.fam[1].n_static);
+    }
   }
   unsigned iter = 0, dec, nprop = 0;
   int cur_buf = 0, next_buf = 1;
@@ -1522,7 +1639,8 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 0;
         const bool lean = P.fam[0].all_plain && P.fam[0].kind_mask == (1 << B_NEQ);
-        n += lean ? sweep_bin<SMEM, true>(c, a, aw4) : sweep_bin<SMEM, false>(c, a, aw4);
+        if (compact) n += sweep_bin_compact<SMEM>(c, a, awc0, awc1);
+        else n += lean ? sweep_bin<SMEM, true>(c, a, aw4) : sweep_bin<SMEM, false>(c, a, aw4);
         seq += a.cnt;
       }
       if (st.fam_cnt[1] > 0) {

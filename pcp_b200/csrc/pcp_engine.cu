@@ -85,6 +85,8 @@ struct HostFamily {
   int static_kind_mask = 0;          // ... among the descriptors covered by the CSR (over-approximation)
   DevBuf<int4> d_desc;
   DevBuf<int2> d_descB;
+  DevBuf<uint2> d_cdesc;    // BIN only: compact 8-byte copies of the static descriptors (see build_csr)
+  size_t n_cdesc = 0;       // descriptors covered by d_cdesc (0: none / not compactable)
   DevBuf<uint32_t> d_active, d_stamp;
   int width = 1;
 };
@@ -478,6 +480,32 @@ void build_csr(pcp_engine* e) {
     CUDA_CHECK(cudaMemcpyAsync(e->d_adj.p, adj.data(), adj.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
   CUDA_CHECK(cudaStreamSynchronize(e->stream));  // host vectors go out of scope
   for (int f = 0; f < 3; ++f) { e->fam[f].n_static = e->fam[f].n; e->fam[f].static_kind_mask = e->fam[f].kind_mask; }
+  // Compact stream for the lean binary sweep: when every static binary descriptor is an XNeqY
+  // over plain variables with 16-bit variable ids and offsets (the n-queens / pairwise-distinct
+  // stores), the sweep reads an 8-byte copy -- {xvar | yvar << 16, (u16)xoff | yoff << 16} --
+  // and half the bytes cross HBM / L2.  The 16-byte descriptors stay the reference copy (rows,
+  // tail, generic loop).
+  {
+    HostFamily& hb = e->fam[F_BIN];
+    hb.n_cdesc = 0;
+    static const bool no_compact = std::getenv("PCP_NO_COMPACT") != nullptr;  // measurement switch
+    bool ok = !no_compact && hb.n > 0 && V <= 65536 && hb.first_nonplain >= hb.n && hb.static_kind_mask == (1 << B_NEQ);
+    std::vector<uint2> cd;
+    if (ok) {
+      cd.resize(hb.n);
+      for (size_t i = 0; i < hb.n && ok; ++i) {
+        const int4& d = hb.desc[i];
+        ok = d.y >= -32768 && d.y <= 32767 && d.w >= -32768 && d.w <= 32767;
+        cd[i] = make_uint2(((unsigned)d.x & 0xffffu) | ((unsigned)d.z << 16), ((unsigned)d.y & 0xffffu) | ((unsigned)d.w << 16));
+      }
+    }
+    if (ok) {
+      hb.d_cdesc.reserve(hb.n, e->stream);
+      CUDA_CHECK(cudaMemcpyAsync(hb.d_cdesc.p, cd.data(), hb.n * sizeof(uint2), cudaMemcpyHostToDevice, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      hb.n_cdesc = hb.n;
+    }
+  }
   e->csr_built = true;
 }
 
@@ -605,6 +633,7 @@ Params prepare(pcp_engine* e) {
     df.n_static = (int)hf.n_static;
     df.all_plain = hf.first_nonplain >= hf.n_static ? 1 : 0;
     df.kind_mask = hf.static_kind_mask;
+    df.cdesc = (f == F_BIN && hf.n_cdesc >= hf.n_static && hf.n_static > 0) ? hf.d_cdesc.p : nullptr;
     P.new_first[f] = (int)hf.active_set;
     P.new_last[f] = (int)hf.n;
     if (hf.active_set < hf.n && hf.active_set < hf.n_static) sync0 = true;  // bits other CTAs will read
@@ -970,7 +999,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (int f = 0; f < 3; ++f) {
-    e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
+    e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_cdesc.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
   }
   e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_active.free();
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
