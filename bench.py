@@ -175,7 +175,6 @@ def device_timed_pass(engine, steps, warmup, flush, torch, device):
 
 
 def run_ours(args):
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from pcp_b200 import Engine, parallel
@@ -368,7 +367,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -430,17 +429,38 @@ def run_reference(args):
         "impl": "reference",
         "metric": "propagations/s (and nodes/s) of the per-node propagation fixpoint",
         "value": cpu["value"], "unit": "propagations/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
-        "steps": steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": args.warmup,
+        "ms_per_step": (1e3 / cpu["nodes_per_s"]) if cpu["nodes_per_s"] else None,  # whole-job: all replicas
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
         "config": {"workload": desc, "step": "one search node = one Consistency::consistency fixpoint"},
         "nodes_per_s": cpu["nodes_per_s"],
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": "propagations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    # stdout carries exactly one JSON line: whatever a library prints on file descriptor 1 (NCCL's
+    # version banner, torchrun notices of child ranks) is sent to stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
