@@ -1564,22 +1564,6 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       }
       __syncthreads();
     }
-    // older tail propagators: CTA 0, every iteration (inline ones were just handled)
-    if (blockIdx.x == 0) {
-      unsigned n = 0;
-      for (unsigned fam = 0; fam < 3; ++fam) {
-        const Family& f = P.fam[fam];
-        const int fn = fam == F_BIN ? bin_n : f.n;
-        for (int p = f.n_static + threadIdx.x; p < fn; p += blockDim.x) {
-          bool is_inl = false;
-          if (iter == 0)
-            for (int i = 0; i < n_inline; ++i) is_inl |= inl[i].fam == fam && inl[i].slot == p;
-          if (!is_inl && is_active(f, p)) { eval_ref<false>(c, fam, p); ++n; }
-        }
-      }
-      nprop += n;
-    }
-
     if (iter == 0) trace_mark(P, 2);
     // ---- the variables narrowed in the previous iteration (iteration 0 of an incremental
     // launch: seeded by the host).  Every CTA derives the same count, hence the same choice
@@ -1621,6 +1605,27 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       }
       trace_mark1(P, iter, 2);
       if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(P, c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
+    }
+    // older tail propagators: CTA 0, every iteration (the posted ones were handled above), after
+    // the refresh so that they read this CTA's snapshot: active word and descriptor in one
+    // round trip, no gather of the domains
+    if (blockIdx.x == 0 && !skip) {
+      unsigned n = 0;
+      for (unsigned fam = 0; fam < 3; ++fam) {
+        const Family& f = P.fam[fam];
+        const int fn = fam == F_BIN ? bin_n : f.n;
+        for (int p = f.n_static + threadIdx.x; p < fn; p += blockDim.x) {
+          bool is_inl = false;
+          if (iter == 0)
+            for (int i = 0; i < n_inline; ++i) is_inl |= inl[i].fam == fam && inl[i].slot == p;
+          if (is_inl) continue;
+          const unsigned word = __ldcg(&f.active[p >> 5]);
+          int4 q0, q1, q2;
+          load_desc(f, fam, p, q0, q1, q2);
+          if ((word >> (p & 31)) & 1u) { eval_loaded<SMEM>(c, fam, p, q0, q1, q2); ++n; }
+        }
+      }
+      nprop += n;
     }
     if (sweep_now && !skip && st.my_chunks > 0) {
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep
