@@ -66,10 +66,12 @@ enum pcp_prop_kind {
   PCP_X_LESS_Y_PLUS_Z = 4,    /* cmp/x_less_y_plus_z.rs:75-128; 3 operands            */
   PCP_X_EQ_Y_PLUS_Z = 5,      /* cmp/x_eq_y_plus_z.rs:26-105; 3 operands              */
   PCP_DISTINCT = 6,           /* distinct.rs:69-126; n >= 1 operands                  */
-  PCP_DISJ2_X_EQ_Y_PLUS_Z = 7 /* logic/disjunction.rs:77-129 over two XEqYPlusZ;
+  PCP_DISJ2_X_EQ_Y_PLUS_Z = 7,/* logic/disjunction.rs:77-129 over two XEqYPlusZ;
                                  6 operands (x1,y1,z1,x2,y2,z2)                       */
+  PCP_X_EQ_Y_MUL_Z = 8        /* cmp/x_eq_y_mul_z.rs:68-116; 3 operands: only x is narrowed,
+                                 to x /\ (y * z) (interval product)                   */
 };
-#define PCP_NUM_KINDS 8
+#define PCP_NUM_KINDS 9
 
 /* Engine configuration (the reference configures through type aliases only:
  * propagation/mod.rs:33-34, variable/mod.rs:35-38). */

@@ -412,16 +412,18 @@ struct XEqYPlusZ : Propagator {
   Formula bclone() const override { return std::make_unique<XEqYPlusZ>(geq->bclone(), leq->bclone()); }
 };
 
-// propagators/cmp/x_eq_y_mul_z.rs:66-123 (oracle only; used by Cumulative).
+// propagators/cmp/x_eq_y_mul_z.rs:68-116.
 struct XEqYMulZ : Propagator {
   Var x, y, z;
   XEqYMulZ(Var x_, Var y_, Var z_) : x(std::move(x_)), y(std::move(y_)), z(std::move(z_)) {}
   SKleene is_subsumed(const VStore& s) const override {
     Interval a = x->read(s), b = y->read(s), c = z->read(s);
+    // x_eq_y_mul_z.rs:73-90: overlap -> True iff y*z and x are both singletons, else Unknown;
+    // no overlap -> False (the product of two intervals can be a singleton without y and z
+    // being singletons: [0,0] * [1,5])
     Interval yz = b.mul(c);
-    if (a.is_singleton() && b.is_singleton() && c.is_singleton() && a == yz) return True;
     if (a.is_disjoint(yz)) return False;
-    return Unknown;
+    return (yz.is_singleton() && a.is_singleton()) ? True : Unknown;
   }
   bool propagate(VStore& s) override {
     Interval a = x->read(s), b = y->read(s), c = z->read(s);
@@ -573,7 +575,7 @@ struct FOp { int32_t var, off; };  // var >= 0: Identity+off; var == -1: Constan
 
 struct FlatProp : Propagator {
   enum Kind : int { LessY = 0, NeqY = 1, EqY = 2, GreaterYPlusZ = 3, LessYPlusZ = 4, EqYPlusZ = 5,
-                    DistinctN = 6, Disj2EqYPlusZ = 7 };
+                    DistinctN = 6, Disj2EqYPlusZ = 7, EqYMulZ = 8 };
   int kind;
   FOp o[6];
   std::vector<FOp> nary;
@@ -645,6 +647,11 @@ struct FlatProp : Propagator {
       case GreaterYPlusZ: return sub_greater(s, o[0], o[1], o[2], 0);
       case LessYPlusZ: return sub_lessyz(s, o[0], o[1], o[2], 0);
       case EqYPlusZ: return sub_eqyz(s, o);
+      case EqYMulZ: {  // x_eq_y_mul_z.rs:73-90
+        Interval a = rd(s, o[0]), yz = rd(s, o[1]).mul(rd(s, o[2]));
+        if (a.is_disjoint(yz)) return False;
+        return (yz.is_singleton() && a.is_singleton()) ? True : Unknown;
+      }
       case DistinctN: {  // Conjunction::is_subsumed over the pairs (conjunction.rs:77-94)
         bool all = true;
         for (size_t i = 0; i + 1 < nary.size(); ++i)
@@ -677,6 +684,10 @@ struct FlatProp : Propagator {
       case GreaterYPlusZ: return prop_greater(s, o[0], o[1], o[2], 0);
       case LessYPlusZ: return prop_lessyz(s, o[0], o[1], o[2], 0);
       case EqYPlusZ: return prop_eqyz(s, o);
+      case EqYMulZ: {  // x_eq_y_mul_z.rs:99-105
+        Interval a = rd(s, o[0]);
+        return up(s, o[0], a.intersection(rd(s, o[1]).mul(rd(s, o[2]))));
+      }
       case DistinctN:  // Conjunction::propagate over the pairs (conjunction.rs:96-105)
         for (size_t i = 0; i + 1 < nary.size(); ++i)
           for (size_t j = i + 1; j < nary.size(); ++j)
@@ -699,7 +710,7 @@ struct FlatProp : Propagator {
     switch (kind) {
       case LessY: dep(d, o[0], Bound); dep(d, o[1], Bound); break;
       case NeqY: case EqY: dep(d, o[0], Inner); dep(d, o[1], Inner); break;
-      case GreaterYPlusZ: case LessYPlusZ: case EqYPlusZ:
+      case GreaterYPlusZ: case LessYPlusZ: case EqYPlusZ: case EqYMulZ:
         for (int i = 0; i < 3; ++i) dep(d, o[i], Bound);
         break;
       case DistinctN: for (auto& a : nary) dep(d, a, Inner); break;

@@ -56,8 +56,8 @@ Formula make_prop(const pcpo_engine* e, int kind, const pcp_operand* ops, int n)
       }
       f.push_back(FOp{op.var, op.off});
     }
-    static const int arity[8] = {2, 2, 2, 3, 3, 3, -1, 6};
-    PCPO_ASSERT(kind >= 0 && kind < 8, "unknown propagator kind");
+    static const int arity[9] = {2, 2, 2, 3, 3, 3, -1, 6, 3};
+    PCPO_ASSERT(kind >= 0 && kind < 9, "unknown propagator kind");
     PCPO_ASSERT(arity[kind] < 0 ? n >= 1 : n == arity[kind], "arity");
     return make_flat(kind, f.data(), n);
   }
@@ -69,6 +69,7 @@ Formula make_prop(const pcpo_engine* e, int kind, const pcp_operand* ops, int n)
     case PCP_X_GREATER_Y_PLUS_Z: PCPO_ASSERT(n == 3, "arity"); return std::make_unique<XGreaterYPlusZ>(v(0), v(1), v(2));
     case PCP_X_LESS_Y_PLUS_Z: PCPO_ASSERT(n == 3, "arity"); return std::make_unique<XLessYPlusZ>(v(0), v(1), v(2));
     case PCP_X_EQ_Y_PLUS_Z: PCPO_ASSERT(n == 3, "arity"); return std::make_unique<XEqYPlusZ>(v(0), v(1), v(2));
+    case PCP_X_EQ_Y_MUL_Z: PCPO_ASSERT(n == 3, "arity"); return std::make_unique<XEqYMulZ>(v(0), v(1), v(2));
     case PCP_DISTINCT: {
       PCPO_ASSERT(n >= 1, "arity");
       std::vector<Var> vars;

@@ -55,7 +55,7 @@ __host__ __device__ inline unsigned make_ref(unsigned fam, unsigned slot) { retu
 
 // kinds inside a family (top 4 bits of descriptor word 0)
 enum BinKind : unsigned { B_LESS = 0, B_NEQ = 1, B_EQ = 2 };
-enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2 };
+enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2, T_MUL = 3 };
 
 enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3 };
 // Worklist iterations: every CTA compacts the dirty bit set into a list that lives in the

@@ -353,11 +353,13 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
     }
     case PCP_X_GREATER_Y_PLUS_Z:
     case PCP_X_LESS_Y_PLUS_Z:
-    case PCP_X_EQ_Y_PLUS_Z: {
+    case PCP_X_EQ_Y_PLUS_Z:
+    case PCP_X_EQ_Y_MUL_Z: {
       PCP_REQUIRE(n_ops == 3, "ternary propagator takes 3 operands");
       for (int i = 0; i < 3; ++i) ops[i] = lower_view(e, raw[i]);
       require_distinct_vars(e, ops, 3);
-      unsigned k = kind == PCP_X_GREATER_Y_PLUS_Z ? T_GREATER : (kind == PCP_X_LESS_Y_PLUS_Z ? T_LESS : T_EQ);
+      unsigned k = kind == PCP_X_GREATER_Y_PLUS_Z ? T_GREATER
+                   : (kind == PCP_X_LESS_Y_PLUS_Z ? T_LESS : (kind == PCP_X_EQ_Y_PLUS_Z ? T_EQ : T_MUL));
       HostFamily& f = e->fam[F_TER];
       if (ops[0].var < 0 || ops[1].var < 0 || ops[2].var < 0) f.first_nonplain = std::min(f.first_nonplain, f.n);
       f.kind_mask |= 1 << k;

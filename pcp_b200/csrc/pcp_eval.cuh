@@ -268,12 +268,32 @@ __device__ __forceinline__ bool stage_tri(UpdSet& us, const Tri& t, IV x0, IV y0
          stage<2>(us, t.zv, t.zo, z0, z.lo, z.hi);
 }
 
+// XEqYMulZ (cmp/x_eq_y_mul_z.rs:68-116): the interval product y * z = [min, max] of the four
+// bound products (64-bit: bounds stay below 2^29 in magnitude).
+struct IV64 { long long lo, hi; };
+__device__ __forceinline__ IV64 mul_iv(IV y, IV z) {
+  const long long p0 = (long long)y.lo * z.lo, p1 = (long long)y.lo * z.hi, p2 = (long long)y.hi * z.lo,
+                  p3 = (long long)y.hi * z.hi;
+  return IV64{min(min(p0, p1), min(p2, p3)), max(max(p0, p1), max(p2, p3))};
+}
 __device__ __forceinline__ Eval eval_ter(int4 a, int2 b, IV x0, IV y0, IV z0, UpdSet& us) {
   unsigned kind = (unsigned)a.x >> 28;
   Tri t{dec_var28((unsigned)a.x), a.y, a.z, a.w, b.x, b.y};
   IV x = x0, y = y0, z = z0;
   const TriRo ro = tri_ro(t);
   int s;
+  if (kind == T_MUL) {
+    // propagate: x <- x /\ (y * z), y and z untouched (x_eq_y_mul_z.rs:99-105); is_subsumed on the
+    // result: no overlap -> False; y * z and x both singletons -> True (x_eq_y_mul_z.rs:73-90)
+    const IV64 yz = mul_iv(y0, z0);
+    const long long nlo = max((long long)x0.lo, yz.lo), nhi = min((long long)x0.hi, yz.hi);
+    if (nlo > nhi) return E_FAIL;
+    x.lo = (int)nlo; x.hi = (int)nhi;
+    if (!stage<0>(us, t.xv, t.xo, x0, x.lo, x.hi)) return E_FAIL;
+    const IV px = ro.x ? x0 : x;  // a multi-term Sum operand is checked, not narrowed (term/sum.rs:62-69)
+    if ((long long)px.hi < yz.lo || yz.hi < (long long)px.lo) return E_FAIL;
+    return (yz.lo == yz.hi && px.lo == px.hi) ? E_ENTAILED : E_UNKNOWN;
+  }
   if (kind == T_EQ) {
     if (!prop_eq(x, y, z, ro)) return E_FAIL;
     s = sub_eq(x, y, z);
@@ -290,6 +310,10 @@ __device__ __forceinline__ Eval eval_ter(int4 a, int2 b, IV x0, IV y0, IV z0, Up
   return s < 0 ? E_FAIL : (s > 0 ? E_ENTAILED : E_UNKNOWN);
 }
 __device__ __forceinline__ bool ter_is_noop(unsigned kind, IV x, IV y, IV z) {
+  if (kind == T_MUL) {
+    const IV64 yz = mul_iv(y, z);
+    return (long long)x.lo >= yz.lo && (long long)x.hi <= yz.hi && !(yz.lo == yz.hi && x.lo == x.hi);
+  }
   if (kind == T_EQ)
     return x.lo >= y.lo + z.lo && y.hi <= x.hi - z.lo && z.hi <= x.hi - y.lo &&
            x.hi <= y.hi + z.hi && y.lo >= x.lo - z.hi && z.lo >= x.lo - y.hi && sub_eq(x, y, z) == 0;

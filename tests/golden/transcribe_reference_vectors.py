@@ -139,6 +139,18 @@ for num, x, y, z, b, a, d, ok in [
 ]:
     add("x_eq_y_plus_z", ref, num, "XEqYPlusZ", [x, y, z], [X, Y, Z], b, a, d, ok)
 
+# --- src/libpcp/propagators/cmp/x_eq_y_mul_z.rs:124-147
+ref = "propagators/cmp/x_eq_y_mul_z.rs:124-147"
+d1_2 = [1, 2]
+for num, x, y, z, b, a, d, ok in [
+    (1, d0_10, d0_10, d0_10, U, U, [], True),
+    (2, d10_11, d5_15, d5_15, F, F, [], False),
+    (3, d10_20, d1_1, d1_1, F, F, [], False),
+    (4, d1_1, d1_1, d1_1, T, T, [], True),
+    (5, d1_2, d1_1, d1_1, U, T, [(0, A)], True),
+]:
+    add("x_eq_y_mul_z", ref, num, "XEqYMulZ", [x, y, z], [X, Y, Z], b, a, d, ok)
+
 # --- src/libpcp/propagators/cmp/x_neq_y.rs:114-133
 ref = "propagators/cmp/x_neq_y.rs:114-133"
 for num, x, y, b, a, d, ok in [

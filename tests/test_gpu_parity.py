@@ -255,8 +255,8 @@ def test_random_mixed_store():
         for e in (dev, ora):
             e.vars_alloc(lo, hi)
         for _ in range(int(rng.integers(1, 60))):
-            kind = int(rng.integers(0, 8))
-            n_ops = {0: 2, 1: 2, 2: 2, 3: 3, 4: 3, 5: 3, 6: int(rng.integers(1, min(V, 12) + 1)), 7: 6}[kind]
+            kind = int(rng.integers(0, 9))
+            n_ops = {0: 2, 1: 2, 2: 2, 3: 3, 4: 3, 5: 3, 6: int(rng.integers(1, min(V, 12) + 1)), 7: 6, 8: 3}[kind]
             if kind == 7:
                 a = rng.choice(V, 3, replace=False)
                 b = rng.choice(V, 3, replace=False)
@@ -499,3 +499,34 @@ def test_sharded_search_single_rank_covers_the_tree():
     models.nqueens(7).load_into(dev)
     out = parallel.sharded_search(dev, 0, 1, node_budget=10**6, sync_every=50, parts_per_rank=6)
     assert out["solutions"] == 40 and out["subtrees"] == out["frontier"] >= 6
+
+
+def test_x_eq_y_mul_z_products_store():
+    """XEqYMulZ (cmp/x_eq_y_mul_z.rs:68-116) at scale: p_i = a_i * b_i with the factors tied by
+    chains of XLessY, signs mixed; fixpoint, status and `active` set against the oracle (a
+    consistent and an inconsistent instance), then 60 search nodes."""
+    rng = np.random.default_rng(77)
+    n = 400
+    lo = np.concatenate([rng.integers(-12, 4, 2 * n), np.full(n, -200)]).astype(np.int32)
+    hi = np.concatenate([lo[:2 * n] + rng.integers(0, 14, 2 * n), np.full(n, 200)]).astype(np.int32)
+    m = models.Model("products", lo, hi)
+    ops = np.zeros((n, 3, 2), np.int32)
+    ops[:, 0, 0] = 2 * n + np.arange(n)   # x = p_i
+    ops[:, 1, 0] = np.arange(n)           # y = a_i
+    ops[:, 2, 0] = n + np.arange(n)       # z = b_i
+    m.add(models.X_EQ_Y_MUL_Z, ops)
+    chain = np.zeros((n - 1, 2, 2), np.int32)
+    chain[:, 0, 0] = 2 * n + np.arange(n - 1)
+    chain[:, 1, 0] = 2 * n + np.arange(1, n)
+    for slack, expect in ((150, 0), (40, -1)):   # p_i < p_{i+1} + slack: consistent / inconsistent
+        mm = models.Model(m.name, m.lo, m.hi, list(m.batches))
+        c = chain.copy()
+        c[:, 1, 1] = slack
+        mm.add(models.X_LESS_Y, c)
+        dev, ora = _engine(), _oracle()
+        mm.load_into(dev)
+        mm.load_into(ora)
+        assert dev.consistency()[0] == ora.consistency()[0] == expect
+        if expect != -1:
+            _assert_same_state(dev, ora)
+        _compare_search(mm, 60)
