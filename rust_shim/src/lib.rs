@@ -35,6 +35,10 @@ pub const PCP_X_LESS_Y_PLUS_Z: i32 = 4;
 pub const PCP_X_EQ_Y_PLUS_Z: i32 = 5;
 pub const PCP_DISTINCT: i32 = 6;
 pub const PCP_DISJ2_X_EQ_Y_PLUS_Z: i32 = 7;
+pub const PCP_X_EQ_Y_MUL_Z: i32 = 8;
+
+pub const PCP_FLAG_INCREMENTAL: u32 = 1;
+pub const PCP_FLAG_HOST_SEARCH: u32 = 2;
 
 extern "C" {
     pub fn pcp_engine_create(cfg: *const PcpConfig, out: *mut *mut PcpEngine) -> c_int;
@@ -48,6 +52,7 @@ extern "C" {
     pub fn pcp_var_update(e: *mut PcpEngine, idx: i32, lo: i32, hi: i32, ok: *mut i32) -> c_int;
     pub fn pcp_label(e: *mut PcpEngine, label: *mut u64) -> c_int;
     pub fn pcp_restore(e: *mut PcpEngine, label: u64) -> c_int;
+    pub fn pcp_stream(e: *mut PcpEngine, stream: *mut *mut std::os::raw::c_void) -> c_int;
 }
 
 /// What a propagator lowers to.  `PropagatorConcept` (libpcp `propagation/concept.rs:21-53`)
@@ -57,7 +62,7 @@ extern "C" {
 /// pub trait DeviceLowering { fn lower(&self) -> Option<Desc> { None } }
 /// ```
 /// implemented for the hot-path propagators (cmp/x_less_y.rs, x_neq_y.rs, x_eq_y.rs,
-/// x_greater_y_plus_z.rs, x_less_y_plus_z.rs, x_eq_y_plus_z.rs, distinct.rs, and a
+/// x_greater_y_plus_z.rs, x_less_y_plus_z.rs, x_eq_y_plus_z.rs, x_eq_y_mul_z.rs, distinct.rs, and a
 /// `Disjunction` of two `XEqYPlusZ`) and for the four views (`Identity` -> (idx, 0),
 /// `Addition` -> inner + v, `Constant` -> (-1, value), `Sum` -> a sum id).  Anything that
 /// returns `None` is an error at `alloc` time: there is no CPU fallback on the fixpoint path.
