@@ -68,10 +68,11 @@ enum pcp_prop_kind {
   PCP_DISTINCT = 6,           /* distinct.rs:69-126; n >= 1 operands                  */
   PCP_DISJ2_X_EQ_Y_PLUS_Z = 7,/* logic/disjunction.rs:77-129 over two XEqYPlusZ;
                                  6 operands (x1,y1,z1,x2,y2,z2)                       */
-  PCP_X_EQ_Y_MUL_Z = 8        /* cmp/x_eq_y_mul_z.rs:68-116; 3 operands: only x is narrowed,
+  PCP_X_EQ_Y_MUL_Z = 8,       /* cmp/x_eq_y_mul_z.rs:68-116; 3 operands: only x is narrowed,
                                  to x /\ (y * z) (interval product)                   */
+  PCP_ALL_EQUAL = 9           /* all_equal.rs:47-103 (chain of XEqY); n >= 1 operands   */
 };
-#define PCP_NUM_KINDS 9
+#define PCP_NUM_KINDS 10
 
 /* Engine configuration (the reference configures through type aliases only:
  * propagation/mod.rs:33-34, variable/mod.rs:35-38). */

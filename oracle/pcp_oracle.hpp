@@ -541,9 +541,11 @@ struct Distinct : Propagator {
   Formula not_() const override { return conj.not_(); }
 };
 
-// propagators/all_equal.rs:47-62 (oracle only): chain of XEqY(vars[i], vars[i+1]).
+// propagators/all_equal.rs:47-103: chain of XEqY(vars[i], vars[i+1]); dependencies are the
+// variables themselves at Inner, each once (all_equal.rs:96-103).
 struct AllEqual : Propagator {
   Conjunction conj;
+  std::vector<Var> vars;
   static std::vector<Formula> chain(const std::vector<Var>& v) {
     PCPO_ASSERT(!v.empty(), "Variable array in `AllEqual` must be non-empty.");
     std::vector<Formula> props;
@@ -551,14 +553,17 @@ struct AllEqual : Propagator {
       props.push_back(std::make_unique<XEqY>(v[i]->bclone(), v[i + 1]->bclone()));
     return props;
   }
-  explicit AllEqual(const std::vector<Var>& v) : conj(chain(v)) {}
-  explicit AllEqual(Conjunction c) : conj(std::move(c.fs)) {}
+  explicit AllEqual(std::vector<Var> v) : conj(chain(v)), vars(std::move(v)) {}
   SKleene is_subsumed(const VStore& s) const override { return conj.is_subsumed(s); }
   bool propagate(VStore& s) override { return conj.propagate(s); }
-  std::vector<Dep> dependencies() const override { return conj.dependencies(); }
+  std::vector<Dep> dependencies() const override {
+    std::vector<Dep> d;
+    for (auto& v : vars) d = cat(std::move(d), v->dependencies(Inner));
+    return d;
+  }
   Formula bclone() const override {
-    std::vector<Formula> c; for (auto& f : conj.fs) c.push_back(f->bclone());
-    return std::make_unique<AllEqual>(Conjunction(std::move(c)));
+    std::vector<Var> c; for (auto& v : vars) c.push_back(v->bclone());
+    return std::make_unique<AllEqual>(std::move(c));
   }
 };
 
@@ -575,7 +580,7 @@ struct FOp { int32_t var, off; };  // var >= 0: Identity+off; var == -1: Constan
 
 struct FlatProp : Propagator {
   enum Kind : int { LessY = 0, NeqY = 1, EqY = 2, GreaterYPlusZ = 3, LessYPlusZ = 4, EqYPlusZ = 5,
-                    DistinctN = 6, Disj2EqYPlusZ = 7, EqYMulZ = 8 };
+                    DistinctN = 6, Disj2EqYPlusZ = 7, EqYMulZ = 8, AllEqualN = 9 };
   int kind;
   FOp o[6];
   std::vector<FOp> nary;
@@ -652,6 +657,15 @@ struct FlatProp : Propagator {
         if (a.is_disjoint(yz)) return False;
         return (yz.is_singleton() && a.is_singleton()) ? True : Unknown;
       }
+      case AllEqualN: {  // Conjunction::is_subsumed over the chain (all_equal.rs:53-57, conjunction.rs:77-94)
+        bool all = true;
+        for (size_t i = 0; i + 1 < nary.size(); ++i) {
+          SKleene k = sub_eq(s, nary[i], nary[i + 1]);
+          if (k == False) return False;
+          if (k == Unknown) all = false;
+        }
+        return all ? True : Unknown;
+      }
       case DistinctN: {  // Conjunction::is_subsumed over the pairs (conjunction.rs:77-94)
         bool all = true;
         for (size_t i = 0; i + 1 < nary.size(); ++i)
@@ -688,6 +702,13 @@ struct FlatProp : Propagator {
         Interval a = rd(s, o[0]);
         return up(s, o[0], a.intersection(rd(s, o[1]).mul(rd(s, o[2]))));
       }
+      case AllEqualN:  // Conjunction::propagate over the chain of XEqY (x_eq_y.rs:102-107)
+        for (size_t i = 0; i + 1 < nary.size(); ++i) {
+          Interval a = rd(s, nary[i]), b = rd(s, nary[i + 1]);
+          Interval n = a.intersection(b);
+          if (!(up(s, nary[i], n) && up(s, nary[i + 1], n))) return false;
+        }
+        return true;
       case DistinctN:  // Conjunction::propagate over the pairs (conjunction.rs:96-105)
         for (size_t i = 0; i + 1 < nary.size(); ++i)
           for (size_t j = i + 1; j < nary.size(); ++j)
@@ -713,7 +734,7 @@ struct FlatProp : Propagator {
       case GreaterYPlusZ: case LessYPlusZ: case EqYPlusZ: case EqYMulZ:
         for (int i = 0; i < 3; ++i) dep(d, o[i], Bound);
         break;
-      case DistinctN: for (auto& a : nary) dep(d, a, Inner); break;
+      case DistinctN: case AllEqualN: for (auto& a : nary) dep(d, a, Inner); break;
       default:
         for (int i = 0; i < 6; ++i) dep(d, o[i], Bound);
         d = sorted_dedup(std::move(d));
@@ -726,7 +747,7 @@ struct FlatProp : Propagator {
 inline Formula make_flat(int kind, const FOp* ops, int n) {
   auto p = std::make_unique<FlatProp>();
   p->kind = kind;
-  if (kind == FlatProp::DistinctN) p->nary.assign(ops, ops + n);
+  if (kind == FlatProp::DistinctN || kind == FlatProp::AllEqualN) p->nary.assign(ops, ops + n);
   else for (int i = 0; i < n && i < 6; ++i) p->o[i] = ops[i];
   return p;
 }

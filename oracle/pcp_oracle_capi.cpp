@@ -56,8 +56,8 @@ Formula make_prop(const pcpo_engine* e, int kind, const pcp_operand* ops, int n)
       }
       f.push_back(FOp{op.var, op.off});
     }
-    static const int arity[9] = {2, 2, 2, 3, 3, 3, -1, 6, 3};
-    PCPO_ASSERT(kind >= 0 && kind < 9, "unknown propagator kind");
+    static const int arity[10] = {2, 2, 2, 3, 3, 3, -1, 6, 3, -1};
+    PCPO_ASSERT(kind >= 0 && kind < 10, "unknown propagator kind");
     PCPO_ASSERT(arity[kind] < 0 ? n >= 1 : n == arity[kind], "arity");
     return make_flat(kind, f.data(), n);
   }
@@ -75,6 +75,12 @@ Formula make_prop(const pcpo_engine* e, int kind, const pcp_operand* ops, int n)
       std::vector<Var> vars;
       for (int i = 0; i < n; ++i) vars.push_back(v(i));
       return std::make_unique<Distinct>(std::move(vars));
+    }
+    case PCP_ALL_EQUAL: {
+      PCPO_ASSERT(n >= 1, "arity");
+      std::vector<Var> vars;
+      for (int i = 0; i < n; ++i) vars.push_back(v(i));
+      return std::make_unique<AllEqual>(std::move(vars));
     }
     case PCP_DISJ2_X_EQ_Y_PLUS_Z: {
       PCPO_ASSERT(n == 6, "arity");

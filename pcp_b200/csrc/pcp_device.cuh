@@ -56,6 +56,7 @@ __host__ __device__ inline unsigned make_ref(unsigned fam, unsigned slot) { retu
 // kinds inside a family (top 4 bits of descriptor word 0)
 enum BinKind : unsigned { B_LESS = 0, B_NEQ = 1, B_EQ = 2 };
 enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2, T_MUL = 3 };
+enum NaryKind : int { N_DISTINCT = 0, N_ALL_EQUAL = 1 };
 
 enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3 };
 // Worklist iterations: every CTA compacts the dirty bit set into a list that lives in the
@@ -120,6 +121,7 @@ struct Params {
   Family fam[3];        // BIN, TER, DJ
   const int* nary_ptr;  // CSR of n-ary Distinct operands
   const int2* nary_ops;
+  const int* nary_kind;  // N_DISTINCT / N_ALL_EQUAL per n-ary propagator
   uint32_t* nary_active;
   int n_nary;
   int nary_max_k;
@@ -934,6 +936,69 @@ __device__ __forceinline__ unsigned eval_distinct(const Params& P, const Ctx& c,
 }
 
 // ---------------------------------------------------------------------------------------
+// n-ary AllEqual (propagators/all_equal.rs:47-103 = Conjunction of XEqY(v_i, v_{i+1}),
+// cmp/x_eq_y.rs:84-107).  Every XEqY replaces both sides by their intersection, so the chain's
+// fixpoint gives every operand the intersection I of all (view-space) domains -- a Constant
+// operand takes part as the singleton it is -- and fails iff I is empty; the conjunction is
+// entailed iff every pair is an equal pair of singletons, i.e. I is a singleton (an array of
+// one variable is the empty conjunction: entailed).  One CTA: block-wide max of the lower and
+// min of the upper bounds, then the write-back.  Returns 1 if evaluated (thread 0 only).
+// ---------------------------------------------------------------------------------------
+template <bool SMEM>
+__device__ __forceinline__ unsigned eval_all_equal(const Params& P, const Ctx& c, int slot, const uint32_t* cur_bits,
+                                                   bool unconditional) {
+  __shared__ int s_lo, s_hi;
+  const int b = __ldg(&P.nary_ptr[slot]), e = __ldg(&P.nary_ptr[slot + 1]);
+  const int k = e - b;
+  __syncthreads();
+  if (threadIdx.x == 0) { s_lo = INT32_MIN; s_hi = INT32_MAX; }
+  int any_dirty = 0, lo = INT32_MIN, hi = INT32_MAX;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const int2 op = __ldg(&P.nary_ops[b + i]);
+    int2 d = make_int2(op.y, op.y);
+    if (op.x >= 0) {
+      const int2 raw = SMEM ? c.sdom[op.x] : ldcg_dom(&P.dom[op.x]);
+      d = make_int2(raw.x + op.y, raw.y + op.y);
+      if (!unconditional && ((__ldcg(&cur_bits[op.x >> 5]) >> (op.x & 31)) & 1u)) any_dirty = 1;
+    }
+    lo = max(lo, d.x);
+    hi = min(hi, d.y);
+  }
+  if (!unconditional) {
+    if (!__syncthreads_or(any_dirty)) return 0;  // nothing it depends on changed (all_equal.rs:96-103)
+  } else {
+    __syncthreads();
+  }
+  for (int o = 16; o; o >>= 1) {
+    lo = max(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = min(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(&s_lo, lo); atomicMin(&s_hi, hi); }
+  __syncthreads();
+  lo = s_lo;
+  hi = s_hi;
+  if (k > 1 && lo > hi) {  // two operands are disjoint: some XEqY of the chain fails
+    if (threadIdx.x == 0) set_failed(c);
+    return 1;
+  }
+  if (k > 1) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      const int2 op = __ldg(&P.nary_ops[b + i]);
+      if (op.x < 0) continue;  // a Constant inside I needs no update (term/constant.rs:43-53)
+      const int2 raw = ldcg_dom(&P.dom[op.x]);
+      const IV cur{raw.x + op.y, raw.y + op.y};
+      if (!tighten(c, op.x, op.y, cur, max(cur.lo, lo), min(cur.hi, hi))) set_failed(c);
+    }
+  }
+  if (threadIdx.x == 0 && (k <= 1 || lo == hi)) {
+    const unsigned bit = 1u << (slot & 31);
+    const unsigned old = atomicAnd(&P.nary_active[slot >> 5], ~bit);
+    if (old & bit) P.trail[atomicAdd(&P.ctl->trail_cnt, 1u)] = make_ref(F_NARY, (unsigned)slot);
+  }
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------
 // device-wide barrier; the last CTA to arrive decides whether the fixpoint is reached
 // (the "block-reduce of a changed flag": every CTA contributes "I narrowed a variable").
 // `decide` = false: plain barrier (after the node prologue).
@@ -1671,7 +1736,9 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       // the last to get one
       for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
         if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-        unsigned ev = eval_distinct<SMEM>(P, c, s, st.ring, cur_bits, iter == 0 && full_sweep);
+        const bool all = iter == 0 && full_sweep;
+        unsigned ev = __ldg(&P.nary_kind[s]) == N_ALL_EQUAL ? eval_all_equal<SMEM>(P, c, s, cur_bits, all)
+                                                             : eval_distinct<SMEM>(P, c, s, st.ring, cur_bits, all);
         if (threadIdx.x == 0) nprop += ev;
       }
     }

@@ -129,6 +129,8 @@ struct pcp_engine {
   HostFamily fam[3];                // BIN, TER, DJ
   std::vector<int> h_nary_ptr{0};
   std::vector<int2> h_nary_ops;
+  std::vector<int> h_nary_kind;     // per n-ary propagator: N_DISTINCT / N_ALL_EQUAL
+  DevBuf<int> d_nary_kind;
   size_t n_nary = 0, nary_uploaded = 0, nary_active_set = 0;
   int nary_max_k = 0;
   DevBuf<int> d_nary_ptr;
@@ -380,13 +382,15 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       e->prop_ref.push_back(make_ref(F_DJ, (unsigned)f.n++));
       break;
     }
-    case PCP_DISTINCT: {
-      PCP_REQUIRE(n_ops >= 1, "Variable array in `Distinct` must be non-empty.");
-      PCP_REQUIRE(n_ops <= 4096, "Distinct over more than 4096 operands is not supported");
+    case PCP_DISTINCT:
+    case PCP_ALL_EQUAL: {
+      PCP_REQUIRE(n_ops >= 1, kind == PCP_DISTINCT ? "Variable array in `Distinct` must be non-empty."
+                                                   : "Variable array in `AllEqual` must be non-empty.");
+      PCP_REQUIRE(n_ops <= 4096, "n-ary propagator over more than 4096 operands is not supported");
       std::vector<pcp_operand> lo(n_ops);
       for (int i = 0; i < n_ops; ++i) {
         lo[i] = lower_view(e, raw[i]);
-        if (lo[i].var <= -2) PCP_FAIL(PCP_ERR_UNSUPPORTED, "Distinct over multi-term Sum views has no device lowering");
+        if (lo[i].var <= -2) PCP_FAIL(PCP_ERR_UNSUPPORTED, "n-ary propagators over multi-term Sum views have no device lowering");
       }
       {
         std::vector<int> vs;
@@ -396,6 +400,7 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       }
       for (auto& o : lo) e->h_nary_ops.push_back(make_int2(o.var, o.off));
       e->h_nary_ptr.push_back((int)e->h_nary_ops.size());
+      e->h_nary_kind.push_back(kind == PCP_DISTINCT ? (int)N_DISTINCT : (int)N_ALL_EQUAL);
       e->nary_max_k = std::max(e->nary_max_k, n_ops);
       e->prop_ref.push_back(make_ref(F_NARY, (unsigned)e->n_nary++));
       // binary/ternary/disjunction propagators allocated after a fixpoint land in the tail,
@@ -421,6 +426,7 @@ void truncate_props(pcp_engine* e, const LabelRec& r) {
   }
   e->n_nary = r.n_fam[F_NARY];
   e->h_nary_ptr.resize(e->n_nary + 1);
+  e->h_nary_kind.resize(e->n_nary);
   e->h_nary_ops.resize(r.n_nary_ops);
   e->nary_uploaded = std::min(e->nary_uploaded, e->n_nary);
   e->nary_active_set = std::min(e->nary_active_set, e->n_nary);
@@ -581,6 +587,7 @@ Params prepare(pcp_engine* e) {
     upload_range(e, e->d_nary_ops, e->h_nary_ops, ops_from, e->h_nary_ops.size());
     size_t pfrom = e->nary_uploaded == 0 ? 0 : e->nary_uploaded + 1;
     upload_range(e, e->d_nary_ptr, e->h_nary_ptr, pfrom, e->n_nary + 1);
+    upload_range(e, e->d_nary_kind, e->h_nary_kind, e->nary_uploaded, e->n_nary);
     e->nary_uploaded = e->n_nary;
   }
   reserve_zeroed(e, e->d_nary_active, (e->n_nary + 31) / 32 + 1, (e->nary_active_set + 31) / 32);
@@ -643,6 +650,7 @@ Params prepare(pcp_engine* e) {
   }
   P.nary_ptr = e->d_nary_ptr.p;
   P.nary_ops = e->d_nary_ops.p;
+  P.nary_kind = e->d_nary_kind.p;
   P.nary_active = e->d_nary_active.p;
   P.nary_active_w = e->d_nary_active.p;
   P.n_nary = (int)e->n_nary;
@@ -1003,7 +1011,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   for (int f = 0; f < 3; ++f) {
     e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_cdesc.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
   }
-  e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_active.free();
+  e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_kind.free(); e->d_nary_active.free();
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
   e->d_dirty_bits.free(); e->d_seed_list.free(); e->d_trail.free(); e->d_stack.free();
   if (e->d_ctl) cudaFree(e->d_ctl);

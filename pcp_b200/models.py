@@ -30,12 +30,13 @@ X_EQ_Y_PLUS_Z = 5
 DISTINCT = 6
 DISJ2_X_EQ_Y_PLUS_Z = 7
 X_EQ_Y_MUL_Z = 8
+ALL_EQUAL = 9
 
 KIND_NAMES = {
     X_LESS_Y: "XLessY", X_NEQ_Y: "XNeqY", X_EQ_Y: "XEqY",
     X_GREATER_Y_PLUS_Z: "XGreaterYPlusZ", X_LESS_Y_PLUS_Z: "XLessYPlusZ",
     X_EQ_Y_PLUS_Z: "XEqYPlusZ", DISTINCT: "Distinct", DISJ2_X_EQ_Y_PLUS_Z: "Disj2XEqYPlusZ",
-    X_EQ_Y_MUL_Z: "XEqYMulZ",
+    X_EQ_Y_MUL_Z: "XEqYMulZ", ALL_EQUAL: "AllEqual",
 }
 KIND_BY_NAME = {v: k for k, v in KIND_NAMES.items()}
 

@@ -36,6 +36,7 @@ pub const PCP_X_EQ_Y_PLUS_Z: i32 = 5;
 pub const PCP_DISTINCT: i32 = 6;
 pub const PCP_DISJ2_X_EQ_Y_PLUS_Z: i32 = 7;
 pub const PCP_X_EQ_Y_MUL_Z: i32 = 8;
+pub const PCP_ALL_EQUAL: i32 = 9;
 
 pub const PCP_FLAG_INCREMENTAL: u32 = 1;
 pub const PCP_FLAG_HOST_SEARCH: u32 = 2;

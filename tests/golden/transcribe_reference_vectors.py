@@ -192,6 +192,21 @@ for num, doms, b, a, d, ok in [
 ]:
     add("distinct", ref, num, "Distinct", doms, [[i, 0] for i in range(len(doms))], b, a, d, ok)
 
+# --- src/libpcp/propagators/all_equal.rs:112-151
+ref = "propagators/all_equal.rs:112-151"
+for num, doms, b, a, d, ok in [
+    (1, [zero, one, two], F, F, [], False),
+    (2, [zero, zero, two], F, F, [], False),
+    (3, [zero, zero, zero], T, T, [], True),
+    (4, [zero, d0_3, d0_3], U, T, [(1, A), (2, A)], True),
+    (5, [d0_1, d0_3, d0_3], U, U, [(1, B), (2, B)], True),
+    (6, [zero, one, d0_2], F, F, [], False),
+    (7, [d0_1, one, d0_1], U, T, [(0, A), (2, A)], True),
+    (8, [d0_3], T, T, [], True),
+    (9, [one], T, T, [], True),
+]:
+    add("all_equal", ref, num, "AllEqual", doms, [[i, 0] for i in range(len(doms))], b, a, d, ok)
+
 # --- variable store semantics: src/libpcp/variable/store.rs:422-526 ---------------------
 store_updates = []
 for ref, num, source, target, events, ok in [

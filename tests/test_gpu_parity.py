@@ -255,8 +255,9 @@ def test_random_mixed_store():
         for e in (dev, ora):
             e.vars_alloc(lo, hi)
         for _ in range(int(rng.integers(1, 60))):
-            kind = int(rng.integers(0, 9))
-            n_ops = {0: 2, 1: 2, 2: 2, 3: 3, 4: 3, 5: 3, 6: int(rng.integers(1, min(V, 12) + 1)), 7: 6, 8: 3}[kind]
+            kind = int(rng.integers(0, 10))
+            n_ops = {0: 2, 1: 2, 2: 2, 3: 3, 4: 3, 5: 3, 6: int(rng.integers(1, min(V, 12) + 1)), 7: 6, 8: 3,
+                     9: int(rng.integers(1, min(V, 6) + 1))}[kind]
             if kind == 7:
                 a = rng.choice(V, 3, replace=False)
                 b = rng.choice(V, 3, replace=False)
@@ -530,3 +531,26 @@ def test_x_eq_y_mul_z_products_store():
         if expect != -1:
             _assert_same_state(dev, ora)
         _compare_search(mm, 60)
+
+
+def test_all_equal_classes_with_distinct_representatives():
+    """AllEqual (all_equal.rs:47-103) at scale: 40 classes of 25 variables each, offsets on the
+    operands, Distinct over one representative per class; root fixpoint, then 200 search nodes,
+    per-node bit-exact against the oracle."""
+    rng = np.random.default_rng(5)
+    classes, size = 40, 25
+    V = classes * size
+    lo = rng.integers(0, 10, V).astype(np.int32)
+    hi = (lo + rng.integers(30, 60, V)).astype(np.int32)
+    m = models.Model("all-equal-classes", lo, hi)
+    for c in range(classes):
+        ops = np.stack([c * size + np.arange(size), rng.integers(-3, 4, size)], axis=1).astype(np.int32)
+        m.add(models.ALL_EQUAL, ops)
+    reps = np.stack([np.arange(classes) * size, np.zeros(classes, np.int64)], axis=1).astype(np.int32)
+    m.add(models.DISTINCT, reps)
+    dev, ora = _engine(), _oracle()
+    m.load_into(dev)
+    m.load_into(ora)
+    assert dev.consistency()[0] == ora.consistency()[0] == 0
+    _assert_same_state(dev, ora)
+    _compare_search(m, 200)
