@@ -216,8 +216,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     V = model.num_vars
 
-    def fresh_engine(host_search=False, timing=True):
-        e = Engine(device=local_rank, timing=timing, max_labels=1 << 16, host_search=host_search)
+    def fresh_engine(host_search=False, timing=True, incremental=False):
+        e = Engine(device=local_rank, timing=timing, max_labels=1 << 16, host_search=host_search,
+                   incremental=incremental)
         model.load_into(e)
         return e
 
@@ -281,6 +282,18 @@ def run_ours(args):
             res[mode] = device_timed_pass(e, args.steps, args.warmup, mode == "flush", torch, device)
             barrier()
             e.close()
+        # the same nodes with PCP_FLAG_INCREMENTAL: a node restored from a label that was a fixpoint
+        # evaluates the posted constraint and what it wakes instead of scheduling every propagator
+        # (store.rs:144-149) -- same domains and statuses (tests/), far fewer propagations
+        e = fresh_engine(incremental=True)
+        if world > 1:
+            paths = parallel.expand_frontier(e, parts=world)
+            root = e.label()
+            parallel.enter_subtree(e, root, paths[rank % len(paths)])
+        barrier()
+        res["incremental"] = device_timed_pass(e, args.steps, args.warmup, True, torch, device)
+        barrier()
+        e.close()
         # e2e through the C++ driver over the C ABI, twice: the host-driven node loop (what a
         # libpcp host does: one launch, one posted descriptor in, status + domains out per node)
         # is the `e2e` key; the device-resident search (same C entry point, branching on the
@@ -312,6 +325,9 @@ def run_ours(args):
     max_ms = reduce_max(f["ms"])
     w = res["warm"]
     w_props, w_nodes, w_ms = reduce_sum(w["propagations"]), reduce_sum(w["nodes"]), reduce_max(w["ms"])
+    inc = res.get("incremental")
+    if inc is not None:
+        i_props, i_nodes, i_ms = reduce_sum(inc["propagations"]), reduce_sum(inc["nodes"]), reduce_max(inc["ms"])
     e_props, e_nodes, e_s = reduce_sum(e2e["propagations"]), reduce_sum(e2e["nodes"]), reduce_max(e2e["seconds"])
     if e2e_dev is not None:
         d_props, d_nodes, d_s = (reduce_sum(e2e_dev["propagations"]), reduce_sum(e2e_dev["nodes"]),
@@ -345,6 +361,11 @@ def run_ours(args):
             "warm": {"value": w_props / (w_ms * 1e-3) if w_ms > 0 else 0.0, "unit": "propagations/s",
                      "nodes_per_s": w_nodes / (w_ms * 1e-3) if w_ms > 0 else 0.0, "ms_per_step": w_ms / max(args.steps, 1),
                      "l2": "not flushed (descriptors L2-resident)"},
+            "incremental": (None if inc is None else {
+                "nodes_per_s": i_nodes / (i_ms * 1e-3) if i_ms > 0 else 0.0, "ms_per_step": i_ms / max(args.steps, 1),
+                "propagations_per_step": inc["propagations"] / max(inc["nodes"], 1),
+                "note": "PCP_FLAG_INCREMENTAL: no schedule-everything first sweep when the restored state was a "
+                        "fixpoint; same domains and statuses, L2 flushed between steps"}),
             "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s",
                     "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "ms_per_step": 1e3 * e_s * world / max(e_nodes, 1),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -2,6 +2,7 @@
 # round-1 final measurements: benches (C2 default, C3, C4, C5), reference arm, launch list, ncu full (C2, C4, C5)
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 300 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
 timeout 200 python bench.py --workload c4 --steps 20 --warmup 3 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; echo "bench c4 rc=$?"
 timeout 200 python bench.py --workload c3 --steps 200 --warmup 10 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
@@ -18,7 +19,7 @@ except Exception as ex:
 PY
 done
 tail -c 400 gpurun_out/bench_ref.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_v7.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
-PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 20 -c 4 -f -o gpurun_out/prof_r1_c2_v7 python bench.py --steps 30 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu c2 rc=$?"
-PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 6 -c 2 -f -o gpurun_out/prof_r1_c5_v7 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/ncu_full_c5.log 2>&1; echo "ncu c5 rc=$?"
-PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 4 -c 2 -f -o gpurun_out/prof_r1_c4_v7 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/ncu_full_c4.log 2>&1; echo "ncu c4 rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_v8.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
+PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 20 -c 4 -f -o gpurun_out/prof_r1_c2_v8 python bench.py --steps 30 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu c2 rc=$?"
+PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 6 -c 2 -f -o gpurun_out/prof_r1_c5_v8 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/ncu_full_c5.log 2>&1; echo "ncu c5 rc=$?"
+PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 4 -c 2 -f -o gpurun_out/prof_r1_c4_v8 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/ncu_full_c4.log 2>&1; echo "ncu c4 rc=$?"
