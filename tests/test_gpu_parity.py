@@ -400,6 +400,37 @@ def test_size_independent_properties_nqueens_1000():
     assert (back[0] == root[0]).all() and (back[1] == root[1]).all()
 
 
+def test_nqueens_5000_full_size():
+    """C5 at full size: V=5000, P=37,492,500 (600 MB of descriptors, 300 MB compact stream, rows
+    of 14,997 entries -- longer than the row staging area).  First 4 DFS nodes bit-exact against
+    the oracle's flat variant, then size-independent properties deeper in the tree: idempotence,
+    monotonicity along a branch, exact restore."""
+    m = models.nqueens(5000)
+    rd, ro, dev, ora = _compare_search(m, 4, oracle_variant=2)
+    del ora
+    dev2 = _engine()
+    m.load_into(dev2)
+    assert dev2.consistency()[0] == 0
+    root = dev2.domains()
+    l0 = dev2.label()
+    prev = root
+    for var, val in [(0, 1), (1, 3), (2, 5), (7, 2499), (8, 4999)]:
+        dev2.prop_alloc(models.X_EQ_Y, [[var, 0], [-1, val]])
+        st, _ = dev2.consistency()
+        assert st == 0
+        cur = dev2.domains()
+        assert (cur[0] >= prev[0]).all() and (cur[1] <= prev[1]).all()
+        st2, stats2 = dev2.consistency()
+        again = dev2.domains()
+        assert st2 == st and (again[0] == cur[0]).all() and (again[1] == cur[1]).all() and stats2.iterations == 1
+        prev = cur
+    # queen 0 sits on value 1, queen 8 on 4999+1-... : the bounds of the free queens moved off them
+    assert int(prev[0][5]) >= 2 and int(prev[1][5]) <= 5000
+    dev2.restore(l0)
+    back = dev2.domains()
+    assert (back[0] == root[0]).all() and (back[1] == root[1]).all()
+
+
 def test_sum_views():
     """term/sum.rs:56-92: a Sum operand reads [sum lo, sum hi]; with more than one term its
     update never prunes (overlap test only, can fail); a single-term Sum delegates.  Random
