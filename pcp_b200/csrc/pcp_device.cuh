@@ -126,6 +126,7 @@ struct Params {
   int2* dom;            // interval per variable: (lo, hi)
   int V;
   int smem_dom;         // 1: domains are staged in shared memory
+  int dirty_bm_off;     // byte offset (in dynamic shared memory) of the CTA's sweep dirty bitmap, 0 = none
   Family fam[3];        // BIN, TER, DJ
   const int* nary_ptr;  // CSR of n-ary Distinct operands
   const int2* nary_ops;
@@ -295,6 +296,7 @@ struct FamSweep {
   uint32_t* next_bits;   // dirty set written in this iteration
   uint32_t flags_s;      // shared-space address of the CTA's {narrowed, failed} flags
   uint32_t tbuf_s;       // shared-space address of the CTA's TrailBuf (entailed propagators of this sweep)
+  uint32_t dbm_s;        // shared-space address of the CTA's dirty bitmap (0: mark the global set directly)
   uint32_t* active_w;    // the family's `active` bit set (writable)
   uint32_t* trail;       // the entailment trail and its length (overflow path of the buffer)
   unsigned* trail_cnt;
@@ -473,9 +475,13 @@ __device__ __forceinline__ bool sweep_upd(const FamSweep& a, int var, int off, I
   const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
   if (lo) atomicMax(&a.dom_w[var].x, n.lo - off);
   if (hi) atomicMin(&a.dom_w[var].y, n.hi - off);
-  // (fire-and-forget: looking the bit up first was measured slower -- the look is a dependent
-  // load on the update path, the reduction is not)
-  if (lo || hi) atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
+  // the variable is queued: in the CTA's bitmap (one coalesced flush into the dirty set after
+  // the sweep instead of a scattered reduction per narrowing), else directly.  (Looking the bit
+  // up first was measured slower: the look is a dependent load on the update path.)
+  if (lo || hi) {
+    if (a.dbm_s) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a.dbm_s + 4u * (unsigned)(var >> 5)), "r"(1u << (var & 31)) : "memory");
+    else atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
+  }
   return lo || hi;
 }
 __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
@@ -1455,6 +1461,7 @@ struct CtaState {
   uint64_t* empty;
   int* flags;
   TrailBuf* tbuf;
+  uint32_t* dbm;     // dirty bitmap of this CTA's sweeps (dynamic shared memory) or nullptr
   // this CTA's share of a sweep: chunk G of the concatenated families belongs to worker
   // G % workers; per family the first chunk index, and the number of chunks
   int workers, wid, my_chunks;
@@ -1485,6 +1492,7 @@ __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& s
   a.next_bits = nullptr;  // set per iteration by the caller
   a.flags_s = smem_u32(st.flags);
   a.tbuf_s = smem_u32(st.tbuf);
+  a.dbm_s = st.dbm ? smem_u32(st.dbm) : 0u;
   a.active_w = P.fam[fam].active;
   a.trail = P.trail;
   a.trail_cnt = &P.ctl->trail_cnt;
@@ -1495,6 +1503,7 @@ __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* sm
                                          uint64_t* s_empty, int* s_flags, bool smem_dom) {
   st.ring = smem;
   st.sdom = smem_dom ? reinterpret_cast<int2*>(smem + kRingBytes) : nullptr;
+  st.dbm = P.dirty_bm_off ? reinterpret_cast<uint32_t*>(smem + P.dirty_bm_off) : nullptr;
   st.full = s_full;
   st.empty = s_empty;
   st.flags = s_flags;
@@ -1736,6 +1745,13 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       }
       if (lane == 0) nprop += n;  // counted per warp
       st.pipe_pos += st.my_chunks;
+      if (st.dbm) {  // what this CTA's sweep narrowed joins the dirty set of the next iteration
+        __syncthreads();
+        for (int w = threadIdx.x; w < W; w += blockDim.x) {
+          const unsigned m = st.dbm[w];
+          if (m) { atomicOr(&c.next_bits[w], m); st.dbm[w] = 0u; }
+        }
+      }
     }
     if (iter <= 1 && P.trace) { __syncthreads(); if (iter == 0) trace_mark(P, 3); else trace_mark1(P, iter, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
@@ -1796,6 +1812,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   // layout: [ring | n-ary staging (aliased)] [domain snapshot]
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
+  if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
   Control* ctl = P.ctl;
 
   if (threadIdx.x == 0) {
@@ -2100,6 +2117,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   __shared__ BurstLocal s_local;
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
+  if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
   Control* ctl = P.ctl;
   BurstCtl* bc = B.bc;
 
