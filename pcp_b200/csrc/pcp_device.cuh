@@ -1422,6 +1422,21 @@ __device__ __forceinline__ void node_prologue(const Params& P, int tid, int nth)
     for (int v = tid; v < P.V; v += nth) P.dom[v] = P.restore_from[v];
   if (P.do_trail) {
     unsigned cnt = *(volatile unsigned*)&P.ctl->trail_cnt;
+    if (P.trail_keep == 0 && cnt > 4096u) {
+      // back to a state in which nothing was entailed (the root of a search, a restart) over a
+      // long trail: every allocated propagator is active again -- whole words instead of one
+      // reduction per trail entry
+      for (int f = 0; f < 4; ++f) {
+        uint32_t* act = f == F_NARY ? P.nary_active_w : P.fam[f].active;
+        const int n = f == F_NARY ? P.n_nary : P.fam[f].n;
+        for (int w = tid; w < (n + 31) / 32; w += nth) {
+          const int bits = min(32, n - w * 32);
+          const unsigned m = bits == 32 ? 0xffffffffu : ((1u << bits) - 1u);
+          if (bits == 32) act[w] = m; else atomicOr(&act[w], m);
+        }
+      }
+      cnt = 0;  // (the loop below has nothing left to do)
+    }
     for (unsigned i = P.trail_keep + tid; i < cnt; i += nth) {
       unsigned ref = P.trail[i];
       unsigned fam = ref >> 29, slot = ref & kSlotMask;
