@@ -292,14 +292,6 @@ struct FamSweep {
   int pipe_pos, first;   // `first` chunks were already issued (pre_issue)
   uint32_t ring_s, full_s, empty_s, sdom_s;
   int have_aw;           // the caller prefetched the active words of the first chunk
-  int2* dom_w;           // the store itself (updates)
-  uint32_t* next_bits;   // dirty set written in this iteration
-  uint32_t flags_s;      // shared-space address of the CTA's {narrowed, failed} flags
-  uint32_t tbuf_s;       // shared-space address of the CTA's TrailBuf (entailed propagators of this sweep)
-  uint32_t dbm_s;        // shared-space address of the CTA's dirty bitmap (0: mark the global set directly)
-  uint32_t* active_w;    // the family's `active` bit set (writable)
-  uint32_t* trail;       // the entailment trail and its length (overflow path of the buffer)
-  unsigned* trail_cnt;
 };
 
 // Propagators found entailed during a sweep: their active bit is cleared with a fire-and-
@@ -310,24 +302,24 @@ struct FamSweep {
 // immaterial: a restore re-activates the whole suffix (store.rs:319-323).
 constexpr int kTrailBuf = 4088;
 struct TrailBuf { unsigned n; unsigned pad; unsigned ref[kTrailBuf]; };
-__device__ __forceinline__ void sweep_deactivate(const FamSweep& a, unsigned fam, int slot) {
-  atomicAnd(&a.active_w[slot >> 5], ~(1u << (slot & 31)));
+__device__ __forceinline__ void sweep_deactivate(const Ctx& c, const FamSweep& a, unsigned fam, int slot) {
+  atomicAnd(const_cast<uint32_t*>(&a.active[slot >> 5]), ~(1u << (slot & 31)));
   const unsigned m = __activemask();
   const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
   unsigned base = 0;
-  if (lane == leader) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(a.tbuf_s), "r"(__popc(m)) : "memory");
+  if (lane == leader) asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(base) : "r"(c.tbuf_s), "r"(__popc(m)) : "memory");
   base = __shfl_sync(m, base, leader);
   const unsigned pos = base + __popc(m & lanemask_lt());
   const unsigned ref = make_ref(fam, (unsigned)slot);
   if (pos < (unsigned)kTrailBuf) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.tbuf_s + 8u + 4u * pos), "r"(ref) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.tbuf_s + 8u + 4u * pos), "r"(ref) : "memory");
   } else {  // buffer full: straight to the trail, one reservation per warp
     const unsigned mo = __activemask();
     const int lo = __ffs(mo) - 1;
     unsigned gb = 0;
-    if (lane == lo) gb = atomicAdd(a.trail_cnt, (unsigned)__popc(mo));
+    if (lane == lo) gb = atomicAdd(c.trail_cnt, (unsigned)__popc(mo));
     gb = __shfl_sync(mo, gb, lo);
-    a.trail[gb + __popc(mo & lanemask_lt())] = ref;
+    c.trail[gb + __popc(mo & lanemask_lt())] = ref;
   }
 }
 // Every thread of the CTA, before the iteration's barrier.
@@ -471,16 +463,17 @@ __device__ __forceinline__ void ring_advance(RingPos& r) {
 // by finish_eval -- geq half, then leq half on the narrowed values (x_eq_y_plus_z.rs:79-81),
 // Kleene entailment on the result, nothing applied on failure -- with the updates issued as
 // fire-and-forget reductions straight from registers.  Entailment (rare) stays out of line.
-__device__ __forceinline__ bool sweep_upd(const FamSweep& a, int var, int off, IV o, IV n) {
+__device__ __forceinline__ bool sweep_upd(const Ctx& c, int var, int off, IV o, IV n) {
   const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
-  if (lo) atomicMax(&a.dom_w[var].x, n.lo - off);
-  if (hi) atomicMin(&a.dom_w[var].y, n.hi - off);
+  if (lo) atomicMax(&c.dom_w[var].x, n.lo - off);
+  if (hi) atomicMin(&c.dom_w[var].y, n.hi - off);
   // the variable is queued: in the CTA's bitmap (one coalesced flush into the dirty set after
   // the sweep instead of a scattered reduction per narrowing), else directly.  (Looking the bit
   // up first was measured slower: the look is a dependent load on the update path.)
   if (lo || hi) {
-    if (a.dbm_s) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a.dbm_s + 4u * (unsigned)(var >> 5)), "r"(1u << (var & 31)) : "memory");
-    else atomicOr(&a.next_bits[var >> 5], 1u << (var & 31));
+    const uint32_t dbm_s = c.dbm_s;
+    if (dbm_s) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(dbm_s + 4u * (unsigned)(var >> 5)), "r"(1u << (var & 31)) : "memory");
+    else atomicOr(&c.next_bits[var >> 5], 1u << (var & 31));
   }
   return lo || hi;
 }
@@ -489,14 +482,14 @@ __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep
   const bool ok = prop_greater(x, y, z, 0) && prop_less(x, y, z, 0);
   const int s = ok ? sub_eq(x, y, z) : -1;
   if (s < 0) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s + 4u), "r"(1) : "memory");  // flags[1]: failure
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s + 4u), "r"(1) : "memory");  // flags[1]: failure
     return;
   }
-  bool ch = sweep_upd(a, (int)((unsigned)d.x & kConstVar28), d.y, x0, x);
-  ch |= sweep_upd(a, d.z, d.w, y0, y);
-  ch |= sweep_upd(a, e.x, e.y, z0, z);
-  if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s), "r"(1) : "memory");  // flags[0]: narrowed
-  if (s > 0) sweep_deactivate(a, F_TER, slot);
+  bool ch = sweep_upd(c, (int)((unsigned)d.x & kConstVar28), d.y, x0, x);
+  ch |= sweep_upd(c, d.z, d.w, y0, y);
+  ch |= sweep_upd(c, e.x, e.y, z0, z);
+  if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s), "r"(1) : "memory");  // flags[0]: narrowed
+  if (s > 0) sweep_deactivate(c, a, F_TER, slot);
 }
 
 // XNeqY over plain variables that is not a no-op: eval_bin's B_NEQ branch + finish_eval inline
@@ -511,13 +504,13 @@ __device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a
   }
   const bool fail = ny.lo > ny.hi || nx.lo > nx.hi || (nx.lo == ny.hi && nx.hi == ny.lo);
   if (fail) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s + 4u), "r"(1) : "memory");
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s + 4u), "r"(1) : "memory");
     return;
   }
-  bool ch = sweep_upd(a, d.z, d.w, y, ny);
-  ch |= sweep_upd(a, (int)((unsigned)d.x & kConstVar28), d.y, x, nx);
-  if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(a.flags_s), "r"(1) : "memory");
-  if (nx.hi < ny.lo || ny.hi < nx.lo) sweep_deactivate(a, F_BIN, slot);
+  bool ch = sweep_upd(c, d.z, d.w, y, ny);
+  ch |= sweep_upd(c, (int)((unsigned)d.x & kConstVar28), d.y, x, nx);
+  if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s), "r"(1) : "memory");
+  if (nx.hi < ny.lo || ny.hi < nx.lo) sweep_deactivate(c, a, F_BIN, slot);
 }
 
 // The streaming sweep of one CTA over the binary family (XLessY / XNeqY / XEqY): warp 0 (one
@@ -1503,14 +1496,6 @@ __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& s
   a.empty_s = smem_u32(st.empty);
   a.sdom_s = st.sdom ? smem_u32(st.sdom) : 0u;
   a.have_aw = 0;
-  a.dom_w = P.dom;
-  a.next_bits = nullptr;  // set per iteration by the caller
-  a.flags_s = smem_u32(st.flags);
-  a.tbuf_s = smem_u32(st.tbuf);
-  a.dbm_s = st.dbm ? smem_u32(st.dbm) : 0u;
-  a.active_w = P.fam[fam].active;
-  a.trail = P.trail;
-  a.trail_cnt = &P.ctl->trail_cnt;
   return a;
 }
 
@@ -1567,13 +1552,67 @@ __device__ __forceinline__ void pre_issue(const Params& P, CtaState& st) {
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// The cold sections of a node -- worklist rows, n-ary propagators, the tail, the prologue, the
+// device search's host step -- are compiled out of line, each with its own register
+// allocation: inlined into the one big kernel body they cost the hot path (snapshot, posted
+// constraint, sweep, barrier) registers, spills and instruction-cache footprint (every feature
+// added there measurably slowed the C2 node).  They read the launch parameters from a copy in
+// shared memory (`PS`; a pointer to the kernel's own parameter space would make every access
+// a generic load).
+// ---------------------------------------------------------------------------------------
+template <bool SMEM>
+__device__ __noinline__ unsigned rows_outlined(const Params* PS, Ctx* c, const int* list, int n_dirty, unsigned cur_epoch,
+                                               char* ring, TrailBuf* tb) {
+  return expand_dirty_rows<SMEM>(*PS, *c, list, n_dirty, cur_epoch, ring, tb);
+}
+template <bool SMEM>
+__device__ __noinline__ unsigned nary_outlined(const Params* PS, const Ctx* c, char* ring, const uint32_t* cur_bits, bool all) {
+  const Params& P = *PS;
+  unsigned n = 0;
+  // dealt from the last CTA backwards: CTA 0 (prologue, posted and tail propagators) is the
+  // last to get one
+  for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
+    if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
+    unsigned ev = __ldg(&P.nary_kind[s]) == N_ALL_EQUAL ? eval_all_equal<SMEM>(P, *c, s, cur_bits, all)
+                                                         : eval_distinct<SMEM>(P, *c, s, ring, cur_bits, all);
+    if (threadIdx.x == 0) n += ev;
+  }
+  return n;
+}
+// older tail propagators: CTA 0, every iteration (the posted ones are handled by the caller),
+// after the refresh so that they read this CTA's snapshot: active word and descriptor in one
+// round trip, no gather of the domains
+template <bool SMEM>
+__device__ __noinline__ unsigned tail_outlined(const Params* PS, const Ctx* c, int bin_n, bool first_iter, int n_inline,
+                                               const InlineProp* inl) {
+  const Params& P = *PS;
+  unsigned n = 0;
+  for (unsigned fam = 0; fam < 3; ++fam) {
+    const Family& f = P.fam[fam];
+    const int fn = fam == F_BIN ? bin_n : f.n;
+    for (int p = f.n_static + threadIdx.x; p < fn; p += blockDim.x) {
+      bool is_inl = false;
+      if (first_iter)
+        for (int i = 0; i < n_inline; ++i) is_inl |= inl[i].fam == fam && inl[i].slot == p;
+      if (is_inl) continue;
+      const unsigned word = __ldcg(&f.active[p >> 5]);
+      int4 q0, q1, q2;
+      load_desc(f, fam, p, q0, q1, q2);
+      if ((word >> (p & 31)) & 1u) { eval_loaded<SMEM>(*c, fam, p, q0, q1, q2); ++n; }
+    }
+  }
+  return n;
+}
+__device__ __noinline__ void prologue_outlined(const Params* PS, int tid, int nth) { node_prologue(*PS, tid, nth); }
+
 // One node's fixpoint: iteration 0 (posted propagators, tail, streaming sweep or seeded
 // worklist) and the worklist / re-sweep iterations, each closed by the deciding barrier.
 // Every thread of every CTA calls it with the same arguments; returns the decision, `iters`
 // the number of iterations.  `bin_n` is the end of the binary tail (dynamic during a burst).
 // On return the three dirty sets are empty again.
 template <bool SMEM>
-__device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st, unsigned epoch0, int bin_n,
+__device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params* PS, CtaState& st, unsigned epoch0, int bin_n,
                                                   int n_inline, const InlineProp* inl, bool full_sweep,
                                                   int seeded, bool pre_issued, unsigned& iters_out) {
   __shared__ unsigned s_wprops[kWarps];
@@ -1595,6 +1634,12 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     c.sdom_s = SMEM ? smem_u32(st.sdom) : 0u;
     c.flags = st.flags;
     c.mirror = false;
+    c.dom_w = P.dom;
+    c.trail = P.trail;
+    c.trail_cnt = &P.ctl->trail_cnt;
+    c.flags_s = smem_u32(st.flags);
+    c.tbuf_s = smem_u32(st.tbuf);
+    c.dbm_s = st.dbm ? smem_u32(st.dbm) : 0u;
   }
   ActiveWords aw;
   aw.w[0] = aw.w[1] = aw.w[2] = aw.w[3] = 0u;
@@ -1701,29 +1746,10 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
         skip = SMEM;
       }
       trace_mark1(P, iter, 2);
-      if (!skip && !sweep_now && n_dirty > 0) nprop += expand_dirty_rows<SMEM>(P, c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
+      if (!skip && !sweep_now && n_dirty > 0) nprop += rows_outlined<SMEM>(PS, &c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
     }
-    // older tail propagators: CTA 0, every iteration (the posted ones were handled above), after
-    // the refresh so that they read this CTA's snapshot: active word and descriptor in one
-    // round trip, no gather of the domains
-    if (blockIdx.x == 0 && !skip) {
-      unsigned n = 0;
-      for (unsigned fam = 0; fam < 3; ++fam) {
-        const Family& f = P.fam[fam];
-        const int fn = fam == F_BIN ? bin_n : f.n;
-        for (int p = f.n_static + threadIdx.x; p < fn; p += blockDim.x) {
-          bool is_inl = false;
-          if (iter == 0)
-            for (int i = 0; i < n_inline; ++i) is_inl |= inl[i].fam == fam && inl[i].slot == p;
-          if (is_inl) continue;
-          const unsigned word = __ldcg(&f.active[p >> 5]);
-          int4 q0, q1, q2;
-          load_desc(f, fam, p, q0, q1, q2);
-          if ((word >> (p & 31)) & 1u) { eval_loaded<SMEM>(c, fam, p, q0, q1, q2); ++n; }
-        }
-      }
-      nprop += n;
-    }
+    if (blockIdx.x == 0 && !skip && (P.fam[0].n_static < bin_n || P.fam[1].n_static < P.fam[1].n || P.fam[2].n_static < P.fam[2].n))
+      nprop += tail_outlined<SMEM>(PS, &c, bin_n, iter == 0, n_inline, inl);
     if (sweep_now && !skip && st.my_chunks > 0) {
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep
       // counting across sweeps so the mbarrier phases stay consistent).  (`skip` is never set
@@ -1738,7 +1764,6 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       int seq = 0;
       if (st.fam_cnt[0] > 0) {
         FamSweep a = fam_sweep(P, st, 0, seq, pre);
-        a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 0;
         const bool lean = P.fam[0].all_plain && P.fam[0].kind_mask == (1 << B_NEQ);
         if (compact) n += sweep_bin_compact<SMEM>(c, a, awc0, awc1);
@@ -1747,7 +1772,6 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
       }
       if (st.fam_cnt[1] > 0) {
         FamSweep a = fam_sweep(P, st, 1, seq, pre);
-        a.next_bits = c.next_bits;
         a.have_aw = have_aw && fam_first == 1;
         const bool lean = P.fam[1].all_plain && P.fam[1].kind_mask == (1 << T_EQ);
         n += lean ? sweep_ter<SMEM, true>(c, a, aw4) : sweep_ter<SMEM, false>(c, a, aw4);
@@ -1770,17 +1794,8 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, CtaState& st,
     }
     if (iter <= 1 && P.trace) { __syncthreads(); if (iter == 0) trace_mark(P, 3); else trace_mark1(P, iter, 3); }
     // n-ary propagators: one CTA each; re-run when one of their operands is dirty.
-    if (P.n_nary > 0 && !skip && (iter > 0 || full_sweep || n_dirty > 0)) {
-      // dealt from the last CTA backwards: CTA 0 (prologue, posted and tail propagators) is
-      // the last to get one
-      for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
-        if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-        const bool all = iter == 0 && full_sweep;
-        unsigned ev = __ldg(&P.nary_kind[s]) == N_ALL_EQUAL ? eval_all_equal<SMEM>(P, c, s, cur_bits, all)
-                                                             : eval_distinct<SMEM>(P, c, s, st.ring, cur_bits, all);
-        if (threadIdx.x == 0) nprop += ev;
-      }
-    }
+    if (P.n_nary > 0 && !skip && (iter > 0 || full_sweep || n_dirty > 0))
+      nprop += nary_outlined<SMEM>(PS, &c, st.ring, cur_bits, iter == 0 && full_sweep);
 
     // block-level propagation count (per-warp partial sums in shared memory, no atomics),
     // then the barrier + decision
@@ -1825,6 +1840,13 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   __shared__ int s_flags[2];
   // layout: [ring | n-ary staging (aliased)] [domain snapshot]
+  __shared__ Params s_P;  // copy of the launch parameters for the out-of-line cold sections
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&P);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = src[i];  // (ordered by the barrier below)
+  }
+  const Params* PS = &s_P;
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
@@ -1849,20 +1871,20 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   trace_mark(P, 0);
 
   if (P.sync0) {
-    node_prologue(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    prologue_outlined(PS, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     grid_barrier(P, st.gen, 0, false, s_flags, 0);  // its last arriver resets trail_cnt (nobody pushes yet)
     if (SMEM) {
       for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
       __syncthreads();
     }
   } else if (blockIdx.x == 0) {
-    node_prologue(P, threadIdx.x, blockDim.x);  // CTA-local effects only (posted propagators)
+    prologue_outlined(PS, threadIdx.x, blockDim.x);  // CTA-local effects only (posted propagators)
     __syncthreads();
   }
   trace_mark(P, 1);
 
   unsigned iters = 0;
-  const unsigned dec = fixpoint_node<SMEM>(P, st, epoch0, P.fam[F_BIN].n, P.n_inline, P.inl, P.full_sweep != 0,
+  const unsigned dec = fixpoint_node<SMEM>(P, PS, st, epoch0, P.fam[F_BIN].n, P.n_inline, P.inl, P.full_sweep != 0,
                                            P.seed_dirty, P.full_sweep != 0, iters);
 
   trace_mark(P, 6);
@@ -1976,7 +1998,7 @@ __device__ __forceinline__ void burst_store(BurstCtl* bc, const BurstLocal* L) {
 // CTA 0, all threads: the host's work between two fixpoints.  `have_node`: a node just reached
 // its decision `dec` (false at the start of a launch).  `scratch`: V int2 of shared memory
 // (CTA 0's snapshot area) or nullptr.  Posts the next node through `bc` or stops the burst.
-__device__ __forceinline__ void burst_host_step(const Params& P, const BurstParams& B, BurstLocal* L, int2* scratch,
+__device__ __noinline__ void burst_host_step(const Params& P, const BurstParams& B, BurstLocal* L, int2* scratch,
                                                 bool have_node, unsigned dec, unsigned iters, unsigned long long done) {
   __shared__ unsigned long long s_best[kWarps];
   __shared__ int4 s_pop;
@@ -2130,6 +2152,19 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   __shared__ int s_cmd, s_slot, s_bin_n;
   __shared__ InlineProp s_inl;
   __shared__ BurstLocal s_local;
+  __shared__ Params s_P;  // copy of the launch parameters for the out-of-line cold sections
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&P);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = src[i];  // (ordered by the barrier below)
+  }
+  const Params* PS = &s_P;
+  __shared__ BurstParams s_B;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&B);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_B);
+    for (int i = threadIdx.x; i < (int)(sizeof(BurstParams) / 4); i += blockDim.x) dst[i] = src[i];
+  }
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
@@ -2155,7 +2190,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   __shared__ unsigned long long s_mnodes, s_sel[kWarps];
   __shared__ unsigned s_tc;
   unsigned long long done = 0;
-  if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, false, 0, 0, done);
+  if (blockIdx.x == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, false, 0, 0, done);
   bool fast = false;  // uniform across the grid
   while (true) {
     if (!fast) {
@@ -2180,7 +2215,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
       if (s_cmd != 0) break;
     }
     unsigned iters = 0;
-    const unsigned dec = fixpoint_node<SMEM>(P, st, epoch, s_bin_n, s_slot >= 0 ? 1 : 0, &s_inl, true, 0, true, iters);
+    const unsigned dec = fixpoint_node<SMEM>(P, PS, st, epoch, s_bin_n, s_slot >= 0 ? 1 : 0, &s_inl, true, 0, true, iters);
     epoch += iters + 1;
     ++done;
     // the next sweep's descriptors can stream in while CTA 0 does the host's work
@@ -2212,7 +2247,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
       fast = unknown && best != ~0ull && !stop && done < B.node_budget && s_mlabels < B.max_labels &&
              s_mbranch + 2 <= B.max_branches && s_mbin < B.bin_cap;
     }
-    if (blockIdx.x == 0) burst_host_step(P, B, &s_local, st.sdom, true, dec, iters, done);
+    if (blockIdx.x == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, true, dec, iters, done);
     if (fast) {
       __syncthreads();  // everybody has read the mirrors (and CTA 0 is done with its snapshot)
       if (threadIdx.x == 0) {

@@ -24,6 +24,14 @@ struct Ctx {
   bool bookkeep;          // entailed propagators are deactivated + trailed
   bool mirror;            // row-local rounds: every update is also applied to this CTA's snapshot
   int* flags;             // shared: [0] this CTA narrowed a variable, [1] saw a failure
+  // what the update paths of the lean sweeps need (CTA-uniform, so kept here and not in the
+  // by-value FamSweep: past 128 bytes that struct travels through local memory)
+  int2* dom_w;            // the store itself
+  uint32_t* trail;        // entailment trail and its length
+  unsigned* trail_cnt;
+  uint32_t flags_s;       // shared-space addresses: flags, the sweep's TrailBuf, its dirty bitmap (0: none)
+  uint32_t tbuf_s;
+  uint32_t dbm_s;
 };
 
 __device__ __forceinline__ void set_failed(const Ctx& c) { c.flags[1] = 1; }

@@ -585,3 +585,12 @@ def test_all_equal_classes_with_distinct_representatives():
     assert dev.consistency()[0] == ora.consistency()[0] == 0
     _assert_same_state(dev, ora)
     _compare_search(m, 200)
+
+
+def test_compact_descriptor_stream_forced(monkeypatch):
+    """The compact 8-byte descriptor stream is only built for stores whose descriptors exceed the
+    L2 working set (C5); PCP_FORCE_COMPACT builds it for any all-XNeqY store, so that the sweep
+    over it is also checked node by node at a size the oracle handles (n-queens N=200 and 64)."""
+    monkeypatch.setenv("PCP_FORCE_COMPACT", "1")
+    _compare_search(models.nqueens(200), 150)
+    _compare_search(models.nqueens(64, "distinct"), 200)
