@@ -701,9 +701,9 @@ bool prologue_pending(const pcp_engine* e) {
 }
 
 __global__ void __launch_bounds__(1024, 1) pcp_prologue_kernel(const __grid_constant__ Params P) {
-  node_prologue(P, threadIdx.x, blockDim.x);  // single CTA
+  full::node_prologue(P, threadIdx.x, blockDim.x);  // single CTA
   __syncthreads();
-  if (threadIdx.x == 0) node_prologue_finish(P);
+  if (threadIdx.x == 0) full::node_prologue_finish(P);
 }
 
 // Bring the device state up to date without running a fixpoint (pcp_domains_read /
@@ -713,6 +713,18 @@ void sync_device_state(pcp_engine* e) {
   Params P = prepare(e);
   pcp_prologue_kernel<<<1, 1024, 0, e->stream>>>(P);
   CUDA_CHECK(cudaGetLastError());
+}
+
+// Kernel variants: `binonly` for stores whose propagators are all binary (no ternary,
+// disjunction or n-ary code in the kernel -- see pcp_body.cuh), `full` otherwise.
+bool bin_only_store(const pcp_engine* e) { return e->fam[F_TER].n == 0 && e->fam[F_DJ].n == 0 && e->n_nary == 0; }
+const void* fixpoint_fn(bool bin_only, bool smem_dom) {
+  if (bin_only) return smem_dom ? (const void*)binonly::pcp_fixpoint_kernel<true> : (const void*)binonly::pcp_fixpoint_kernel<false>;
+  return smem_dom ? (const void*)full::pcp_fixpoint_kernel<true> : (const void*)full::pcp_fixpoint_kernel<false>;
+}
+const void* burst_fn(bool bin_only, bool smem_dom) {
+  if (bin_only) return smem_dom ? (const void*)binonly::pcp_burst_kernel<true> : (const void*)binonly::pcp_burst_kernel<false>;
+  return smem_dom ? (const void*)full::pcp_burst_kernel<true> : (const void*)full::pcp_burst_kernel<false>;
 }
 
 // The persistent kernels need every CTA co-resident (they meet at a device-wide barrier):
@@ -802,7 +814,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
       smem += bm_bytes;
     }
   }
-  const void* fn = smem_dom ? (const void*)pcp_fixpoint_kernel<true> : (const void*)pcp_fixpoint_kernel<false>;
+  const void* fn = fixpoint_fn(bin_only_store(e), smem_dom);
 
   static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (trace_on) {
@@ -986,8 +998,8 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     {
       // dynamic shared memory every persistent kernel may use = the opt-in maximum minus its own
       // static part; configured once (an engine never lowers what another engine relies on)
-      const void* fns[4] = {(const void*)pcp_fixpoint_kernel<false>, (const void*)pcp_fixpoint_kernel<true>,
-                            (const void*)pcp_burst_kernel<false>, (const void*)pcp_burst_kernel<true>};
+      const void* fns[8] = {fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
+                            fixpoint_fn(true, false),  fixpoint_fn(true, true),  burst_fn(true, false),  burst_fn(true, true)};
       size_t max_static = 0;
       for (const void* fn : fns) {
         cudaFuncAttributes fa;
@@ -1362,7 +1374,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
         smem += bm_bytes;
       }
     }
-    const void* fn = smem_dom ? (const void*)pcp_burst_kernel<true> : (const void*)pcp_burst_kernel<false>;
+    const void* fn = burst_fn(bin_only_store(e), smem_dom);
     CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
     void* args[] = {&P, &B};
     launch_persistent(fn, grid, args, smem, e->stream);

@@ -7,9 +7,9 @@
 // issues the staged updates as fire-and-forget reductions on the bounds and on the dirty
 // bit set.  A cheap inline "would this evaluation change anything?" test keeps the common
 // case of a sweep free of calls.
-#pragma once
+// (No include guard and no namespace of its own: pcp_body.cuh includes this file inside the
+// namespace of the kernel variant being compiled.)
 
-namespace pcpd {
 
 struct IV { int lo, hi; };
 
@@ -389,12 +389,15 @@ template <bool SMEM>
 __device__ __forceinline__ void eval_full(const Ctx& c, unsigned fam, int slot, int4 q0, int4 q1, int4 q2) {
   if (fam == F_BIN) {
     eval_full_bin(c, slot, q0, rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), rd<SMEM>(c, q0.z, q0.w));
-  } else if (fam == F_TER) {
+  }
+#ifndef PCP_BIN_ONLY
+  else if (fam == F_TER) {
     eval_full_ter(c, slot, q0, make_int2(q1.x, q1.y), rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), rd<SMEM>(c, q0.z, q0.w),
                   rd<SMEM>(c, q1.x, q1.y));
   } else {
     eval_full_dj<SMEM>(c, slot, q0, q1, q2);
   }
+#endif
 }
 
 // Gather one descriptor from global memory (worklist expansion, tail).
@@ -418,12 +421,15 @@ __device__ __forceinline__ void eval_loaded(const Ctx& c, unsigned fam, int slot
   if (fam == F_BIN) {
     IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w);
     if (!bin_is_noop((unsigned)q0.x >> 28, x, y)) eval_full_bin(c, slot, q0, x, y);
-  } else if (fam == F_TER) {
+  }
+#ifndef PCP_BIN_ONLY
+  else if (fam == F_TER) {
     IV x = rd<SMEM>(c, dec_var28((unsigned)q0.x), q0.y), y = rd<SMEM>(c, q0.z, q0.w), z = rd<SMEM>(c, q1.x, q1.y);
     if (!ter_is_noop((unsigned)q0.x >> 28, x, y, z)) eval_full_ter(c, slot, q0, make_int2(q1.x, q1.y), x, y, z);
   } else {
     if (!dj_is_noop<SMEM>(c, q0, q1, q2)) eval_full_dj<SMEM>(c, slot, q0, q1, q2);
   }
+#endif
 }
 template <bool SMEM>
 __device__ __forceinline__ void eval_ref(const Ctx& c, unsigned fam, int slot) {
@@ -436,4 +442,3 @@ __device__ __forceinline__ bool is_active(const Family& f, int slot) {
   return (__ldcg(&f.active[slot >> 5]) >> (slot & 31)) & 1u;
 }
 
-}  // namespace pcpd
