@@ -19,7 +19,7 @@ except Exception as ex:
 PY
 done
 tail -c 400 gpurun_out/bench_ref.json
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_v9.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
-PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 20 -c 4 -f -o gpurun_out/prof_r1_c2_v9 python bench.py --steps 30 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu c2 rc=$?"
-PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 6 -c 2 -f -o gpurun_out/prof_r1_c5_v9 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/ncu_full_c5.log 2>&1; echo "ncu c5 rc=$?"
-PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 4 -c 2 -f -o gpurun_out/prof_r1_c4_v9 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/ncu_full_c4.log 2>&1; echo "ncu c4 rc=$?"
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1_v10.csv python bench.py --steps 20 --warmup 3 > gpurun_out/ncu_b.log 2>&1; echo "ncu list rc=$?"
+PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 20 -c 4 -f -o gpurun_out/prof_r1_c2_v10 python bench.py --steps 30 --warmup 3 > gpurun_out/ncu_full.log 2>&1; echo "ncu c2 rc=$?"
+PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 6 -c 2 -f -o gpurun_out/prof_r1_c5_v10 python bench.py --workload c5 --steps 4 --warmup 3 > gpurun_out/ncu_full_c5.log 2>&1; echo "ncu c5 rc=$?"
+PCP_NO_BURST=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:pcp_fixpoint -s 4 -c 2 -f -o gpurun_out/prof_r1_c4_v10 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/ncu_full_c4.log 2>&1; echo "ncu c4 rc=$?"
