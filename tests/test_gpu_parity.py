@@ -594,3 +594,30 @@ def test_compact_descriptor_stream_forced(monkeypatch):
     monkeypatch.setenv("PCP_FORCE_COMPACT", "1")
     _compare_search(models.nqueens(200), 150)
     _compare_search(models.nqueens(64, "distinct"), 200)
+
+
+def test_result_paths_agree():
+    """pcp_consistency returns status + domains three ways -- zero-copy into the mapped mirror
+    (default), copy + synchronise (timing enabled), header only + explicit copy (more than 8192
+    variables) -- and pcp_stream hands out the stream the launches run on."""
+    import torch
+    for n in (300, 9000):   # 9000 variables: the domains are not part of the zero-copy result
+        m = models.chained_lt(n, 0, n + 3)
+        a, b = _engine(), _engine(timing=True)
+        m.load_into(a)
+        m.load_into(b)
+        sa, _ = a.consistency()
+        sb, stb = b.consistency()
+        assert sa == sb == 0 and stb.kernel_ms > 0
+        la, ha = a.domains()
+        lb, hb = b.domains()
+        assert (la == lb).all() and (ha == hb).all()
+        assert (la == np.arange(n)).all() and (ha == np.arange(n) + 4).all()
+        # work queued on the engine's stream is ordered before the next fixpoint
+        s = torch.cuda.ExternalStream(a.cuda_stream(), device=torch.device("cuda", 0))
+        with torch.cuda.stream(s):
+            torch.zeros(1 << 20, device="cuda").add_(1)
+        a.prop_alloc(models.X_LESS_Y, [[0, 0], [-1, 1]])      # x0 < 1
+        assert a.consistency()[0] == 0
+        la2, ha2 = a.domains()
+        assert int(ha2[0]) == 0 and (la2 == la).all()
