@@ -202,6 +202,13 @@ int pcp_search_open(pcp_engine* e, const pcp_search_config* cfg, int32_t* trace_
                     uint64_t* trace_hash, int32_t* trace_lo, int32_t* trace_hi,
                     uint64_t trace_capacity, pcp_search** out);
 int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res);
+/* BranchAndBound's incumbent (search/branch_and_bound.rs:69-94) seen from outside: between two
+ * pcp_search_step slices a rank adopts the best objective value any rank has found (the one-word
+ * all-reduce of SURVEY 8e).  `value` replaces the local incumbent only when it improves on it
+ * (smaller when minimising, larger when maximising); every node entered afterwards posts
+ * `bb_var < value` (`>` when maximising) exactly as branch_and_bound.rs:76-87 does with its own
+ * incumbent.  PCP_ERR_INVALID when the search was opened without bb_mode. */
+int pcp_search_set_incumbent(pcp_search* s, int32_t value);
 void pcp_search_close(pcp_search* s);
 
 #ifdef __cplusplus

@@ -234,6 +234,8 @@ class _Counters:
 
     def __init__(self):
         self.status = 0
+        self.has_bb_value = 0
+        self.bb_value = 0
         self.num_nodes = self.num_solution = self.num_failed_node = self.num_prune = 0
         self.propagations = self.iterations = 0
         self.seconds = self.kernel_seconds = 0.0
@@ -244,8 +246,11 @@ class PySearchHandle:
     surface (restore / prop_alloc / consistency / domains / label).  Any `EngineBase` can use
     it; the device engine overrides `search_open` with the native driver."""
 
-    def __init__(self, engine: "EngineBase", all_solutions: bool = False, node_limit: int = 0, warmup_nodes: int = 0):
+    def __init__(self, engine: "EngineBase", all_solutions: bool = False, node_limit: int = 0, warmup_nodes: int = 0,
+                 bb_mode: int = 0, bb_var: int = 0):
         self.e = engine
+        self.bb_mode = bb_mode
+        self.bb_var = bb_var
         self.all_solutions = all_solutions
         self.node_limit = node_limit
         self.warmup = warmup_nodes
@@ -258,8 +263,13 @@ class PySearchHandle:
     def _enter_child(self) -> int:
         import time
         t0 = time.perf_counter()
-        st, stats = self.e.consistency()
         r = self.res
+        if self.bb_mode and r.has_bb_value:  # branch_and_bound.rs:76-87
+            if self.bb_mode == 1:
+                self.e.prop_alloc(0, [[self.bb_var, 0], [-1, r.bb_value]])   # var < incumbent
+            else:
+                self.e.prop_alloc(0, [[-1, r.bb_value], [self.bb_var, 0]])   # var > incumbent
+        st, stats = self.e.consistency()
         if r.num_nodes >= self.warmup:
             r.propagations += int(stats.propagations)
             r.iterations += int(stats.iterations)
@@ -273,6 +283,9 @@ class PySearchHandle:
             label = self.e.label()
             self.stack.append((label, var, val, 1))
             self.stack.append((label, var, val, 0))
+        if st == TRUE and self.bb_mode:  # branch_and_bound.rs:89-92
+            lo, _ = self.e.domains(self.bb_var, 1)
+            r.has_bb_value, r.bb_value = 1, int(lo[0])
         r.num_nodes += 1
         stop = self.node_limit and r.num_nodes >= self.node_limit
         if stop:
@@ -320,12 +333,21 @@ class PySearchHandle:
                 r.status = 1
                 return r
 
+    def set_incumbent(self, value: int) -> None:
+        """pcp_search_set_incumbent: adopt a better incumbent found elsewhere."""
+        assert self.bb_mode, "search opened without bb_mode"
+        r = self.res
+        if not r.has_bb_value or (value < r.bb_value if self.bb_mode == 1 else value > r.bb_value):
+            r.has_bb_value, r.bb_value = 1, int(value)
+
     def close(self) -> None:
         pass
 
 
-def _search_open(self, node_limit: int = 0, all_solutions: bool = False, warmup_nodes: int = 0, **_kw):
-    return PySearchHandle(self, all_solutions=all_solutions, node_limit=node_limit, warmup_nodes=warmup_nodes)
+def _search_open(self, node_limit: int = 0, all_solutions: bool = False, warmup_nodes: int = 0, bb_mode: int = 0,
+                 bb_var: int = 0, **_kw):
+    return PySearchHandle(self, all_solutions=all_solutions, node_limit=node_limit, warmup_nodes=warmup_nodes,
+                          bb_mode=bb_mode, bb_var=bb_var)
 
 
 EngineBase.search_open = _search_open

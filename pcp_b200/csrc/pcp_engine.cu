@@ -41,6 +41,10 @@ struct Error {
 #define PCP_FAIL(code, msg) throw Error{code, msg}
 #define PCP_REQUIRE(cond, msg) \
   do { if (!(cond)) PCP_FAIL(PCP_ERR_INVALID, msg); } while (0)
+// While a device-resident search is open its launch parameters cache raw device pointers and the
+// search state lives on the device: the store entry points that would reallocate or change
+// either are contract violations until pcp_search_close.
+#define PCP_REQUIRE_NO_BURST(e) PCP_REQUIRE(!(e)->burst.open, "a device search is open on this engine (pcp_search_close it first)")
 #define CUDA_CHECK(expr)                                                                      \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -50,6 +54,12 @@ struct Error {
   } while (0)
 
 constexpr size_t kPad = 64;  // slack elements behind every device array (TMA tails)
+// All device bound arithmetic (view offsets, y.hi - 1, y.lo + z.lo + strict, the segmented sum
+// of a Sum view, MiddleVal's lo + hi) is plain 32-bit: every bound, offset and worst-case Sum
+// range must stay below 2^29 in magnitude.  Rust release builds wrap and debug builds panic
+// on overflow (SURVEY 7 "hard parts" iv), so such inputs are outside the pinned contract:
+// they are rejected with PCP_ERR_INVALID instead of wrapping silently.
+constexpr long long kBoundLimit = 1ll << 29;
 
 // Growable device array.
 template <class T>
@@ -61,12 +71,17 @@ struct DevBuf {
     size_t ncap = std::max<size_t>(n, cap + cap / 2 + 64);
     T* q = nullptr;
     CUDA_CHECK(cudaMalloc(&q, (ncap + kPad) * sizeof(T)));
-    CUDA_CHECK(cudaMemsetAsync(q + ncap, 0, kPad * sizeof(T), st));
-    if (p) {
-      if (keep_n) CUDA_CHECK(cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
-      CUDA_CHECK(cudaStreamSynchronize(st));
-      cudaFree(p);
+    try {
+      CUDA_CHECK(cudaMemsetAsync(q + ncap, 0, kPad * sizeof(T), st));
+      if (p) {
+        if (keep_n) CUDA_CHECK(cudaMemcpyAsync(q, p, keep_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+      }
+    } catch (...) {
+      cudaFree(q);  // the old array stays valid
+      throw;
     }
+    if (p) cudaFree(p);
     p = q;
     cap = ncap;
   }
@@ -115,6 +130,7 @@ struct pcp_engine {
 
   // variables
   std::vector<int2> h_dom_pending;  // variables allocated but not yet uploaded
+  std::vector<int2> h_dom_init;     // the domains as allocated (range validation of Sum views)
   size_t V = 0, V_uploaded = 0;
   char* d_block = nullptr;          // [Result | dom ...]
   size_t block_cap_vars = 0;
@@ -290,8 +306,13 @@ inline unsigned enc_var28(int var) {
 }
 
 void check_operand(const pcp_engine* e, pcp_operand op) {
-  if (op.var >= 0) PCP_REQUIRE((size_t)op.var < e->V, "operand variable not registered in the store");
-  else if (op.var <= -2) PCP_REQUIRE((size_t)(-2 - op.var) < e->sums.size(), "unknown sum view");
+  PCP_REQUIRE(op.off > -kBoundLimit && op.off < kBoundLimit, "view offset / constant outside (-2^29, 2^29)");
+  if (op.var >= 0) {
+    PCP_REQUIRE((size_t)op.var < e->V, "operand variable not registered in the store");
+    const int2 d = e->h_dom_init[(size_t)op.var];  // the view's range (domains only shrink)
+    PCP_REQUIRE((long long)d.x + op.off > -kBoundLimit && (long long)d.y + op.off < kBoundLimit,
+                "range of the view var + offset outside (-2^29, 2^29)");
+  } else if (op.var <= -2) PCP_REQUIRE((size_t)(-2 - op.var) < e->sums.size(), "unknown sum view");
   PCP_REQUIRE(op.var < (int)kSumBase28, "variable index too large");
 }
 
@@ -1071,11 +1092,14 @@ int pcp_stream(pcp_engine* e, void** stream) {
 int pcp_vars_alloc(pcp_engine* e, const int32_t* lo, const int32_t* hi, int32_t n, int32_t* first_idx) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(n >= 0 && (n == 0 || (lo && hi)), "bad arguments");
     for (int i = 0; i < n; ++i) PCP_REQUIRE(lo[i] <= hi[i], "alloc of an empty domain");  // variable/store.rs:136
+    for (int i = 0; i < n; ++i)
+      PCP_REQUIRE(lo[i] > -kBoundLimit && hi[i] < kBoundLimit, "domain bound outside (-2^29, 2^29)");
     PCP_REQUIRE(e->V + (size_t)n < (size_t)kConstVar28, "too many variables");
     if (first_idx) *first_idx = (int32_t)e->V;
-    for (int i = 0; i < n; ++i) e->h_dom_pending.push_back(make_int2(lo[i], hi[i]));
+    for (int i = 0; i < n; ++i) { e->h_dom_pending.push_back(make_int2(lo[i], hi[i])); e->h_dom_init.push_back(make_int2(lo[i], hi[i])); }
     e->V += (size_t)n;
     e->at_fixpoint = false;
     e->snapshot_valid = false;
@@ -1085,8 +1109,20 @@ int pcp_vars_alloc(pcp_engine* e, const int32_t* lo, const int32_t* hi, int32_t 
 int pcp_sum_alloc(pcp_engine* e, const pcp_operand* terms, int32_t n, int32_t* sum_id) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(n >= 1 && terms, "At least one variable in sum.");
-    for (int i = 0; i < n; ++i) { PCP_REQUIRE(terms[i].var >= -1, "nested sums are not supported"); check_operand(e, terms[i]); }
+    long long worst = 0;  // largest magnitude the segmented sum can reach (domains only shrink)
+    for (int i = 0; i < n; ++i) {
+      PCP_REQUIRE(terms[i].var >= -1, "nested sums are not supported");
+      check_operand(e, terms[i]);
+      long long m = terms[i].off < 0 ? -(long long)terms[i].off : terms[i].off;
+      if (terms[i].var >= 0) {
+        const int2 d = e->h_dom_init[(size_t)terms[i].var];
+        m = std::max(std::llabs((long long)d.x + terms[i].off), std::llabs((long long)d.y + terms[i].off));
+      }
+      worst += m;
+    }
+    PCP_REQUIRE(worst < kBoundLimit, "worst-case range of the Sum view outside (-2^29, 2^29)");
     e->sums.emplace_back(terms, terms + n);
     for (int i = 0; i < n; ++i) e->h_sum_terms.push_back(make_int2(terms[i].var, terms[i].off));
     e->h_sum_ptr.push_back((int)e->h_sum_terms.size());
@@ -1097,6 +1133,7 @@ int pcp_sum_alloc(pcp_engine* e, const pcp_operand* terms, int32_t n, int32_t* s
 int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops, int64_t n_props, int32_t* first_idx) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(n_props >= 0 && n_ops >= 0 && (n_props == 0 || ops), "bad arguments");
     PCP_REQUIRE(e->num_props() + (size_t)n_props < (size_t)kSlotMask, "too many propagators");
     // all-or-nothing: remember the sizes and roll back on a contract violation
@@ -1129,6 +1166,7 @@ int pcp_prop_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t 
 int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   if (!e || !status) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     CUDA_CHECK(cudaSetDevice(e->device));
     run_fixpoint(e, status, stats);
   });
@@ -1151,6 +1189,7 @@ int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32
 int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* ok) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(idx >= 0 && (size_t)idx < e->V, "Variable not registered in the store.");
     CUDA_CHECK(cudaSetDevice(e->device));
     fetch_domains(e);
@@ -1200,6 +1239,7 @@ int pcp_active_read(pcp_engine* e, int32_t first, int32_t n, uint8_t* out) {
 int pcp_label(pcp_engine* e, uint64_t* label) {
   if (!e || !label) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(e->labels.size() < e->max_labels, "label stack full (pcp_config.max_labels)");
     size_t idx = e->labels.size();
     const bool have = e->snapshot_valid && e->snapshot_version == e->dom_version && !prologue_pending(e);
@@ -1207,7 +1247,8 @@ int pcp_label(pcp_engine* e, uint64_t* label) {
       CUDA_CHECK(cudaSetDevice(e->device));
       sync_device_state(e);
       if (e->stack_stride != e->V) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = e->V; }
-      e->d_stack.reserve((idx + 1) * std::max<size_t>(e->stack_stride, 1), e->stream, idx * e->stack_stride);
+      if ((idx + 1) * std::max<size_t>(e->stack_stride, 1) > e->d_stack.cap)  // grow in big steps: a reallocation copies the stack
+        e->d_stack.reserve(std::max<size_t>((idx + 1) * 2, 16) * std::max<size_t>(e->stack_stride, 1), e->stream, idx * e->stack_stride);
       if (e->V)
         CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride, e->d_dom(), e->V * sizeof(int2),
                                    cudaMemcpyDeviceToDevice, e->stream));
@@ -1229,6 +1270,7 @@ int pcp_label(pcp_engine* e, uint64_t* label) {
 int pcp_restore(pcp_engine* e, uint64_t label) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(label < e->labels.size(), "unknown label (invalidated by an earlier restore?)");
     const LabelRec r = e->labels[label];
     e->labels.resize(label + 1);
@@ -1252,6 +1294,11 @@ int pcp_restore(pcp_engine* e, uint64_t label) {
 // ---------------------------------------------------------------------------------------
 // device-resident search bursts (private interface, pcp_internal.h)
 // ---------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kBurstStackBudget = (size_t)8 << 30;  // bytes of label slots a device search may reserve
+size_t burst_depth(const pcp_engine* e) { return std::max<size_t>(e->max_labels, 16384); }
+}  // namespace
+
 int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, uint64_t trace_capacity) {
   if (!e || !cfg) return 0;
   static const bool off = std::getenv("PCP_NO_BURST") != nullptr;
@@ -1259,6 +1306,9 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
   if (cfg->var_sel != 0 || cfg->val_sel != 0 || cfg->distributor != 0 || cfg->bb_mode != 0) return 0;
   if (e->V == 0 || e->V > (size_t)(1 << 20)) return 0;
   if ((e->flags & (PCP_FLAG_INCREMENTAL | PCP_FLAG_HOST_SEARCH))) return 0;
+  // the device search pre-reserves its whole label stack (burst_depth(e) slots of V domains):
+  // a store too wide for that budget takes the host-driven node loop, which grows on demand
+  if (burst_depth(e) * e->V * sizeof(int2) > kBurstStackBudget) return 0;
   // the device trace keeps full domains for the traced nodes
   if (trace_capacity * e->V * sizeof(int2) > (size_t)1 << 30) return 0;
   return 1;
@@ -1267,15 +1317,15 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
 int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node_limit, uint64_t trace_capacity,
                              int32_t trace_domains) {
   if (!e) return PCP_ERR_INVALID;
+  if (e->burst.open) { e->err = "a device search is already open on this engine"; return PCP_ERR_INVALID; }
   int rc = pcp_label(e, &e->burst.root_label);  // flushes everything pending; the root of the search
   if (rc != PCP_OK) return rc;
-  return guarded(e, [&] {
+  rc = guarded(e, [&] {
     CUDA_CHECK(cudaSetDevice(e->device));
     auto& b = e->burst;
-    PCP_REQUIRE(!b.open, "a device search is already open on this engine");
     const size_t V = e->V;
     // room for the search: label slots, branching constraints in the binary tail, trail
-    const size_t depth = std::max<size_t>(e->max_labels, 16384);
+    const size_t depth = burst_depth(e);
     b.max_labels = (int)(e->labels.size() + depth);
     e->stack_stride = V;
     e->d_stack.reserve((size_t)b.max_labels * V, e->stream, e->labels.size() * V);
@@ -1324,6 +1374,8 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
     b.kernel_seconds = 0;
     b.open = true;
   });
+  if (rc != PCP_OK) e->labels.resize((size_t)e->burst.root_label);  // give the root label back
+  return rc;
 }
 
 int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result* res) {

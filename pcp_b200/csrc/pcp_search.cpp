@@ -269,6 +269,14 @@ int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res) {
   return rc;
 }
 
+int pcp_search_set_incumbent(pcp_search* s, int32_t value) {
+  if (!s || s->cfg.bb_mode == 0) return PCP_ERR_INVALID;
+  pcp_search_result& r = s->res;
+  const bool better = !r.has_bb_value || (s->cfg.bb_mode == 1 ? value < r.bb_value : value > r.bb_value);
+  if (better) { r.has_bb_value = 1; r.bb_value = value; }
+  return PCP_OK;
+}
+
 void pcp_search_close(pcp_search* s) {
   if (!s) return;
   if (s->d.burst_begun) pcp_internal_burst_end(s->d.e);  // the engine goes back to the search root

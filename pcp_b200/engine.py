@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_stream", "pcp_vars_alloc",
     "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_consistency", "pcp_domains_read",
     "pcp_var_update", "pcp_active_read", "pcp_label", "pcp_restore", "pcp_num_vars", "pcp_num_props",
-    "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_close",
+    "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_set_incumbent", "pcp_search_close",
 ]
 
 _lib = None
@@ -52,6 +52,8 @@ def load_library() -> C.CDLL:
                                         C.POINTER(C.c_void_p)]
         lib.pcp_search_step.restype = C.c_int
         lib.pcp_search_step.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SearchResult)]
+        lib.pcp_search_set_incumbent.restype = C.c_int
+        lib.pcp_search_set_incumbent.argtypes = [C.c_void_p, C.c_int32]
         lib.pcp_search_close.restype = None
         lib.pcp_search_close.argtypes = [C.c_void_p]
         _lib = lib
@@ -108,6 +110,10 @@ class SearchHandle:
         res = SearchResult()
         self._engine._check(self._lib.pcp_search_step(self._h, max_nodes, C.byref(res)))
         return res
+
+    def set_incumbent(self, value: int) -> None:
+        """Adopt another rank's incumbent (pcp_search_set_incumbent)."""
+        self._engine._check(self._lib.pcp_search_set_incumbent(self._h, int(value)))
 
     def close(self) -> None:
         if self._h:

@@ -103,24 +103,39 @@ class StopFlag:
 
 
 def sharded_search(engine, rank: int, world: int, node_budget: int, sync_every: int = 64, stop_flag=None,
-                   stop_on_solution: bool = False, warmup_nodes: int = 0, parts_per_rank: int = 4):
+                   stop_on_solution: bool = False, warmup_nodes: int = 0, parts_per_rank: int = 4,
+                   bb_mode: int = 0, bb_var: int = 0):
     """Run this rank's share of a sharded DFS.
 
     Every rank expands the same frontier, takes its round-robin slice and spends `node_budget`
     nodes on it, subtree after subtree, in rounds of `sync_every` nodes; after each round the
-    stop word is exchanged (every rank executes the same number of rounds, so the collective
-    always matches).  Returns a dict of counters; `seconds` is host wall clock inside the
-    search driver, `kernel_seconds` device time of the fixpoint launches."""
+    one-word collective of the path runs (every rank executes the same number of rounds, so
+    the collective always matches): the max of the `found` flag, and -- with `bb_mode` 1
+    (minimise) / 2 (maximise) `bb_var` -- the min / max of the incumbent, which every rank then
+    adopts (`set_incumbent`) so that its next nodes post `bb_var < best` like
+    search/branch_and_bound.rs:76-92 does within one process.
+
+    Returns a dict of counters.  `seconds` is the host wall clock of the search driver,
+    `kernel_seconds` device time of the fixpoint launches, `exchange_seconds` the wall clock of
+    the collectives, `wall_seconds` the whole round loop (driver + collectives) after the
+    warm-up round(s): the end-to-end time of the sharded search."""
+    import time
     paths = expand_frontier(engine, parts=max(world, 1) * parts_per_rank)
     mine = my_slice(paths, rank, world)
     root = engine.label()
     out = {"nodes": 0, "propagations": 0, "iterations": 0, "solutions": 0, "seconds": 0.0, "kernel_seconds": 0.0,
-           "subtrees": 0, "frontier": len(paths), "stopped": False}
+           "subtrees": 0, "frontier": len(paths), "stopped": False, "exchanges": 0, "exchange_seconds": 0.0,
+           "wall_seconds": 0.0, "incumbent": None}
     keys = (("nodes", "num_nodes"), ("propagations", "propagations"), ("iterations", "iterations"),
             ("solutions", "num_solution"), ("seconds", "seconds"), ("kernel_seconds", "kernel_seconds"))
     rounds = (node_budget + sync_every - 1) // sync_every
     handle, prev, idx, found = None, None, 0, 0
+    INF = 2**31 - 1
+    best = None  # the global incumbent as of the last exchange
+    t_wall = None
     for _ in range(rounds):
+        if t_wall is None and out["nodes"] >= warmup_nodes:
+            t_wall = time.perf_counter()
         round_used = 0
         while round_used < sync_every and out["nodes"] < node_budget:
             if handle is None:
@@ -128,8 +143,10 @@ def sharded_search(engine, rank: int, world: int, node_budget: int, sync_every: 
                     break
                 enter_subtree(engine, root, mine[idx])
                 idx += 1
-                handle = engine.search_open(all_solutions=not stop_on_solution,
+                handle = engine.search_open(all_solutions=not stop_on_solution, bb_mode=bb_mode, bb_var=bb_var,
                                             warmup_nodes=warmup_nodes if out["subtrees"] == 0 else 0)
+                if bb_mode and best is not None:
+                    handle.set_incumbent(best)
                 prev = {k: 0 for k, _ in keys}
                 out["subtrees"] += 1
             before = out["nodes"]
@@ -139,6 +156,10 @@ def sharded_search(engine, rank: int, world: int, node_budget: int, sync_every: 
                 out[k] += cur - prev[k]
                 prev[k] = cur
             round_used += out["nodes"] - before
+            if bb_mode and res.has_bb_value:
+                v = int(res.bb_value)
+                if best is None or (v < best if bb_mode == 1 else v > best):
+                    best = v
             if res.status == 1 and stop_on_solution:
                 found = 1
             if res.status != 0:
@@ -147,12 +168,35 @@ def sharded_search(engine, rank: int, world: int, node_budget: int, sync_every: 
             if found:
                 break
         if stop_flag is not None:
-            if stop_flag.exchange(found):
+            t0 = time.perf_counter()
+            # one word carries both "some rank found a solution" and "every rank ran out of work"
+            idle = 1 if (handle is None and idx >= len(mine)) or out["nodes"] >= node_budget else 0
+            word = stop_flag.exchange(found + (idle << 16), op="sum")
+            stop = (word & 0xffff) > 0
+            all_idle = (word >> 16) >= max(world, 1)
+            if bb_mode:
+                if bb_mode == 1:
+                    g = stop_flag.exchange(INF if best is None else best, op="min")
+                    best = None if g == INF else g
+                else:
+                    g = stop_flag.exchange(-INF if best is None else best, op="max")
+                    best = None if g == -INF else g
+                if best is not None and handle is not None:
+                    handle.set_incumbent(best)
+                out["exchanges"] += 1
+            out["exchanges"] += 1
+            out["exchange_seconds"] += time.perf_counter() - t0
+            if stop:
                 out["stopped"] = True
+                break
+            if all_idle:
                 break
         elif found:
             out["stopped"] = True
             break
+    if t_wall is not None:
+        out["wall_seconds"] = time.perf_counter() - t_wall
     if handle is not None:
         handle.close()
+    out["incumbent"] = best
     return out

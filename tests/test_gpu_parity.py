@@ -115,6 +115,9 @@ def test_snapshot_capacity_boundary(n):
     _compare_search(m, 40, oracle_variant=2)
 
 
+_ORACLE_TRACES = {}  # (model name, node limit) -> the oracle's (result, trace) of the last _compare_search
+
+
 def _compare_search(model, node_limit, dev_kw=None, all_solutions=True, oracle_variant=1, **skw):
     dev, ora = _engine(**(dev_kw or {})), _oracle(oracle_variant)
     model.load_into(dev)
@@ -123,6 +126,8 @@ def _compare_search(model, node_limit, dev_kw=None, all_solutions=True, oracle_v
                         trace_domains=True, **skw)
     ro, to = ora.search(node_limit=node_limit, all_solutions=all_solutions, trace=node_limit or 100000,
                         trace_domains=True, **skw)
+    _ORACLE_TRACES.clear()
+    _ORACLE_TRACES[(model.name, node_limit)] = (ro, to)
     assert rd.num_nodes == ro.num_nodes
     assert rd.status == ro.status
     assert rd.num_solution == ro.num_solution and rd.num_failed_node == ro.num_failed_node
@@ -326,6 +331,65 @@ def test_incremental_mode_same_fixpoints(model):
     assert rd.propagations <= rf.propagations
 
 
+@pytest.mark.parametrize("model,nodes", [(models.nqueens(1000), 150), (models.all_interval(500), 60)],
+                         ids=["c2-nqueens-1000", "c3-all-interval-500"])
+def test_incremental_mode_full_size(model, nodes):
+    """PCP_FLAG_INCREMENTAL at the sizes bench.py reports it for (C2, C3; C5 rides in
+    test_nqueens_5000_full_size): every node's status and domains against the oracle."""
+    rd, ro, _, _ = _compare_search(model, nodes, dev_kw={"incremental": True}, oracle_variant=2)
+    assert rd.num_nodes == nodes
+
+
+def test_bounds_outside_the_contract_are_rejected():
+    """Device bound arithmetic is 32-bit: bounds, offsets, view ranges and worst-case Sum ranges
+    must stay inside (-2^29, 2^29) (SURVEY 7 iv); anything else is PCP_ERR_INVALID at
+    allocation time instead of a silent wrap-around."""
+    from pcp_b200 import ContractViolation
+    L = 1 << 29
+    dev = _engine()
+    for lo, hi in ((0, L), (-L, 0), (-(1 << 31), (1 << 31) - 1)):
+        with pytest.raises(ContractViolation):
+            dev.vars_alloc([lo], [hi])
+    assert dev.num_vars == 0
+    dev.vars_alloc([-(L - 1), 0, 0], [L - 1, 10, 10])
+    with pytest.raises(ContractViolation):
+        dev.prop_alloc(models.X_LESS_Y, [[1, L], [2, 0]])          # offset
+    with pytest.raises(ContractViolation):
+        dev.prop_alloc(models.X_LESS_Y, [[0, 5], [1, 0]])          # range of the view x0 + 5
+    with pytest.raises(ContractViolation):
+        dev.prop_alloc(models.X_LESS_Y, [[1, 0], [-1, -L]])        # constant
+    with pytest.raises(ContractViolation):
+        dev.sum_alloc([[0, 0], [1, 0]])                            # worst case of the sum
+    assert dev.num_props == 0
+    dev.prop_alloc(models.X_LESS_Y, [[1, 0], [0, 0]])              # at the limit: fine
+    assert dev.consistency()[0] == 0
+    lo, hi = dev.domains()
+    assert int(lo[0]) == 1 and int(hi[1]) == 10
+
+
+def test_store_calls_are_refused_while_a_device_search_is_open():
+    """The device-resident search caches launch parameters: store entry points that would
+    reallocate or change state underneath it return PCP_ERR_INVALID until pcp_search_close."""
+    from pcp_b200 import ContractViolation
+    dev = _engine()
+    models.nqueens(12).load_into(dev)
+    h = dev.search_open(all_solutions=True)
+    assert h.step(5).status == 0
+    for call in (lambda: dev.prop_alloc(models.X_LESS_Y, [[0, 0], [1, 0]]), lambda: dev.consistency(),
+                 lambda: dev.label(), lambda: dev.restore(0), lambda: dev.vars_alloc([0], [1]),
+                 lambda: dev.var_update(0, 1, 1)):
+        with pytest.raises(ContractViolation):
+            call()
+    res = None
+    for _ in range(100000):
+        res = h.step(50)
+        if res.status != 0:
+            break
+    h.close()
+    assert res.num_solution == 14200
+    assert dev.consistency()[0] in (0, 1, -1)  # usable again after close
+
+
 def test_var_update_and_contract_violations():
     from pcp_b200 import ContractViolation
     dev, ora = _engine(incremental=True), _oracle()
@@ -402,12 +466,24 @@ def test_size_independent_properties_nqueens_1000():
 
 def test_nqueens_5000_full_size():
     """C5 at full size: V=5000, P=37,492,500 (600 MB of descriptors, 300 MB compact stream, rows
-    of 14,997 entries -- longer than the row staging area).  First 4 DFS nodes bit-exact against
-    the oracle's flat variant, then size-independent properties deeper in the tree: idempotence,
-    monotonicity along a branch, exact restore."""
+    of 14,997 entries -- longer than the row staging area).  The first 32 DFS nodes bit-exact
+    against the oracle's flat variant -- the descent passes nodes that need worklist iterations
+    after the sweep (asserted) -- for the default engine and for PCP_FLAG_INCREMENTAL; then
+    size-independent properties deeper in the tree: idempotence, monotonicity along a branch,
+    exact restore."""
     m = models.nqueens(5000)
-    rd, ro, dev, ora = _compare_search(m, 4, oracle_variant=2)
+    rd, ro, dev, ora = _compare_search(m, 32, oracle_variant=2)
+    assert rd.iterations > rd.num_nodes  # at least one node went through a worklist iteration
     del ora
+    _, to = _ORACLE_TRACES[(m.name, 32)]
+    inc = _engine(incremental=True)
+    m.load_into(inc)
+    ri, ti = inc.search(node_limit=32, all_solutions=True, trace=32, trace_domains=True)
+    assert ri.num_nodes == 32 and (ti["status"] == to["status"]).all() and (ti["hash"] == to["hash"]).all()
+    ok = ti["status"] != -1
+    assert (ti["lo"][ok] == to["lo"][ok]).all() and (ti["hi"][ok] == to["hi"][ok]).all()
+    assert ri.propagations < rd.propagations
+    del inc
     dev2 = _engine()
     m.load_into(dev2)
     assert dev2.consistency()[0] == 0
@@ -531,6 +607,59 @@ def test_sharded_search_single_rank_covers_the_tree():
     models.nqueens(7).load_into(dev)
     out = parallel.sharded_search(dev, 0, 1, node_budget=10**6, sync_every=50, parts_per_rank=6)
     assert out["solutions"] == 40 and out["subtrees"] == out["frontier"] >= 6
+
+
+def _nccl_rank(rank, world, port, n, q):
+    import os as _os, sys as _sys
+    _sys.path.insert(0, ROOT)
+    _os.environ["MASTER_ADDR"] = "127.0.0.1"
+    _os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from pcp_b200 import Engine, parallel
+    out = {}
+    for key, kw in (("all", {}), ("bb", {"bb_mode": 1, "bb_var": 3})):
+        e = Engine(device=rank, max_labels=1 << 12)
+        models.nqueens(n).load_into(e)
+        flag = parallel.StopFlag(torch.device("cuda", rank))
+        out[key] = parallel.sharded_search(e, rank, world, node_budget=10**6, sync_every=32, stop_flag=flag, **kw)
+        e.close()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_search_two_gpus_nccl():
+    """The N>1 path with the *device* engine under NCCL (world = 2, one GPU per rank): the two
+    ranks' subtrees hold every solution of n-queens N=9 (352, all_solution.rs:67-74), the
+    collectives match, and with BranchAndBound both ranks end with the incumbent one process
+    finds alone (the all-reduced minimum of q_3)."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_rank, args=(r, 2, port, 9, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[0]["all"]["solutions"] + res[1]["all"]["solutions"] == 352
+    assert res[0]["all"]["exchanges"] == res[1]["all"]["exchanges"] >= 1
+    solo = _oracle(2)
+    models.nqueens(9).load_into(solo)
+    ref, _ = solo.search(all_solutions=True, bb_mode=1, bb_var=3)
+    assert res[0]["bb"]["incumbent"] == res[1]["bb"]["incumbent"] == ref.bb_value
 
 
 def test_x_eq_y_mul_z_products_store():

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.oracle_api import FAITHFUL, TUNED, Fifo, OracleEngine, Reactor, event_new
+from oracle.oracle_api import FAITHFUL, FLAT, TUNED, Fifo, OracleEngine, Reactor, event_new
 from pcp_b200 import models
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -26,9 +26,12 @@ def _engine_for(vec, variant=FAITHFUL):
 
 
 @pytest.mark.parametrize("vec", GOLDEN["propagators"], ids=lambda v: v["name"])
-def test_propagator_vector(vec):
-    """propagators/mod.rs:110-129: is_subsumed, propagate, exact delta, is_subsumed."""
-    e, p = _engine_for(vec)
+@pytest.mark.parametrize("variant", [FAITHFUL, FLAT], ids=["faithful", "flat"])
+def test_propagator_vector(vec, variant):
+    """propagators/mod.rs:110-129: is_subsumed, propagate, exact delta, is_subsumed.  The FLAT
+    variant (inline (var, off) descriptors -- the timed CPU baseline, the reference arm and the
+    checker of the full-size GPU tests) replays every vector too."""
+    e, p = _engine_for(vec, variant)
     before, ok, delta, after = e.test_propagation(p)
     assert before == vec["before"], vec["ref"]
     assert ok == vec["ok"], vec["ref"]
@@ -41,7 +44,7 @@ def test_propagator_vector(vec):
 
 
 @pytest.mark.parametrize("vec", GOLDEN["propagators"], ids=lambda v: v["name"])
-@pytest.mark.parametrize("variant", [FAITHFUL, TUNED])
+@pytest.mark.parametrize("variant", [FAITHFUL, TUNED, FLAT])
 def test_propagator_vector_through_loop(vec, variant):
     """The same vectors through Store::consistency: status False iff propagate failed or the
     propagator is disentailed; otherwise the after-entailment decides True/Unknown once the
@@ -186,7 +189,7 @@ def test_relaxed_fifo():
     assert Fifo(3).unschedule(3) == -1
 
 
-@pytest.mark.parametrize("variant", [FAITHFUL, TUNED])
+@pytest.mark.parametrize("variant", [FAITHFUL, TUNED, FLAT])
 def test_nqueens_all_solutions(variant):
     """search/engine/all_solution.rs:67-74 (counts are propagation-strength independent)."""
     g = GOLDEN["search"]["nqueens_all_solutions"]
@@ -255,7 +258,7 @@ def test_binary_split_children():
             assert [int(lo[var]), int(hi[var])] == child
 
 
-@pytest.mark.parametrize("variant", [FAITHFUL, TUNED])
+@pytest.mark.parametrize("variant", [FAITHFUL, TUNED, FLAT])
 def test_chained_lt_and_root(variant):
     """propagation/store.rs:362-392 (dead tests): loop-level known answers on Interval."""
     for n, status in GOLDEN["search"]["chained_lt"]["status"].items():
@@ -277,19 +280,29 @@ def test_chained_lt_and_root(variant):
         assert (lo == 1).all() and (hi == int(n)).all()
 
 
-def test_faithful_and_tuned_agree_on_search_trace():
-    """Same node sequence, statuses and domains from both oracle variants."""
+def test_all_variants_agree_on_search_trace():
+    """Same node sequence, statuses and domains from the three oracle variants (FLAT is what the
+    full-size GPU tests and the CPU baseline use)."""
+    rng = np.random.default_rng(7)
+    mixed = models.Model("mixed", rng.integers(-5, 5, 14).astype(np.int32), rng.integers(6, 15, 14).astype(np.int32))
+    for kind, n_ops in ((0, 2), (1, 2), (2, 2), (3, 3), (4, 3), (5, 3), (8, 3)):
+        for _ in range(3):
+            vs = rng.choice(14, n_ops, replace=False)
+            mixed.add(kind, np.stack([vs, rng.integers(-3, 4, n_ops)], axis=1).astype(np.int32))
+    mixed.add(models.ALL_EQUAL, [[0, 0], [5, 1], [9, -1]])
+    mixed.add(models.DISTINCT, [[1, 0], [2, 0], [3, 0], [4, 2]])
     for model in (models.nqueens(12, "example"), models.nqueens(10, "distinct"), models.all_interval(7),
-                  models.all_interval(6, decompose_distinct=True)):
+                  models.all_interval(6, decompose_distinct=True), mixed):
         traces = []
-        for variant in (FAITHFUL, TUNED):
+        for variant in (FAITHFUL, TUNED, FLAT):
             e = OracleEngine(variant)
             model.load_into(e)
             res, tr = e.search(node_limit=400, all_solutions=True, trace=400, trace_domains=True)
             traces.append((res.num_nodes, res.num_solution, tr))
-        assert traces[0][0] == traces[1][0] and traces[0][1] == traces[1][1]
-        for k in ("status", "hash", "lo", "hi"):
-            assert (traces[0][2][k] == traces[1][2][k]).all(), (model.name, k)
+        for other in traces[1:]:
+            assert traces[0][0] == other[0] and traces[0][1] == other[1]
+            for k in ("status", "hash", "lo", "hi"):
+                assert (traces[0][2][k] == other[2][k]).all(), (model.name, k)
 
 
 def test_label_restore():

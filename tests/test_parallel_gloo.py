@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, budget, stop_on_solution, q):
+def _worker(rank, world, port, n, budget, stop_on_solution, q, bb_mode=0, bb_var=0):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,18 +33,19 @@ def _worker(rank, world, port, n, budget, stop_on_solution, q):
     paths = parallel.expand_frontier(e, parts=world * 4)
     flag = parallel.StopFlag()
     out = parallel.sharded_search(e, rank, world, node_budget=budget, sync_every=16, stop_flag=flag,
-                                  stop_on_solution=stop_on_solution)
+                                  stop_on_solution=stop_on_solution, bb_mode=bb_mode, bb_var=bb_var)
     lo, hi = e.domains()
     q.put((rank, [tuple(map(tuple, p)) for p in paths], out, bool((lo == hi).all())))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _run(world, n, budget, stop_on_solution):
+def _run(world, n, budget, stop_on_solution, bb_mode=0, bb_var=0):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, budget, stop_on_solution, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, budget, stop_on_solution, q, bb_mode, bb_var))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
@@ -70,6 +71,28 @@ def test_stop_flag_reaches_every_rank():
     assert all(o["stopped"] for o in outs)                 # the finder's flag stops both ranks
     assert sum(o["solutions"] for o in outs) >= 1
     assert any(r[3] for r in res)                          # the finder holds a full assignment
+
+
+@pytest.mark.parametrize("bb_mode", [1, 2])
+def test_incumbent_exchange_branch_and_bound(bb_mode):
+    """BranchAndBound across ranks (search/branch_and_bound.rs:76-92 + SURVEY 8e): every rank
+    all-reduces the incumbent (min / max) after each round and adopts it, so both ranks end
+    with the global optimum -- the value one process finds alone -- and the rank that did not
+    find it itself still prunes with it (fewer nodes than the subtrees cost without exchange)."""
+    sys.path.insert(0, ROOT)
+    from oracle.oracle_api import FLAT, OracleEngine
+    from pcp_b200 import models
+    n, var = 9, 4
+    solo = OracleEngine(FLAT)
+    models.nqueens(n).load_into(solo)
+    ref, _ = solo.search(all_solutions=True, bb_mode=bb_mode, bb_var=var)
+    assert ref.has_bb_value
+    res = _run(2, n, 10**6, False, bb_mode=bb_mode, bb_var=var)
+    outs = [r[2] for r in res]
+    assert [o["incumbent"] for o in outs] == [ref.bb_value, ref.bb_value]
+    assert all(o["exchanges"] >= 2 for o in outs) and outs[0]["exchanges"] == outs[1]["exchanges"]
+    plain = _run(2, n, 10**6, False)                      # the same subtrees searched exhaustively
+    assert sum(o["nodes"] for o in outs) < sum(r[2]["nodes"] for r in plain)
 
 
 def test_frontier_slices_partition_the_tree():
