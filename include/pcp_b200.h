@@ -80,6 +80,10 @@ enum pcp_prop_kind {
                                    engine can prove the restored state was a fixpoint
                                    (same domains/status; fewer propagations than
                                    store.rs:144-149)                                  */
+#define PCP_FLAG_INTERVAL_SET 4u /* domains are IntervalSet<i32> (VStoreSet, variable/mod.rs:38 -- what
+                                   FDSpace and example/src/nqueens.rs use): a bit set per variable
+                                   beside the cached bounds; XNeqY removes interior values.  Default:
+                                   Interval<i32> (VStoreFD, variable/mod.rs:37)                   */
 #define PCP_FLAG_HOST_SEARCH 2u /* pcp_search_* drive every node from the host through the
                                    store surface (restore / prop_alloc / consistency /
                                    domains_read / label, one launch and one D2H copy per
@@ -124,6 +128,32 @@ int pcp_sum_alloc(pcp_engine* e, const pcp_operand* terms, int32_t n, int32_t* s
  * active and returns its index. */
 int pcp_prop_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops, int32_t* idx);
 
+/* ---- formula trees (logic/: Conjunction, Disjunction, Boolean, BooleanNeg, f.not()) ------------
+ * Allocates ONE propagator whose body is a tree of connectives over leaf propagators, exactly as
+ * `cstore.alloc(Box::new(Disjunction::new(vec![..])))` does in the reference (logic/disjunction.rs:
+ * 29-33,77-129; logic/conjunction.rs:77-118; logic/boolean.rs:108-141; logic/boolean_neg.rs:77-98;
+ * implication / equivalence = logic/mod.rs:30-45; the user of all of them: propagators/
+ * cumulative.rs:59-114).  Prefix encoding in int32 words:
+ *     PCP_F_CONJUNCTION n child_1 .. child_n          PCP_F_DISJUNCTION n child_1 .. child_n
+ *     PCP_F_BOOLEAN var off                           PCP_F_BOOLEAN_NEG var off
+ *     PCP_F_NOT child      (the reference's `f.not()`, applied when the tree is built: De Morgan on
+ *                           connectives, the cmp/mod.rs:34-86 complements on leaves)
+ *     PCP_F_LEAF + kind, then (var, off) per operand; kind one of PCP_X_LESS_Y, PCP_X_NEQ_Y,
+ *                           PCP_X_EQ_Y, PCP_X_GREATER_Y_PLUS_Z, PCP_X_LESS_Y_PLUS_Z, PCP_X_EQ_Y_PLUS_Z
+ * The operand of Boolean / BooleanNeg is a variable the caller allocated with domain [0, 1]
+ * (Boolean::new, boolean.rs:35-40).  A tree whose subsumption / propagation the device cannot
+ * evaluate (more than PCP_F_MAX_NODES nodes or PCP_F_MAX_VARS distinct variables, Sum operands,
+ * not() of XEqYPlusZ -- unimplemented!() in the reference too) is PCP_ERR_UNSUPPORTED.           */
+#define PCP_F_CONJUNCTION 1
+#define PCP_F_DISJUNCTION 2
+#define PCP_F_BOOLEAN 3
+#define PCP_F_BOOLEAN_NEG 4
+#define PCP_F_NOT 5
+#define PCP_F_LEAF 16
+#define PCP_F_MAX_NODES 32
+#define PCP_F_MAX_VARS 12
+int pcp_formula_alloc(pcp_engine* e, const int32_t* words, int32_t n_words, int32_t* idx);
+
 /* The same for `n_props` propagators of one kind with `n_ops` operands each,
  * operands laid out prop-major (model upload: millions of descriptors). */
 int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t n_ops,
@@ -135,6 +165,16 @@ int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats /* may be N
 
 /* Index<usize> on the variable store (variable/store.rs:175-181), batched. */
 int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32_t* hi);
+
+/* Cardinality::size() of each domain (what FirstSmallestVar compares, search/branching/
+ * first_smallest_var.rs:30-39): hi - lo + 1 on Interval domains, the number of values on
+ * IntervalSet domains. */
+int pcp_domains_size_read(pcp_engine* e, int32_t first, int32_t n, uint32_t* size);
+
+/* The values of each domain as a bit window: bit (v - base) of the `words` 32-bit words of
+ * variable i is set iff v is in its domain (IntervalSet iteration; on Interval engines one run
+ * of ones).  Every value of the domains read must fall inside the window. */
+int pcp_domains_read_bits(pcp_engine* e, int32_t first, int32_t n, int32_t base, int32_t words, uint32_t* out);
 
 /* MonotonicUpdate::update (variable/store.rs:151-166): *ok = 0 when [lo,hi] is
  * empty (store untouched); widening is a contract violation. */

@@ -17,13 +17,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libpcp_oracle.so")
 
 FAITHFUL, TUNED, FLAT = 0, 1, 2
+SET = 4  # + SET: IntervalSet<i32> domains (libpcp's VStoreSet / FDSpace) instead of Interval<i32>
 
 
 def build(force: bool = False) -> str:
     """Compile the oracle with g++ (oracle/Makefile)."""
     if force or not os.path.exists(_SO) or any(
             os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_SO)
-            for f in ("pcp_oracle.hpp", "pcp_oracle_capi.cpp", "Makefile")):
+            for f in ("pcp_oracle.hpp", "pcp_oracle_common.hpp", "pcp_oracle_body.hpp", "pcp_oracle_capi.cpp",
+                  "pcp_oracle_capi_body.hpp", "Makefile")):
         subprocess.run(["make", "-C", _HERE, "-B", "libpcp_oracle.so"], check=True, capture_output=True)
     return _SO
 
@@ -44,6 +46,8 @@ def lib() -> C.CDLL:
         _lib.pcpo_test_propagation.argtypes = [C.c_void_p, C.c_int32, _i32p, _i32p, _i32p, _i32p, _i32p]
         _lib.pcpo_prop_dependencies.restype = C.c_int
         _lib.pcpo_prop_dependencies.argtypes = [C.c_void_p, C.c_int32, _i32p, _i32p]
+        _lib.pcpo_store_is_subsumed.restype = C.c_int
+        _lib.pcpo_store_is_subsumed.argtypes = [C.c_void_p, _i32p]
         _lib.pcpo_reactor_new.restype = C.c_void_p
         _lib.pcpo_reactor_new.argtypes = [C.c_int32, C.c_int32]
         _lib.pcpo_reactor_free.argtypes = [C.c_void_p]
@@ -89,6 +93,12 @@ class OracleEngine(EngineBase):
                                                     delta.ctypes.data_as(_i32p), C.byref(n)))
         d = [(int(delta[2 * i]), int(delta[2 * i + 1])) for i in range(n.value)]
         return before.value, bool(ok.value), d, after.value
+
+    def store_is_subsumed(self) -> int:
+        """Subsumption for Store (propagation/store.rs:231-237)."""
+        k = C.c_int32()
+        self._check(self._lib.pcpo_store_is_subsumed(self._h, C.byref(k)))
+        return k.value
 
     def dependencies(self, prop: int):
         deps = np.zeros(2 * 65536, np.int32)

@@ -55,6 +55,7 @@ class SearchResult(C.Structure):
 
 
 _i32p = C.POINTER(C.c_int32)
+_u32p = C.POINTER(C.c_uint32)
 _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
 _opp = C.POINTER(Operand)
@@ -67,7 +68,10 @@ _COMMON = {
     "sum_alloc": (C.c_int, [C.c_void_p, _opp, C.c_int32, _i32p]),
     "prop_alloc": (C.c_int, [C.c_void_p, C.c_int32, _opp, C.c_int32, _i32p]),
     "props_alloc": (C.c_int, [C.c_void_p, C.c_int32, _opp, C.c_int32, C.c_int64, _i32p]),
+    "formula_alloc": (C.c_int, [C.c_void_p, _i32p, C.c_int32, _i32p]),
     "consistency": (C.c_int, [C.c_void_p, _i32p, C.POINTER(Stats)]),
+    "domains_size_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _u32p]),
+    "domains_read_bits": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u32p]),
     "domains_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p]),
     "var_update": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, _i32p]),
     "active_read": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _u8p]),
@@ -158,6 +162,13 @@ class EngineBase:
                                             C.byref(first)))
         return first.value
 
+    # --- a formula tree as one propagator (logic/*.rs; prefix words, see pcp_formula_alloc)
+    def formula_alloc(self, words) -> int:
+        a = np.ascontiguousarray(np.asarray(words, dtype=np.int32).reshape(-1))
+        idx = C.c_int32(-1)
+        self._check(self._fn("formula_alloc")(self._h, a.ctypes.data_as(_i32p), a.shape[0], C.byref(idx)))
+        return idx.value
+
     # --- Consistency::consistency (propagation/store.rs:247-257)
     def consistency(self) -> Tuple[int, Stats]:
         st = C.c_int32(0)
@@ -172,6 +183,22 @@ class EngineBase:
         hi = np.empty(n, np.int32)
         self._check(self._fn("domains_read")(self._h, first, n, lo.ctypes.data_as(_i32p), hi.ctypes.data_as(_i32p)))
         return lo, hi
+
+    def domain_sizes(self, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """Cardinality::size() per variable (first_smallest_var.rs:30-39)."""
+        if n is None:
+            n = self.num_vars - first
+        out = np.empty(n, np.uint32)
+        self._check(self._fn("domains_size_read")(self._h, first, n, out.ctypes.data_as(_u32p)))
+        return out
+
+    def domain_bits(self, base: int, words: int, first: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """The values of each domain as a bit window [n, words] starting at value `base`."""
+        if n is None:
+            n = self.num_vars - first
+        out = np.zeros((n, words), np.uint32)
+        self._check(self._fn("domains_read_bits")(self._h, first, n, base, words, out.ctypes.data_as(_u32p)))
+        return out
 
     # --- MonotonicUpdate::update (variable/store.rs:151-166)
     def var_update(self, idx: int, lo: int, hi: int) -> bool:

@@ -17,11 +17,13 @@ LIB_PATH = os.environ.get("PCP_B200_LIB") or os.path.join(_HERE, "libpcp_b200.so
 
 FLAG_INCREMENTAL = 1
 FLAG_HOST_SEARCH = 2
+FLAG_INTERVAL_SET = 4
 
 # every symbol include/pcp_b200.h declares
 ABI_SYMBOLS = [
     "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_stream", "pcp_vars_alloc",
-    "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_consistency", "pcp_domains_read",
+    "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_formula_alloc", "pcp_consistency", "pcp_domains_read",
+    "pcp_domains_size_read", "pcp_domains_read_bits",
     "pcp_var_update", "pcp_active_read", "pcp_label", "pcp_restore", "pcp_num_vars", "pcp_num_props",
     "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_set_incumbent", "pcp_search_close",
 ]
@@ -66,9 +68,10 @@ class Engine(EngineBase):
     _prefix = "pcp_"
 
     def __init__(self, device: int = 0, incremental: bool = False, max_labels: int = 0, tail_limit: int = 0,
-                 timing: bool = False, host_search: bool = False):
+                 timing: bool = False, host_search: bool = False, interval_set: bool = False):
         self._lib = load_library()
-        flags = (FLAG_INCREMENTAL if incremental else 0) | (FLAG_HOST_SEARCH if host_search else 0)
+        flags = ((FLAG_INCREMENTAL if incremental else 0) | (FLAG_HOST_SEARCH if host_search else 0) |
+                 (FLAG_INTERVAL_SET if interval_set else 0))
         cfg = Config(device, flags, max_labels, tail_limit)
         h = C.c_void_p()
         rc = self._lib.pcp_engine_create(C.byref(cfg), C.byref(h))
