@@ -151,7 +151,11 @@ template <bool SMEM>
 __device__ __noinline__ void sweep_slow_bin(const Ctx& c, int slot, uint32_t desc_s) {
   const int4 d = lds128(desc_s);
   const IV x = rd<SMEM>(c, dec_var28((unsigned)d.x), d.y), y = rd<SMEM>(c, d.z, d.w);
+#ifdef PCP_SET
+  if (!bin_is_noop_set(c, d, x, y)) eval_full_bin(c, slot, d, x, y);
+#else
   if (!bin_is_noop((unsigned)d.x >> 28, x, y)) eval_full_bin(c, slot, d, x, y);
+#endif
 }
 template <bool SMEM>
 __device__ __noinline__ void sweep_slow_ter(const Ctx& c, int slot, uint32_t a_s, uint32_t b_s) {
@@ -255,6 +259,10 @@ __device__ __forceinline__ bool sweep_upd(const Ctx& c, int var, int off, IV o, 
   return lo || hi;
 }
 __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
+#ifdef PCP_SET
+  eval_full_ter(c, slot, d, e, x0, y0, z0);  // (bounds land on set elements: the staged path knows how)
+  return;
+#endif
   IV x = x0, y = y0, z = z0;
   const bool ok = prop_greater(x, y, z, 0) && prop_less(x, y, z, 0);
   const int s = ok ? sub_eq(x, y, z) : -1;
@@ -272,6 +280,48 @@ __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep
 // XNeqY over plain variables that is not a no-op: eval_bin's B_NEQ branch + finish_eval inline
 // (x_neq_y.rs:82-93 on Interval: a singleton side trims the matching bound of the other side;
 // is_subsumed = not XEqY, x_neq_y.rs:71-73).
+#ifdef PCP_SET
+// IntervalSet: the assigned side's value leaves the other domain wherever it sits (a bound moves to
+// the next value still in the set, an interior value is cleared), after which the two are
+// disjoint and the propagator is entailed; two unassigned sides are entailed when their sets are
+// disjoint (decided exactly here: the hot loop only found no witness at the larger lower bound).
+__device__ __noinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, IV x, IV y) {
+  const SetW sw = set_of(*c.P);
+  const int xv = (int)((unsigned)d.x & kConstVar28), yv = d.z;
+  const bool xs = x.lo == x.hi, ys = y.lo == y.hi;
+  if (xs || ys) {
+    const int v = xs ? x.lo : y.lo;                    // the assigned side's value (view space)
+    const int tv = xs ? yv : xv, to = xs ? d.w : d.y;  // the other side
+    const IV t = xs ? y : x;
+    if (v >= t.lo && v <= t.hi) {
+      if (t.lo == t.hi) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s + 4u), "r"(1) : "memory"); return; }
+      bool ch;
+      if (v == t.lo) {
+        const int r = sb_next(sw, tv, v - to + 1, t.hi - to);
+        if (r == INT32_MAX) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s + 4u), "r"(1) : "memory"); return; }
+        ch = sweep_upd(c, tv, to, t, IV{r + to, t.hi});
+      } else if (v == t.hi) {
+        const int r = sb_prev(sw, tv, v - to - 1, t.lo - to);
+        if (r == INT32_MIN) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s + 4u), "r"(1) : "memory"); return; }
+        ch = sweep_upd(c, tv, to, t, IV{t.lo, r + to});
+      } else {
+        ch = sb_clear(sw, tv, v - to);
+        if (ch) {
+          const uint32_t dbm_s = c.dbm_s;
+          if (dbm_s) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(dbm_s + 4u * (unsigned)(tv >> 5)), "r"(1u << (tv & 31)) : "memory");
+          else atomicOr(&c.next_bits[tv >> 5], 1u << (tv & 31));
+        }
+      }
+      if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s), "r"(1) : "memory");
+    }
+    sweep_deactivate(c, a, F_BIN, slot);
+    return;
+  }
+  if (x.hi < y.lo || y.hi < x.lo) { sweep_deactivate(c, a, F_BIN, slot); return; }
+  if (sb_witness(sw, xv, x.lo - d.y, x.hi - d.y, d.y, yv, y.lo - d.w, y.hi - d.w, d.w)) return;
+  if (sb_disjoint(sw, xv, x.lo - d.y, x.hi - d.y, d.y, yv, y.lo - d.w, y.hi - d.w, d.w)) sweep_deactivate(c, a, F_BIN, slot);
+}
+#else
 __device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, IV x, IV y) {
   IV nx = x, ny = y;
   if (x.lo == x.hi) {
@@ -289,6 +339,7 @@ __device__ __forceinline__ void sweep_neq_update(const Ctx& c, const FamSweep& a
   if (ch) asm volatile("st.shared.u32 [%0], %1;" ::"r"(c.flags_s), "r"(1) : "memory");
   if (nx.hi < ny.lo || ny.hi < nx.lo) sweep_deactivate(c, a, F_BIN, slot);
 }
+#endif
 
 // The streaming sweep of one CTA over the binary family (XLessY / XNeqY / XEqY): warp 0 (one
 // lane) keeps the ring full, every other warp owns 128 consecutive descriptors of each chunk
@@ -310,6 +361,9 @@ __device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, uint4
   }
   const unsigned lane_bit = 1u << lane;
   const uint32_t lane_off = (uint32_t)((warp - 1) * (32 * G) + lane) * 16u;
+#ifdef PCP_SET
+  const SetW sw = set_of(*c.P);
+#endif
   const int stride = a.workers * kChunkBin;
   int base = a.g0 * kChunkBin + (warp - 1) * (32 * G);  // this warp's first descriptor of the chunk
   if (!a.have_aw) aw = load_active<G>(a.active, base, a.n);
@@ -345,12 +399,43 @@ __device__ __noinline__ unsigned sweep_bin(const Ctx& c, const FamSweep a, uint4
       dy[g] = rd_plain<SMEM>(a.sdom_s, a.dom, plain[g] ? d[g].z : 0);
     }
     bool any = false;
+#ifdef PCP_SET
+    // IntervalSet: two unassigned overlapping views make an XNeqY a no-op only if they share a value.
+    // One bit test proves it in the common case (dense domains): the larger lower bound belongs to
+    // its own set, is it in the other one?  The probes of all groups are in flight together.
+    unsigned pw[G], pbit[G];
+    bool cand[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
+      const unsigned kind = NEQ_PLAIN ? (unsigned)B_NEQ : (unsigned)d[g].x >> 28;
+      cand[g] = on[g] && plain[g] && kind == B_NEQ && x.lo != x.hi && y.lo != y.hi && !(x.hi < y.lo || y.hi < x.lo);
+      pw[g] = 0u;
+      pbit[g] = 0u;
+      if (cand[g]) {
+        const bool lx = x.lo >= y.lo;
+        const int pv = lx ? d[g].z : (int)((unsigned)d[g].x & kConstVar28);
+        const unsigned b = (unsigned)((lx ? x.lo - d[g].w : y.lo - d[g].y) - sw.base);
+        pw[g] = __ldcg(sw.bits + (size_t)pv * (unsigned)sw.W + (b >> 5));
+        pbit[g] = b & 31u;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
+      const unsigned kind = NEQ_PLAIN ? (unsigned)B_NEQ : (unsigned)d[g].x >> 28;
+      const bool noop = cand[g] ? ((pw[g] >> pbit[g]) & 1u) != 0u : (plain[g] && kind == B_LESS && bin_is_noop(B_LESS, x, y));
+      need[g] = on[g] && !noop;
+      any |= need[g];
+    }
+#else
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       const IV x{dx[g].x + d[g].y, dx[g].y + d[g].y}, y{dy[g].x + d[g].w, dy[g].y + d[g].w};
       need[g] = on[g] && !(plain[g] && bin_is_noop(NEQ_PLAIN ? (unsigned)B_NEQ : (unsigned)d[g].x >> 28, x, y));
       any |= need[g];
     }
+#endif
     if (any) {
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -719,6 +804,133 @@ __device__ __forceinline__ unsigned eval_distinct(const Params& P, const Ctx& c,
   return 1;
 }
 
+#ifdef PCP_SET
+// ---------------------------------------------------------------------------------------
+// n-ary Distinct on IntervalSet domains: the same conjunction of pairwise XNeqY
+// (distinct.rs:69-126), whose fixpoint on sets is: every assigned operand's value leaves the
+// set of every other operand -- bounds and interior alike -- an operand that becomes assigned
+// joins in, two equal assigned operands fail.  Entailed iff the operands' sets are pairwise
+// disjoint (Conjunction::is_subsumed, conjunction.rs:77-94, over XNeqY::is_subsumed).
+// smem (the idle ring): int2 ops[k]; int2 iv[k]; int tab[tabsz]; int newv[k].
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ bool views_disjoint(const SetW& sw, int2 oa, int2 a, int2 ob, int2 b) {
+  if (a.y < b.x || b.y < a.x) return true;
+  if (a.x == a.y || oa.x < 0) {           // a is a single value
+    if (b.x == b.y || ob.x < 0) return false;   // (the bounds overlap: the same value)
+    return !sb_test(sw, ob.x, a.x - ob.y);
+  }
+  if (b.x == b.y || ob.x < 0) return !sb_test(sw, oa.x, b.x - oa.y);
+  return sb_disjoint(sw, oa.x, a.x - oa.y, a.y - oa.y, oa.y, ob.x, b.x - ob.y, b.y - ob.y, ob.y);
+}
+template <bool SMEM>
+__device__ __forceinline__ unsigned eval_distinct_set(const Params& P, const Ctx& c, int slot, char* smem_nary, const uint32_t* cur_bits,
+                                                      bool unconditional) {
+  __shared__ int s_nnew;
+  const SetW sw = set_of(P);
+  const int b = __ldg(&P.nary_ptr[slot]), e = __ldg(&P.nary_ptr[slot + 1]);
+  const int k = e - b;
+  int2* ops = reinterpret_cast<int2*>(smem_nary);
+  int2* iv = ops + P.nary_max_k;
+  int* tab = reinterpret_cast<int*>(iv + P.nary_max_k);
+  unsigned tabsz = 4;
+  while (tabsz < 2u * (unsigned)k) tabsz <<= 1;
+  const unsigned mask = tabsz - 1;
+  int* newv = tab + tabsz;
+  __syncthreads();
+  int any_dirty = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    int2 op = __ldg(&P.nary_ops[b + i]);
+    ops[i] = op;
+    if (op.x >= 0) {
+      int2 d = SMEM ? c.sdom[op.x] : ldcg_dom(&P.dom[op.x]);
+      iv[i] = make_int2(d.x + op.y, d.y + op.y);
+      if (!unconditional && ((__ldcg(&cur_bits[op.x >> 5]) >> (op.x & 31)) & 1u)) any_dirty = 1;
+    } else {
+      iv[i] = make_int2(op.y, op.y);
+    }
+  }
+  for (unsigned i = threadIdx.x; i < tabsz; i += blockDim.x) tab[i] = kHashEmpty;
+  if (!unconditional) {
+    if (!__syncthreads_or(any_dirty)) return 0;
+  } else {
+    __syncthreads();
+  }
+  unsigned inserted_bits = 0, inner_bits = 0;  // per owned operand j (k <= 32 * blockDim)
+  while (true) {
+    if (threadIdx.x == 0) s_nnew = 0;
+    __syncthreads();
+    int fail = 0, j = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x, ++j) {
+      const int2 d = iv[i];
+      if (d.x == d.y && !((inserted_bits >> j) & 1u)) {
+        inserted_bits |= 1u << j;
+        if (!hs_insert(tab, mask, d.x)) fail = 1;            // two equal assigned operands
+        else newv[atomicAdd(&s_nnew, 1)] = d.x;
+      }
+    }
+    if (__syncthreads_or(fail)) { set_failed(c); return 1; }
+    const int n = s_nnew;
+    if (n == 0) break;
+    j = 0;
+    for (int i = threadIdx.x; i < k; i += blockDim.x, ++j) {
+      const int2 op = ops[i];
+      int2 d = iv[i];
+      if (op.x < 0 || d.x == d.y) continue;
+      bool moved = false;
+      for (int q = 0; q < n && d.x <= d.y; ++q) {
+        const int v = newv[q];
+        if (v < d.x || v > d.y) continue;
+        if (v == d.x) {
+          const int r = sb_next(sw, op.x, v - op.y + 1, d.y - op.y);
+          d.x = r == INT32_MAX ? d.y + 1 : r + op.y;
+          moved = true;
+        } else if (v == d.y) {
+          const int r = sb_prev(sw, op.x, v - op.y - 1, d.x - op.y);
+          d.y = r == INT32_MIN ? d.x - 1 : r + op.y;
+          moved = true;
+        } else if (sb_clear(sw, op.x, v - op.y)) {
+          inner_bits |= 1u << j;
+        }
+      }
+      if (d.x > d.y) { fail = 1; continue; }
+      if (moved) iv[i] = d;
+    }
+    if (__syncthreads_or(fail)) { set_failed(c); return 1; }
+  }
+  // write back: bounds through the staged path, interior removals are already in the sets
+  int j = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x, ++j) {
+    const int2 op = ops[i];
+    if (op.x < 0) continue;
+    const int2 d = iv[i];
+    const int2 cur = ldcg_dom(&P.dom[op.x]);
+    const IV curv{cur.x + op.y, cur.y + op.y};
+    if (!tighten(c, op.x, op.y, curv, max(curv.lo, d.x), min(curv.hi, d.y))) set_failed(c);
+    if (((inner_bits >> j) & 1u) && c.mark_dirty) {
+      atomicOr(&c.next_bits[op.x >> 5], 1u << (op.x & 31));
+      c.flags[0] = 1;
+    }
+  }
+  __syncthreads();
+  bool entailed = k <= 1;
+  if (k > 1) {
+    int overlap = 0;
+    for (int i = threadIdx.x; i < k && !overlap; i += blockDim.x) {
+      const int2 oa = ops[i], a = iv[i];
+      for (int q = i + 1; q < k; ++q)
+        if (!views_disjoint(sw, oa, a, ops[q], iv[q])) { overlap = 1; break; }
+    }
+    entailed = !__syncthreads_or(overlap);
+  }
+  if (threadIdx.x == 0 && entailed) {
+    unsigned bit = 1u << (slot & 31);
+    unsigned old = atomicAnd(&P.nary_active[slot >> 5], ~bit);
+    if (old & bit) P.trail[atomicAdd(&P.ctl->trail_cnt, 1u)] = make_ref(F_NARY, (unsigned)slot);
+  }
+  return 1;
+}
+#endif  // PCP_SET
+
 // ---------------------------------------------------------------------------------------
 // n-ary AllEqual (propagators/all_equal.rs:47-103 = Conjunction of XEqY(v_i, v_{i+1}),
 // cmp/x_eq_y.rs:84-107).  Every XEqY replaces both sides by their intersection, so the chain's
@@ -989,7 +1201,9 @@ __device__ __forceinline__ bool row_eval_entry(const Params& P, Ctx& c, unsigned
   const unsigned fam = ref >> 29;
   const int slot = (int)(ref & kSlotMask);
   if (fam == F_BIN) {
+#ifndef PCP_SET  // (IntervalSet: the staged path does the set work; no crawling on sets)
     if (SMEM && is_plain_neq(q)) return row_eval_neq(P, c, q);
+#endif
     eval_loaded<SMEM>(c, F_BIN, slot, q, make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0));
   } else {
     eval_ref<SMEM>(c, fam, slot);
@@ -1019,7 +1233,11 @@ __device__ __forceinline__ unsigned expand_rows_local(const Params& P, Ctx& c, c
     trace_seq(P, 100);
     for (int round = 0;; ++round) {
       const int2 d0 = s_before;                   // v at the start of the round
+#ifdef PCP_SET
+      const bool crawl = false;                   // a set loses a value wherever it sits: nothing crawls
+#else
       const bool crawl = SMEM && d0.x < d0.y;     // an unassigned v can crawl
+#endif
       if (crawl && threadIdx.x < 2 * (kJumpBits / 32)) (&s_win.bm[0][0])[threadIdx.x] = 0u;
       if (round == 0 && staged) {
         // Round 0 of a row that fits the staging area: gather it from L2 in batches -- all
@@ -1190,6 +1408,13 @@ __device__ __forceinline__ unsigned expand_dirty_rows(const Params& P, Ctx& c, c
 __device__ __forceinline__ void node_prologue(const Params& P, int tid, int nth) {
   if (P.restore_from)
     for (int v = tid; v < P.V; v += nth) P.dom[v] = P.restore_from[v];
+#ifdef PCP_SET
+  if (P.restore_from) {  // the label slot holds the bit sets behind the bounds
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.restore_from + P.V);
+    const long long nw = (long long)P.V * P.bits_W;
+    for (long long i = tid; i < nw; i += nth) P.bits[i] = src[i];
+  }
+#endif
   if (P.do_trail) {
     unsigned cnt = *(volatile unsigned*)&P.ctl->trail_cnt;
     if (P.trail_keep == 0 && cnt > 4096u) {
@@ -1352,7 +1577,11 @@ __device__ __noinline__ unsigned nary_outlined(const Params* PS, const Ctx* c, c
   for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
     if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
     unsigned ev = __ldg(&P.nary_kind[s]) == N_ALL_EQUAL ? eval_all_equal<SMEM>(P, *c, s, cur_bits, all)
+#ifdef PCP_SET
+                                                         : eval_distinct_set<SMEM>(P, *c, s, ring, cur_bits, all);
+#else
                                                          : eval_distinct<SMEM>(P, *c, s, ring, cur_bits, all);
+#endif
     if (threadIdx.x == 0) n += ev;
   }
   return n;
@@ -1382,6 +1611,26 @@ __device__ __noinline__ unsigned tail_outlined(const Params* PS, const Ctx* c, i
   return n;
 }
 __device__ __noinline__ void prologue_outlined(const Params* PS, int tid, int nth) { node_prologue(*PS, tid, nth); }
+
+#ifdef PCP_SET
+// Bring the cached bounds of a narrowed variable back onto elements of its set: two concurrent
+// updates can leave lo on a value that a third thread removed meanwhile (the set itself is
+// always right: bits are only cleared).  Every CTA does this when it refreshes its view of the
+// dirty variables; the result also goes back to the store (idempotent reductions, not a
+// narrowing of the domain: nobody is re-scheduled for it).  Returns 1 when the domain is empty.
+__device__ __forceinline__ int set_normalise(const Params& P, int v, int2& d) {
+  if (d.x > d.y) return 1;
+  const SetW sw = set_of(P);
+  const int lo = sb_next(sw, v, d.x, d.y);
+  if (lo == INT32_MAX) { d.x = d.y + 1; return 1; }
+  const int hi = sb_prev(sw, v, d.y, lo);
+  if (lo != d.x) atomicMax(&P.dom[v].x, lo);
+  if (hi != d.y) atomicMin(&P.dom[v].y, hi);
+  d.x = lo;
+  d.y = hi;
+  return 0;
+}
+#endif
 
 // One node's fixpoint: iteration 0 (posted propagators, tail, streaming sweep or seeded
 // worklist) and the worklist / re-sweep iterations, each closed by the deciding barrier.
@@ -1464,6 +1713,13 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
       // already sees their effect.
       if (threadIdx.x == 0) {
         c.mark_dirty = !full_sweep;
+#ifdef PCP_SET
+        // A posted XLessY (what BinarySplit and BranchAndBound post) only moves bounds, which every
+        // CTA applies to its own snapshot; anything else may clear bits of the shared sets behind the
+        // back of a CTA that is already sweeping, so what it narrows is queued like any other change.
+        for (int i = 0; i < n_inline; ++i)
+          if (inl[i].fam != F_BIN || ((unsigned)inl[i].q[0].x >> 28) != B_LESS) c.mark_dirty = true;
+#endif
         if (blockIdx.x == 0 || !SMEM) {  // the global store: counted and book-kept by CTA 0
           c.bookkeep = blockIdx.x == 0;
           for (int i = 0; i < n_inline; ++i)
@@ -1504,6 +1760,9 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
         const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
         for (int v = r0; v < P.V; v += rs) {  // coalesced re-read of everything beats gathers
           int2 d = ldcg_dom(&P.dom[v]);
+#ifdef PCP_SET
+          bad |= set_normalise(P, v, d);
+#endif
           if (SMEM) st.sdom[v] = d;
           bad |= d.x > d.y;
         }
@@ -1513,6 +1772,9 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
         for (int i = r0; i < n_dirty; i += rs) {
           int v = list[i];
           int2 d = ldcg_dom(&P.dom[v]);
+#ifdef PCP_SET
+          bad |= set_normalise(P, v, d);
+#endif
           if (SMEM) st.sdom[v] = d;
           bad |= d.x > d.y;
         }
@@ -1669,6 +1931,15 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
                                            P.seed_dirty, P.full_sweep != 0, iters);
 
   trace_mark(P, 6);
+#ifdef PCP_SET
+  // the label copy of the bit sets: every CTA takes a slice (at a fixpoint nobody writes them any more)
+  if (P.snapshot_to && dec == D_FIXPOINT) {
+    uint32_t* dst = reinterpret_cast<uint32_t*>(P.snapshot_to + P.V);
+    const long long nw = (long long)P.V * P.bits_W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x)
+      dst[i] = __ldcg(&P.bits[i]);
+  }
+#endif
   if (blockIdx.x == 0) {
     // Branch::distribute takes a label right after an Unknown node (branch.rs:36-49): leave the
     // copy of the fixpoint domains in the next label slot so that pcp_label is free.
@@ -1680,6 +1951,15 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       int2* hd = reinterpret_cast<int2*>(P.host_result + 1);
       const bool from_snapshot = SMEM && dec == D_FIXPOINT;
       for (int v = threadIdx.x; v < P.V; v += blockDim.x) hd[v] = from_snapshot ? st.sdom[v] : ldcg_dom(&P.dom[v]);
+#ifdef PCP_SET
+      if (P.host_sizes && dec != D_FAILED) {  // Cardinality::size() per variable, for the host's FirstSmallestVar
+        const SetW sw = set_of(P);
+        for (int v = threadIdx.x; v < P.V; v += blockDim.x) {
+          const int2 d = from_snapshot ? st.sdom[v] : ldcg_dom(&P.dom[v]);
+          P.host_sizes[v] = d.x > d.y ? 0u : sb_count(sw, v, d.x, d.y);
+        }
+      }
+#endif
       __threadfence_system();
     }
     if (P.host_result) __syncthreads();

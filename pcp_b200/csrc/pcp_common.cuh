@@ -136,6 +136,14 @@ struct Params {
   unsigned host_seq;          //   Result::seq, so the host polls instead of copying + synchronising
   // ---- debug: per-CTA phase timestamps (PCP_TRACE=1), 8 slots per CTA
   unsigned long long* trace;
+  // ---- IntervalSet domains (PCP_FLAG_INTERVAL_SET; the `set` kernel variants): one bit per value
+  // of the window [bits_base, bits_base + 32 * bits_W) and variable; the domain of v is
+  // bits[v] /\ [dom[v].lo, dom[v].hi] (bits outside the cached bounds are don't-care).  A label
+  // slot holds the V domains followed by the V * bits_W words (stack_stride counts both).
+  uint32_t* bits;
+  int bits_W;
+  int bits_base;
+  uint32_t* host_sizes;       // mapped pinned: Cardinality::size() per variable, stored by the epilogue
 };
 
 constexpr int kTraceIter1 = 8 * 256 + 4 * 32 + 64;  // second mark region: phases of iteration 1
@@ -232,6 +240,7 @@ struct BurstParams {
   long long props_base;             // allocated propagators = props_base + bin_n
   int* t_status;                    // per-node trace (device buffers), indexed by node number
   int2* t_dom;
+  uint32_t* t_bits;                 // set variants: V * bits_W words per traced node
   unsigned long long t_cap;
 };
 

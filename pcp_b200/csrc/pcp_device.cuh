@@ -44,3 +44,19 @@ namespace pcpd { namespace binonly {
 #include "pcp_body.cuh"
 } }  // namespace pcpd::binonly
 #undef PCP_BIN_ONLY
+
+// The same two variants for IntervalSet<i32> domains (PCP_FLAG_INTERVAL_SET; libpcp's VStoreSet,
+// variable/mod.rs:38): a bit set per variable beside the cached bounds, XNeqY removes interior
+// values (x_neq_y.rs:82-93 on IntervalSet::difference), bound updates land on the next value
+// that is still in the set, entailment of XNeqY / XEqY / Distinct is decided on the sets.
+// Kept as separate compilations so that the Interval kernels stay exactly what they were.
+#define PCP_SET 1
+namespace pcpd { namespace full_set {
+#include "pcp_body.cuh"
+} }  // namespace pcpd::full_set
+#define PCP_BIN_ONLY 1
+namespace pcpd { namespace binonly_set {
+#include "pcp_body.cuh"
+} }  // namespace pcpd::binonly_set
+#undef PCP_BIN_ONLY
+#undef PCP_SET

@@ -132,6 +132,12 @@ struct pcp_engine {
   std::vector<int2> h_dom_pending;  // variables allocated but not yet uploaded
   std::vector<int2> h_dom_init;     // the domains as allocated (range validation of Sum views)
   size_t V = 0, V_uploaded = 0;
+  // IntervalSet domains (PCP_FLAG_INTERVAL_SET): one bit per value of the window
+  // [set_base, set_base + 32 * set_W) and variable, fixed when the first variables are uploaded
+  bool set_mode = false;
+  int set_base = 0, set_W = 0;
+  DevBuf<uint32_t> d_bits;
+  bool sizes_valid = false;         // the size mirror behind the host domains is current
   char* d_block = nullptr;          // [Result | dom ...]
   size_t block_cap_vars = 0;
   char* h_block = nullptr;          // pinned mirror of d_block (mapped: the fixpoint kernel stores into it)
@@ -226,6 +232,10 @@ struct pcp_engine {
   int2* d_dom() const { return reinterpret_cast<int2*>(d_block + sizeof(Result)); }
   Result* h_result() const { return reinterpret_cast<Result*>(h_block); }
   int2* h_dom() const { return reinterpret_cast<int2*>(h_block + sizeof(Result)); }
+  uint32_t* h_sizes() const { return reinterpret_cast<uint32_t*>(h_block + sizeof(Result) + h_block_cap_vars * sizeof(int2)); }
+  uint32_t* h_sizes_dev() const { return reinterpret_cast<uint32_t*>(h_block_dev + sizeof(Result) + h_block_cap_vars * sizeof(int2)); }
+  // a label slot: the V domains, then (set mode) the V * set_W words of the bit sets, in int2 units
+  size_t slot_stride() const { return V + (set_mode ? (V * (size_t)set_W + 1) / 2 : 0); }
   size_t num_props() const { return prop_ref.size(); }
 };
 
@@ -250,7 +260,8 @@ void ensure_var_capacity(pcp_engine* e, size_t nvars) {
   if (nvars > e->h_block_cap_vars) {
     size_t ncap = std::max<size_t>(nvars, e->h_block_cap_vars * 2 + 256);
     char* q = nullptr;
-    CUDA_CHECK(cudaHostAlloc(&q, sizeof(Result) + ncap * sizeof(int2), cudaHostAllocMapped));
+    CUDA_CHECK(cudaHostAlloc(&q, sizeof(Result) + ncap * (sizeof(int2) + sizeof(uint32_t)), cudaHostAllocMapped));
+    e->sizes_valid = false;
     if (e->h_block) {
       std::memcpy(q, e->h_block, sizeof(Result) + e->h_block_cap_vars * sizeof(int2));
       cudaFreeHost(e->h_block);
@@ -359,6 +370,17 @@ void require_distinct_vars(const pcp_engine* e, const pcp_operand* ops, int n) {
 
 void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
   pcp_operand ops[6];
+  if (e->set_mode) {
+    // What has no device lowering on IntervalSet domains (loud, not a fallback): the arithmetic of
+    // XEqYMulZ and of multi-term Sum views needs `set * set` / `set + set` (whose reference result
+    // depends on interior values while the propagators subscribe to Bound only: the reference's
+    // own fixpoint is schedule-dependent there), AllEqual needs an n-way set intersection.
+    if (kind == PCP_X_EQ_Y_MUL_Z || kind == PCP_ALL_EQUAL)
+      PCP_FAIL(PCP_ERR_UNSUPPORTED, "XEqYMulZ / AllEqual have no device lowering on IntervalSet domains");
+    for (int i = 0; i < n_ops; ++i)
+      if (raw[i].var <= -2 && (size_t)(-2 - raw[i].var) < e->sums.size() && e->sums[(size_t)(-2 - raw[i].var)].size() > 1)
+        PCP_FAIL(PCP_ERR_UNSUPPORTED, "multi-term Sum views have no device lowering on IntervalSet domains");
+  }
   switch (kind) {
     case PCP_X_LESS_Y:
     case PCP_X_NEQ_Y:
@@ -548,7 +570,7 @@ size_t nary_smem_bytes(const pcp_engine* e) {
   size_t k = (size_t)e->nary_max_k;
   size_t tab = 4;
   while (tab < 2 * k) tab <<= 1;
-  return k * 16 + tab * 4;
+  return k * 16 + tab * 4 + (e->set_mode ? k * 4 : 0);  // (set variants: + the list of newly assigned values)
 }
 
 // Everything except the few "inline" propagators is brought to the device here: new
@@ -566,6 +588,21 @@ Params prepare(pcp_engine* e) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
     e->h_dom_pending.clear();
     size_t oldV = e->V_uploaded;
+    if (e->set_mode) {
+      int mn = INT32_MAX, mx = INT32_MIN;
+      for (size_t v = oldV; v < V; ++v) { mn = std::min(mn, e->h_dom_init[v].x); mx = std::max(mx, e->h_dom_init[v].y); }
+      if (e->set_W == 0) {  // the window is fixed by the first variables
+        const long long words = ((long long)mx - mn + 1 + 31) / 32;
+        if (words > 4096) PCP_FAIL(PCP_ERR_UNSUPPORTED, "IntervalSet domains spanning more than 131072 values are not supported");
+        e->set_base = mn;
+        e->set_W = (int)((words + 1) & ~1ll);  // even: a label slot stays 8-byte aligned
+      } else if (mn < e->set_base || (long long)mx >= (long long)e->set_base + 32ll * e->set_W) {
+        PCP_FAIL(PCP_ERR_UNSUPPORTED, "IntervalSet variable outside the value window fixed by the first variables");
+      }
+      // every value of the window starts in the set: bits outside the bounds are don't-care
+      e->d_bits.reserve(V * (size_t)e->set_W, e->stream, oldV * (size_t)e->set_W);
+      fill_u32(e, e->d_bits.p + oldV * (size_t)e->set_W, 0xffffffffu, (V - oldV) * (size_t)e->set_W);
+    }
     e->V_uploaded = V;
     e->mirror_valid = false;
     ++e->dom_version;
@@ -576,7 +613,7 @@ Params prepare(pcp_engine* e) {
     CUDA_CHECK(cudaMemsetAsync(e->d_dirty_bits.p, 0, e->d_dirty_bits.cap * sizeof(uint32_t), e->stream));
     // the label stack is laid out with stride V: a label taken with fewer variables cannot be
     // restored after more were allocated
-    if (e->stack_stride != V) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = V; }
+    if (e->stack_stride != e->slot_stride()) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = e->slot_stride(); }
     e->csr_built = false;  // adj_ptr has V+1 entries
     for (int f = 0; f < 3; ++f) e->fam[f].n_static = 0;
   }
@@ -693,6 +730,9 @@ Params prepare(pcp_engine* e) {
   P.dirty_words = (int)e->dirty_words;
   P.trail = e->d_trail.p;
   P.ctl = e->d_ctl;
+  P.bits = e->d_bits.p;
+  P.bits_W = e->set_W;
+  P.bits_base = e->set_base;
   P.max_iterations = e->max_iterations;
   P.gen0 = e->bar_gen;
   P.epoch0 = e->epoch;
@@ -726,19 +766,38 @@ __global__ void __launch_bounds__(1024, 1) pcp_prologue_kernel(const __grid_cons
   __syncthreads();
   if (threadIdx.x == 0) full::node_prologue_finish(P);
 }
+__global__ void __launch_bounds__(1024, 1) pcp_prologue_set_kernel(const __grid_constant__ Params P) {
+  full_set::node_prologue(P, threadIdx.x, blockDim.x);  // (restores the bit sets as well)
+  __syncthreads();
+  if (threadIdx.x == 0) full_set::node_prologue_finish(P);
+}
+// Cardinality::size() of every IntervalSet domain (when the fixpoint kernel did not leave them
+// in the host mirror: stores too large for the zero-copy result, reads after a restore).
+__global__ void pcp_set_sizes_kernel(const int2* dom, const uint32_t* bits, int W, int base, int V, uint32_t* out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  const int2 d = dom[v];
+  full_set::SetW sw{const_cast<uint32_t*>(bits), W, base};
+  out[v] = d.x > d.y ? 0u : full_set::sb_count(sw, v, d.x, d.y);
+}
 
 // Bring the device state up to date without running a fixpoint (pcp_domains_read /
 // pcp_label / pcp_active_read right after a restore or an alloc).
 void sync_device_state(pcp_engine* e) {
   if (!prologue_pending(e)) return;
   Params P = prepare(e);
-  pcp_prologue_kernel<<<1, 1024, 0, e->stream>>>(P);
+  if (e->set_mode) pcp_prologue_set_kernel<<<1, 1024, 0, e->stream>>>(P);
+  else pcp_prologue_kernel<<<1, 1024, 0, e->stream>>>(P);
   CUDA_CHECK(cudaGetLastError());
 }
 
 // Kernel variants: `binonly` for stores whose propagators are all binary (no ternary,
 // disjunction or n-ary code in the kernel -- see pcp_body.cuh), `full` otherwise.
 bool bin_only_store(const pcp_engine* e) { return e->fam[F_TER].n == 0 && e->fam[F_DJ].n == 0 && e->n_nary == 0; }
+const void* fixpoint_set_fn(bool bin_only, bool smem_dom) {
+  if (bin_only) return smem_dom ? (const void*)binonly_set::pcp_fixpoint_kernel<true> : (const void*)binonly_set::pcp_fixpoint_kernel<false>;
+  return smem_dom ? (const void*)full_set::pcp_fixpoint_kernel<true> : (const void*)full_set::pcp_fixpoint_kernel<false>;
+}
 const void* fixpoint_fn(bool bin_only, bool smem_dom) {
   if (bin_only) return smem_dom ? (const void*)binonly::pcp_fixpoint_kernel<true> : (const void*)binonly::pcp_fixpoint_kernel<false>;
   return smem_dom ? (const void*)full::pcp_fixpoint_kernel<true> : (const void*)full::pcp_fixpoint_kernel<false>;
@@ -801,7 +860,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
 
   // label slot for the epilogue snapshot (Branch::distribute labels right after an Unknown node)
   e->snapshot_valid = false;
-  const bool want_snapshot = V > 0 && V <= 16384 && e->labels.size() < e->max_labels && e->stack_stride == V;
+  const bool want_snapshot = V > 0 && V <= 16384 && e->labels.size() < e->max_labels && e->stack_stride == e->slot_stride();
   if (want_snapshot) {
     size_t idx = e->labels.size();
     if ((idx + 1) * e->stack_stride > e->d_stack.cap) {
@@ -835,7 +894,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
       smem += bm_bytes;
     }
   }
-  const void* fn = fixpoint_fn(bin_only_store(e), smem_dom);
+  const void* fn = e->set_mode ? fixpoint_set_fn(bin_only_store(e), smem_dom) : fixpoint_fn(bin_only_store(e), smem_dom);
 
   static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (trace_on) {
@@ -853,7 +912,9 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     P.host_result = reinterpret_cast<Result*>(e->h_block_dev);
     P.host_dom = eager_dom ? 1 : 0;
     P.host_seq = ++e->host_seq ? e->host_seq : ++e->host_seq;  // never 0
+    if (e->set_mode && eager_dom) P.host_sizes = e->h_sizes_dev();
   }
+  e->sizes_valid = false;
   const double hp2 = now_s();
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
   void* args[] = {&P};
@@ -881,6 +942,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
   }
   e->mirror_valid = eager_dom;
+  e->sizes_valid = P.host_sizes != nullptr && !e->h_result()->failed;
   {
     const double hp4 = now_s();
     static unsigned long long skip = 0;
@@ -969,6 +1031,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
 void fetch_domains(pcp_engine* e) {
   sync_device_state(e);
   if (e->mirror_valid) return;
+  e->sizes_valid = false;
   if (e->V) {
     CUDA_CHECK(cudaMemcpyAsync(e->h_dom(), e->d_dom(), e->V * sizeof(int2), cudaMemcpyDeviceToHost, e->stream));
     CUDA_CHECK(cudaStreamSynchronize(e->stream));
@@ -1001,6 +1064,7 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
   int rc = guarded(e, [&] {
     e->device = cfg ? cfg->device : 0;
     e->flags = cfg ? cfg->flags : 0;
+    e->set_mode = (e->flags & PCP_FLAG_INTERVAL_SET) != 0;
     if (cfg && cfg->max_labels) e->max_labels = cfg->max_labels;
     if (cfg && cfg->tail_limit) e->tail_limit = cfg->tail_limit;
     int count = 0;
@@ -1019,8 +1083,10 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     {
       // dynamic shared memory every persistent kernel may use = the opt-in maximum minus its own
       // static part; configured once (an engine never lowers what another engine relies on)
-      const void* fns[8] = {fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
-                            fixpoint_fn(true, false),  fixpoint_fn(true, true),  burst_fn(true, false),  burst_fn(true, true)};
+      const void* fns[12] = {fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
+                             fixpoint_fn(true, false),  fixpoint_fn(true, true),  burst_fn(true, false),  burst_fn(true, true),
+                             fixpoint_set_fn(false, false), fixpoint_set_fn(false, true), fixpoint_set_fn(true, false),
+                             fixpoint_set_fn(true, true)};
       size_t max_static = 0;
       for (const void* fn : fns) {
         cudaFuncAttributes fa;
@@ -1062,7 +1128,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   }
   e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_kind.free(); e->d_nary_active.free();
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
-  e->d_dirty_bits.free(); e->d_seed_list.free(); e->d_trail.free(); e->d_stack.free();
+  e->d_dirty_bits.free(); e->d_seed_list.free(); e->d_trail.free(); e->d_stack.free(); e->d_bits.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
   if (e->burst.d_bc) cudaFree(e->burst.d_bc);
   e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_bmeta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free();
@@ -1186,6 +1252,76 @@ int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32
   });
 }
 
+int pcp_domains_size_read(pcp_engine* e, int32_t first, int32_t n, uint32_t* size) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(first >= 0 && n >= 0 && (size_t)first + (size_t)n <= e->V && (n == 0 || size), "Variable not registered in the store.");
+    if (n == 0) return;
+    if (!e->mirror_valid || prologue_pending(e)) {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      fetch_domains(e);
+      e->sizes_valid = false;
+    }
+    if (!e->set_mode) {  // Interval::size()
+      const int2* d = e->h_dom() + first;
+      for (int i = 0; i < n; ++i) size[i] = d[i].x > d[i].y ? 0u : (uint32_t)(d[i].y - d[i].x) + 1u;
+      return;
+    }
+    if (!e->sizes_valid) {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      pcp_set_sizes_kernel<<<(int)((e->V + 255) / 256), 256, 0, e->stream>>>(e->d_dom(), e->d_bits.p, e->set_W, e->set_base, (int)e->V,
+                                                                             e->h_sizes_dev());
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      e->sizes_valid = true;
+    }
+    std::memcpy(size, e->h_sizes() + first, (size_t)n * sizeof(uint32_t));
+  });
+}
+
+int pcp_domains_read_bits(pcp_engine* e, int32_t first, int32_t n, int32_t base, int32_t words, uint32_t* out) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE(first >= 0 && n >= 0 && words >= 0 && (size_t)first + (size_t)n <= e->V && (n == 0 || words == 0 || out),
+                "Variable not registered in the store.");
+    if (n == 0 || words == 0) return;
+    if (!e->mirror_valid || prologue_pending(e)) {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      fetch_domains(e);
+    }
+    std::vector<uint32_t> raw;
+    if (e->set_mode) {
+      raw.resize((size_t)n * e->set_W);
+      CUDA_CHECK(cudaSetDevice(e->device));
+      CUDA_CHECK(cudaMemcpyAsync(raw.data(), e->d_bits.p + (size_t)first * e->set_W, raw.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    }
+    std::memset(out, 0, (size_t)n * (size_t)words * 4);
+    for (int i = 0; i < n; ++i) {
+      const int2 d = e->h_dom()[first + i];
+      for (long long v = d.x; v <= d.y; ++v) {
+        if (e->set_mode) {
+          const unsigned b = (unsigned)(v - e->set_base);
+          if (!((raw[(size_t)i * e->set_W + (b >> 5)] >> (b & 31)) & 1u)) continue;
+        }
+        const long long o = v - base;
+        PCP_REQUIRE(o >= 0 && o < (long long)words * 32, "value outside the requested bit window");
+        out[(size_t)i * words + (size_t)(o >> 5)] |= 1u << (o & 31);
+      }
+    }
+  });
+}
+
+int pcp_formula_alloc(pcp_engine* e, const int32_t* words, int32_t n_words, int32_t* idx) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
+    PCP_REQUIRE(words && n_words > 0, "bad arguments");
+    (void)idx;
+    PCP_FAIL(PCP_ERR_UNSUPPORTED, "formula trees: not built yet");
+  });
+}
+
 int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* ok) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
@@ -1197,6 +1333,16 @@ int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* 
     bool empty = lo > hi;
     // variable/store.rs:153-156: dom must be a subset of the current domain (empty is)
     PCP_REQUIRE(empty || (lo >= cur.x && hi <= cur.y), "Domain update must be monotonic.");
+    if (!empty && e->set_mode) {
+      // IntervalSet: the new domain is cur /\ [lo, hi]; its bounds are the extreme values left
+      std::vector<uint32_t> w((size_t)e->set_W);
+      CUDA_CHECK(cudaMemcpyAsync(w.data(), e->d_bits.p + (size_t)idx * e->set_W, w.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+      CUDA_CHECK(cudaStreamSynchronize(e->stream));
+      auto has = [&](int v) { unsigned b = (unsigned)(v - e->set_base); return (w[b >> 5] >> (b & 31)) & 1u; };
+      while (lo <= hi && !has(lo)) ++lo;
+      while (hi >= lo && !has(hi)) --hi;
+      empty = lo > hi;
+    }
     if (empty) { if (ok) *ok = 0; return; }
     if (lo != cur.x || hi != cur.y) {
       int2* st = static_cast<int2*>(stage(e, sizeof(int2)));
@@ -1204,6 +1350,7 @@ int pcp_var_update(pcp_engine* e, int32_t idx, int32_t lo, int32_t hi, int32_t* 
       CUDA_CHECK(cudaMemcpyAsync(e->d_dom() + idx, st, sizeof(int2), cudaMemcpyHostToDevice, e->stream));
       CUDA_CHECK(cudaStreamSynchronize(e->stream));
       e->h_dom()[idx] = make_int2(lo, hi);
+      e->sizes_valid = false;
       e->host_dirty.push_back(idx);
       ++e->dom_version;
       e->snapshot_valid = false;
@@ -1246,12 +1393,15 @@ int pcp_label(pcp_engine* e, uint64_t* label) {
     if (!have) {
       CUDA_CHECK(cudaSetDevice(e->device));
       sync_device_state(e);
-      if (e->stack_stride != e->V) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = e->V; }
+      if (e->stack_stride != e->slot_stride()) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = e->slot_stride(); }
       if ((idx + 1) * std::max<size_t>(e->stack_stride, 1) > e->d_stack.cap)  // grow in big steps: a reallocation copies the stack
         e->d_stack.reserve(std::max<size_t>((idx + 1) * 2, 16) * std::max<size_t>(e->stack_stride, 1), e->stream, idx * e->stack_stride);
       if (e->V)
         CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride, e->d_dom(), e->V * sizeof(int2),
                                    cudaMemcpyDeviceToDevice, e->stream));
+      if (e->V && e->set_mode)
+        CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride + e->V, e->d_bits.p,
+                                   e->V * (size_t)e->set_W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
     }
     e->snapshot_valid = false;
     LabelRec r;
@@ -1276,6 +1426,7 @@ int pcp_restore(pcp_engine* e, uint64_t label) {
     e->labels.resize(label + 1);
     truncate_props(e, r);
     e->snapshot_valid = false;
+    e->sizes_valid = false;
     e->host_dirty.clear();
     e->at_fixpoint = r.at_fixpoint;
     // restoring the label that was just taken from the current domains (the left child of
@@ -1306,6 +1457,7 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
   if (cfg->var_sel != 0 || cfg->val_sel != 0 || cfg->distributor != 0 || cfg->bb_mode != 0) return 0;
   if (e->V == 0 || e->V > (size_t)(1 << 20)) return 0;
   if ((e->flags & (PCP_FLAG_INCREMENTAL | PCP_FLAG_HOST_SEARCH))) return 0;
+  if (e->set_mode) return 0;  // IntervalSet engines: the host-driven node loop (sizes and bit sets per label)
   // the device search pre-reserves its whole label stack (burst_depth(e) slots of V domains):
   // a store too wide for that budget takes the host-driven node loop, which grows on demand
   if (burst_depth(e) * e->V * sizeof(int2) > kBurstStackBudget) return 0;
@@ -1526,6 +1678,8 @@ int pcp_internal_burst_end(pcp_engine* e) {
     e->at_fixpoint = false;
   });
 }
+
+int pcp_internal_interval_set(const pcp_engine* e) { return e && e->set_mode ? 1 : 0; }
 
 int pcp_num_vars(const pcp_engine* e, int32_t* n) {
   if (!e || !n) return PCP_ERR_INVALID;

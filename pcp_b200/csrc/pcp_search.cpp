@@ -24,6 +24,27 @@ struct Branch {
   int32_t var, val;
 };
 
+// FNV-1a over the (lb, ub) words of every maximal run of values of every domain, from a bit window
+// (IntervalSet engines; a domain without holes hashes like its (lo, hi) pair below)
+uint64_t hash_domain_bits(const int32_t* lo, const int32_t* hi, size_t n, int32_t base, int32_t words, const uint32_t* bits) {
+  uint64_t h = 1469598103934665603ull;
+  auto feed = [&](uint32_t w) { for (int b = 0; b < 4; ++b) { h ^= (w >> (8 * b)) & 0xffu; h *= 1099511628211ull; } };
+  for (size_t i = 0; i < n; ++i) {
+    const uint32_t* w = bits + i * (size_t)words;
+    auto has = [&](int64_t v) { const int64_t o = v - base; return (w[o >> 5] >> (o & 31)) & 1u; };
+    int64_t v = lo[i];
+    while (v <= hi[i]) {
+      if (!has(v)) { ++v; continue; }
+      int64_t u = v;
+      while (u + 1 <= hi[i] && has(u + 1)) ++u;
+      feed((uint32_t)(int32_t)v);
+      feed((uint32_t)(int32_t)u);
+      v = u + 1;
+    }
+  }
+  return h;
+}
+
 uint64_t hash_domains(const int32_t* lo, const int32_t* hi, size_t n) {  // FNV-1a over (lo,hi) words
   uint64_t h = 1469598103934665603ull;
   for (size_t i = 0; i < n; ++i) {
@@ -45,6 +66,8 @@ struct Driver {
   uint64_t t_cap;
   std::vector<Branch> queue;  // VectorStack: DFS, left child first
   std::vector<int32_t> lo, hi;
+  std::vector<uint32_t> size, bits;  // Cardinality::size() per variable; bit window of the traced domains
+  bool set_domains = false;          // IntervalSet engine: sizes and hashes come from the sets
   bool started = false;
   uint64_t nodes_explored = 0;
   int32_t V = 0;
@@ -88,8 +111,9 @@ struct Driver {
       // first_smallest_var.rs:30-39 / input_order.rs; middle_val.rs:25-27 / min_val.rs
       int32_t var = -1;
       uint32_t best = 0;
+      if (set_domains) TRY(pcp_domains_size_read(e, 0, V, size.data()));
       for (int32_t i = 0; i < V; ++i) {
-        uint32_t sz = (uint32_t)(hi[i] - lo[i]) + 1u;
+        uint32_t sz = set_domains ? size[i] : (uint32_t)(hi[i] - lo[i]) + 1u;
         if (sz > 1 && (var < 0 || (cfg->var_sel == 0 && sz < best))) { var = i; best = sz; if (cfg->var_sel == 1) break; }
       }
       if (var < 0) return PCP_ERR_INVALID;  // "Cannot select a variable in a space where all variables are assigned."
@@ -103,7 +127,14 @@ struct Driver {
     uint64_t n = res->num_nodes;
     if (n < t_cap) {
       if (t_status) t_status[n] = k;
-      if (t_hash) t_hash[n] = k == PCP_FALSE ? 0 : hash_domains(lo.data(), hi.data(), (size_t)V);
+      if (t_hash && k != PCP_FALSE && set_domains) {
+        int32_t mn = lo[0], mx = hi[0];
+        for (int32_t i = 1; i < V; ++i) { mn = std::min(mn, lo[i]); mx = std::max(mx, hi[i]); }
+        const int32_t words = (int32_t)(((int64_t)mx - mn + 32) / 32);
+        bits.resize((size_t)V * (size_t)words);
+        TRY(pcp_domains_read_bits(e, 0, V, mn, words, bits.data()));
+        t_hash[n] = hash_domain_bits(lo.data(), hi.data(), (size_t)V, mn, words, bits.data());
+      } else if (t_hash) t_hash[n] = k == PCP_FALSE ? 0 : hash_domains(lo.data(), hi.data(), (size_t)V);
       if (cfg->trace_domains && t_lo && t_hi && k != PCP_FALSE) {
         std::memcpy(t_lo + n * (size_t)V, lo.data(), sizeof(int32_t) * (size_t)V);
         std::memcpy(t_hi + n * (size_t)V, hi.data(), sizeof(int32_t) * (size_t)V);
@@ -215,6 +246,8 @@ struct Driver {
       TRY(pcp_num_vars(e, &V));
       lo.assign((size_t)V, 0);
       hi.assign((size_t)V, 0);
+      size.assign((size_t)V, 0);
+      set_domains = pcp_internal_interval_set(e) != 0;
     }
     if (stopped) { *out = 2; return PCP_OK; }
     while (true) {
