@@ -112,6 +112,11 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out);
 void pcp_engine_destroy(pcp_engine* e);
 const char* pcp_last_error(const pcp_engine* e);
 int pcp_set_timing(pcp_engine* e, int32_t enabled);
+/* Several engines can run their fixpoints side by side on one GPU (independent subtrees of one
+ * search: SURVEY 8e applied inside a device; pcp_consistency_batch).  A fixpoint launch is a
+ * persistent grid of one CTA per SM; this caps the CTAs a launch of this engine uses so that the
+ * engines' grids are co-resident (0 = all SMs, the default). */
+int pcp_set_grid_limit(pcp_engine* e, int32_t max_ctas);
 /* The CUDA stream (cudaStream_t, returned as an opaque pointer) every launch and copy of this
  * engine is issued on: lets a caller order its own device work -- e.g. a benchmark's L2
  * flush -- directly before a fixpoint without a host synchronisation in between. */
@@ -162,6 +167,16 @@ int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t
 /* Consistency::consistency (propagation/store.rs:247-257): runs the propagation
  * fixpoint on the device.  *status is PCP_FALSE / PCP_UNKNOWN / PCP_TRUE. */
 int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats /* may be NULL */);
+
+/* Consistency::consistency for `n` engines at once: every engine's fixpoint is launched before the
+ * first result is awaited, so the fixpoints of independent search nodes -- sibling subtrees held
+ * by separate (vstore, cstore) pairs, the multi-GPU partitioning of SURVEY 8e applied inside one
+ * GPU -- run side by side instead of one after the other (launch latency, device barriers and
+ * worklist iterations of one node overlap the sweeps of the others).  status / stats have n
+ * entries (stats may be NULL).  Engines without a pcp_set_grid_limit get an equal share of the
+ * SMs for the call.  With timing enabled on engines[0], stats[0].kernel_ms is the device time of
+ * the whole batch (first launch to last completion). */
+int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status, pcp_stats* stats);
 
 /* Index<usize> on the variable store (variable/store.rs:175-181), batched. */
 int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32_t* hi);
@@ -242,6 +257,12 @@ int pcp_search_open(pcp_engine* e, const pcp_search_config* cfg, int32_t* trace_
                     uint64_t* trace_hash, int32_t* trace_lo, int32_t* trace_hi,
                     uint64_t trace_capacity, pcp_search** out);
 int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res);
+/* pcp_search_step for `n` searches at once -- independent subtrees of one model, each opened on its
+ * own engine (SURVEY 8e inside one GPU): the device-resident searches run concurrently; host-driven
+ * searches advance in lockstep, one node per search and round, with the fixpoints of a round
+ * launched together (pcp_consistency_batch).  res has n entries (may be NULL); a search that is
+ * finished or has used up `max_nodes` simply sits out the remaining rounds. */
+int pcp_search_step_many(pcp_search* const* searches, int32_t n, uint64_t max_nodes, pcp_search_result* res);
 /* BranchAndBound's incumbent (search/branch_and_bound.rs:69-94) seen from outside: between two
  * pcp_search_step slices a rank adopts the best objective value any rank has found (the one-word
  * all-reduce of SURVEY 8e).  `value` replaces the local incumbent only when it improves on it

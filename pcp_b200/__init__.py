@@ -6,7 +6,7 @@ creating an `Engine` does.
 """
 from . import models
 from ._capi import FALSE, TRUE, UNKNOWN, ContractViolation, PcpError
-from .engine import ABI_SYMBOLS, LIB_PATH, Engine, load_library
+from .engine import ABI_SYMBOLS, LIB_PATH, Engine, consistency_batch, load_library, search_step_many
 
-__all__ = ["Engine", "models", "load_library", "ABI_SYMBOLS", "LIB_PATH", "PcpError", "ContractViolation",
+__all__ = ["Engine", "consistency_batch", "search_step_many", "models", "load_library", "ABI_SYMBOLS", "LIB_PATH", "PcpError", "ContractViolation",
            "TRUE", "FALSE", "UNKNOWN"]

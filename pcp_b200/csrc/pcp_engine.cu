@@ -122,8 +122,10 @@ struct pcp_engine {
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_done = nullptr, ev_batch0 = nullptr, ev_batch1 = nullptr;  // pcp_consistency_batch: fork / join across engines' streams
   bool timing = false;
   int num_sms = 0;
+  int grid_limit = 0;               // pcp_set_grid_limit: CTAs a launch of this engine may use (0 = all SMs)
   int max_smem_optin = 0;
   size_t static_smem = 0;           // largest static shared memory of the persistent kernels
   std::string err;
@@ -220,6 +222,15 @@ struct pcp_engine {
     double kernel_seconds = 0;
     Params P;
   } burst;
+
+  // the fixpoint launched by fixpoint_launch and not yet collected by fixpoint_wait
+  struct Inflight {
+    bool active = false;
+    Params P;
+    int grid = 0;
+    bool want_snapshot = false, eager_dom = false, zero_copy = false;
+    double hp0 = 0, hp1 = 0, hp2 = 0, hp3 = 0;
+  } inflight;
 
   // debug timeline (PCP_TRACE=1)
   unsigned long long* d_trace = nullptr;
@@ -817,6 +828,16 @@ void launch_persistent(const void* fn, int grid, void** args, size_t smem, cudaS
   else CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, stream));
 }
 
+// CTAs a persistent launch of this engine may occupy: all SMs, or the share it was given when
+// several engines run their fixpoints side by side on one GPU (pcp_set_grid_limit)
+int launch_ctas(const pcp_engine* e) {
+  static const int env = [] { const char* v = std::getenv("PCP_MAX_CTAS"); return v ? std::atoi(v) : 0; }();  // measurement switch
+  int n = e->num_sms;
+  if (e->grid_limit > 0) n = std::min(n, e->grid_limit);
+  if (env > 0) n = std::min(n, env);
+  return std::max(n, 2);  // (CTA 0 keeps the books, the others sweep)
+}
+
 struct HostProf {
   double prepare = 0, launch = 0, wait = 0, total = 0;
   unsigned long long n = 0;
@@ -829,7 +850,12 @@ struct HostProf {
 static HostProf g_hostprof;
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+// One fixpoint = fixpoint_launch (node prologue parameters, launch geometry, the launch itself) +
+// fixpoint_wait (result header and domains back, host bookkeeping).  pcp_consistency runs them back
+// to back; pcp_consistency_batch launches several engines' fixpoints before it waits for any, so
+// that their persistent grids run side by side on the GPU.
+void fixpoint_launch(pcp_engine* e) {
+  PCP_REQUIRE(!e->inflight.active, "a fixpoint of this engine is already in flight");
   const double hp0 = now_s();
   Params P = prepare(e);
   const double hp1 = now_s();
@@ -876,7 +902,7 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   // launch geometry: one CTA per SM, fewer for small stores (cheaper barrier)
   size_t total = e->n_nary * 4096;
   for (int f = 0; f < 3; ++f) total += e->fam[f].n;
-  int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 4095) / 4096));
+  int grid = (int)std::min<size_t>((size_t)launch_ctas(e), std::max<size_t>(1, (total + 4095) / 4096));
   size_t nary_bytes = nary_smem_bytes(e);
   PCP_REQUIRE(nary_bytes <= (size_t)kRingBytes, "Distinct too wide for shared memory");
   size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
@@ -922,6 +948,26 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
   const double hp3 = now_s();
   ++e->dom_version;
+  pcp_engine::Inflight& f = e->inflight;
+  f.active = true;
+  f.P = P;
+  f.grid = grid;
+  f.want_snapshot = want_snapshot;
+  f.eager_dom = eager_dom;
+  f.zero_copy = zero_copy;
+  f.hp0 = hp0; f.hp1 = hp1; f.hp2 = hp2; f.hp3 = hp3;
+}
+
+void fixpoint_wait(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  pcp_engine::Inflight& f = e->inflight;
+  PCP_REQUIRE(f.active, "no fixpoint of this engine is in flight");
+  f.active = false;
+  const Params& P = f.P;
+  const size_t V = e->V;
+  const int grid = f.grid;
+  const bool want_snapshot = f.want_snapshot, eager_dom = f.eager_dom, zero_copy = f.zero_copy;
+  const double hp0 = f.hp0, hp1 = f.hp1, hp2 = f.hp2, hp3 = f.hp3;
+  static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
   if (zero_copy) {
     volatile unsigned* seq = &e->h_result()->seq;
     for (unsigned long long spins = 1; *seq != P.host_seq; ++spins) {
@@ -1028,6 +1074,11 @@ void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
   }
 }
 
+void run_fixpoint(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  fixpoint_launch(e);
+  fixpoint_wait(e, status, stats);
+}
+
 void fetch_domains(pcp_engine* e) {
   sync_device_state(e);
   if (e->mirror_valid) return;
@@ -1067,6 +1118,9 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     e->set_mode = (e->flags & PCP_FLAG_INTERVAL_SET) != 0;
     if (cfg && cfg->max_labels) e->max_labels = cfg->max_labels;
     if (cfg && cfg->tail_limit) e->tail_limit = cfg->tail_limit;
+    // engines running side by side need their streams on distinct hardware queues (default: 8);
+    // only effective when set before the process creates its CUDA context, never overrides the user
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0) PCP_FAIL(PCP_ERR_CUDA, "no CUDA device: the propagation engine has no CPU fallback");
@@ -1100,6 +1154,9 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     CUDA_CHECK(cudaEventCreate(&e->ev0));
     CUDA_CHECK(cudaEventCreate(&e->ev1));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreate(&e->ev_batch0));
+    CUDA_CHECK(cudaEventCreate(&e->ev_batch1));
     CUDA_CHECK(cudaMalloc(&e->d_ctl, sizeof(Control)));
     Control c;
     std::memset(&c, 0, sizeof(c));
@@ -1137,6 +1194,9 @@ void pcp_engine_destroy(pcp_engine* e) {
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev_done) cudaEventDestroy(e->ev_done);
+  if (e->ev_batch0) cudaEventDestroy(e->ev_batch0);
+  if (e->ev_batch1) cudaEventDestroy(e->ev_batch1);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -1146,6 +1206,12 @@ const char* pcp_last_error(const pcp_engine* e) { return e ? e->err.c_str() : "n
 int pcp_set_timing(pcp_engine* e, int32_t enabled) {
   if (!e) return PCP_ERR_INVALID;
   e->timing = enabled != 0;
+  return PCP_OK;
+}
+
+int pcp_set_grid_limit(pcp_engine* e, int32_t max_ctas) {
+  if (!e || max_ctas < 0) return PCP_ERR_INVALID;
+  e->grid_limit = max_ctas;
   return PCP_OK;
 }
 
@@ -1236,6 +1302,58 @@ int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     CUDA_CHECK(cudaSetDevice(e->device));
     run_fixpoint(e, status, stats);
   });
+}
+
+int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status, pcp_stats* stats) {
+  if (!engines || n < 0 || !status) return PCP_ERR_INVALID;
+  for (int i = 0; i < n; ++i)
+    if (!engines[i]) return PCP_ERR_INVALID;
+  if (n == 0) return PCP_OK;
+  // every launch first, then every wait: the engines' persistent grids run side by side.  An
+  // engine without a grid limit of its own gets an equal share of the SMs for this call.
+  int rc = PCP_OK, launched = 0;
+  pcp_engine* lead = engines[0];
+  const bool timed = lead->timing;
+  std::vector<int> saved((size_t)n);
+  for (int i = 0; i < n; ++i) saved[(size_t)i] = engines[i]->grid_limit;
+  for (int i = 0; i < n && rc == PCP_OK; ++i) {
+    pcp_engine* e = engines[i];
+    rc = guarded(e, [&] {
+      PCP_REQUIRE_NO_BURST(e);
+      CUDA_CHECK(cudaSetDevice(e->device));
+      if (e->grid_limit == 0 && n > 1) e->grid_limit = std::max(2, e->num_sms / n);
+      if (timed && i == 0) CUDA_CHECK(cudaEventRecord(lead->ev_batch0, lead->stream));
+      if (timed && i > 0) CUDA_CHECK(cudaStreamWaitEvent(e->stream, lead->ev_batch0, 0));
+      fixpoint_launch(e);
+      if (timed && i > 0) {
+        CUDA_CHECK(cudaEventRecord(e->ev_done, e->stream));
+        CUDA_CHECK(cudaStreamWaitEvent(lead->stream, e->ev_done, 0));
+      }
+    });
+    if (rc == PCP_OK) ++launched;
+  }
+  if (timed && launched == n) {
+    int r2 = guarded(lead, [&] { CUDA_CHECK(cudaSetDevice(lead->device)); CUDA_CHECK(cudaEventRecord(lead->ev_batch1, lead->stream)); });
+    if (rc == PCP_OK) rc = r2;
+  }
+  for (int i = 0; i < launched; ++i) {
+    pcp_engine* e = engines[i];
+    int r2 = guarded(e, [&] {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      fixpoint_wait(e, &status[i], stats ? &stats[i] : nullptr);
+    });
+    if (rc == PCP_OK) rc = r2;
+  }
+  for (int i = 0; i < n; ++i) engines[i]->grid_limit = saved[(size_t)i];
+  if (timed && launched == n && rc == PCP_OK && stats) {
+    rc = guarded(lead, [&] {
+      CUDA_CHECK(cudaEventSynchronize(lead->ev_batch1));
+      float ms = 0;
+      CUDA_CHECK(cudaEventElapsedTime(&ms, lead->ev_batch0, lead->ev_batch1));
+      stats[0].kernel_ms = ms;  // the whole batch: first launch to last completion
+    });
+  }
+  return rc;
 }
 
 int pcp_domains_read(pcp_engine* e, int32_t first, int32_t n, int32_t* lo, int32_t* hi) {
@@ -1565,7 +1683,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     P.epoch0 = e->epoch;
     size_t total = e->n_nary * 4096;
     for (int f = 0; f < 3; ++f) total += e->fam[f].n;
-    int grid = (int)std::min<size_t>((size_t)e->num_sms, std::max<size_t>(1, (total + 4095) / 4096));
+    int grid = (int)std::min<size_t>((size_t)launch_ctas(e), std::max<size_t>(1, (total + 4095) / 4096));
     size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
     bool smem_dom = (size_t)kRingBytes + dom_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin;
     size_t smem = (size_t)kRingBytes + (smem_dom ? dom_bytes : 0);

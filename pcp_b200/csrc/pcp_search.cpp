@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/pcp_b200.h"
@@ -86,9 +87,12 @@ struct Driver {
     return pcp_prop_alloc(e, kind, ops, 2, nullptr);
   }
 
-  // Propagation::enter + Brancher::enter (+ BranchAndBound, StopNode, Monitor/Statistics).
+  // Propagation::enter + Brancher::enter (+ BranchAndBound, StopNode, Monitor/Statistics), in
+  // three steps so that several drivers can put their fixpoints on the GPU together
+  // (pcp_search_step_many): enter_pre posts what the node needs, the fixpoint runs
+  // (pcp_consistency here, pcp_consistency_batch there), enter_post reads the result and branches.
   // *out: 1 Satisfiable, -1 Unsatisfiable, 0 Unknown (branches pushed), 2 EndOfSearch.
-  int enter_child(int* out) {
+  int enter_pre() {
     if (cfg->bb_mode != 0 && res->has_bb_value) {  // branch_and_bound.rs:76-87
       pcp_operand v{cfg->bb_var, 0}, b{PCP_VAR_CONSTANT, res->bb_value};
       pcp_operand ops[2];
@@ -96,9 +100,16 @@ struct Driver {
       TRY(pcp_prop_alloc(e, PCP_X_LESS_Y, ops, 2, nullptr));
     }
     if (res->num_nodes == (uint64_t)cfg->warmup_nodes) t_start = std::chrono::steady_clock::now();
+    return PCP_OK;
+  }
+  int enter_child(int* out) {
+    TRY(enter_pre());
     int32_t k = 0;
     pcp_stats st;
     TRY(pcp_consistency(e, &k, &st));  // propagation.rs:49
+    return enter_post(k, st, out);
+  }
+  int enter_post(int32_t k, const pcp_stats& st, int* out) {
     if (res->num_nodes >= (uint64_t)cfg->warmup_nodes) {
       res->propagations += st.propagations;
       res->iterations += st.iterations;
@@ -300,6 +311,93 @@ int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res) {
   int rc = s->d.step(max_nodes ? max_nodes : ~0ull, &status);
   if (res) *res = s->res;
   return rc;
+}
+
+// Several searches -- independent subtrees of one model, one engine each -- advanced together:
+// device-resident searches run on one host thread each (their launches last for whole slices of
+// nodes); host-driven searches move in lockstep, one node per search and round, the fixpoints of
+// a round launched together through pcp_consistency_batch.
+int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, pcp_search_result* res) {
+  if (!ss || n < 0) return PCP_ERR_INVALID;
+  for (int i = 0; i < n; ++i) if (!ss[i]) return PCP_ERR_INVALID;
+  if (n == 0) return PCP_OK;
+  const uint64_t budget = max_nodes ? max_nodes : ~0ull;
+  bool all_burst = true, any_burst = false;
+  for (int i = 0; i < n; ++i) { all_burst &= ss[i]->d.burst; any_burst |= ss[i]->d.burst; }
+  if (any_burst && !all_burst) return PCP_ERR_INVALID;
+  if (all_burst) {
+    std::vector<int> rcs((size_t)n, PCP_OK);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i)
+      th.emplace_back([&, i] { rcs[(size_t)i] = pcp_search_step(ss[i], max_nodes, res ? &res[i] : nullptr); });
+    for (auto& t : th) t.join();
+    for (int rc : rcs) if (rc != PCP_OK) return rc;
+    return PCP_OK;
+  }
+  std::vector<uint64_t> start((size_t)n);
+  std::vector<char> done((size_t)n, 0);
+  for (int i = 0; i < n; ++i) {
+    Driver& d = ss[i]->d;
+    start[(size_t)i] = d.res->num_nodes;
+    if (d.V == 0 && !d.started) {
+      TRY(pcp_num_vars(d.e, &d.V));
+      d.lo.assign((size_t)d.V, 0);
+      d.hi.assign((size_t)d.V, 0);
+      d.size.assign((size_t)d.V, 0);
+      d.set_domains = pcp_internal_interval_set(d.e) != 0;
+    }
+    if (d.stopped) { d.res->status = 2; done[(size_t)i] = 1; }
+  }
+  std::vector<pcp_engine*> engines;
+  std::vector<int> who;
+  std::vector<int32_t> ks;
+  std::vector<pcp_stats> sts;
+  while (true) {
+    engines.clear();
+    who.clear();
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; ++i) {
+      if (done[(size_t)i]) continue;
+      Driver& d = ss[i]->d;
+      if (d.started && d.queue.empty()) {  // fully explored (one_solution.rs:66-68)
+        if (d.cfg->all_solutions || d.exhausted_reported) d.res->status = 2;
+        else { d.exhausted_reported = true; d.res->status = -1; }
+        done[(size_t)i] = 1;
+        continue;
+      }
+      if (d.res->num_nodes - start[(size_t)i] >= budget) { d.res->status = 0; done[(size_t)i] = 1; continue; }
+      if (!d.started) {
+        d.started = true;
+      } else {
+        Branch b = d.queue.back();
+        d.queue.pop_back();
+        TRY(pcp_restore(d.e, b.label));  // Branch::commit (branch.rs:51-55)
+        TRY(d.apply_alternative(b));
+      }
+      TRY(d.enter_pre());
+      engines.push_back(d.e);
+      who.push_back(i);
+    }
+    if (engines.empty()) break;
+    ks.assign(engines.size(), 0);
+    sts.assign(engines.size(), pcp_stats{});
+    TRY(pcp_consistency_batch(engines.data(), (int32_t)engines.size(), ks.data(), sts.data()));
+    for (size_t j = 0; j < who.size(); ++j) {
+      Driver& d = ss[who[j]]->d;
+      int child = 0;
+      TRY(d.enter_post(ks[j], sts[j], &child));
+      if (child == 2) { d.stopped = true; d.res->status = 2; done[(size_t)who[j]] = 1; }
+      else if (child == 1 && !d.cfg->all_solutions) { d.res->status = 1; done[(size_t)who[j]] = 1; }
+    }
+    // the wall clock of a round belongs to every search that took part in it
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (int i : who) {
+      Driver& d = ss[i]->d;
+      if (d.res->num_nodes > (uint64_t)d.cfg->warmup_nodes) d.res->seconds += dt;
+    }
+  }
+  if (res) for (int i = 0; i < n; ++i) res[i] = ss[i]->res;
+  return PCP_OK;
 }
 
 int pcp_search_set_incumbent(pcp_search* s, int32_t value) {

@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._capi import Config, EngineBase, PcpError, SearchConfig, SearchResult, bind
+from ._capi import Config, EngineBase, PcpError, SearchConfig, SearchResult, Stats, bind
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # PCP_B200_LIB: development override (kernel variants built side by side for A/B timing)
@@ -21,11 +21,11 @@ FLAG_INTERVAL_SET = 4
 
 # every symbol include/pcp_b200.h declares
 ABI_SYMBOLS = [
-    "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_stream", "pcp_vars_alloc",
-    "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_formula_alloc", "pcp_consistency", "pcp_domains_read",
+    "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_set_grid_limit", "pcp_stream", "pcp_vars_alloc",
+    "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_formula_alloc", "pcp_consistency", "pcp_consistency_batch", "pcp_domains_read",
     "pcp_domains_size_read", "pcp_domains_read_bits",
     "pcp_var_update", "pcp_active_read", "pcp_label", "pcp_restore", "pcp_num_vars", "pcp_num_props",
-    "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_set_incumbent", "pcp_search_close",
+    "pcp_search_run", "pcp_search_open", "pcp_search_step", "pcp_search_step_many", "pcp_search_set_incumbent", "pcp_search_close",
 ]
 
 _lib = None
@@ -46,6 +46,8 @@ def load_library() -> C.CDLL:
         lib.pcp_engine_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
         lib.pcp_set_timing.restype = C.c_int
         lib.pcp_set_timing.argtypes = [C.c_void_p, C.c_int32]
+        lib.pcp_set_grid_limit.restype = C.c_int
+        lib.pcp_set_grid_limit.argtypes = [C.c_void_p, C.c_int32]
         lib.pcp_stream.restype = C.c_int
         lib.pcp_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         i32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
@@ -54,6 +56,10 @@ def load_library() -> C.CDLL:
                                         C.POINTER(C.c_void_p)]
         lib.pcp_search_step.restype = C.c_int
         lib.pcp_search_step.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SearchResult)]
+        lib.pcp_consistency_batch.restype = C.c_int
+        lib.pcp_consistency_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int32, i32p, C.POINTER(Stats)]
+        lib.pcp_search_step_many.restype = C.c_int
+        lib.pcp_search_step_many.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_uint64, C.POINTER(SearchResult)]
         lib.pcp_search_set_incumbent.restype = C.c_int
         lib.pcp_search_set_incumbent.argtypes = [C.c_void_p, C.c_int32]
         lib.pcp_search_close.restype = None
@@ -84,6 +90,10 @@ class Engine(EngineBase):
     def set_timing(self, enabled: bool) -> None:
         self._check(self._lib.pcp_set_timing(self._h, int(enabled)))
 
+    def set_grid_limit(self, max_ctas: int) -> None:
+        """Cap the CTAs of this engine's launches (engines running side by side on one GPU)."""
+        self._check(self._lib.pcp_set_grid_limit(self._h, int(max_ctas)))
+
     def cuda_stream(self) -> int:
         """The engine's cudaStream_t as an integer (torch.cuda.ExternalStream(ptr) wraps it)."""
         p = C.c_void_p()
@@ -97,6 +107,32 @@ class Engine(EngineBase):
         cfg = SearchConfig(node_limit, int(all_solutions), var_sel, val_sel, distributor, bb_mode, bb_var, 0,
                            warmup_nodes)
         return SearchHandle(self, cfg)
+
+
+def consistency_batch(engines):
+    """pcp_consistency_batch: the fixpoints of several engines launched together (they run side by
+    side on the GPU).  Returns (statuses, stats) with one entry per engine."""
+    n = len(engines)
+    hs = (C.c_void_p * n)(*[e._h for e in engines])
+    status = (C.c_int32 * n)()
+    stats = (Stats * n)()
+    rc = engines[0]._lib.pcp_consistency_batch(hs, n, status, stats)
+    for e in engines:
+        if rc != 0:
+            e._check(rc)
+    return [int(x) for x in status], list(stats)
+
+
+def search_step_many(handles, max_nodes: int = 0):
+    """pcp_search_step_many: advance several open searches (one engine each) together."""
+    n = len(handles)
+    hs = (C.c_void_p * n)(*[h._h for h in handles])
+    res = (SearchResult * n)()
+    rc = handles[0]._lib.pcp_search_step_many(hs, n, max_nodes, res)
+    if rc != 0:
+        for h in handles:
+            h._engine._check(rc)
+    return list(res)
 
 
 class SearchHandle:

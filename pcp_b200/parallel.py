@@ -200,3 +200,48 @@ def sharded_search(engine, rank: int, world: int, node_budget: int, sync_every: 
         handle.close()
     out["incumbent"] = best
     return out
+
+
+class SubtreeContexts:
+    """K engines side by side on ONE GPU, each holding the model and searching its own subtree
+    (SURVEY 8e applied inside a device).  One fixpoint of n-queens N=1000 leaves most of a B200
+    idle between its phases (launch, prologue, device barriers, worklist iterations: 23 us per
+    node of which the sweep is 4); K contexts on num_sms / K CTAs each overlap those phases of
+    one node with the sweeps of the others.  Every context is an ordinary (vstore, cstore) pair
+    behind the C ABI -- per-node results are exactly those of a lone engine on that subtree."""
+
+    def __init__(self, make_engine, model, k: int, paths: Sequence[List[Decision]] = None, device_sms: int = 148):
+        self.engines = []
+        self.paths = []
+        for i in range(k):
+            e = make_engine()
+            model.load_into(e)
+            if k > 1:
+                e.set_grid_limit(max(2, device_sms // k))
+            self.engines.append(e)
+        frontier = list(paths) if paths is not None else expand_frontier(self.engines[0], parts=k)
+        for i, e in enumerate(self.engines):
+            if i or paths is not None:
+                e.consistency()  # builds the reactor CSR, uploads the store
+            root = e.label()
+            path = frontier[i % len(frontier)]
+            enter_subtree(e, root, path)
+            self.paths.append(path)
+        self.handles = None
+
+    def open(self, **kw):
+        self.handles = [e.search_open(**kw) for e in self.engines]
+        return self.handles
+
+    def step(self, max_nodes: int = 0):
+        from .engine import search_step_many
+        return search_step_many(self.handles, max_nodes)
+
+    def close(self):
+        if self.handles:
+            for h in self.handles:
+                h.close()
+            self.handles = None
+        for e in self.engines:
+            e.close()
+        self.engines = []

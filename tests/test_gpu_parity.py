@@ -662,6 +662,83 @@ def test_sharded_search_two_gpus_nccl():
     assert res[0]["bb"]["incumbent"] == res[1]["bb"]["incumbent"] == ref.bb_value
 
 
+@pytest.mark.parametrize("k", [2, 5])
+def test_consistency_batch_matches_lone_engines(k):
+    """pcp_consistency_batch: k engines, each on its own subtree of n-queens N=120, advance a
+    host-driven DFS in lockstep (the k fixpoints of a round are launched together and run side
+    by side on the GPU); after every round each engine's status, domains and `active` set equal
+    those of the oracle replaying the same subtree alone."""
+    import pcp_b200
+    from pcp_b200 import parallel
+    m = models.nqueens(120)
+    probe = _engine()
+    m.load_into(probe)
+    paths = parallel.expand_frontier(probe, parts=k)[:k]
+    devs, oras, stacks = [], [], []
+    for p in paths:
+        d, o = _engine(), _oracle(2)
+        for e in (d, o):
+            m.load_into(e)
+            e.consistency()
+            parallel.enter_subtree(e, e.label(), p)
+        d.set_grid_limit(148 // k)
+        devs.append(d)
+        oras.append(o)
+        stacks.append(None)  # None: the subtree's root is the next node
+    for rnd in range(40):
+        live = [i for i in range(k) if stacks[i] is None or stacks[i]]
+        if not live:
+            break
+        for i in live:
+            if stacks[i] is None:
+                stacks[i] = []
+                continue
+            (dl, ol), dec = stacks[i].pop()
+            devs[i].restore(dl)
+            oras[i].restore(ol)
+            parallel.post_decision(devs[i], dec)
+            parallel.post_decision(oras[i], dec)
+        sts, stats = pcp_b200.consistency_batch([devs[i] for i in live])
+        for i, st in zip(live, sts):
+            assert st == oras[i].consistency()[0], (rnd, i)
+            if st == -1:
+                continue
+            _assert_same_state(devs[i], oras[i])
+            if st == 0:
+                lo, hi = devs[i].domains()
+                var, val = parallel.select_branch(lo, hi)
+                labels = (devs[i].label(), oras[i].label())
+                stacks[i].append((labels, (var, val, 1)))
+                stacks[i].append((labels, (var, val, 0)))
+        assert all(s.propagations > 0 for s in stats)
+
+
+@pytest.mark.parametrize("host_search", [False, True], ids=["device-search", "host-lockstep"])
+def test_search_step_many_matches_lone_searches(host_search):
+    """pcp_search_step_many over 4 subtree contexts (device-resident searches on one host thread
+    each / host-driven searches in lockstep): every context counts the nodes, failures and
+    solutions of a lone search of its subtree, and together they hold every solution of n-queens
+    N=9 (352, all_solution.rs:67-74)."""
+    from pcp_b200 import Engine, parallel
+    m = models.nqueens(9)
+    ctx = parallel.SubtreeContexts(lambda: Engine(host_search=host_search), m, 4)
+    ctx.open(all_solutions=True)
+    res = None
+    for _ in range(100000):
+        res = ctx.step(37)
+        if all(r.status != 0 for r in res):
+            break
+    assert sum(r.num_solution for r in res) == 352
+    for path, r in zip(ctx.paths, res):
+        lone = _oracle(2)
+        m.load_into(lone)
+        lone.consistency()
+        parallel.enter_subtree(lone, lone.label(), path)
+        ro, _ = lone.search(all_solutions=True)
+        assert (r.num_nodes, r.num_solution, r.num_failed_node) == (ro.num_nodes, ro.num_solution, ro.num_failed_node)
+    ctx.close()
+
+
 def test_x_eq_y_mul_z_products_store():
     """XEqYMulZ (cmp/x_eq_y_mul_z.rs:68-116) at scale: p_i = a_i * b_i with the factors tied by
     chains of XLessY, signs mixed; fixpoint, status and `active` set against the oracle (a
