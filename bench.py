@@ -40,6 +40,9 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 BYTES_PER_PROP = {"c2": 32, "c5": 32, "c4": 48, "c3": 32}  # SURVEY 8d "algorithmic bytes per propagation"
+# what a sweep actually streams per propagation (the domains come from shared memory / L2):
+# 16-byte binary descriptors, the compact 8-byte stream at C5, 24-byte ternary descriptors
+STREAM_BYTES = {"c2": 16, "c5": 8, "c4": 24, "c3": 16}
 
 
 def build_model(workload: str):
@@ -113,7 +116,7 @@ class ClockSampler:
 
 class PyDfs:
     """The reference search node by node through the engine surface (used for the device-timed
-    passes so that an L2 flush can be slotted between two nodes)."""
+    passes so that an L2 flush can be slotted between two rounds of nodes)."""
 
     def __init__(self, engine):
         from pcp_b200 import parallel
@@ -144,37 +147,46 @@ class PyDfs:
         self.stack.append((label, (var, val, 0)))
 
 
-def device_timed_pass(engine, steps, warmup, flush, torch, device):
-    """K nodes timed with CUDA events on the engine stream (stats.kernel_ms covers the node
-    prologue + the fixpoint kernel); optional L2 flush (write 512 MiB) between nodes."""
-    dfs = PyDfs(engine)
+def device_timed_pass(engines, steps, warmup, flush, torch, device, skip=0):
+    """K engines side by side (K = len(engines)), each on its own subtree.  A step = one round:
+    every engine's next DFS node is posted, then the K fixpoints are launched together
+    (pcp_consistency_batch) and timed as one region with CUDA events on the engines' streams
+    (fork after the optional L2 flush on the lead stream, join after the last kernel)."""
+    import pcp_b200
+    dfs = [PyDfs(e) for e in engines]
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=device) if flush else None
-    # the flush runs on the engine's own stream, directly before the timed launch: the events
-    # then bracket the kernel, not the host's launch latency on an idle stream
-    ext = torch.cuda.ExternalStream(engine.cuda_stream(), device=device)
+    # the flush runs on the lead engine's own stream, directly before the timed launches: the
+    # events then bracket the kernels, not the host's launch latency on an idle stream
+    ext = torch.cuda.ExternalStream(engines[0].cuda_stream(), device=device)
     torch.cuda.synchronize(device)
-    props = iters = 0
+    props = iters = nodes = launches = 0
     ms = 0.0
-    launches = 0
     n = 0
-    while n < warmup + steps:
-        if not dfs.next_node():
+    live = list(range(len(engines)))
+    while n < skip + warmup + steps and live:
+        live = [i for i in live if dfs[i].next_node()]
+        if not live:
             break
-        if flush:
+        timed = n >= skip + warmup
+        if flush and n >= skip:
             with torch.cuda.stream(ext):
                 flush_buf.add_(1)
-        st, stats = engine.consistency()
-        if n >= warmup:
-            props += stats.propagations
-            iters += stats.iterations
-            ms += stats.kernel_ms
-            launches += 1  # pcp_fixpoint_kernel (restore, posted constraint and label copy ride inside)
-        dfs.after_fixpoint(st)
+        sts, stats = pcp_b200.consistency_batch([engines[i] for i in live])
+        if timed:
+            props += sum(int(s.propagations) for s in stats)
+            iters += sum(int(s.iterations) for s in stats)
+            ms += float(stats[0].kernel_ms)   # the whole round: first launch to last completion
+            nodes += len(live)
+            launches += len(live)             # one pcp_fixpoint_kernel per node (restore, posted constraint, label copy inside)
+        for i, st in zip(live, sts):
+            dfs[i].after_fixpoint(st)
         n += 1
-    return {"nodes": max(n - warmup, 0), "propagations": props, "iterations": iters, "ms": ms, "launches": launches}
+    return {"nodes": nodes, "propagations": props, "iterations": iters, "ms": ms, "launches": launches,
+            "rounds": max(n - skip - warmup, 0)}
 
 
 def run_ours(args):
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per context's stream
     import torch
     import torch.distributed as dist
     from pcp_b200 import Engine, parallel
@@ -187,10 +199,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
-    workload = args.workload or ("c2" if world == 1 else "c2")
+    workload = args.workload or "c2"
     model, desc = build_model(workload)
     bpp = BYTES_PER_PROP.get(workload, 32)
     peak, peak_src = peaks()
+    set_domains = args.domains == "set"
+    if set_domains:
+        desc += " -- IntervalSet<i32> domains (FDSpace, as example/src/nqueens.rs allocates them)"
+    # contexts per GPU: engines side by side, each on its own subtree.  The streaming-bound
+    # stores (C5: DRAM-bound sweep, C4: one fixpoint) gain nothing from it.
+    K = args.contexts if args.contexts > 0 else {"c2": 12, "c3": 12}.get(workload, 1)
+    if workload.startswith("nq"):
+        K = args.contexts if args.contexts > 0 else 12
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -198,30 +218,47 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def reduce_max(x):
+    def reduce(x, op):
         if world == 1:
             return float(x)
         t = torch.tensor([float(x)], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def reduce_sum(x):
-        if world == 1:
-            return float(x)
-        t = torch.tensor([float(x)], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    reduce_max = lambda x: reduce(x, dist.ReduceOp.MAX)  # noqa: E731
+    reduce_sum = lambda x: reduce(x, dist.ReduceOp.SUM)  # noqa: E731
 
     single_fixpoint = workload == "c4"
     sampler = ClockSampler(local_rank) if rank == 0 else None
     V = model.num_vars
+    sms = torch.cuda.get_device_properties(device).multi_processor_count
 
-    def fresh_engine(host_search=False, timing=True, incremental=False):
-        e = Engine(device=local_rank, timing=timing, max_labels=1 << 16, host_search=host_search,
-                   incremental=incremental)
-        model.load_into(e)
+    def fresh_engine(mdl=None, host_search=False, timing=True, incremental=False, interval_set=None):
+        e = Engine(device=local_rank, timing=timing, max_labels=1 << 14, host_search=host_search,
+                   incremental=incremental, interval_set=set_domains if interval_set is None else interval_set)
+        (mdl or model).load_into(e)
         return e
 
+    def contexts(k, mdl=None, **kw):
+        """k engines of this rank, each entered into its own frontier subtree (rank-major slices of
+        the same breadth-first frontier on every rank)."""
+        engines = [fresh_engine(mdl, **kw) for _ in range(k)]
+        parts = world * k
+        paths = parallel.expand_frontier(engines[0], parts=parts) if parts > 1 else [[]]
+        for i, e in enumerate(engines):
+            if i:
+                e.consistency()
+            if k > 1:
+                e.set_grid_limit(max(2, sms // k))
+            root = e.label()
+            parallel.enter_subtree(e, root, paths[(rank * k + i) % len(paths)])
+        return engines
+
+    def close_all(engines):
+        for e in engines:
+            e.close()
+
+    extra = {}
     if single_fixpoint:
         # C4: a step = one whole fixpoint from the initial domains (root label restored per step)
         e = fresh_engine()
@@ -230,7 +267,6 @@ def run_ours(args):
         res = {}
         for mode in ("flush", "warm"):
             e2 = fresh_engine()
-            lo0, hi0 = e2.domains()
             root = e2.label()
             ext = torch.cuda.ExternalStream(e2.cuda_stream(), device=device)
             torch.cuda.synchronize(device)
@@ -249,7 +285,7 @@ def run_ours(args):
                     ms += stats.kernel_ms
             barrier()
             res[mode] = {"nodes": args.steps, "propagations": props, "iterations": iters, "ms": ms,
-                         "launches": args.steps}
+                         "launches": args.steps, "rounds": args.steps}
             e2.close()
         # e2e: restore + consistency + domains through the ABI, wall clock
         e3 = fresh_engine(timing=False)
@@ -269,52 +305,75 @@ def run_ours(args):
         e2e = {"propagations": props_e2e, "seconds": e2e_s, "nodes": args.steps}
         e2e_dev = None
         h2d, d2h = 0, 64 + 8 * V
+        K = 1
     else:
         res = {}
         for mode in ("flush", "warm"):
-            e = fresh_engine()
-            if world > 1:
-                # every rank works on its own subtree: replay the decision path of frontier node `rank`
-                paths = parallel.expand_frontier(e, parts=world)
-                root = e.label()
-                parallel.enter_subtree(e, root, paths[rank % len(paths)])
+            engines = contexts(K)
             barrier()
-            res[mode] = device_timed_pass(e, args.steps, args.warmup, mode == "flush", torch, device)
+            res[mode] = device_timed_pass(engines, args.steps, args.warmup, mode == "flush", torch, device, skip=args.skip_nodes)
             barrier()
-            e.close()
+            close_all(engines)
+        if K > 1:
+            # one context with the whole GPU: the round-1 measurement, one node per step
+            engines = contexts(1)
+            barrier()
+            res["single"] = device_timed_pass(engines, args.steps, args.warmup, True, torch, device, skip=args.skip_nodes)
+            barrier()
+            close_all(engines)
         # the same nodes with PCP_FLAG_INCREMENTAL: a node restored from a label that was a fixpoint
         # evaluates the posted constraint and what it wakes instead of scheduling every propagator
         # (store.rs:144-149) -- same domains and statuses (tests/), far fewer propagations
-        e = fresh_engine(incremental=True)
-        if world > 1:
-            paths = parallel.expand_frontier(e, parts=world)
-            root = e.label()
-            parallel.enter_subtree(e, root, paths[rank % len(paths)])
+        engines = contexts(1, incremental=True)
         barrier()
-        res["incremental"] = device_timed_pass(e, args.steps, args.warmup, True, torch, device)
+        res["incremental"] = device_timed_pass(engines, args.steps, args.warmup, True, torch, device)
         barrier()
-        e.close()
-        # e2e through the C++ driver over the C ABI, twice: the host-driven node loop (what a
-        # libpcp host does: one launch, one posted descriptor in, status + domains out per node)
-        # is the `e2e` key; the device-resident search (same C entry point, branching on the
-        # GPU, results copied back when the search stops) is reported beside it
+        close_all(engines)
+
+        # e2e through the C++ driver over the C ABI with host buffers, twice: the host-driven node
+        # loop (what a libpcp host does per node: restore, post one descriptor, fixpoint, status +
+        # domains back, label) over the K contexts in lockstep is the `e2e` key; the device-resident
+        # searches (same entry points, branching on the GPU) are reported beside it.  With more than
+        # one rank the one-word collective (stop flag; sum all-reduce) runs inside the timed loop
+        # after every round of `sync_every` nodes per context.
         def e2e_pass(host_search):
-            e = fresh_engine(host_search=host_search, timing=False)  # wall clock only: no event records, zero-copy results
+            engines = contexts(K, host_search=host_search, timing=False)  # wall clock only: no event records, zero-copy results
+            from pcp_b200 import search_step_many
+            handles = [e.search_open(all_solutions=True) for e in engines]
             stop = parallel.StopFlag(device) if world > 1 else None
+            search_step_many(handles, args.warmup)   # untimed: CSR, buffers, first nodes
+            base = [(int(r.propagations), int(r.num_nodes)) for r in search_step_many(handles, 1)]
             barrier()
-            if world > 1:
-                out = parallel.sharded_search(e, rank, world, node_budget=args.warmup + args.steps, sync_every=64,
-                                              stop_flag=stop, warmup_nodes=args.warmup, parts_per_rank=1)
-                res_ = {"propagations": out["propagations"], "seconds": out["seconds"], "nodes": out["nodes"] - args.warmup}
-            else:
-                r, _ = e.search(node_limit=args.warmup + args.steps, all_solutions=True, warmup_nodes=args.warmup)
-                res_ = {"propagations": int(r.propagations), "seconds": float(r.seconds), "nodes": int(r.num_nodes) - args.warmup}
+            sync_every = max(1, min(args.sync_every, args.steps))
+            done = exch = 0
+            exch_s = 0.0
+            t0 = time.perf_counter()
+            last = None
+            while done < args.steps:
+                n = min(sync_every, args.steps - done)
+                last = search_step_many(handles, n)
+                done += n
+                if stop is not None:
+                    t1 = time.perf_counter()
+                    stop.exchange(0, op="sum")
+                    exch_s += time.perf_counter() - t1
+                    exch += 1
+            wall = time.perf_counter() - t0
+            out = {"propagations": sum(int(r.propagations) - b[0] for r, b in zip(last, base)),
+                   "nodes": sum(int(r.num_nodes) - b[1] for r, b in zip(last, base)), "seconds": wall,
+                   "exchanges": exch, "exchange_seconds": exch_s}
             barrier()
-            e.close()
-            return res_
+            for h in handles:
+                h.close()
+            close_all(engines)
+            return out
         e2e = e2e_pass(True)
-        e2e_dev = e2e_pass(False)
-        h2d, d2h = 16, 64 + 8 * V  # one posted descriptor in, result header + domains out
+        e2e_dev = e2e_pass(False) if not set_domains else None
+        h2d, d2h = 16 * K, (64 + 8 * V) * K  # per step = per round of K nodes: one posted descriptor in, header + domains out, per context
+
+        if world > 1 and workload == "c2" and not args.no_c5:
+            extra["c5"] = run_c5(args, torch, dist, device, rank, world, local_rank, barrier, reduce_sum, reduce_max, peak)
+            extra["branch_and_bound"] = run_bb(torch, device, rank, world, local_rank, barrier)
 
     clocks = sampler.stop() if sampler else None
 
@@ -325,6 +384,9 @@ def run_ours(args):
     max_ms = reduce_max(f["ms"])
     w = res["warm"]
     w_props, w_nodes, w_ms = reduce_sum(w["propagations"]), reduce_sum(w["nodes"]), reduce_max(w["ms"])
+    one = res.get("single")
+    if one is not None:
+        o_props, o_nodes, o_ms = reduce_sum(one["propagations"]), reduce_sum(one["nodes"]), reduce_max(one["ms"])
     inc = res.get("incremental")
     if inc is not None:
         i_props, i_nodes, i_ms = reduce_sum(inc["propagations"]), reduce_sum(inc["nodes"]), reduce_max(inc["ms"])
@@ -336,7 +398,7 @@ def run_ours(args):
 
     if rank == 0:
         # ---- CPU baseline: the oracle (flat variant), 1 thread, same first nodes of the same DFS
-        cpu = cpu_baseline(workload, model, args)
+        cpu = cpu_baseline(workload, model, args, set_domains=set_domains)
         value = tot_props / (max_ms * 1e-3) if max_ms > 0 else 0.0
         achieved = (f["propagations"] * bpp) / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
         traffic = None
@@ -346,59 +408,157 @@ def run_ours(args):
                 traffic = json.load(open(tp)).get(workload)
             except Exception:
                 traffic = None
+        rounds = max(f["rounds"], 1)
         line = {
             "metric": "propagations/s (and nodes/s) of the per-node propagation fixpoint",
             "value": value, "unit": "propagations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": max_ms / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": max_ms / rounds, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": desc, "l2": "flushed between steps (512 MiB read-modify-write on the engine stream directly before each timed launch)",
-                       "step": "one search node = one Consistency::consistency fixpoint",
-                       "parallelism": f"subtree-sharding x{world}" if world > 1 else "single engine",
-                       "timing": "CUDA events on the engine stream per step, summed; max over ranks"},
+            "config": {"workload": desc, "l2": "flushed between steps (512 MiB read-modify-write on the lead engine's stream directly before each timed round)",
+                       "step": (f"one round of {K} search nodes, one per subtree context: {K} Consistency::consistency fixpoints launched together "
+                                "(pcp_consistency_batch), each on its own (vstore, cstore) pair" if K > 1 else
+                                "one search node = one Consistency::consistency fixpoint"),
+                       "contexts_per_gpu": K, "skip_nodes": args.skip_nodes,
+                       "parallelism": (f"subtree sharding: {world} GPU(s) x {K} context(s)"),
+                       "timing": "CUDA events per step (fork after the flush on the lead stream, join after the last context's kernel), summed; max over ranks"},
             "nodes_per_s": tot_nodes / (max_ms * 1e-3) if max_ms > 0 else 0.0,
-            "propagations_per_step": f["propagations"] / max(f["nodes"], 1),
-            "iterations_per_step": f["iterations"] / max(f["nodes"], 1),
+            "us_per_node": 1e3 * max_ms * world / max(tot_nodes, 1),
+            "propagations_per_node": f["propagations"] / max(f["nodes"], 1),
+            "iterations_per_node": f["iterations"] / max(f["nodes"], 1),
             "warm": {"value": w_props / (w_ms * 1e-3) if w_ms > 0 else 0.0, "unit": "propagations/s",
-                     "nodes_per_s": w_nodes / (w_ms * 1e-3) if w_ms > 0 else 0.0, "ms_per_step": w_ms / max(args.steps, 1),
+                     "nodes_per_s": w_nodes / (w_ms * 1e-3) if w_ms > 0 else 0.0, "ms_per_step": w_ms / max(w["rounds"], 1),
                      "l2": "not flushed (descriptors L2-resident)"},
+            "single_context": (None if one is None else {
+                "value": o_props / (o_ms * 1e-3) if o_ms > 0 else 0.0, "unit": "propagations/s",
+                "nodes_per_s": o_nodes / (o_ms * 1e-3) if o_ms > 0 else 0.0, "ms_per_step": o_ms / max(one["rounds"], 1),
+                "roofline_frac": ((one["propagations"] * bpp) / (one["ms"] * 1e-3) / 1e9 / peak) if one["ms"] > 0 else None,
+                "note": "one context with the whole GPU, one node per step, L2 flushed (the round-1 headline measurement)"}),
             "incremental": (None if inc is None else {
-                "nodes_per_s": i_nodes / (i_ms * 1e-3) if i_ms > 0 else 0.0, "ms_per_step": i_ms / max(args.steps, 1),
-                "propagations_per_step": inc["propagations"] / max(inc["nodes"], 1),
-                "note": "PCP_FLAG_INCREMENTAL: no schedule-everything first sweep when the restored state was a "
-                        "fixpoint; same domains and statuses, L2 flushed between steps"}),
+                "nodes_per_s": i_nodes / (i_ms * 1e-3) if i_ms > 0 else 0.0, "ms_per_step": i_ms / max(inc["rounds"], 1),
+                "propagations_per_node": inc["propagations"] / max(inc["nodes"], 1),
+                "note": "PCP_FLAG_INCREMENTAL, one context: no schedule-everything first sweep when the restored state "
+                        "was a fixpoint; same domains and statuses, L2 flushed between steps"}),
             "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s",
-                    "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "ms_per_step": 1e3 * e_s * world / max(e_nodes, 1),
+                    "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "us_per_node": 1e6 * e_s * world / max(e_nodes, 1),
+                    "ms_per_step": 1e3 * e_s / max(args.steps, 1),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "exchanges": e2e.get("exchanges"), "exchange_seconds": e2e.get("exchange_seconds"),
                     "path": ("restore + pcp_consistency + pcp_domains_read per step through the C ABI (ctypes), L2 not flushed"
                              if single_fixpoint else
-                             "host-driven node loop: C++ search driver -> C ABI (pcp_restore / pcp_prop_alloc / "
-                             "pcp_consistency / pcp_domains_read / pcp_label per node), wall clock, L2 not flushed")},
+                             f"host-driven node loop over {K} context(s) in lockstep: C++ search driver -> C ABI (pcp_restore / "
+                             "pcp_prop_alloc / pcp_consistency_batch / pcp_domains_read / pcp_label per node and context), "
+                             "wall clock, L2 not flushed" + ("; 1 x int32 NCCL all-reduce every round inside the timed loop" if world > 1 else ""))},
             "e2e_device_search": (None if e2e_dev is None else {
                 "value": d_props / d_s if d_s > 0 else 0.0, "unit": "propagations/s",
-                "nodes_per_s": d_nodes / d_s if d_s > 0 else 0.0, "ms_per_step": 1e3 * d_s * world / max(d_nodes, 1),
+                "nodes_per_s": d_nodes / d_s if d_s > 0 else 0.0, "us_per_node": 1e6 * d_s * world / max(d_nodes, 1),
                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "path": "pcp_search_run with the device-resident DFS (pcp_burst_kernel): branching, label/restore and "
-                        "the fixpoints in one launch per budget slice; counters copied back when it stops"}),
+                "path": f"pcp_search_step_many over {K} device-resident searches (pcp_burst_kernel: branching, label/restore and "
+                        "the fixpoints in one launch per budget slice and context); counters copied back when a slice ends"}),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "pcp_fixpoint_kernel (node prologue, TMA sweep, worklist iterations, label snapshot)",
+                         "kernel": "pcp_fixpoint_kernel (node prologue, TMA sweep, worklist iterations, label snapshot)"
+                                   + (f", {K} launches side by side per step" if K > 1 else ""),
                          "algorithmic_bytes_per_propagation": bpp,
+                         "streamed_bytes_per_propagation": STREAM_BYTES.get(workload, bpp),
+                         "streamed_frac": ((f["propagations"] * STREAM_BYTES.get(workload, bpp)) / (f["ms"] * 1e-3) / 1e9 / peak) if f["ms"] > 0 else None,
                          "warm_frac": ((w["propagations"] * bpp) / (w["ms"] * 1e-3) / 1e9 / peak) if w["ms"] > 0 else None},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
+        line.update(extra)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(workload, model, args, threads: int = 1, budget_s: float = 20.0):
+def run_c5(args, torch, dist, device, rank, world, local_rank, barrier, reduce_sum, reduce_max, peak):
+    """BASELINE configs[4]: n-queens N=5000 (V=5000, P=37,492,500; 600 MB of descriptors, 300 MB
+    compact stream per GPU) as a parallel-subtree search over the ranks: one context per GPU (the
+    sweep is DRAM-bound), device-timed nodes and the host-driven sharded search with the one-word
+    NCCL exchange inside the timed loop."""
+    from pcp_b200 import Engine, models, parallel
+    m = models.nqueens(5000)
+    steps, warm = min(args.steps, 10), 3
+
+    def engine(**kw):
+        e = Engine(device=local_rank, max_labels=1 << 10, **kw)
+        m.load_into(e)
+        paths = parallel.expand_frontier(e, parts=world)
+        parallel.enter_subtree(e, e.label(), paths[rank % len(paths)])
+        return e
+
+    e = engine(timing=True)
+    barrier()
+    dev = device_timed_pass([e], steps, warm, True, torch, device)
+    barrier()
+    e.close()
+    e = engine(timing=False, host_search=True)
+    stop = parallel.StopFlag(device)
+    h = e.search_open(all_solutions=True)
+    h.step(warm)
+    base = h.step(1)
+    base = (int(base.propagations), int(base.num_nodes))
+    barrier()
+    t0 = time.perf_counter()
+    exch_s, last = 0.0, None
+    for _ in range(steps):
+        last = h.step(1)
+        t1 = time.perf_counter()
+        stop.exchange(0, op="sum")
+        exch_s += time.perf_counter() - t1
+    wall = time.perf_counter() - t0
+    barrier()
+    h.close()
+    e.close()
+    props, nodes, ms = reduce_sum(dev["propagations"]), reduce_sum(dev["nodes"]), reduce_max(dev["ms"])
+    e_props = reduce_sum(int(last.propagations) - base[0])
+    e_nodes = reduce_sum(int(last.num_nodes) - base[1])
+    e_s = reduce_max(wall)
+    return {"workload": "n-queens N=5000 (V=5000, P=37492500 XNeqY), subtree-sharded DFS, one context per GPU",
+            "value": props / (ms * 1e-3) if ms > 0 else 0.0, "unit": "propagations/s", "steps": steps, "warmup": warm,
+            "nodes_per_s": nodes / (ms * 1e-3) if ms > 0 else 0.0, "ms_per_step": ms / max(steps, 1),
+            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s",
+                         "streamed_bytes_per_propagation": 8,
+                         "streamed_frac": (dev["propagations"] * 8) / (dev["ms"] * 1e-3) / 1e9 / peak if dev["ms"] > 0 else None,
+                         "algorithmic_frac": (dev["propagations"] * 32) / (dev["ms"] * 1e-3) / 1e9 / peak if dev["ms"] > 0 else None,
+                         "note": "the sweep streams the compact 8-byte descriptors from HBM and reads the domains from shared memory: "
+                                 "the fraction against the bytes it must stream is the meaningful one"},
+            "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s", "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0,
+                    "exchanges": steps, "exchange_seconds": exch_s,
+                    "path": "host-driven node loop through the C ABI, 1 x int32 NCCL all-reduce after every node inside the timed loop"}}
+
+
+def run_bb(torch, device, rank, world, local_rank, barrier):
+    """BranchAndBound across ranks (search/branch_and_bound.rs:76-92 + SURVEY 8e): minimise the
+    middle queen of n-queens N=32 on IntervalSet engines, subtrees sharded over the ranks, the
+    incumbent all-reduced (min) after every round of 32 nodes and adopted by every rank."""
+    from pcp_b200 import Engine, models, parallel
+    n = 32
+    e = Engine(device=local_rank, interval_set=True, host_search=True, max_labels=1 << 12)
+    models.nqueens(n).load_into(e)
+    flag = parallel.StopFlag(device)
+    barrier()
+    t0 = time.perf_counter()
+    out = parallel.sharded_search(e, rank, world, node_budget=3000, sync_every=32, stop_flag=flag, bb_mode=1, bb_var=n // 2,
+                                  parts_per_rank=2)
+    wall = time.perf_counter() - t0
+    barrier()
+    e.close()
+    return {"workload": f"n-queens N={n} on IntervalSet domains, minimise q[{n // 2}], node budget 3000 per rank",
+            "incumbent": out["incumbent"], "nodes_rank0": out["nodes"], "solutions_rank0": out["solutions"],
+            "exchanges": out["exchanges"], "exchange_seconds": out["exchange_seconds"], "wall_seconds": wall,
+            "collective": "NCCL all-reduce, 1 x int32: sum (stop / idle word) + min (incumbent) per round"}
+
+
+def cpu_baseline(workload, model, args, threads: int = 1, budget_s: float = 20.0, set_domains: bool = False,
+                 faithful: bool = True):
     """Time the oracle's flat variant on a bounded sample of the same workload."""
-    from oracle.oracle_api import FLAT, OracleEngine
+    from oracle.oracle_api import FAITHFUL, FLAT, SET, OracleEngine
+    dom = SET if set_domains else 0
 
     def one(nodes, out, i):
-        e = OracleEngine(FLAT)
+        e = OracleEngine(FLAT + dom)
         model.load_into(e)
         if workload == "c4":
             t0 = time.perf_counter()
@@ -425,7 +585,19 @@ def cpu_baseline(workload, model, args, threads: int = 1, budget_s: float = 20.0
     props = sum(o[0] for o in out)
     secs = max(o[1] for o in out)
     nn = sum(o[2] for o in out)
+    faith = None
+    if faithful and workload in ("c2", "c3") and threads == 1:
+        # the reference's own algorithmic structure (BASELINE.md 3 "cpu-faithful"): reactor rebuilt at
+        # every node with the duplicate-subscription scan (indexed_deps.rs:69-77, store.rs:125-149),
+        # boxed view trees -- 3 nodes of the same DFS
+        e = OracleEngine(FAITHFUL + dom)
+        model.load_into(e)
+        r, _ = e.search(node_limit=3, all_solutions=True)
+        faith = {"value": r.propagations / r.seconds if r.seconds > 0 else 0.0, "nodes_per_s": r.num_nodes / r.seconds if r.seconds > 0 else 0.0,
+                 "sample": "3 nodes, oracle faithful variant (per-node reactor rebuild incl. duplicate scan, boxed views), 1 thread"}
+        e.close()
     return {"value": props / secs if secs > 0 else 0.0, "unit": "propagations/s", "cores": threads, "kind": "port",
+            "faithful": faith,
             "nodes_per_s": nn / secs if secs > 0 else 0.0,
             "sample": (f"{out[0][2]} node(s) per thread of the same DFS, oracle flat variant (static CSR reactor, inline "
                        f"descriptors), {threads} thread(s), wall {wall:.1f}s incl. model load"),
@@ -444,7 +616,7 @@ def run_reference(args):
     model, desc = build_model(workload)
     threads = max(1, os.cpu_count() or 1)
     threads = min(threads, 64)
-    cpu = cpu_baseline(workload, model, args, threads=threads, budget_s=40.0)
+    cpu = cpu_baseline(workload, model, args, threads=threads, budget_s=40.0, set_domains=args.domains == "set", faithful=False)
     steps = args.steps
     line = {
         "impl": "reference",
@@ -488,6 +660,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c2 (default) | c3 | c4 | c5 | nq<N>")
+    ap.add_argument("--contexts", type=int, default=0, help="engines side by side per GPU (0 = per-workload default: 12 for c2/c3, 1 for c4/c5)")
+    ap.add_argument("--domains", default="interval", choices=["interval", "set"], help="Interval<i32> (VStoreFD) or IntervalSet<i32> (FDSpace) domains")
+    ap.add_argument("--skip-nodes", type=int, default=0, help="advance every context by this many DFS nodes before the timed window (deep nodes)")
+    ap.add_argument("--sync-every", type=int, default=8, help="multi-GPU e2e: nodes per context between two exchanges of the stop word")
+    ap.add_argument("--no-c5", action="store_true", help="multi-GPU: skip the nested C5 (N=5000) and branch-and-bound runs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -225,8 +225,10 @@ struct pcp_engine {
 
   // the fixpoint launched by fixpoint_launch and not yet collected by fixpoint_wait
   struct Inflight {
-    bool active = false;
+    bool prepared = false, active = false;
     Params P;
+    const void* fn = nullptr;
+    size_t smem = 0;
     int grid = 0;
     bool want_snapshot = false, eager_dom = false, zero_copy = false;
     double hp0 = 0, hp1 = 0, hp2 = 0, hp3 = 0;
@@ -302,7 +304,7 @@ void* stage(pcp_engine* e, size_t bytes) {
 template <class T>
 void upload_range(pcp_engine* e, DevBuf<T>& dst, const std::vector<T>& src, size_t from, size_t to) {
   if (to <= from) return;
-  dst.reserve(src.size(), e->stream, from);
+  if (src.size() > dst.cap) dst.reserve(src.size() + 3 * e->tail_limit, e->stream, from);  // (headroom: see prepare)
   CUDA_CHECK(cudaMemcpyAsync(dst.p + from, src.data() + from, (to - from) * sizeof(T), cudaMemcpyHostToDevice, e->stream));
   CUDA_CHECK(cudaStreamSynchronize(e->stream));  // pageable source: keep it simple and safe
 }
@@ -639,16 +641,19 @@ Params prepare(pcp_engine* e) {
     HostFamily& hf = e->fam[f];
     const size_t w = (size_t)hf.width;
     if (use_inline) {
-      hf.d_desc.reserve(hf.desc.size(), e->stream, hf.uploaded * w);
-      if (f == F_TER) hf.d_descB.reserve(hf.descB.size(), e->stream, hf.uploaded);
+      if (hf.desc.size() > hf.d_desc.cap) hf.d_desc.reserve(hf.desc.size() + e->tail_limit * w, e->stream, hf.uploaded * w);
+      if (f == F_TER && hf.descB.size() > hf.d_descB.cap) hf.d_descB.reserve(hf.descB.size() + e->tail_limit, e->stream, hf.uploaded);
     } else {
       upload_range(e, hf.d_desc, hf.desc, hf.uploaded * w, hf.n * w);
       if (f == F_TER) upload_range(e, hf.d_descB, hf.descB, hf.uploaded, hf.n);
     }
-    reserve_zeroed(e, hf.d_active, (hf.n + 31) / 32 + 1, (hf.active_set + 31) / 32);
+    // (room for a whole tail: the branching constraints of a search are posted one by one, and a
+    // reallocation -- cudaMalloc, copy, device synchronisation -- in the middle of it costs milliseconds)
+    if ((hf.n + 31) / 32 + 1 > hf.d_active.cap)
+      reserve_zeroed(e, hf.d_active, (hf.n + e->tail_limit + 31) / 32 + 2, (hf.active_set + 31) / 32);
     if (hf.n > hf.d_stamp.cap) {
       size_t valid = std::min(hf.d_stamp.cap, hf.active_set);
-      hf.d_stamp.reserve(hf.n, e->stream, valid);
+      hf.d_stamp.reserve(hf.n + e->tail_limit, e->stream, valid);
       fill_u32(e, hf.d_stamp.p + valid, 0u, hf.d_stamp.cap - valid);
     }
     if (!hf.d_desc.p) hf.d_desc.reserve(1, e->stream);
@@ -671,7 +676,7 @@ Params prepare(pcp_engine* e) {
     upload_range(e, e->d_sum_ptr, e->h_sum_ptr, e->sums_uploaded == 0 ? 0 : e->sums_uploaded + 1, e->sums.size() + 1);
     e->sums_uploaded = e->sums.size();
   }
-  e->d_trail.reserve(total + 64, e->stream, e->trail_len);
+  if (total + 64 > e->d_trail.cap) e->d_trail.reserve(total + e->tail_limit + 64, e->stream, e->trail_len);
 
   Params P;
   std::memset(&P, 0, sizeof(P));
@@ -850,11 +855,11 @@ struct HostProf {
 static HostProf g_hostprof;
 static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// One fixpoint = fixpoint_launch (node prologue parameters, launch geometry, the launch itself) +
-// fixpoint_wait (result header and domains back, host bookkeeping).  pcp_consistency runs them back
+// One fixpoint = fixpoint_prepare (uploads, node prologue parameters, launch geometry) +
+// fixpoint_fire (the launch) + fixpoint_wait (result header and domains back, host bookkeeping).  pcp_consistency runs them back
 // to back; pcp_consistency_batch launches several engines' fixpoints before it waits for any, so
 // that their persistent grids run side by side on the GPU.
-void fixpoint_launch(pcp_engine* e) {
+void fixpoint_prepare(pcp_engine* e) {
   PCP_REQUIRE(!e->inflight.active, "a fixpoint of this engine is already in flight");
   const double hp0 = now_s();
   Params P = prepare(e);
@@ -941,21 +946,36 @@ void fixpoint_launch(pcp_engine* e) {
     if (e->set_mode && eager_dom) P.host_sizes = e->h_sizes_dev();
   }
   e->sizes_valid = false;
-  const double hp2 = now_s();
-  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
-  void* args[] = {&P};
-  launch_persistent(fn, grid, args, smem, e->stream);
-  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
-  const double hp3 = now_s();
-  ++e->dom_version;
   pcp_engine::Inflight& f = e->inflight;
-  f.active = true;
+  f.prepared = true;
   f.P = P;
+  f.fn = fn;
+  f.smem = smem;
   f.grid = grid;
   f.want_snapshot = want_snapshot;
   f.eager_dom = eager_dom;
   f.zero_copy = zero_copy;
-  f.hp0 = hp0; f.hp1 = hp1; f.hp2 = hp2; f.hp3 = hp3;
+  f.hp0 = hp0; f.hp1 = hp1;
+}
+
+// the launch itself: nothing but the (cooperative) launch call between the two timing events
+void fixpoint_fire(pcp_engine* e) {
+  pcp_engine::Inflight& f = e->inflight;
+  PCP_REQUIRE(f.prepared && !f.active, "fixpoint not prepared");
+  f.hp2 = now_s();
+  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
+  void* args[] = {&f.P};
+  launch_persistent(f.fn, f.grid, args, f.smem, e->stream);
+  if (e->timing) CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
+  f.hp3 = now_s();
+  ++e->dom_version;
+  f.prepared = false;
+  f.active = true;
+}
+
+void fixpoint_launch(pcp_engine* e) {
+  fixpoint_prepare(e);
+  fixpoint_fire(e);
 }
 
 void fixpoint_wait(pcp_engine* e, int32_t* status, pcp_stats* stats) {
@@ -1316,15 +1336,29 @@ int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status
   const bool timed = lead->timing;
   std::vector<int> saved((size_t)n);
   for (int i = 0; i < n; ++i) saved[(size_t)i] = engines[i]->grid_limit;
+  // host work first (uploads, buffer growth, parameters), then the launches back to back
+  int prepared = 0;
   for (int i = 0; i < n && rc == PCP_OK; ++i) {
     pcp_engine* e = engines[i];
     rc = guarded(e, [&] {
       PCP_REQUIRE_NO_BURST(e);
       CUDA_CHECK(cudaSetDevice(e->device));
       if (e->grid_limit == 0 && n > 1) e->grid_limit = std::max(2, e->num_sms / n);
+      fixpoint_prepare(e);
+    });
+    if (rc == PCP_OK) ++prepared;
+  }
+  // (an engine whose preparation failed is left out; the ones already prepared have consumed their
+  // pending restore / uploads and must run, so the call goes on for them and reports the error)
+  const int first_rc = rc;
+  rc = PCP_OK;
+  for (int i = 0; i < prepared && rc == PCP_OK; ++i) {
+    pcp_engine* e = engines[i];
+    rc = guarded(e, [&] {
+      CUDA_CHECK(cudaSetDevice(e->device));
       if (timed && i == 0) CUDA_CHECK(cudaEventRecord(lead->ev_batch0, lead->stream));
       if (timed && i > 0) CUDA_CHECK(cudaStreamWaitEvent(e->stream, lead->ev_batch0, 0));
-      fixpoint_launch(e);
+      fixpoint_fire(e);
       if (timed && i > 0) {
         CUDA_CHECK(cudaEventRecord(e->ev_done, e->stream));
         CUDA_CHECK(cudaStreamWaitEvent(lead->stream, e->ev_done, 0));
@@ -1345,6 +1379,7 @@ int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status
     if (rc == PCP_OK) rc = r2;
   }
   for (int i = 0; i < n; ++i) engines[i]->grid_limit = saved[(size_t)i];
+  if (first_rc != PCP_OK) return first_rc;
   if (timed && launched == n && rc == PCP_OK && stats) {
     rc = guarded(lead, [&] {
       CUDA_CHECK(cudaEventSynchronize(lead->ev_batch1));
