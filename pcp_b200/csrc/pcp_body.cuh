@@ -994,6 +994,187 @@ __device__ __forceinline__ unsigned eval_all_equal(const Params& P, const Ctx& c
   return 1;
 }
 
+#if !defined(PCP_BIN_ONLY) && !defined(PCP_SET)
+// ---------------------------------------------------------------------------------------
+// Formula trees: one propagator = a tree of Conjunction / Disjunction / Boolean / BooleanNeg over
+// cmp leaves, evaluated by one thread on a private copy of the domains of the tree's variables
+// (at most kTreeMaxVars), exactly as the reference walks its boxed formulas:
+//   Conjunction  propagate = children in order, stop at the first failure (conjunction.rs:96-105);
+//                is_subsumed = Kleene and (conjunction.rs:77-94)
+//   Disjunction  propagate = read every child's is_subsumed: one True -> nothing to do; all False ->
+//                fail; all but one False -> propagate the remaining child (disjunction.rs:96-116);
+//                is_subsumed = Kleene or (disjunction.rs:77-94)
+//   Boolean b    is_subsumed: b assigned -> (b == 1), else Unknown; propagate: b <- 1
+//                (boolean.rs:108-135); BooleanNeg the mirror image (boolean_neg.rs:77-98)
+//   leaves       the cmp propagators of pcp_eval.cuh on the private copy
+// Both walks are iterative over the prefix node array (no recursion in the kernel): subsumption is
+// a reverse scan with a value stack, propagation a work list of node indices.
+// ---------------------------------------------------------------------------------------
+struct TreeCtx {
+  const int* nodes;   // the tree's node array
+  IV d[kTreeMaxVars];
+};
+__device__ __forceinline__ IV tree_rd(const TreeCtx& t, const int* nd, int i) {
+  const int slot = nd[3 + 2 * i], off = nd[4 + 2 * i];
+  if (slot < 0) return IV{off, off};
+  return IV{t.d[slot].lo + off, t.d[slot].hi + off};
+}
+// narrow operand i of a leaf to [nlo, nhi] (view space); false = empty / Constant outside
+__device__ __forceinline__ bool tree_wr(TreeCtx& t, const int* nd, int i, IV cur, int nlo, int nhi) {
+  nlo = max(nlo, cur.lo);
+  nhi = min(nhi, cur.hi);
+  if (nlo > nhi) return false;
+  const int slot = nd[3 + 2 * i], off = nd[4 + 2 * i];
+  if (slot >= 0) { t.d[slot].lo = nlo - off; t.d[slot].hi = nhi - off; }
+  return true;
+}
+__device__ __noinline__ int tree_leaf_subsumed(const TreeCtx& t, const int* nd) {
+  const int type = nd[0];
+  if (type == TN_BOOL || type == TN_BOOL_NEG) {
+    const IV b = tree_rd(t, nd, 0);
+    if (b.lo != b.hi) return 0;
+    return ((b.lo == 1) == (type == TN_BOOL)) ? 1 : -1;
+  }
+  if (type >= TN_LEAF3) {
+    const IV x = tree_rd(t, nd, 0), y = tree_rd(t, nd, 1), z = tree_rd(t, nd, 2);
+    const int k = type - TN_LEAF3;
+    return k == T_GREATER ? sub_greater(x, y, z, 1) : (k == T_LESS ? sub_less(x, y, z, 1) : sub_eq(x, y, z));
+  }
+  const IV x = tree_rd(t, nd, 0), y = tree_rd(t, nd, 1);
+  const int k = type - TN_LEAF;
+  if (k == B_LESS) return x.lo >= y.hi ? -1 : (x.hi < y.lo ? 1 : 0);
+  const bool same_singleton = x.lo == y.hi && x.hi == y.lo;
+  const bool disjoint = x.hi < y.lo || y.hi < x.lo;
+  if (k == B_NEQ) return same_singleton ? -1 : (disjoint ? 1 : 0);
+  return same_singleton ? 1 : (disjoint ? -1 : 0);
+}
+__device__ __noinline__ bool tree_leaf_propagate(TreeCtx& t, const int* nd) {
+  const int type = nd[0];
+  if (type == TN_BOOL || type == TN_BOOL_NEG) {
+    const IV b = tree_rd(t, nd, 0);
+    const int v = type == TN_BOOL ? 1 : 0;
+    return tree_wr(t, nd, 0, b, v, v);  // (outside the domain: the reference's update panics; here the node fails)
+  }
+  if (type >= TN_LEAF3) {
+    IV x = tree_rd(t, nd, 0), y = tree_rd(t, nd, 1), z = tree_rd(t, nd, 2);
+    const IV x0 = x, y0 = y, z0 = z;
+    const int k = type - TN_LEAF3;
+    bool ok;
+    if (k == T_GREATER) ok = prop_greater(x, y, z, 1);
+    else if (k == T_LESS) ok = prop_less(x, y, z, 1);
+    else ok = prop_greater(x, y, z, 0) && prop_less(x, y, z, 0);
+    if (!ok) return false;
+    return tree_wr(t, nd, 0, x0, x.lo, x.hi) && tree_wr(t, nd, 1, y0, y.lo, y.hi) && tree_wr(t, nd, 2, z0, z.lo, z.hi);
+  }
+  const IV x = tree_rd(t, nd, 0), y = tree_rd(t, nd, 1);
+  const int k = type - TN_LEAF;
+  if (k == B_LESS)  // x_less_y.rs:101-108: x first, then y against the old x.lo
+    return tree_wr(t, nd, 0, x, x.lo, y.hi - 1) && tree_wr(t, nd, 1, y, x.lo + 1, y.hi);
+  if (k == B_EQ) {  // x_eq_y.rs:102-107
+    const int lo = max(x.lo, y.lo), hi = min(x.hi, y.hi);
+    return tree_wr(t, nd, 0, x, lo, hi) && tree_wr(t, nd, 1, y, lo, hi);
+  }
+  // XNeqY on Interval: only a value on a bound goes (x_neq_y.rs:82-93)
+  if (x.lo == x.hi) {
+    if (y.lo == x.lo) return tree_wr(t, nd, 1, y, y.lo + 1, y.hi);
+    if (y.hi == x.lo) return tree_wr(t, nd, 1, y, y.lo, y.hi - 1);
+  } else if (y.lo == y.hi) {
+    if (x.lo == y.lo) return tree_wr(t, nd, 0, x, x.lo + 1, x.hi);
+    if (x.hi == y.lo) return tree_wr(t, nd, 0, x, x.lo, x.hi - 1);
+  }
+  return true;
+}
+// is_subsumed of the subtree rooted at node r: reverse prefix scan, children's values on a stack
+__device__ __noinline__ int tree_subsumed(const TreeCtx& t, int r) {
+  signed char val[kTreeMaxNodes];
+  int sp = 0;
+  const int end = t.nodes[r * kTreeNodeInts + 2];
+  for (int i = end - 1; i >= r; --i) {
+    const int* nd = t.nodes + i * kTreeNodeInts;
+    const int type = nd[0];
+    int v;
+    if (type == TN_CONJ || type == TN_DISJ) {
+      const int n = nd[1];
+      v = type == TN_CONJ ? 1 : -1;
+      for (int q = 0; q < n; ++q) {
+        const int cv = val[--sp];
+        v = type == TN_CONJ ? min(v, cv) : max(v, cv);
+      }
+    } else {
+      v = tree_leaf_subsumed(t, nd);
+    }
+    val[sp++] = (signed char)v;
+  }
+  return val[0];
+}
+__device__ __noinline__ bool tree_propagate(TreeCtx& t) {
+  short work[kTreeMaxNodes];
+  int sp = 0;
+  work[sp++] = 0;
+  while (sp > 0) {
+    const int i = work[--sp];
+    const int* nd = t.nodes + i * kTreeNodeInts;
+    const int type = nd[0];
+    if (type == TN_CONJ) {
+      // children in order: push them in reverse (child q starts where child q - 1 ends)
+      short kids[kTreeMaxNodes];
+      const int n = nd[1];
+      int ch = i + 1;
+      for (int q = 0; q < n; ++q) { kids[q] = (short)ch; ch = t.nodes[ch * kTreeNodeInts + 2]; }
+      for (int q = n - 1; q >= 0; --q) work[sp++] = kids[q];
+    } else if (type == TN_DISJ) {
+      const int n = nd[1];
+      int ch = i + 1, num_disentailed = 0, unknown = -1;
+      bool entailed = false;
+      for (int q = 0; q < n; ++q) {
+        const int k = tree_subsumed(t, ch);
+        if (k > 0) { entailed = true; break; }
+        if (k < 0) ++num_disentailed; else unknown = ch;
+        ch = t.nodes[ch * kTreeNodeInts + 2];
+      }
+      if (entailed) continue;
+      if (num_disentailed == n) return false;
+      if (num_disentailed == n - 1) work[sp++] = (short)unknown;
+    } else if (!tree_leaf_propagate(t, nd)) {
+      return false;
+    }
+  }
+  return true;
+}
+// One tree propagator (thread 0 of the CTA that got the slot).  Returns 1 if evaluated.
+template <bool SMEM>
+__device__ __noinline__ unsigned eval_tree(const Params& P, const Ctx& c, int slot, const uint32_t* cur_bits, bool unconditional) {
+  if (threadIdx.x != 0) return 0;
+  const int b = __ldg(&P.nary_ptr[slot]), k = __ldg(&P.nary_ptr[slot + 1]) - b;
+  TreeCtx t;
+  t.nodes = P.tree_nodes + __ldg(&P.tree_ptr[slot]);
+  IV before[kTreeMaxVars];
+  bool any_dirty = unconditional;
+  for (int i = 0; i < k; ++i) {
+    const int v = __ldg(&P.nary_ops[b + i]).x;
+    const int2 d = SMEM ? c.sdom[v] : ldcg_dom(&P.dom[v]);
+    t.d[i] = before[i] = IV{d.x, d.y};
+    if (!unconditional && ((__ldcg(&cur_bits[v >> 5]) >> (v & 31)) & 1u)) any_dirty = true;
+  }
+  if (!any_dirty) return 0;
+  if (!tree_propagate(t)) { set_failed(c); return 1; }
+  const int sub = tree_subsumed(t, 0);
+  if (sub < 0) { set_failed(c); return 1; }
+  for (int i = 0; i < k; ++i) {
+    if (t.d[i].lo == before[i].lo && t.d[i].hi == before[i].hi) continue;
+    const int v = __ldg(&P.nary_ops[b + i]).x;
+    const int2 cur = ldcg_dom(&P.dom[v]);
+    if (!tighten(c, v, 0, IV{cur.x, cur.y}, max(cur.x, t.d[i].lo), min(cur.y, t.d[i].hi))) set_failed(c);
+  }
+  if (sub > 0) {
+    const unsigned bit = 1u << (slot & 31);
+    const unsigned old = atomicAnd(&P.nary_active[slot >> 5], ~bit);
+    if (old & bit) P.trail[atomicAdd(&P.ctl->trail_cnt, 1u)] = make_ref(F_NARY, (unsigned)slot);
+  }
+  return 1;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------
 // device-wide barrier; the last CTA to arrive decides whether the fixpoint is reached
 // (the "block-reduce of a changed flag": every CTA contributes "I narrowed a variable").
@@ -1576,11 +1757,17 @@ __device__ __noinline__ unsigned nary_outlined(const Params* PS, const Ctx* c, c
   // last to get one
   for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
     if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
-    unsigned ev = __ldg(&P.nary_kind[s]) == N_ALL_EQUAL ? eval_all_equal<SMEM>(P, *c, s, cur_bits, all)
+    const int kind = __ldg(&P.nary_kind[s]);
+    unsigned ev;
+#if !defined(PCP_BIN_ONLY) && !defined(PCP_SET)
+    if (kind == N_TREE) ev = eval_tree<SMEM>(P, *c, s, cur_bits, all);
+    else
+#endif
+    if (kind == N_ALL_EQUAL) ev = eval_all_equal<SMEM>(P, *c, s, cur_bits, all);
 #ifdef PCP_SET
-                                                         : eval_distinct_set<SMEM>(P, *c, s, ring, cur_bits, all);
+    else ev = eval_distinct_set<SMEM>(P, *c, s, ring, cur_bits, all);
 #else
-                                                         : eval_distinct<SMEM>(P, *c, s, ring, cur_bits, all);
+    else ev = eval_distinct<SMEM>(P, *c, s, ring, cur_bits, all);
 #endif
     if (threadIdx.x == 0) n += ev;
   }

@@ -37,7 +37,17 @@ __host__ __device__ inline unsigned make_ref(unsigned fam, unsigned slot) { retu
 // kinds inside a family (top 4 bits of descriptor word 0)
 enum BinKind : unsigned { B_LESS = 0, B_NEQ = 1, B_EQ = 2 };
 enum TerKind : unsigned { T_GREATER = 0, T_LESS = 1, T_EQ = 2, T_MUL = 3 };
-enum NaryKind : int { N_DISTINCT = 0, N_ALL_EQUAL = 1 };
+enum NaryKind : int { N_DISTINCT = 0, N_ALL_EQUAL = 1, N_TREE = 2 };
+// Formula trees (logic/: Conjunction, Disjunction, Boolean, BooleanNeg over cmp leaves) ride in the
+// n-ary family: the operands of the n-ary slot are the tree's distinct variables, its nodes sit
+// in Params::tree_nodes from tree_ptr[slot] on, kTreeNodeInts ints each, in prefix order:
+//   [0] type: TN_* or TN_LEAF + BinKind / TN_LEAF3 + TerKind   [1] number of children
+//   [2] index (relative to the tree's first node) one past the node's subtree
+//   [3 + 2i], [4 + 2i]  operand i of a leaf / the Boolean: slot in the variable table (or -1:
+//                       Constant) and offset
+constexpr int kTreeNodeInts = 9;
+constexpr int kTreeMaxNodes = 32, kTreeMaxVars = 12;
+enum TreeNode : int { TN_CONJ = 1, TN_DISJ = 2, TN_BOOL = 3, TN_BOOL_NEG = 4, TN_LEAF = 16, TN_LEAF3 = 32 };
 
 enum Decision : unsigned { D_CONTINUE = 0, D_FIXPOINT = 1, D_FAILED = 2, D_ITER_CAP = 3 };
 // Worklist iterations: every CTA compacts the dirty bit set into a list that lives in the
@@ -103,7 +113,9 @@ struct Params {
   Family fam[3];        // BIN, TER, DJ
   const int* nary_ptr;  // CSR of n-ary Distinct operands
   const int2* nary_ops;
-  const int* nary_kind;  // N_DISTINCT / N_ALL_EQUAL per n-ary propagator
+  const int* nary_kind;  // N_DISTINCT / N_ALL_EQUAL / N_TREE per n-ary propagator
+  const int* tree_ptr;   // N_TREE: first int of the propagator's nodes in tree_nodes
+  const int* tree_nodes;
   uint32_t* nary_active;
   int n_nary;
   int nary_max_k;

@@ -109,6 +109,7 @@ struct HostFamily {
 struct LabelRec {
   size_t n_fam[4];
   size_t n_nary_ops;
+  size_t n_tree_ints;
   size_t n_props;
   unsigned trail_len;
   bool at_fixpoint;
@@ -153,8 +154,11 @@ struct pcp_engine {
   HostFamily fam[3];                // BIN, TER, DJ
   std::vector<int> h_nary_ptr{0};
   std::vector<int2> h_nary_ops;
-  std::vector<int> h_nary_kind;     // per n-ary propagator: N_DISTINCT / N_ALL_EQUAL
+  std::vector<int> h_nary_kind;     // per n-ary propagator: N_DISTINCT / N_ALL_EQUAL / N_TREE
   DevBuf<int> d_nary_kind;
+  std::vector<int> h_tree_ptr;      // per n-ary propagator: first int of its nodes in h_tree_nodes (-1: not a tree)
+  std::vector<int> h_tree_nodes;    // formula trees, kTreeNodeInts ints per node (pcp_common.cuh)
+  DevBuf<int> d_tree_ptr, d_tree_nodes;
   size_t n_nary = 0, nary_uploaded = 0, nary_active_set = 0;
   int nary_max_k = 0;
   DevBuf<int> d_nary_ptr;
@@ -457,6 +461,7 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
       for (auto& o : lo) e->h_nary_ops.push_back(make_int2(o.var, o.off));
       e->h_nary_ptr.push_back((int)e->h_nary_ops.size());
       e->h_nary_kind.push_back(kind == PCP_DISTINCT ? (int)N_DISTINCT : (int)N_ALL_EQUAL);
+      e->h_tree_ptr.push_back(-1);
       e->nary_max_k = std::max(e->nary_max_k, n_ops);
       e->prop_ref.push_back(make_ref(F_NARY, (unsigned)e->n_nary++));
       // binary/ternary/disjunction propagators allocated after a fixpoint land in the tail,
@@ -484,6 +489,8 @@ void truncate_props(pcp_engine* e, const LabelRec& r) {
   e->h_nary_ptr.resize(e->n_nary + 1);
   e->h_nary_kind.resize(e->n_nary);
   e->h_nary_ops.resize(r.n_nary_ops);
+  e->h_tree_ptr.resize(e->n_nary);
+  e->h_tree_nodes.resize(r.n_tree_ints);
   e->nary_uploaded = std::min(e->nary_uploaded, e->n_nary);
   e->nary_active_set = std::min(e->nary_active_set, e->n_nary);
   e->prop_ref.resize(r.n_props);
@@ -667,6 +674,13 @@ Params prepare(pcp_engine* e) {
     size_t pfrom = e->nary_uploaded == 0 ? 0 : e->nary_uploaded + 1;
     upload_range(e, e->d_nary_ptr, e->h_nary_ptr, pfrom, e->n_nary + 1);
     upload_range(e, e->d_nary_kind, e->h_nary_kind, e->nary_uploaded, e->n_nary);
+    upload_range(e, e->d_tree_ptr, e->h_tree_ptr, e->nary_uploaded, e->n_nary);
+    {  // the nodes of the trees among the new propagators
+      size_t first = e->h_tree_nodes.size();
+      for (size_t q = e->nary_uploaded; q < e->n_nary; ++q)
+        if (e->h_tree_ptr[q] >= 0) { first = (size_t)e->h_tree_ptr[q]; break; }
+      upload_range(e, e->d_tree_nodes, e->h_tree_nodes, first, e->h_tree_nodes.size());
+    }
     e->nary_uploaded = e->n_nary;
   }
   reserve_zeroed(e, e->d_nary_active, (e->n_nary + 31) / 32 + 1, (e->nary_active_set + 31) / 32);
@@ -730,6 +744,8 @@ Params prepare(pcp_engine* e) {
   P.nary_ptr = e->d_nary_ptr.p;
   P.nary_ops = e->d_nary_ops.p;
   P.nary_kind = e->d_nary_kind.p;
+  P.tree_ptr = e->d_tree_ptr.p;
+  P.tree_nodes = e->d_tree_nodes.p;
   P.nary_active = e->d_nary_active.p;
   P.nary_active_w = e->d_nary_active.p;
   P.n_nary = (int)e->n_nary;
@@ -1204,6 +1220,7 @@ void pcp_engine_destroy(pcp_engine* e) {
     e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_cdesc.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
   }
   e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_kind.free(); e->d_nary_active.free();
+  e->d_tree_ptr.free(); e->d_tree_nodes.free();
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
   e->d_dirty_bits.free(); e->d_seed_list.free(); e->d_trail.free(); e->d_stack.free(); e->d_bits.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
@@ -1293,6 +1310,7 @@ int pcp_props_alloc(pcp_engine* e, int32_t kind, const pcp_operand* ops, int32_t
     for (int f = 0; f < 3; ++f) mark.n_fam[f] = e->fam[f].n;
     mark.n_fam[F_NARY] = e->n_nary;
     mark.n_nary_ops = e->h_nary_ops.size();
+    mark.n_tree_ints = e->h_tree_nodes.size();
     mark.n_props = e->num_props();
     int old_max_k = e->nary_max_k;
     if (first_idx) *first_idx = (int32_t)e->num_props();
@@ -1465,13 +1483,154 @@ int pcp_domains_read_bits(pcp_engine* e, int32_t first, int32_t n, int32_t base,
   });
 }
 
+static_assert(PCP_F_MAX_NODES == kTreeMaxNodes && PCP_F_MAX_VARS == kTreeMaxVars, "header limits out of step with the device");
+namespace {
+// Host form of a formula tree (pcp_formula_alloc): parsed from the prefix words, negations pushed to
+// the leaves the way the reference's NotFormula impls do, then flattened for the device.
+struct FTree {
+  int type = 0;                 // TN_CONJ, TN_DISJ, TN_BOOL, TN_BOOL_NEG, TN_LEAF + BinKind, TN_LEAF3 + TerKind
+  std::vector<FTree> kids;
+  pcp_operand op[3];
+  int nops = 0;
+};
+
+FTree ftree_negate(const FTree& f) {
+  FTree g;
+  switch (f.type) {
+    case TN_CONJ: case TN_DISJ:  // De Morgan (conjunction.rs:66-74, disjunction.rs:66-74)
+      g.type = f.type == TN_CONJ ? TN_DISJ : TN_CONJ;
+      for (const FTree& k : f.kids) g.kids.push_back(ftree_negate(k));
+      return g;
+    case TN_BOOL: g = f; g.type = TN_BOOL_NEG; return g;       // boolean.rs:70-79
+    case TN_BOOL_NEG: g = f; g.type = TN_BOOL; return g;       // boolean_neg.rs:58-66
+    case TN_LEAF + B_LESS:   // not (x < y) = x >= y = x_greater_y(x + 1, y) = XLessY(y, x + 1)  (x_less_y.rs:57-65, cmp/mod.rs:40-52)
+      g.type = TN_LEAF + B_LESS; g.nops = 2; g.op[0] = f.op[1]; g.op[1] = f.op[0]; g.op[1].off += 1; return g;
+    case TN_LEAF + B_NEQ: g = f; g.type = TN_LEAF + B_EQ; return g;    // x_neq_y.rs:56-64
+    case TN_LEAF + B_EQ: g = f; g.type = TN_LEAF + B_NEQ; return g;    // x_eq_y.rs:57-65
+    case TN_LEAF3 + T_GREATER:  // not (x > y + z) = x <= y + z = XLessYPlusZ(x - 1, y, z)  (cmp/mod.rs:78-86)
+      g = f; g.type = TN_LEAF3 + T_LESS; g.op[0].off -= 1; return g;
+    case TN_LEAF3 + T_LESS:     // not (x < y + z) = x >= y + z = XGreaterYPlusZ(x + 1, y, z)  (cmp/mod.rs:70-76)
+      g = f; g.type = TN_LEAF3 + T_GREATER; g.op[0].off += 1; return g;
+    default:                    // XEqYPlusZ::not is unimplemented!() in the reference (x_eq_y_plus_z.rs:70-77)
+      PCP_FAIL(PCP_ERR_UNSUPPORTED, "not() of XEqYPlusZ is unimplemented in the reference");
+  }
+}
+
+FTree ftree_parse(pcp_engine* e, const int32_t*& p, const int32_t* end, int depth) {
+  PCP_REQUIRE(p < end, "truncated formula");
+  PCP_REQUIRE(depth < 16, "formula nested too deeply");
+  const int32_t tag = *p++;
+  FTree f;
+  auto operand = [&](int i) {
+    PCP_REQUIRE(p + 2 <= end, "truncated formula");
+    pcp_operand raw{p[0], p[1]};
+    p += 2;
+    f.op[i] = lower_view(e, raw);
+    if (f.op[i].var <= -2) PCP_FAIL(PCP_ERR_UNSUPPORTED, "multi-term Sum views inside a formula tree have no device lowering");
+  };
+  if (tag == PCP_F_CONJUNCTION || tag == PCP_F_DISJUNCTION) {
+    PCP_REQUIRE(p < end && *p >= 1, "connective without children");
+    const int32_t n = *p++;
+    f.type = tag == PCP_F_CONJUNCTION ? TN_CONJ : TN_DISJ;
+    for (int32_t i = 0; i < n; ++i) f.kids.push_back(ftree_parse(e, p, end, depth + 1));
+    return f;
+  }
+  if (tag == PCP_F_NOT) return ftree_negate(ftree_parse(e, p, end, depth + 1));
+  if (tag == PCP_F_BOOLEAN || tag == PCP_F_BOOLEAN_NEG) {
+    f.type = tag == PCP_F_BOOLEAN ? TN_BOOL : TN_BOOL_NEG;
+    f.nops = 1;
+    operand(0);
+    PCP_REQUIRE(f.op[0].var >= 0 && f.op[0].off == 0, "Boolean reads a variable");
+    const int2 d = e->h_dom_init[(size_t)f.op[0].var];
+    PCP_REQUIRE(d.x >= 0 && d.y <= 1, "Boolean variables have the domain [0, 1] (boolean.rs:35-40)");
+    return f;
+  }
+  const int kind = tag - PCP_F_LEAF;
+  switch (kind) {
+    case PCP_X_LESS_Y: f.type = TN_LEAF + B_LESS; f.nops = 2; break;
+    case PCP_X_NEQ_Y: f.type = TN_LEAF + B_NEQ; f.nops = 2; break;
+    case PCP_X_EQ_Y: f.type = TN_LEAF + B_EQ; f.nops = 2; break;
+    case PCP_X_GREATER_Y_PLUS_Z: f.type = TN_LEAF3 + T_GREATER; f.nops = 3; break;
+    case PCP_X_LESS_Y_PLUS_Z: f.type = TN_LEAF3 + T_LESS; f.nops = 3; break;
+    case PCP_X_EQ_Y_PLUS_Z: f.type = TN_LEAF3 + T_EQ; f.nops = 3; break;
+    default: PCP_FAIL(PCP_ERR_UNSUPPORTED, "unknown formula node / leaf kind without a device lowering");
+  }
+  for (int i = 0; i < f.nops; ++i) operand(i);
+  require_distinct_vars(e, f.op, f.nops);  // a leaf subscribing twice to one variable (indexed_deps.rs:69-77)
+  return f;
+}
+
+// Conjunction / Disjunction::dependencies sort and de-duplicate (variable, event) pairs
+// (conjunction.rs:107-118, disjunction.rs:118-129), so one variable may be read by several leaves
+// -- but only at one event: XLessY / the ternaries / Boolean subscribe at Bound, XNeqY / XEqY at
+// Inner, and a propagator that ends up on two lists of one variable trips the assert of
+// IndexedDeps::subscribe (indexed_deps.rs:69-77) when the store prepares.  ev[var] = bit set of events.
+void ftree_events(const FTree& f, std::vector<std::pair<int, int>>& ev) {
+  for (const FTree& k : f.kids) ftree_events(k, ev);
+  if (f.type == TN_CONJ || f.type == TN_DISJ) return;
+  const bool inner = f.type == TN_LEAF + B_NEQ || f.type == TN_LEAF + B_EQ;
+  for (int i = 0; i < f.nops; ++i)
+    if (f.op[i].var >= 0) ev.emplace_back(f.op[i].var, inner ? 2 : 1);
+}
+
+int ftree_count(const FTree& f) {
+  int n = 1;
+  for (const FTree& k : f.kids) n += ftree_count(k);
+  return n;
+}
+// prefix order; node indices are relative to the tree's first node
+void ftree_flatten(const FTree& f, std::vector<int>& out, std::vector<int>& vars, int base_node) {
+  const size_t at = out.size();
+  out.resize(at + kTreeNodeInts, 0);
+  out[at + 0] = f.type;
+  out[at + 1] = (int)f.kids.size();
+  for (int i = 0; i < 3; ++i) {
+    int slot = -1, off = 0;
+    if (i < f.nops) {
+      off = f.op[i].off;
+      if (f.op[i].var >= 0) {
+        auto it = std::find(vars.begin(), vars.end(), f.op[i].var);
+        if (it == vars.end()) { vars.push_back(f.op[i].var); it = vars.end() - 1; }
+        slot = (int)(it - vars.begin());
+      }
+    }
+    out[at + 3 + 2 * i] = slot;
+    out[at + 4 + 2 * i] = off;
+  }
+  for (const FTree& k : f.kids) ftree_flatten(k, out, vars, base_node);
+  out[at + 2] = (int)((out.size() - (size_t)base_node) / kTreeNodeInts);
+}
+}  // namespace
+
 int pcp_formula_alloc(pcp_engine* e, const int32_t* words, int32_t n_words, int32_t* idx) {
   if (!e) return PCP_ERR_INVALID;
   return guarded(e, [&] {
     PCP_REQUIRE_NO_BURST(e);
     PCP_REQUIRE(words && n_words > 0, "bad arguments");
-    (void)idx;
-    PCP_FAIL(PCP_ERR_UNSUPPORTED, "formula trees: not built yet");
+    if (e->set_mode) PCP_FAIL(PCP_ERR_UNSUPPORTED, "formula trees have no device lowering on IntervalSet domains");
+    const int32_t* p = words;
+    const FTree f = ftree_parse(e, p, words + n_words, 0);
+    PCP_REQUIRE(p == words + n_words, "trailing words after the formula");
+    {
+      std::vector<std::pair<int, int>> ev;
+      ftree_events(f, ev);
+      std::sort(ev.begin(), ev.end());
+      for (size_t i = 1; i < ev.size(); ++i)
+        PCP_REQUIRE(ev[i].first != ev[i - 1].first || ev[i].second == ev[i - 1].second, "propagator already subscribed to this variable");
+    }
+    if (ftree_count(f) > kTreeMaxNodes) PCP_FAIL(PCP_ERR_UNSUPPORTED, "formula tree with more than PCP_F_MAX_NODES nodes");
+    std::vector<int> nodes, vars;
+    ftree_flatten(f, nodes, vars, 0);
+    if ((int)vars.size() > kTreeMaxVars) PCP_FAIL(PCP_ERR_UNSUPPORTED, "formula tree over more than PCP_F_MAX_VARS variables");
+    if (idx) *idx = (int32_t)e->num_props();
+    e->h_tree_ptr.push_back((int)e->h_tree_nodes.size());
+    e->h_tree_nodes.insert(e->h_tree_nodes.end(), nodes.begin(), nodes.end());
+    for (int v : vars) e->h_nary_ops.push_back(make_int2(v, 0));  // the variable table = the n-ary operands
+    e->h_nary_ptr.push_back((int)e->h_nary_ops.size());
+    e->h_nary_kind.push_back((int)N_TREE);
+    e->nary_max_k = std::max(e->nary_max_k, (int)vars.size());
+    e->prop_ref.push_back(make_ref(F_NARY, (unsigned)e->n_nary++));
+    e->at_fixpoint = false;  // a new n-ary propagator needs a full first sweep
   });
 }
 
@@ -1561,6 +1720,7 @@ int pcp_label(pcp_engine* e, uint64_t* label) {
     for (int f = 0; f < 3; ++f) r.n_fam[f] = e->fam[f].n;
     r.n_fam[F_NARY] = e->n_nary;
     r.n_nary_ops = e->h_nary_ops.size();
+    r.n_tree_ints = e->h_tree_nodes.size();
     r.n_props = e->num_props();
     r.trail_len = e->trail_len;
     r.at_fixpoint = e->at_fixpoint;
@@ -1809,6 +1969,7 @@ int pcp_internal_burst_end(pcp_engine* e) {
         r.n_fam[F_DJ] = e->fam[F_DJ].n;
         r.n_fam[F_NARY] = e->n_nary;
         r.n_nary_ops = e->h_nary_ops.size();
+        r.n_tree_ints = e->h_tree_nodes.size();
         r.n_props = (size_t)(b.props_base + m.x);
         r.trail_len = (unsigned)m.y;
         r.at_fixpoint = true;

@@ -42,6 +42,9 @@ KIND_BY_NAME = {v: k for k, v in KIND_NAMES.items()}
 
 VAR_CONSTANT = -1
 
+# formula-tree node tags (pcp_formula_alloc, include/pcp_b200.h)
+F_CONJUNCTION, F_DISJUNCTION, F_BOOLEAN, F_BOOLEAN_NEG, F_NOT, F_LEAF = 1, 2, 3, 4, 5, 16
+
 
 def var_sum(sum_id: int) -> int:
     return -2 - sum_id
@@ -62,7 +65,11 @@ class Model:
 
     @property
     def num_props(self) -> int:
-        return int(sum(b[1].shape[0] for b in self.batches))
+        return int(sum(1 if b[0] < 0 else b[1].shape[0] for b in self.batches))
+
+    def add_formula(self, words) -> None:
+        """One propagator given as a formula tree (prefix words of pcp_formula_alloc)."""
+        self.batches.append((-1, np.ascontiguousarray(np.asarray(words, dtype=np.int32).reshape(-1))))
 
     def add(self, kind: int, ops) -> None:
         a = np.ascontiguousarray(np.asarray(ops, dtype=np.int32))
@@ -77,7 +84,10 @@ class Model:
         for s in self.sums:
             engine.sum_alloc(s)
         for kind, ops in self.batches:
-            engine.props_alloc(kind, ops)
+            if kind < 0:
+                engine.formula_alloc(ops)
+            else:
+                engine.props_alloc(kind, ops)
 
 
 def _queens_diagonals(n: int) -> np.ndarray:
@@ -208,4 +218,87 @@ def random_arith_csp(num_vars: int = 100_000, num_props: int = 1_000_000,
     ops[:, 1, 0] = y
     ops[:, 2, 0] = z
     m.add(X_EQ_Y_PLUS_Z, ops)
+    return m
+
+
+def f_leaf(kind: int, *ops) -> list:
+    """A leaf propagator inside a formula tree: tag, then (var, off) per operand."""
+    w = [F_LEAF + kind]
+    for var, off in ops:
+        w += [int(var), int(off)]
+    return w
+
+
+def f_not(f: list) -> list:
+    return [F_NOT] + list(f)
+
+
+def f_and(*fs) -> list:
+    return [F_CONJUNCTION, len(fs)] + [w for f in fs for w in f]
+
+
+def f_or(*fs) -> list:
+    return [F_DISJUNCTION, len(fs)] + [w for f in fs for w in f]
+
+
+def f_implication(f: list, g: list) -> list:
+    """logic/mod.rs:30-35 (as written there: Disjunction[f, g.not()])."""
+    return f_or(f, f_not(g))
+
+
+def f_equivalence(f: list, g: list) -> list:
+    """logic/mod.rs:37-45."""
+    return f_and(f_implication(f, g), f_implication(g, f))
+
+
+def cumulative(starts, durations, resources, capacity, constant: bool = False) -> Model:
+    r"""`Cumulative::join` (propagators/cumulative.rs:59-114: the decomposition of Schutt et al.)
+    on the instance the reference's tests build (cumulative.rs:161-232): tasks given as
+    (lo, hi) domains; with `constant`, assigned domains become Constant views instead of
+    variables.  Allocation order of the propagators as in the reference: per task j and other
+    task i: equivalence(b_ij, s_i <= s_j /\ s_j < s_i + d_i), r_ij = b_ij * r_i; then
+    c >= r_j + sum_i r_ij."""
+    lo, hi = [], []
+
+    def alloc(d):
+        lo.append(int(d[0]))
+        hi.append(int(d[1]))
+        return (len(lo) - 1, 0)
+
+    def create(d):
+        if d[0] == d[1] and constant:
+            return (VAR_CONSTANT, int(d[0]))
+        return alloc(d)
+
+    s_ = [create(d) for d in starts]
+    d_ = [create(d) for d in durations]
+    r_ = [create(d) for d in resources]
+    r_ub = [int(d[1]) for d in resources]
+    cap = alloc(capacity)
+    tasks = len(s_)
+    m = Model(f"cumulative-{tasks}", np.zeros(0, np.int32), np.zeros(0, np.int32))
+
+    def plus(view, c):
+        return (view[0], view[1] + c)
+
+    if tasks == 1:
+        m.add(X_LESS_Y, [r_[0], plus(cap, 1)])           # c >= r[0]: x_geq_y (cmp/mod.rs:44-52)
+    else:
+        for j in range(tasks):
+            terms = []
+            for i in range(tasks):
+                if i == j:
+                    continue
+                conj = f_and(f_leaf(X_LESS_Y, s_[i], plus(s_[j], 1)),             # s[i] <= s[j]
+                             f_leaf(X_LESS_Y_PLUS_Z, s_[j], s_[i], d_[i]))        # s[j] < s[i] + d[i]
+                b = alloc((0, 1))                                                 # Boolean::new
+                m.add_formula(f_equivalence([F_BOOLEAN, b[0], 0], conj))
+                r = alloc((0, r_ub[i]))
+                m.add(X_EQ_Y_MUL_Z, [r, b, r_[i]])                                # r = b * r[i]
+                terms.append(r)
+            m.sums.append(np.array(terms, np.int32))
+            sid = len(m.sums) - 1
+            m.add(X_GREATER_Y_PLUS_Z, [plus(cap, 1), r_[j], (var_sum(sid), 0)])   # c >= r[j] + sum
+    m.lo = np.array(lo, np.int32)
+    m.hi = np.array(hi, np.int32)
     return m
