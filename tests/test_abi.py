@@ -52,3 +52,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), f
+
+
+@pytest.mark.gpu
+def test_plain_c_client_solves_nqueens_8():
+    """tests/abi_client.c (built by __graft_entry__.build()): a C program that only includes
+    include/pcp_b200.h drives example/src/nqueens.rs at N = 8 to its 92 solutions -- host-driven
+    node loop on Interval and IntervalSet domains, pcp_search_run, and two engines through
+    pcp_consistency_batch -- and sees contract violations as PCP_ERR_INVALID."""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "abi_client")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "92 solutions" in r.stdout and "pcp_search_run 92" in r.stdout and "two engines 92" in r.stdout
