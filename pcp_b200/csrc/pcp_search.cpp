@@ -10,7 +10,10 @@
 // sides -- so its timings are end-to-end timings of the boundary.
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -286,10 +289,23 @@ struct Driver {
 
 }  // namespace
 
+// A worker thread that belongs to one search: pcp_search_step_many hands it slices of nodes, so
+// that several searches (one engine, one host thread each -- the threading contract of the
+// header) advance at the same time without a thread being created per call.
+struct Worker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  bool has_job = false, done = false, quit = false;
+  uint64_t max_nodes = 0;
+  int rc = PCP_OK;
+};
+
 struct pcp_search {
   pcp_search_config cfg;
   pcp_search_result res;
   Driver d;
+  Worker* worker = nullptr;
 };
 
 extern "C" {
@@ -325,14 +341,49 @@ int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, p
   bool all_burst = true, any_burst = false;
   for (int i = 0; i < n; ++i) { all_burst &= ss[i]->d.burst; any_burst |= ss[i]->d.burst; }
   if (any_burst && !all_burst) return PCP_ERR_INVALID;
-  if (all_burst) {
-    std::vector<int> rcs((size_t)n, PCP_OK);
-    std::vector<std::thread> th;
-    for (int i = 0; i < n; ++i)
-      th.emplace_back([&, i] { rcs[(size_t)i] = pcp_search_step(ss[i], max_nodes, res ? &res[i] : nullptr); });
-    for (auto& t : th) t.join();
-    for (int rc : rcs) if (rc != PCP_OK) return rc;
-    return PCP_OK;
+  // Host-driven searches can move in lockstep on the calling thread (PCP_SEARCH_LOCKSTEP=1: one
+  // pcp_consistency_batch per round) or -- the default, like the device-resident ones -- each on
+  // its own worker thread, so that a search that needs a worklist iteration does not hold up the
+  // round and the host work of one node (post, launch, read back, branch) overlaps the others'.
+  static const bool lockstep = [] { const char* v = std::getenv("PCP_SEARCH_LOCKSTEP"); return v && v[0] == '1'; }();
+  if (all_burst || (!lockstep && n > 1)) {
+    for (int i = 0; i < n; ++i) {
+      pcp_search* s = ss[i];
+      if (!s->worker) {
+        s->worker = new Worker();
+        Worker* w = s->worker;
+        w->th = std::thread([s, w] {
+          std::unique_lock<std::mutex> lk(w->mu);
+          while (true) {
+            w->cv.wait(lk, [w] { return w->has_job || w->quit; });
+            if (w->quit) return;
+            w->has_job = false;
+            const uint64_t budget_w = w->max_nodes;
+            lk.unlock();
+            const int rc = pcp_search_step(s, budget_w, nullptr);
+            lk.lock();
+            w->rc = rc;
+            w->done = true;
+            w->cv.notify_all();
+          }
+        });
+      }
+      Worker* w = s->worker;
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->max_nodes = max_nodes;
+      w->done = false;
+      w->has_job = true;
+      w->cv.notify_all();
+    }
+    int rc = PCP_OK;
+    for (int i = 0; i < n; ++i) {
+      Worker* w = ss[i]->worker;
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv.wait(lk, [w] { return w->done; });
+      if (w->rc != PCP_OK && rc == PCP_OK) rc = w->rc;
+      if (res) res[i] = ss[i]->res;
+    }
+    return rc;
   }
   std::vector<uint64_t> start((size_t)n);
   std::vector<char> done((size_t)n, 0);
@@ -410,6 +461,11 @@ int pcp_search_set_incumbent(pcp_search* s, int32_t value) {
 
 void pcp_search_close(pcp_search* s) {
   if (!s) return;
+  if (s->worker) {
+    { std::lock_guard<std::mutex> lk(s->worker->mu); s->worker->quit = true; s->worker->cv.notify_all(); }
+    s->worker->th.join();
+    delete s->worker;
+  }
   if (s->d.burst_begun) pcp_internal_burst_end(s->d.e);  // the engine goes back to the search root
   delete s;
 }
