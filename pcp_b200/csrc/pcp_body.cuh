@@ -1894,12 +1894,27 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
     if (iter > 0 && blockIdx.x == 0)
       for (int w = threadIdx.x; w < W; w += blockDim.x) P.dirty_bits[(size_t)spare_buf * W + w] = 0u;
 
+    // Incremental launch (no schedule-everything sweep): the variables of the posted propagators go
+    // straight into the worklist of THIS iteration -- every CTA has applied the posted propagators to
+    // its own view, so the rows can be expanded at once instead of after a first barrier (one
+    // iteration per node instead of two when nothing else moves).  Only for posted binary
+    // propagators over plain / constant operands in a store without n-ary propagators (those find
+    // their dirty operands in the shared bit set).
+    bool posted_rows = false;
+    if (iter == 0 && !full_sweep && !seeded && n_inline > 0 && P.n_nary == 0) {
+      posted_rows = true;
+      for (int i = 0; i < n_inline; ++i)
+        posted_rows = posted_rows && inl[i].fam == F_BIN && dec_var28((unsigned)inl[i].q[0].x) >= -1 && inl[i].q[0].z >= -1;
+#ifdef PCP_SET
+      for (int i = 0; i < n_inline; ++i) posted_rows = posted_rows && ((unsigned)inl[i].q[0].x >> 28) == B_LESS;
+#endif
+    }
     if (iter == 0 && n_inline > 0) {
       // Propagators posted since the last node.  With a full sweep ahead they need not enter
       // the worklist: every CTA applies them to its own view of the domains first, so the sweep
       // already sees their effect.
       if (threadIdx.x == 0) {
-        c.mark_dirty = !full_sweep;
+        c.mark_dirty = !full_sweep && !posted_rows;
 #ifdef PCP_SET
         // A posted XLessY (what BinarySplit and BranchAndBound post) only moves bounds, which every
         // CTA applies to its own snapshot; anything else may clear bits of the shared sets behind the
@@ -1932,8 +1947,28 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
     // between expanding their rows and sweeping again.
     int n_dirty = 0;
     bool sweep_now = iter == 0 && full_sweep, skip = false;
-    if (iter > 0 || (!full_sweep && seeded)) {
-      n_dirty = dirty_compact(cur_bits, W, list, kListCap);
+    if (iter > 0 || (!full_sweep && (seeded || posted_rows))) {
+      n_dirty = (iter > 0 || seeded) ? dirty_compact(cur_bits, W, list, kListCap) : 0;
+      const int n_refresh = n_dirty;  // (the posted variables appended below are current in every CTA's own view)
+      if (posted_rows && n_dirty + 2 * kMaxInline <= kListCap) {
+        __shared__ int s_nd;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int n = n_dirty;
+          for (int i = 0; i < n_inline; ++i) {
+            const int vs[2] = {dec_var28((unsigned)inl[i].q[0].x), inl[i].q[0].z};
+            for (int q = 0; q < 2; ++q) {
+              if (vs[q] < 0) continue;
+              bool have = false;
+              for (int j = 0; j < n; ++j) have |= list[j] == vs[q];
+              if (!have) list[n++] = vs[q];
+            }
+          }
+          s_nd = n;
+        }
+        __syncthreads();
+        n_dirty = s_nd;
+      }
       trace_mark1(P, iter, 1);
       // many dirty variables: their CSR rows cover most of the store, and a streaming sweep is
       // cheaper than gathering the rows
@@ -1956,7 +1991,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
       } else {
         const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
         const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
-        for (int i = r0; i < n_dirty; i += rs) {
+        for (int i = r0; i < n_refresh; i += rs) {
           int v = list[i];
           int2 d = ldcg_dom(&P.dom[v]);
 #ifdef PCP_SET
@@ -1965,6 +2000,17 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
           if (SMEM) st.sdom[v] = d;
           bad |= d.x > d.y;
         }
+      }
+      if (SMEM && posted_rows && sweep_now) {
+        // the whole snapshot was just re-read from the store, where CTA 0's application of the posted
+        // propagators may not have landed yet: apply them to this CTA's view again
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          c.local = true; c.bookkeep = false; c.mark_dirty = false;
+          for (int i = 0; i < n_inline; ++i) eval_full<true>(c, inl[i].fam, inl[i].slot, inl[i].q[0], inl[i].q[1], inl[i].q[2]);
+          c.local = false; c.bookkeep = true; c.mark_dirty = true;
+        }
+        __syncthreads();
       }
       if (__syncthreads_or(bad)) {
         // failed: with a snapshot every CTA sees it and the iteration's work is skipped
