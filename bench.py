@@ -242,12 +242,15 @@ def run_ours(args):
     def contexts(k, mdl=None, **kw):
         """k engines of this rank, each entered into its own frontier subtree (rank-major slices of
         the same breadth-first frontier on every rank)."""
-        engines = [fresh_engine(mdl, **kw) for _ in range(k)]
+        first = fresh_engine(mdl, **kw)
         parts = world * k
-        paths = parallel.expand_frontier(engines[0], parts=parts) if parts > 1 else [[]]
+        paths = parallel.expand_frontier(first, parts=parts) if parts > 1 else [[]]
+        if parts == 1:
+            first.consistency()
+        # the other contexts are forks of the first one at the root fixpoint: one upload and one reactor
+        # build of the model, its static part shared on the device (pcp_engine_fork)
+        engines = [first] + [first.fork() for _ in range(k - 1)]
         for i, e in enumerate(engines):
-            if i:
-                e.consistency()
             if k > 1:
                 e.set_grid_limit(max(2, sms // k))
             root = e.label()

@@ -110,6 +110,16 @@ typedef struct pcp_stats {
 
 int pcp_engine_create(const pcp_config* cfg, pcp_engine** out);
 void pcp_engine_destroy(pcp_engine* e);
+/* A second (vstore, cstore) pair over the same model: `Space::clone` without copying the model.  The
+ * new engine starts from the parent's current state (domains, propagators, `active` set; no labels)
+ * and shares the parent's immutable static part -- descriptors, reactor CSR -- on the device; tail,
+ * domains, `active` set, trail and label stack are its own.  For the K subtree contexts of one GPU
+ * (pcp_consistency_batch, pcp_search_step_many) this replaces K uploads and K reactor builds of the
+ * same model by one, and keeps one copy of the descriptors in L2.  An engine that has to rebuild
+ * its reactor (tail_limit reached) or is restored to a label older than the shared part lets go
+ * of the shared block and uploads its own copy.  Call after the first pcp_consistency (the
+ * reactor is built there); not while a search is open. */
+int pcp_engine_fork(pcp_engine* parent, pcp_engine** out);
 const char* pcp_last_error(const pcp_engine* e);
 int pcp_set_timing(pcp_engine* e, int32_t enabled);
 /* Several engines can run their fixpoints side by side on one GPU (independent subtrees of one

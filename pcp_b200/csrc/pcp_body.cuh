@@ -1633,9 +1633,10 @@ __device__ __forceinline__ void node_prologue(const Params& P, int tid, int nth)
   if (tid < P.n_inline) {
     const InlineProp& ip = P.inl[tid];
     const Family& f = P.fam[ip.fam];
-    if (ip.fam == F_BIN) f.desc[ip.slot] = ip.q[0];
-    else if (ip.fam == F_TER) { f.desc[ip.slot] = ip.q[0]; f.descB[ip.slot] = make_int2(ip.q[1].x, ip.q[1].y); }
-    else { f.desc[3 * (size_t)ip.slot] = ip.q[0]; f.desc[3 * (size_t)ip.slot + 1] = ip.q[1]; f.desc[3 * (size_t)ip.slot + 2] = ip.q[2]; }
+    // (freshly posted propagators are tail slots)
+    if (ip.fam == F_BIN) f.tdesc[ip.slot] = ip.q[0];
+    else if (ip.fam == F_TER) { f.tdesc[ip.slot] = ip.q[0]; f.tdescB[ip.slot] = make_int2(ip.q[1].x, ip.q[1].y); }
+    else { f.tdesc[3 * (size_t)ip.slot] = ip.q[0]; f.tdesc[3 * (size_t)ip.slot + 1] = ip.q[1]; f.tdesc[3 * (size_t)ip.slot + 2] = ip.q[2]; }
   }
 }
 __device__ __forceinline__ void node_prologue_finish(const Params& P) {
@@ -2380,7 +2381,7 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
     else {
       int4 d = br.w == 0 ? make_int4((int)((B_LESS << 28) | (unsigned)br.y), 0, -1, br.z + 1)    // x <= val
                          : make_int4((int)((B_LESS << 28) | kConstVar28), br.z, br.y, 0);         // val < x
-      P.fam[F_BIN].desc[slot] = d;
+      P.fam[F_BIN].tdesc[slot] = d;
       atomicOr(&P.fam[F_BIN].active[slot >> 5], 1u << (slot & 31));
       bc->inl_desc = d;
       bc->inl_slot = slot;

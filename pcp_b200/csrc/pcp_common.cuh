@@ -87,6 +87,12 @@ static_assert(sizeof(Result) == 64, "Result header is 64 bytes");
 struct Family {
   int4* desc;           // BIN: 1 int4/prop; TER: int4 (x,y) plane; DJ: 3 int4/prop
   int2* descB;          // TER: (z) plane
+  // The descriptors of the tail (slots >= n_static: branching constraints and whatever was posted
+  // after the reactor CSR was built), indexed by slot like `desc`.  The same arrays as desc / descB
+  // unless the static part is shared with other engines (pcp_engine_fork): then the tail is this
+  // engine's own array, biased so that tdesc[slot * width] is slot's descriptor.
+  int4* tdesc;
+  int2* tdescB;
   uint32_t* active;     // bit set, 1 = active (propagation/store.rs:34)
   uint32_t* stamp;      // epoch of the last worklist evaluation
   int n;                // allocated propagators

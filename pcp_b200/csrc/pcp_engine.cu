@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -70,6 +71,7 @@ struct DevBuf {
     if (n <= cap) return;
     size_t ncap = std::max<size_t>(n, cap + cap / 2 + 64);
     T* q = nullptr;
+    if (std::getenv("PCP_DEBUG_ALLOC")) std::fprintf(stderr, "[pcp alloc] %zu -> %zu elements of %zu bytes\n", cap, ncap, sizeof(T));
     CUDA_CHECK(cudaMalloc(&q, (ncap + kPad) * sizeof(T)));
     try {
       CUDA_CHECK(cudaMemsetAsync(q + ncap, 0, kPad * sizeof(T), st));
@@ -98,12 +100,29 @@ struct HostFamily {
   size_t first_nonplain = SIZE_MAX;  // first descriptor with a Constant / Sum operand (lean sweep variant)
   int kind_mask = 0;                 // kinds ever allocated in this family
   int static_kind_mask = 0;          // ... among the descriptors covered by the CSR (over-approximation)
-  DevBuf<int4> d_desc;
+  DevBuf<int4> d_desc;      // static part + tail; a *view* into StaticBlock when the engine shares its static model
   DevBuf<int2> d_descB;
+  DevBuf<int4> d_tdesc;     // shared static model only: this engine's tail, slot s at [(s - tail_base) * width]
+  DevBuf<int2> d_tdescB;
+  size_t tail_base = 0;     // first slot of d_tdesc (= n_static when the static part became shared)
   DevBuf<uint2> d_cdesc;    // BIN only: compact 8-byte copies of the static descriptors (see build_csr)
   size_t n_cdesc = 0;       // descriptors covered by d_cdesc (0: none / not compactable)
   DevBuf<uint32_t> d_active, d_stamp;
   int width = 1;
+};
+
+// The immutable part of a loaded model -- static descriptors, compact stream, reactor CSR -- once it
+// is shared between engines (pcp_engine_fork): freed with the last engine that refers to it.
+struct StaticBlock {
+  DevBuf<int4> desc[3];
+  DevBuf<int2> descB;
+  DevBuf<uint2> cdesc;
+  DevBuf<int> adj_ptr;
+  DevBuf<uint32_t> adj;
+  ~StaticBlock() {
+    for (auto& d : desc) d.free();
+    descB.free(); cdesc.free(); adj_ptr.free(); adj.free();
+  }
 };
 
 struct LabelRec {
@@ -174,8 +193,9 @@ struct pcp_engine {
   size_t sums_uploaded = 0;
 
   // reactor CSR
-  DevBuf<int> d_adj_ptr;
+  DevBuf<int> d_adj_ptr;            // (views into `shared` when set)
   DevBuf<uint32_t> d_adj;
+  std::shared_ptr<StaticBlock> shared;  // the static model is shared with other engines (pcp_engine_fork)
   bool csr_built = false;
   size_t tail_limit = 4096;
 
@@ -474,7 +494,11 @@ void append_prop(pcp_engine* e, int kind, const pcp_operand* raw, int n_ops) {
   }
 }
 
+void unshare_static(pcp_engine* e);
 void truncate_props(pcp_engine* e, const LabelRec& r) {
+  if (e->shared)
+    for (int f = 0; f < 3; ++f)
+      if (r.n_fam[f] < e->fam[f].tail_base) { unshare_static(e); break; }
   for (int f = 0; f < 3; ++f) {
     HostFamily& hf = e->fam[f];
     hf.n = r.n_fam[f];
@@ -496,10 +520,49 @@ void truncate_props(pcp_engine* e, const LabelRec& r) {
   e->prop_ref.resize(r.n_props);
 }
 
+// pcp_engine_fork: the static arrays move into a refcounted block; this engine keeps views of them
+// and puts its tail (everything at and behind n_static) into arrays of its own.
+void share_static(pcp_engine* e) {
+  if (e->shared) return;
+  auto blk = std::make_shared<StaticBlock>();
+  for (int f = 0; f < 3; ++f) {
+    HostFamily& hf = e->fam[f];
+    blk->desc[f] = hf.d_desc;  // (plain structs: pointer + capacity; the block owns them from here on)
+    hf.tail_base = hf.n_static;
+    hf.uploaded = std::min(hf.uploaded, hf.n_static);  // the tail is uploaded again, into d_tdesc
+  }
+  blk->descB = e->fam[F_TER].d_descB;
+  blk->cdesc = e->fam[F_BIN].d_cdesc;
+  blk->adj_ptr = e->d_adj_ptr;
+  blk->adj = e->d_adj;
+  e->shared = blk;
+}
+// Before anything that rewrites the static part (CSR rebuild, a restore below the shared prefix):
+// let go of the shared block and upload everything again into arrays of this engine's own.
+void unshare_static(pcp_engine* e) {
+  if (!e->shared) return;
+  e->shared.reset();
+  for (int f = 0; f < 3; ++f) {
+    HostFamily& hf = e->fam[f];
+    hf.d_desc = DevBuf<int4>();
+    hf.d_descB = DevBuf<int2>();
+    hf.d_cdesc = DevBuf<uint2>();
+    hf.uploaded = 0;
+    hf.n_static = 0;
+    hf.n_cdesc = 0;
+    hf.tail_base = 0;
+  }
+  e->d_adj_ptr = DevBuf<int>();
+  e->d_adj = DevBuf<uint32_t>();
+  e->csr_built = false;
+  e->at_fixpoint = false;
+}
+
 // Static reactor: CSR var -> refs of the propagators that depend on it, rows grouped by
 // family (so the lanes of a warp expanding a row stay on one code path).
 void build_csr(pcp_engine* e) {
   const size_t V = e->V;
+  if (std::getenv("PCP_DEBUG_ALLOC")) std::fprintf(stderr, "[pcp csr] build V=%zu\n", V);
   std::vector<int> ptr(V + 1, 0);
   // dependencies of one lowered operand: the variable itself, or every term of a sum view
   auto dep = [&](int var, unsigned ref, auto&& fn) { for_each_dep_var(e, var, [&](int v) { fn(v, ref); }); };
@@ -641,13 +704,31 @@ Params prepare(pcp_engine* e) {
   size_t tail = 0, pending = 0;
   for (int f = 0; f < 3; ++f) { tail += e->fam[f].n - e->fam[f].n_static; pending += e->fam[f].n - e->fam[f].uploaded; }
   const bool rebuild = (!e->csr_built && tail > 0) || tail > e->tail_limit;
+  if (rebuild && e->shared) {  // the static part is about to change: no longer the shared one
+    unshare_static(e);
+    pending = 0;
+    for (int f = 0; f < 3; ++f) pending += e->fam[f].n;
+  }
   // --- descriptors
   const bool use_inline = !rebuild && pending > 0 && pending <= (size_t)kMaxInline;
   size_t total = 0;
   for (int f = 0; f < 3; ++f) {
     HostFamily& hf = e->fam[f];
     const size_t w = (size_t)hf.width;
-    if (use_inline) {
+    if (e->shared) {
+      // shared static model: the tail [tail_base, n) lives in this engine's own arrays
+      const size_t t0 = hf.tail_base, have = hf.uploaded - t0, need = hf.n - t0;
+      if (need * w > hf.d_tdesc.cap) hf.d_tdesc.reserve((need + e->tail_limit) * w, e->stream, have * w);
+      if (f == F_TER && need > hf.d_tdescB.cap) hf.d_tdescB.reserve(need + e->tail_limit, e->stream, have);
+      if (!use_inline && need > have) {
+        CUDA_CHECK(cudaMemcpyAsync(hf.d_tdesc.p + have * w, hf.desc.data() + hf.uploaded * w, (need - have) * w * sizeof(int4),
+                                   cudaMemcpyHostToDevice, e->stream));
+        if (f == F_TER)
+          CUDA_CHECK(cudaMemcpyAsync(hf.d_tdescB.p + have, hf.descB.data() + hf.uploaded, (need - have) * sizeof(int2),
+                                     cudaMemcpyHostToDevice, e->stream));
+        CUDA_CHECK(cudaStreamSynchronize(e->stream));  // pageable source
+      }
+    } else if (use_inline) {
       if (hf.desc.size() > hf.d_desc.cap) hf.d_desc.reserve(hf.desc.size() + e->tail_limit * w, e->stream, hf.uploaded * w);
       if (f == F_TER && hf.descB.size() > hf.d_descB.cap) hf.d_descB.reserve(hf.descB.size() + e->tail_limit, e->stream, hf.uploaded);
     } else {
@@ -663,8 +744,10 @@ Params prepare(pcp_engine* e) {
       hf.d_stamp.reserve(hf.n + e->tail_limit, e->stream, valid);
       fill_u32(e, hf.d_stamp.p + valid, 0u, hf.d_stamp.cap - valid);
     }
-    if (!hf.d_desc.p) hf.d_desc.reserve(1, e->stream);
-    if (!hf.d_descB.p) hf.d_descB.reserve(1, e->stream);
+    if (!hf.d_desc.p && !e->shared) hf.d_desc.reserve(1, e->stream);
+    if (!hf.d_descB.p && !e->shared) hf.d_descB.reserve(1, e->stream);
+    if (e->shared && !hf.d_tdesc.p) hf.d_tdesc.reserve(1, e->stream);
+    if (e->shared && !hf.d_tdescB.p) hf.d_tdescB.reserve(1, e->stream);
     if (!hf.d_stamp.p) { hf.d_stamp.reserve(1, e->stream); fill_u32(e, hf.d_stamp.p, 0u, hf.d_stamp.cap); }
     total += hf.n;
   }
@@ -729,6 +812,8 @@ Params prepare(pcp_engine* e) {
     HostFamily& hf = e->fam[f];
     df.desc = hf.d_desc.p;
     df.descB = hf.d_descB.p;
+    df.tdesc = e->shared ? hf.d_tdesc.p - (ptrdiff_t)(hf.tail_base * (size_t)hf.width) : hf.d_desc.p;
+    df.tdescB = e->shared ? hf.d_tdescB.p - (ptrdiff_t)hf.tail_base : hf.d_descB.p;
     df.active = hf.d_active.p;
     df.stamp = hf.d_stamp.p;
     df.n = (int)hf.n;
@@ -1212,13 +1297,142 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
   return PCP_OK;
 }
 
+int pcp_engine_fork(pcp_engine* parent, pcp_engine** out) {
+  if (!parent || !out) return PCP_ERR_INVALID;
+  *out = nullptr;
+  // bring the parent's device state up to date, then share its static model
+  int rc = guarded(parent, [&] {
+    PCP_REQUIRE_NO_BURST(parent);
+    PCP_REQUIRE(!parent->inflight.active, "a fixpoint of this engine is in flight");
+    CUDA_CHECK(cudaSetDevice(parent->device));
+    sync_device_state(parent);
+    if (!parent->csr_built) {  // the reactor is built by the first fixpoint: run the prologue path that builds it
+      size_t tail = 0;
+      for (int f = 0; f < 3; ++f) tail += parent->fam[f].n - parent->fam[f].n_static;
+      PCP_REQUIRE(tail == 0, "fork before the first pcp_consistency of a store with propagators");
+    }
+    CUDA_CHECK(cudaStreamSynchronize(parent->stream));
+    share_static(parent);
+  });
+  if (rc != PCP_OK) return rc;
+  pcp_engine* e = new pcp_engine();
+  rc = guarded(e, [&] {
+    const pcp_engine* p = parent;
+    e->device = p->device;
+    e->flags = p->flags;
+    e->set_mode = p->set_mode;
+    e->set_base = p->set_base;
+    e->set_W = p->set_W;
+    e->max_labels = p->max_labels;
+    e->tail_limit = p->tail_limit;
+    e->num_sms = p->num_sms;
+    e->max_smem_optin = p->max_smem_optin;
+    e->static_smem = p->static_smem;
+    e->max_iterations = p->max_iterations;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreate(&e->ev0));
+    CUDA_CHECK(cudaEventCreate(&e->ev1));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreate(&e->ev_batch0));
+    CUDA_CHECK(cudaEventCreate(&e->ev_batch1));
+    stage(e, 1 << 16);
+    // ---- variables: the parent's current domains (and bit sets)
+    e->V = e->V_uploaded = p->V;
+    e->h_dom_init = p->h_dom_init;
+    ensure_var_capacity(e, std::max<size_t>(e->V, 1));
+    if (e->V) CUDA_CHECK(cudaMemcpyAsync(e->d_dom(), p->d_dom(), e->V * sizeof(int2), cudaMemcpyDeviceToDevice, e->stream));
+    if (e->set_mode && e->V) {
+      e->d_bits.reserve(e->V * (size_t)e->set_W, e->stream);
+      CUDA_CHECK(cudaMemcpyAsync(e->d_bits.p, p->d_bits.p, e->V * (size_t)e->set_W * 4, cudaMemcpyDeviceToDevice, e->stream));
+    }
+    e->dirty_words = p->dirty_words;
+    e->d_dirty_bits.reserve(std::max<size_t>(3 * e->dirty_words, 1), e->stream);
+    CUDA_CHECK(cudaMemsetAsync(e->d_dirty_bits.p, 0, e->d_dirty_bits.cap * sizeof(uint32_t), e->stream));
+    e->stack_stride = e->slot_stride();
+    // ---- propagators: host descriptors copied, static device arrays shared, tail / active / stamps own
+    e->shared = p->shared;
+    for (int f = 0; f < 3; ++f) {
+      const HostFamily& pf = p->fam[f];
+      HostFamily& hf = e->fam[f];
+      hf.desc = pf.desc;
+      hf.descB = pf.descB;
+      hf.n = pf.n;
+      hf.n_static = pf.n_static;
+      hf.tail_base = pf.tail_base;
+      hf.uploaded = pf.tail_base;          // this engine's tail is uploaded by its first prepare()
+      hf.active_set = pf.active_set;
+      hf.first_nonplain = pf.first_nonplain;
+      hf.kind_mask = pf.kind_mask;
+      hf.static_kind_mask = pf.static_kind_mask;
+      hf.width = pf.width;
+      hf.n_cdesc = pf.n_cdesc;
+      hf.d_desc = pf.d_desc;               // views of the shared block
+      hf.d_descB = pf.d_descB;
+      hf.d_cdesc = pf.d_cdesc;
+      const size_t words = (hf.n + e->tail_limit + 31) / 32 + 2;
+      hf.d_active.reserve(words, e->stream);
+      fill_u32(e, hf.d_active.p, 0u, hf.d_active.cap);
+      const size_t pw = std::min(words, (pf.active_set + 31) / 32);
+      if (pw) CUDA_CHECK(cudaMemcpyAsync(hf.d_active.p, pf.d_active.p, pw * 4, cudaMemcpyDeviceToDevice, e->stream));
+      hf.d_stamp.reserve(hf.n + e->tail_limit + 1, e->stream);
+      fill_u32(e, hf.d_stamp.p, 0u, hf.d_stamp.cap);
+    }
+    e->d_adj_ptr = p->d_adj_ptr;
+    e->d_adj = p->d_adj;
+    e->csr_built = p->csr_built;
+    e->h_nary_ptr = p->h_nary_ptr;
+    e->h_nary_ops = p->h_nary_ops;
+    e->h_nary_kind = p->h_nary_kind;
+    e->h_tree_ptr = p->h_tree_ptr;
+    e->h_tree_nodes = p->h_tree_nodes;
+    e->n_nary = p->n_nary;
+    e->nary_max_k = p->nary_max_k;
+    e->nary_uploaded = 0;                  // small arrays: uploaded again by the first prepare()
+    e->nary_active_set = p->nary_active_set;
+    e->d_nary_active.reserve((e->n_nary + 31) / 32 + 1, e->stream);
+    fill_u32(e, e->d_nary_active.p, 0u, e->d_nary_active.cap);
+    if (p->nary_active_set)
+      CUDA_CHECK(cudaMemcpyAsync(e->d_nary_active.p, p->d_nary_active.p, ((p->nary_active_set + 31) / 32) * 4, cudaMemcpyDeviceToDevice, e->stream));
+    e->prop_ref = p->prop_ref;
+    e->sums = p->sums;
+    e->h_sum_ptr = p->h_sum_ptr;
+    e->h_sum_terms = p->h_sum_terms;
+    e->sums_uploaded = 0;
+    // ---- trail and control block
+    e->trail_len = p->trail_len;
+    e->d_trail.reserve(e->num_props() + e->tail_limit + 64, e->stream);
+    if (e->trail_len) CUDA_CHECK(cudaMemcpyAsync(e->d_trail.p, p->d_trail.p, (size_t)e->trail_len * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CUDA_CHECK(cudaMalloc(&e->d_ctl, sizeof(Control)));
+    Control c;
+    std::memset(&c, 0, sizeof(c));
+    c.epoch = 1;
+    c.trail_cnt = e->trail_len;
+    CUDA_CHECK(cudaMemcpyAsync(e->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    e->at_fixpoint = p->at_fixpoint;
+    e->mirror_valid = false;
+    e->grid_limit = p->grid_limit;
+    e->timing = p->timing;
+  });
+  if (rc != PCP_OK) {
+    parent->err = e->err;
+    pcp_engine_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return PCP_OK;
+}
+
 void pcp_engine_destroy(pcp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (int f = 0; f < 3; ++f) {
-    e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_cdesc.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
+    if (!e->shared) { e->fam[f].d_desc.free(); e->fam[f].d_descB.free(); e->fam[f].d_cdesc.free(); }  // (else: views of the shared block)
+    e->fam[f].d_tdesc.free(); e->fam[f].d_tdescB.free(); e->fam[f].d_active.free(); e->fam[f].d_stamp.free();
   }
+  if (e->shared) { e->d_adj_ptr = DevBuf<int>(); e->d_adj = DevBuf<uint32_t>(); e->shared.reset(); }
   e->d_nary_ptr.free(); e->d_nary_ops.free(); e->d_nary_kind.free(); e->d_nary_active.free();
   e->d_tree_ptr.free(); e->d_tree_nodes.free();
   e->d_adj_ptr.free(); e->d_adj.free(); e->d_sum_ptr.free(); e->d_sum_terms.free();
@@ -1707,7 +1921,8 @@ int pcp_label(pcp_engine* e, uint64_t* label) {
       sync_device_state(e);
       if (e->stack_stride != e->slot_stride()) { PCP_REQUIRE(e->labels.empty(), "variables allocated while labels are live"); e->stack_stride = e->slot_stride(); }
       if ((idx + 1) * std::max<size_t>(e->stack_stride, 1) > e->d_stack.cap)  // grow in big steps: a reallocation copies the stack
-        e->d_stack.reserve(std::max<size_t>((idx + 1) * 2, 16) * std::max<size_t>(e->stack_stride, 1), e->stream, idx * e->stack_stride);
+        e->d_stack.reserve(std::max<size_t>((idx + 1) * 2, std::min<size_t>(e->max_labels, 256)) * std::max<size_t>(e->stack_stride, 1),
+                           e->stream, idx * e->stack_stride);
       if (e->V)
         CUDA_CHECK(cudaMemcpyAsync(e->d_stack.p + idx * e->stack_stride, e->d_dom(), e->V * sizeof(int2),
                                    cudaMemcpyDeviceToDevice, e->stream));
@@ -1796,7 +2011,12 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
     e->d_stack.reserve((size_t)b.max_labels * V, e->stream, e->labels.size() * V);
     HostFamily& hb = e->fam[F_BIN];
     b.bin_cap = (int)(hb.n + depth);
-    hb.d_desc.reserve((size_t)b.bin_cap, e->stream, hb.n);
+    if (e->shared) {
+      const size_t t0 = hb.tail_base;
+      if ((size_t)b.bin_cap - t0 > hb.d_tdesc.cap) hb.d_tdesc.reserve((size_t)b.bin_cap - t0, e->stream, hb.n - t0);
+    } else {
+      hb.d_desc.reserve((size_t)b.bin_cap, e->stream, hb.n);
+    }
     reserve_zeroed(e, hb.d_active, ((size_t)b.bin_cap + 31) / 32 + 1, (hb.active_set + 31) / 32 + 1);
     if ((size_t)b.bin_cap > hb.d_stamp.cap) {
       size_t valid = std::min(hb.d_stamp.cap, hb.n);
@@ -1979,7 +2199,8 @@ int pcp_internal_burst_end(pcp_engine* e) {
     }
     if ((size_t)bc.bin_n > hb.n) {
       std::vector<int4> tail((size_t)bc.bin_n - hb.n);
-      CUDA_CHECK(cudaMemcpy(tail.data(), hb.d_desc.p + hb.n, tail.size() * sizeof(int4), cudaMemcpyDeviceToHost));
+      const int4* src = e->shared ? hb.d_tdesc.p + (hb.n - hb.tail_base) : hb.d_desc.p + hb.n;
+      CUDA_CHECK(cudaMemcpy(tail.data(), src, tail.size() * sizeof(int4), cudaMemcpyDeviceToHost));
       for (const int4& d : tail) {
         hb.desc.push_back(d);
         e->prop_ref.push_back(make_ref(F_BIN, (unsigned)hb.n++));

@@ -600,14 +600,15 @@ __device__ __forceinline__ void eval_full(const Ctx& c, unsigned fam, int slot, 
 __device__ __forceinline__ void load_desc(const Family& f, unsigned fam, int slot, int4& q0, int4& q1, int4& q2) {
   q1 = make_int4(0, 0, 0, 0);
   q2 = q1;
+  const int4* desc = slot < f.n_static ? f.desc : f.tdesc;  // (a shared static part keeps the tail apart)
   if (fam == F_BIN) {
-    q0 = __ldg(&f.desc[slot]);
+    q0 = __ldg(&desc[slot]);
   } else if (fam == F_TER) {
-    q0 = __ldg(&f.desc[slot]);
-    int2 b = __ldg(&f.descB[slot]);
+    q0 = __ldg(&desc[slot]);
+    int2 b = __ldg(&(slot < f.n_static ? f.descB : f.tdescB)[slot]);
     q1.x = b.x; q1.y = b.y;
   } else {
-    const int4* q = &f.desc[3 * (size_t)slot];
+    const int4* q = &desc[3 * (size_t)slot];
     q0 = __ldg(q); q1 = __ldg(q + 1); q2 = __ldg(q + 2);
   }
 }

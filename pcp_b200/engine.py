@@ -21,7 +21,7 @@ FLAG_INTERVAL_SET = 4
 
 # every symbol include/pcp_b200.h declares
 ABI_SYMBOLS = [
-    "pcp_engine_create", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_set_grid_limit", "pcp_stream", "pcp_vars_alloc",
+    "pcp_engine_create", "pcp_engine_fork", "pcp_engine_destroy", "pcp_last_error", "pcp_set_timing", "pcp_set_grid_limit", "pcp_stream", "pcp_vars_alloc",
     "pcp_sum_alloc", "pcp_prop_alloc", "pcp_props_alloc", "pcp_formula_alloc", "pcp_consistency", "pcp_consistency_batch", "pcp_domains_read",
     "pcp_domains_size_read", "pcp_domains_read_bits",
     "pcp_var_update", "pcp_active_read", "pcp_label", "pcp_restore", "pcp_num_vars", "pcp_num_props",
@@ -44,6 +44,8 @@ def load_library() -> C.CDLL:
         bind(lib, "pcp_")
         lib.pcp_engine_create.restype = C.c_int
         lib.pcp_engine_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+        lib.pcp_engine_fork.restype = C.c_int
+        lib.pcp_engine_fork.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         lib.pcp_set_timing.restype = C.c_int
         lib.pcp_set_timing.argtypes = [C.c_void_p, C.c_int32]
         lib.pcp_set_grid_limit.restype = C.c_int
@@ -86,6 +88,16 @@ class Engine(EngineBase):
         self._h = h
         if timing:
             self.set_timing(True)
+
+    def fork(self) -> "Engine":
+        """pcp_engine_fork: another (vstore, cstore) pair in this engine's current state that shares
+        the static model (descriptors, reactor) on the device."""
+        child = Engine.__new__(Engine)
+        child._lib = self._lib
+        h = C.c_void_p()
+        self._check(self._lib.pcp_engine_fork(self._h, C.byref(h)))
+        child._h = h
+        return child
 
     def set_timing(self, enabled: bool) -> None:
         self._check(self._lib.pcp_set_timing(self._h, int(enabled)))

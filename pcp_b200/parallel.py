@@ -210,19 +210,29 @@ class SubtreeContexts:
     one node with the sweeps of the others.  Every context is an ordinary (vstore, cstore) pair
     behind the C ABI -- per-node results are exactly those of a lone engine on that subtree."""
 
-    def __init__(self, make_engine, model, k: int, paths: Sequence[List[Decision]] = None, device_sms: int = 148):
-        self.engines = []
+    def __init__(self, make_engine, model, k: int, paths: Sequence[List[Decision]] = None, device_sms: int = 148,
+                 fork: bool = True):
+        """`make_engine()` creates the first engine; the others are `fork()`s of it at the root
+        fixpoint (one upload and one reactor build of the model, static part shared on the
+        device) unless `fork=False` (every context loads the model itself)."""
+        first = make_engine()
+        model.load_into(first)
+        frontier = list(paths) if paths is not None else (expand_frontier(first, parts=k) if k > 1 else [[]])
+        if paths is not None or k == 1:
+            first.consistency()  # builds the reactor CSR, uploads the store
+        self.engines = [first]
+        for i in range(1, k):
+            if fork and hasattr(first, "fork"):
+                e = first.fork()
+            else:
+                e = make_engine()
+                model.load_into(e)
+                e.consistency()
+            self.engines.append(e)
         self.paths = []
-        for i in range(k):
-            e = make_engine()
-            model.load_into(e)
+        for i, e in enumerate(self.engines):
             if k > 1:
                 e.set_grid_limit(max(2, device_sms // k))
-            self.engines.append(e)
-        frontier = list(paths) if paths is not None else expand_frontier(self.engines[0], parts=k)
-        for i, e in enumerate(self.engines):
-            if i or paths is not None:
-                e.consistency()  # builds the reactor CSR, uploads the store
             root = e.label()
             path = frontier[i % len(frontier)]
             enter_subtree(e, root, path)

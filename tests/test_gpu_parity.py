@@ -713,6 +713,65 @@ def test_consistency_batch_matches_lone_engines(k):
         assert all(s.propagations > 0 for s in stats)
 
 
+def test_fork_shares_the_static_model_and_lets_go_of_it():
+    """pcp_engine_fork: the child starts in the parent's state and shares its descriptors and
+    reactor on the device; both then go their own way (own tail, domains, `active`, trail, labels).
+    An engine that must rewrite its static part -- reactor rebuild when the tail limit is reached,
+    restore to a label older than the shared prefix -- lets go of the shared block; the other keeps
+    working on it.  Every engine against its own oracle after every step."""
+    from pcp_b200 import parallel
+    m = models.nqueens(40)
+    parent, po = _engine(tail_limit=6), _oracle(2)
+    early = None
+    for e in (parent, po):
+        e.vars_alloc(m.lo, m.hi)
+        e.props_alloc(*m.batches[0][:1], m.batches[0][1][:10])      # ten propagators, then a label
+    early = (parent.label(), po.label())
+    for e in (parent, po):
+        e.props_alloc(m.batches[0][0], m.batches[0][1][10:])
+        e.props_alloc(*m.batches[1])
+        assert e.consistency()[0] == 0
+    child, co = parent.fork(), _oracle(2)
+    m.load_into(co)
+    assert co.consistency()[0] == 0
+    _assert_same_state(child, co)
+    _assert_same_state(parent, po)
+    # different decisions on the two engines; the child posts past its tail limit (reactor rebuild -> own copy)
+    for step in range(10):
+        for (d, o, var) in ((parent, po, step), (child, co, 39 - step)):
+            if d is parent and step >= 4:
+                continue
+            lo, hi = d.domains()
+            dec = (var, int((int(lo[var]) + int(hi[var])) / 2), step & 1)
+            parallel.post_decision(d, dec)
+            parallel.post_decision(o, dec)
+            st = d.consistency()[0]
+            assert st == o.consistency()[0], step
+            if st == -1:
+                return
+            _assert_same_state(d, o)
+    # the parent goes back to a label older than the shared static part
+    parent.restore(early[0])
+    po.restore(early[1])
+    assert parent.num_props == po.num_props == 10
+    for e in (parent, po):
+        e.prop_alloc(models.X_LESS_Y, [[0, 0], [1, 0]])
+    assert parent.consistency()[0] == po.consistency()[0]
+    _assert_same_state(parent, po)
+    assert child.consistency()[0] == co.consistency()[0]
+    _assert_same_state(child, co)
+    # a search on a fork (device-resident: the tail of a shared model is the engine's own array)
+    a, b = _engine(), _oracle(2)
+    models.nqueens(30).load_into(a)
+    models.nqueens(30).load_into(b)
+    a.consistency()
+    f = a.fork()
+    a.close()                                            # the shared block outlives the parent
+    rf, tf = f.search(node_limit=300, all_solutions=True, trace=300, trace_domains=True)
+    rb, tb = b.search(node_limit=300, all_solutions=True, trace=300, trace_domains=True)
+    assert rf.num_nodes == rb.num_nodes and (tf["status"] == tb["status"]).all() and (tf["hash"] == tb["hash"]).all()
+
+
 @pytest.mark.parametrize("host_search", [False, True], ids=["device-search", "host-lockstep"])
 def test_search_step_many_matches_lone_searches(host_search):
     """pcp_search_step_many over 4 subtree contexts (device-resident searches on one host thread
