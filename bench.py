@@ -208,9 +208,13 @@ def run_ours(args):
         desc += " -- IntervalSet<i32> domains (FDSpace, as example/src/nqueens.rs allocates them)"
     # contexts per GPU: engines side by side, each on its own subtree.  The streaming-bound
     # stores (C5: DRAM-bound sweep, C4: one fixpoint) gain nothing from it.
-    K = args.contexts if args.contexts > 0 else {"c2": 12, "c3": 12}.get(workload, 1)
-    if workload.startswith("nq"):
-        K = args.contexts if args.contexts > 0 else 12
+    multi = workload in ("c2", "c3") or workload.startswith("nq")
+    K = args.contexts if args.contexts > 0 else (24 if multi else 1)
+    # the host-driven loop runs one host thread per context, the device-resident searches one blocked
+    # thread: their best context counts differ from the device-timed rounds' (measured: DESIGN 6)
+    K_e2e = min(K, args.e2e_contexts) if multi else 1
+    K_dev = min(max(K, 1), 20) if multi else 1
+    K_inc = 30 if multi and args.contexts == 0 else K
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -339,21 +343,22 @@ def run_ours(args):
         # searches (same entry points, branching on the GPU) are reported beside it.  With more than
         # one rank the one-word collective (stop flag; sum all-reduce) runs inside the timed loop
         # after every round of `sync_every` nodes per context.
-        def e2e_pass(host_search):
-            engines = contexts(K, host_search=host_search, timing=False)  # wall clock only: no event records, zero-copy results
+        def e2e_pass(host_search, k, incremental=False, steps=None):
+            steps = steps or args.steps
+            engines = contexts(k, host_search=host_search, timing=False, incremental=incremental)  # wall clock only: no event records, zero-copy results
             from pcp_b200 import search_step_many
             handles = [e.search_open(all_solutions=True) for e in engines]
             stop = parallel.StopFlag(device) if world > 1 else None
             search_step_many(handles, args.warmup)   # untimed: CSR, buffers, first nodes
             base = [(int(r.propagations), int(r.num_nodes)) for r in search_step_many(handles, 1)]
             barrier()
-            sync_every = max(1, min(args.sync_every, args.steps))
+            sync_every = max(1, min(args.sync_every, steps)) if world > 1 else steps  # (one slice when there is nobody to talk to)
             done = exch = 0
             exch_s = 0.0
             t0 = time.perf_counter()
             last = None
-            while done < args.steps:
-                n = min(sync_every, args.steps - done)
+            while done < steps:
+                n = min(sync_every, steps - done)
                 last = search_step_many(handles, n)
                 done += n
                 if stop is not None:
@@ -364,15 +369,19 @@ def run_ours(args):
             wall = time.perf_counter() - t0
             out = {"propagations": sum(int(r.propagations) - b[0] for r, b in zip(last, base)),
                    "nodes": sum(int(r.num_nodes) - b[1] for r, b in zip(last, base)), "seconds": wall,
-                   "exchanges": exch, "exchange_seconds": exch_s}
+                   "exchanges": exch, "exchange_seconds": exch_s, "contexts": k, "nodes_per_context": steps}
             barrier()
             for h in handles:
                 h.close()
             close_all(engines)
             return out
-        e2e = e2e_pass(True)
-        e2e_dev = e2e_pass(False) if not set_domains else None
-        h2d, d2h = 16 * K, (64 + 8 * V) * K  # per step = per round of K nodes: one posted descriptor in, header + domains out, per context
+        e2e = e2e_pass(True, K_e2e)
+        e2e_dev = e2e_pass(False, K_dev) if not set_domains else None
+        # PCP_FLAG_INCREMENTAL with the device-resident searches: nodes below the root evaluate their
+        # posted constraint and the row of its variable instead of scheduling every propagator
+        # (same statuses and domains: tests/); far fewer propagations per node, so nodes/s is its number
+        e2e_inc = e2e_pass(False, K_inc, incremental=True, steps=max(args.steps, 400)) if (multi and not set_domains) else None
+        h2d, d2h = 16 * K_e2e, (64 + 8 * V) * K_e2e  # per e2e step = one node on each of the K_e2e contexts: one posted descriptor in, header + domains out, each
 
         if world > 1 and workload == "c2" and not args.no_c5:
             extra["c5"] = run_c5(args, torch, dist, device, rank, world, local_rank, barrier, reduce_sum, reduce_max, peak)
@@ -397,6 +406,10 @@ def run_ours(args):
     if e2e_dev is not None:
         d_props, d_nodes, d_s = (reduce_sum(e2e_dev["propagations"]), reduce_sum(e2e_dev["nodes"]),
                                  reduce_max(e2e_dev["seconds"]))
+    e2e_inc = locals().get("e2e_inc")
+    if e2e_inc is not None:
+        n_props, n_nodes, n_s = (reduce_sum(e2e_inc["propagations"]), reduce_sum(e2e_inc["nodes"]),
+                                 reduce_max(e2e_inc["seconds"]))
     launches = int(reduce_sum(f["launches"]))
 
     if rank == 0:
@@ -443,20 +456,28 @@ def run_ours(args):
                         "was a fixpoint; same domains and statuses, L2 flushed between steps"}),
             "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s",
                     "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "us_per_node": 1e6 * e_s * world / max(e_nodes, 1),
-                    "ms_per_step": 1e3 * e_s / max(args.steps, 1),
+                    "ms_per_step": 1e3 * e_s / max(args.steps, 1), "contexts_per_gpu": e2e.get("contexts", 1),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "exchanges": e2e.get("exchanges"), "exchange_seconds": e2e.get("exchange_seconds"),
                     "path": ("restore + pcp_consistency + pcp_domains_read per step through the C ABI (ctypes), L2 not flushed"
                              if single_fixpoint else
-                             f"host-driven node loop over {K} context(s) in lockstep: C++ search driver -> C ABI (pcp_restore / "
-                             "pcp_prop_alloc / pcp_consistency_batch / pcp_domains_read / pcp_label per node and context), "
-                             "wall clock, L2 not flushed" + ("; 1 x int32 NCCL all-reduce every round inside the timed loop" if world > 1 else ""))},
+                             f"host-driven node loop over {K_e2e} context(s), one host thread each (pcp_search_step_many): C++ search "
+                             "driver -> C ABI (pcp_restore / pcp_prop_alloc / pcp_consistency / pcp_domains_read / pcp_label per node "
+                             "and context), wall clock, L2 not flushed" + ("; 1 x int32 NCCL all-reduce every round inside the timed loop" if world > 1 else ""))},
             "e2e_device_search": (None if e2e_dev is None else {
                 "value": d_props / d_s if d_s > 0 else 0.0, "unit": "propagations/s",
                 "nodes_per_s": d_nodes / d_s if d_s > 0 else 0.0, "us_per_node": 1e6 * d_s * world / max(d_nodes, 1),
-                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                "path": f"pcp_search_step_many over {K} device-resident searches (pcp_burst_kernel: branching, label/restore and "
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "contexts_per_gpu": e2e_dev.get("contexts"),
+                "path": f"pcp_search_step_many over {K_dev} device-resident searches (pcp_burst_kernel: branching, label/restore and "
                         "the fixpoints in one launch per budget slice and context); counters copied back when a slice ends"}),
+            "incremental_device_search": (None if e2e_inc is None else {
+                "nodes_per_s": n_nodes / n_s if n_s > 0 else 0.0, "us_per_node": 1e6 * n_s * world / max(n_nodes, 1),
+                "value": n_props / n_s if n_s > 0 else 0.0, "unit": "propagations/s",
+                "propagations_per_node": n_props / max(n_nodes, 1), "contexts_per_gpu": e2e_inc.get("contexts"),
+                "nodes_per_context": e2e_inc.get("nodes_per_context"),
+                "note": "PCP_FLAG_INCREMENTAL + device-resident searches: below the root a node evaluates its posted constraint "
+                        "and what it wakes (the reference schedules every propagator at every node, store.rs:144-149; statuses "
+                        "and domains are the same).  Wall clock through pcp_search_step_many."}),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
@@ -663,7 +684,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c2 (default) | c3 | c4 | c5 | nq<N>")
-    ap.add_argument("--contexts", type=int, default=0, help="engines side by side per GPU (0 = per-workload default: 12 for c2/c3, 1 for c4/c5)")
+    ap.add_argument("--contexts", type=int, default=0, help="engines side by side per GPU in the device-timed rounds (0 = default: 24 for c2/c3, 1 for c4/c5)")
+    ap.add_argument("--e2e-contexts", type=int, default=12, help="contexts of the host-driven e2e loop (one host thread each)")
     ap.add_argument("--domains", default="interval", choices=["interval", "set"], help="Interval<i32> (VStoreFD) or IntervalSet<i32> (FDSpace) domains")
     ap.add_argument("--skip-nodes", type=int, default=0, help="advance every context by this many DFS nodes before the timed window (deep nodes)")
     ap.add_argument("--sync-every", type=int, default=8, help="multi-GPU e2e: nodes per context between two exchanges of the stop word")

@@ -2429,7 +2429,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kConsumerWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    pre_issue(P, st);  // descriptors never depend on the node
+    if (!B.incremental) pre_issue(P, st);  // descriptors never depend on the node
   } else if (threadIdx.x == 32) {
     if (blockIdx.x == 0) burst_load(bc, &s_local);
   }
@@ -2468,11 +2468,16 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
       if (s_cmd != 0) break;
     }
     unsigned iters = 0;
-    const unsigned dec = fixpoint_node<SMEM>(P, PS, st, epoch, s_bin_n, s_slot >= 0 ? 1 : 0, &s_inl, true, 0, true, iters);
+    // Incremental search (PCP_FLAG_INCREMENTAL): a node = a label that was a fixpoint + one posted
+    // constraint, so only that constraint and what it wakes are evaluated (its variable's row goes into
+    // the worklist of iteration 0); the root schedules everything (store.rs:144-149).  No descriptors
+    // are pre-issued then: the ring is the worklist's scratch memory.
+    const bool sweep_first = !B.incremental || s_slot < 0;
+    const unsigned dec = fixpoint_node<SMEM>(P, PS, st, epoch, s_bin_n, s_slot >= 0 ? 1 : 0, &s_inl, sweep_first, 0, !B.incremental, iters);
     epoch += iters + 1;
     ++done;
     // the next sweep's descriptors can stream in while CTA 0 does the host's work
-    if (threadIdx.x == 0 && dec != D_ITER_CAP) pre_issue(P, st);
+    if (threadIdx.x == 0 && dec != D_ITER_CAP && !B.incremental) pre_issue(P, st);
 
     // Fast descent.  At a fixpoint every CTA's snapshot is the store (the last iteration narrowed
     // nothing), so every CTA can derive what CTA 0 is about to do: if the node is Unknown and
@@ -2529,7 +2534,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     }
   }
   // drain the chunks that were pre-issued for a node that will not run in this launch
-  if (threadIdx.x >> 5 > 0 && st.my_chunks > 0) {
+  if (threadIdx.x >> 5 > 0 && st.my_chunks > 0 && !B.incremental) {
     const int n = min(st.my_chunks, kStages);
     for (int i = 0; i < n; ++i) {
       const int q = st.pipe_pos + i, s = q % kStages;

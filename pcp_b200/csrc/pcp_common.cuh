@@ -253,6 +253,7 @@ struct BurstParams {
   long long stack_stride;
   int max_labels, max_branches, bin_cap;
   int all_solutions;
+  int incremental;                  // PCP_FLAG_INCREMENTAL: nodes below the root evaluate their posted constraint and what it wakes
   unsigned long long node_budget;   // nodes to run in this launch
   unsigned long long node_limit;    // StopNode (search/stop_node.rs:54-61), 0 = none
   long long props_base;             // allocated propagators = props_base + bin_n

@@ -142,6 +142,7 @@ struct pcp_engine {
   uint32_t flags = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_sleep = nullptr;   // cudaEventBlockingSync: waits that put the host thread to sleep
   cudaEvent_t ev_done = nullptr, ev_batch0 = nullptr, ev_batch1 = nullptr;  // pcp_consistency_batch: fork / join across engines' streams
   bool timing = false;
   int num_sms = 0;
@@ -1276,6 +1277,7 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     CUDA_CHECK(cudaEventCreate(&e->ev0));
     CUDA_CHECK(cudaEventCreate(&e->ev1));
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_sleep, cudaEventDisableTiming | cudaEventBlockingSync));
     CUDA_CHECK(cudaEventCreate(&e->ev_batch0));
     CUDA_CHECK(cudaEventCreate(&e->ev_batch1));
     CUDA_CHECK(cudaMalloc(&e->d_ctl, sizeof(Control)));
@@ -1334,6 +1336,7 @@ int pcp_engine_fork(pcp_engine* parent, pcp_engine** out) {
     CUDA_CHECK(cudaEventCreate(&e->ev0));
     CUDA_CHECK(cudaEventCreate(&e->ev1));
     CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_done, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_sleep, cudaEventDisableTiming | cudaEventBlockingSync));
     CUDA_CHECK(cudaEventCreate(&e->ev_batch0));
     CUDA_CHECK(cudaEventCreate(&e->ev_batch1));
     stage(e, 1 << 16);
@@ -1446,6 +1449,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->ev_done) cudaEventDestroy(e->ev_done);
+  if (e->ev_sleep) cudaEventDestroy(e->ev_sleep);
   if (e->ev_batch0) cudaEventDestroy(e->ev_batch0);
   if (e->ev_batch1) cudaEventDestroy(e->ev_batch1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -1984,7 +1988,7 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
   if (off) return 0;
   if (cfg->var_sel != 0 || cfg->val_sel != 0 || cfg->distributor != 0 || cfg->bb_mode != 0) return 0;
   if (e->V == 0 || e->V > (size_t)(1 << 20)) return 0;
-  if ((e->flags & (PCP_FLAG_INCREMENTAL | PCP_FLAG_HOST_SEARCH))) return 0;
+  if ((e->flags & PCP_FLAG_HOST_SEARCH)) return 0;
   if (e->set_mode) return 0;  // IntervalSet engines: the host-driven node loop (sizes and bit sets per label)
   // the device search pre-reserves its whole label stack (burst_depth(e) slots of V domains):
   // a store too wide for that budget takes the host-driven node loop, which grows on demand
@@ -2082,6 +2086,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     B.max_branches = (int)b.d_branches.cap;
     B.bin_cap = b.bin_cap;
     B.all_solutions = b.all_solutions;
+    B.incremental = (e->flags & PCP_FLAG_INCREMENTAL) ? 1 : 0;
     B.node_budget = max_nodes ? max_nodes : ~0ull;
     B.node_limit = b.node_limit;
     B.props_base = b.props_base;
@@ -2119,7 +2124,10 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     BurstCtl bc;
     CUDA_CHECK(cudaMemcpyAsync(&bc, b.d_bc, sizeof(bc), cudaMemcpyDeviceToHost, e->stream));
     CUDA_CHECK(cudaMemcpyAsync(e->h_block, e->d_block, sizeof(Result), cudaMemcpyDeviceToHost, e->stream));
-    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    // (a blocking wait: with many searches side by side -- one host thread each -- spinning threads
+    // would outnumber the cores)
+    CUDA_CHECK(cudaEventRecord(e->ev_sleep, e->stream));
+    CUDA_CHECK(cudaEventSynchronize(e->ev_sleep));
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     b.kernel_seconds += ms * 1e-3;

@@ -390,6 +390,16 @@ def test_store_calls_are_refused_while_a_device_search_is_open():
     assert dev.consistency()[0] in (0, 1, -1)  # usable again after close
 
 
+@pytest.mark.parametrize("model,nodes", [(models.nqueens(64), 400), (models.nqueens(300), 300), (models.all_interval(12), 300),
+                                         (models.nqueens(20, "distinct"), 400)], ids=lambda m: getattr(m, "name", str(m)))
+def test_incremental_mode_host_driven_and_device_search(model, nodes):
+    """PCP_FLAG_INCREMENTAL through both search paths: the device-resident search (a node below the
+    root evaluates its posted constraint and the row of its variable in iteration 0) and the
+    host-driven node loop -- the same per-node statuses and domains as the oracle's full fixpoints."""
+    _compare_search(model, nodes, dev_kw={"incremental": True})
+    _compare_search(model, nodes, dev_kw={"incremental": True, "host_search": True})
+
+
 def test_var_update_and_contract_violations():
     from pcp_b200 import ContractViolation
     dev, ora = _engine(incremental=True), _oracle()
