@@ -212,7 +212,10 @@ def run_ours(args):
     K = args.contexts if args.contexts > 0 else (24 if multi else 1)
     # the host-driven loop runs one host thread per context, the device-resident searches one blocked
     # thread: their best context counts differ from the device-timed rounds' (measured: DESIGN 6)
-    K_e2e = min(K, args.e2e_contexts) if multi else 1
+    K_e2e = max(1, min(K, args.e2e_contexts)) if multi else 1
+    # host threads of the host-driven loop: the rank's share of the cores; each thread pipelines its
+    # share of the contexts (pcp_search_step_many)
+    os.environ.setdefault("PCP_SEARCH_THREADS", str(max(1, min(K_e2e, 6, (os.cpu_count() or 8) // max(world, 1) - 1))))
     K_dev = min(max(K, 1), 20) if multi else 1
     K_inc = 30 if multi and args.contexts == 0 else K
 

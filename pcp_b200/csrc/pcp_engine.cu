@@ -2224,6 +2224,29 @@ int pcp_internal_burst_end(pcp_engine* e) {
 
 int pcp_internal_interval_set(const pcp_engine* e) { return e && e->set_mode ? 1 : 0; }
 
+// Split-phase pcp_consistency for a host thread that drives several engines (pcp_search_step_many):
+// begin = prepare + launch, poll = "has the result arrived?" without blocking, end = collect.
+int pcp_internal_consistency_begin(pcp_engine* e) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    PCP_REQUIRE_NO_BURST(e);
+    CUDA_CHECK(cudaSetDevice(e->device));
+    fixpoint_launch(e);
+  });
+}
+int pcp_internal_consistency_poll(pcp_engine* e) {
+  if (!e || !e->inflight.active) return 1;
+  if (e->inflight.zero_copy) return *(volatile unsigned*)&e->h_result()->seq == e->inflight.P.host_seq ? 1 : 0;
+  return cudaStreamQuery(e->stream) == cudaErrorNotReady ? 0 : 1;
+}
+int pcp_internal_consistency_end(pcp_engine* e, int32_t* status, pcp_stats* stats) {
+  if (!e || !status) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    CUDA_CHECK(cudaSetDevice(e->device));
+    fixpoint_wait(e, status, stats);
+  });
+}
+
 int pcp_num_vars(const pcp_engine* e, int32_t* n) {
   if (!e || !n) return PCP_ERR_INVALID;
   *n = (int32_t)e->V;

@@ -27,6 +27,10 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
 /* copies the per-node trace of nodes [first, first+n): status and (if recorded) domains */
 int pcp_internal_burst_trace(pcp_engine* e, uint64_t first, uint64_t n, int32_t* status, int32_t* lo, int32_t* hi);
 int pcp_internal_burst_end(pcp_engine* e);
+/* split-phase pcp_consistency: launch / non-blocking "result there?" / collect */
+int pcp_internal_consistency_begin(pcp_engine* e);
+int pcp_internal_consistency_poll(pcp_engine* e);
+int pcp_internal_consistency_end(pcp_engine* e, int32_t* status, pcp_stats* stats);
 /* 1 when the engine was created with PCP_FLAG_INTERVAL_SET */
 int pcp_internal_interval_set(const pcp_engine* e);
 

@@ -299,6 +299,7 @@ struct Worker {
   bool has_job = false, done = false, quit = false;
   uint64_t max_nodes = 0;
   int rc = PCP_OK;
+  std::vector<pcp_search*> group;  // the searches this thread advances (host-driven: pipelined over them)
 };
 
 struct pcp_search {
@@ -329,6 +330,84 @@ int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res) {
   return rc;
 }
 
+// One host thread, several host-driven searches: every search always has its next fixpoint in
+// flight; the thread goes round, collects what has finished (pcp_internal_consistency_poll reads
+// the result's sequence word in the mapped mirror), does that node's host work -- read the domains,
+// branch, label, restore, post -- and launches the next one.  The searches never wait for each
+// other (no rounds), and a host with fewer cores than contexts still keeps every context busy.
+static int run_group_pipelined(const std::vector<pcp_search*>& g, uint64_t max_nodes) {
+  const uint64_t budget = max_nodes ? max_nodes : ~0ull;
+  const size_t n = g.size();
+  std::vector<uint64_t> start(n);
+  std::vector<char> done(n, 0), inflight(n, 0);
+  std::vector<std::chrono::steady_clock::time_point> t0(n);
+  for (size_t i = 0; i < n; ++i) {
+    Driver& d = g[i]->d;
+    start[i] = d.res->num_nodes;
+    if (d.V == 0 && !d.started) {
+      TRY(pcp_num_vars(d.e, &d.V));
+      d.lo.assign((size_t)d.V, 0);
+      d.hi.assign((size_t)d.V, 0);
+      d.size.assign((size_t)d.V, 0);
+      d.set_domains = pcp_internal_interval_set(d.e) != 0;
+    }
+    if (d.stopped) { d.res->status = 2; done[i] = 1; }
+    t0[i] = std::chrono::steady_clock::now();
+  }
+  size_t open_n = 0;
+  for (size_t i = 0; i < n; ++i) open_n += done[i] ? 0 : 1;
+  // one visit of search i: collect its finished fixpoint (if any), then launch its next node
+  auto visit = [&](size_t i) -> int {
+    Driver& d = g[i]->d;
+    if (inflight[i]) {
+      if (!pcp_internal_consistency_poll(d.e)) return PCP_OK;
+      int32_t k = 0;
+      pcp_stats st;
+      inflight[i] = 0;
+      TRY(pcp_internal_consistency_end(d.e, &k, &st));
+      int child = 0;
+      TRY(d.enter_post(k, st, &child));
+      if (child == 2) { d.stopped = true; d.res->status = 2; done[i] = 1; }
+      else if (child == 1 && !d.cfg->all_solutions) { d.res->status = 1; done[i] = 1; }
+      if (done[i]) { --open_n; return PCP_OK; }
+    }
+    if (d.started && d.queue.empty()) {  // fully explored (one_solution.rs:66-68)
+      if (d.cfg->all_solutions || d.exhausted_reported) d.res->status = 2;
+      else { d.exhausted_reported = true; d.res->status = -1; }
+      done[i] = 1; --open_n;
+      return PCP_OK;
+    }
+    if (d.res->num_nodes - start[i] >= budget) { d.res->status = 0; done[i] = 1; --open_n; return PCP_OK; }
+    if (!d.started) {
+      d.started = true;
+    } else {
+      Branch b = d.queue.back();
+      d.queue.pop_back();
+      TRY(pcp_restore(d.e, b.label));  // Branch::commit (branch.rs:51-55)
+      TRY(d.apply_alternative(b));
+    }
+    TRY(d.enter_pre());
+    TRY(pcp_internal_consistency_begin(d.e));
+    inflight[i] = 1;
+    return PCP_OK;
+  };
+  int rc = PCP_OK;
+  while (open_n > 0 && rc == PCP_OK)
+    for (size_t i = 0; i < n && rc == PCP_OK; ++i)
+      if (!done[i]) rc = visit(i);
+  if (rc != PCP_OK) {  // leave no fixpoint in flight behind an error
+    for (size_t i = 0; i < n; ++i)
+      if (inflight[i]) { int32_t k; pcp_internal_consistency_end(g[i]->d.e, &k, nullptr); }
+    return rc;
+  }
+  const auto t1 = std::chrono::steady_clock::now();
+  for (size_t i = 0; i < n; ++i) {
+    Driver& d = g[i]->d;
+    if (d.res->num_nodes > (uint64_t)d.cfg->warmup_nodes) d.res->seconds += std::chrono::duration<double>(t1 - t0[i]).count();
+  }
+  return PCP_OK;
+}
+
 // Several searches -- independent subtrees of one model, one engine each -- advanced together:
 // device-resident searches run on one host thread each (their launches last for whole slices of
 // nodes); host-driven searches move in lockstep, one node per search and round, the fixpoints of
@@ -347,8 +426,20 @@ int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, p
   // round and the host work of one node (post, launch, read back, branch) overlaps the others'.
   static const bool lockstep = [] { const char* v = std::getenv("PCP_SEARCH_LOCKSTEP"); return v && v[0] == '1'; }();
   if (all_burst || (!lockstep && n > 1)) {
-    for (int i = 0; i < n; ++i) {
-      pcp_search* s = ss[i];
+    // device-resident searches: one (sleeping) thread each.  Host-driven searches: T threads, each
+    // pipelining its share of the searches; T = PCP_SEARCH_THREADS, else what the machine has.
+    int T = n;
+    if (!all_burst) {
+      const char* v = std::getenv("PCP_SEARCH_THREADS");
+      const int hw = (int)std::thread::hardware_concurrency();
+      T = v ? std::atoi(v) : (hw > 1 ? hw - 1 : 1);
+      T = std::max(1, std::min(T, n));
+    }
+    // searches are dealt to the leaders' groups round-robin; the leaders are ss[0 .. T)
+    std::vector<std::vector<pcp_search*>> groups((size_t)T);
+    for (int i = 0; i < n; ++i) groups[(size_t)(i % T)].push_back(ss[i]);
+    for (int t = 0; t < T; ++t) {
+      pcp_search* s = ss[t];
       if (!s->worker) {
         s->worker = new Worker();
         Worker* w = s->worker;
@@ -360,7 +451,7 @@ int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, p
             w->has_job = false;
             const uint64_t budget_w = w->max_nodes;
             lk.unlock();
-            const int rc = pcp_search_step(s, budget_w, nullptr);
+            const int rc = (w->group.size() > 1 || !s->d.burst) ? run_group_pipelined(w->group, budget_w) : pcp_search_step(s, budget_w, nullptr);
             lk.lock();
             w->rc = rc;
             w->done = true;
@@ -370,17 +461,21 @@ int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, p
       }
       Worker* w = s->worker;
       std::lock_guard<std::mutex> lk(w->mu);
+      w->group = groups[(size_t)t];
       w->max_nodes = max_nodes;
       w->done = false;
       w->has_job = true;
       w->cv.notify_all();
     }
     int rc = PCP_OK;
-    for (int i = 0; i < n; ++i) {
-      Worker* w = ss[i]->worker;
+    for (int t = 0; t < T; ++t) {
+      Worker* w = ss[t]->worker;
       std::unique_lock<std::mutex> lk(w->mu);
       w->cv.wait(lk, [w] { return w->done; });
       if (w->rc != PCP_OK && rc == PCP_OK) rc = w->rc;
+    }
+    for (int i = 0; i < n; ++i) {
+      ss[i]->res.status = ss[i]->d.res->status;
       if (res) res[i] = ss[i]->res;
     }
     return rc;
