@@ -379,11 +379,11 @@ def run_ours(args):
             close_all(engines)
             return out
         e2e = e2e_pass(True, K_e2e)
-        e2e_dev = e2e_pass(False, K_dev) if not set_domains else None
+        e2e_dev = e2e_pass(False, K_dev)
         # PCP_FLAG_INCREMENTAL with the device-resident searches: nodes below the root evaluate their
         # posted constraint and the row of its variable instead of scheduling every propagator
         # (same statuses and domains: tests/); far fewer propagations per node, so nodes/s is its number
-        e2e_inc = e2e_pass(False, K_inc, incremental=True, steps=max(args.steps, 400)) if (multi and not set_domains) else None
+        e2e_inc = e2e_pass(False, K_inc, incremental=True, steps=max(args.steps, 400)) if multi else None
         h2d, d2h = 16 * K_e2e, (64 + 8 * V) * K_e2e  # per e2e step = one node on each of the K_e2e contexts: one posted descriptor in, header + domains out, each
 
         if world > 1 and workload == "c2" and not args.no_c5:

@@ -2272,7 +2272,11 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
     for (int v = tid; v < P.V; v += blockDim.x) {
       int2 d = from_snapshot ? scratch[v] : ldcg_dom(&P.dom[v]);
       if (scratch && !from_snapshot) scratch[v] = d;
+#ifdef PCP_SET
+      unsigned size = d.x >= d.y ? (unsigned)(d.y - d.x) + 1u : sb_count(set_of(P), v, d.x, d.y);  // Cardinality::size()
+#else
       unsigned size = (unsigned)(d.y - d.x) + 1u;
+#endif
       if (size > 1u) best = min(best, ((unsigned long long)size << 32) | (unsigned)v);
     }
     // propagation/store.rs:250-256
@@ -2284,6 +2288,12 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
       if (B.t_dom && status != -1)
         for (int v = tid; v < P.V; v += blockDim.x)
           B.t_dom[n * (unsigned long long)P.V + v] = scratch ? scratch[v] : ldcg_dom(&P.dom[v]);
+#ifdef PCP_SET
+      if (B.t_bits && status != -1) {
+        const long long nw = (long long)P.V * P.bits_W;
+        for (long long i = tid; i < nw; i += blockDim.x) B.t_bits[n * (unsigned long long)nw + i] = __ldcg(&P.bits[i]);
+      }
+#endif
     }
     if (status == 0 && !stop) {
       // FirstSmallestVar: min over (size, index) of the variables with size > 1
@@ -2302,6 +2312,13 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
         const int val = (d.x + d.y) / 2;  // MiddleVal: truncating division
         int2* dst = B.stack + (long long)slot * B.stack_stride;
         for (int v = tid; v < P.V; v += blockDim.x) dst[v] = scratch ? scratch[v] : ldcg_dom(&P.dom[v]);
+#ifdef PCP_SET
+        {  // the label slot holds the bit sets behind the bounds
+          uint32_t* dbits = reinterpret_cast<uint32_t*>(dst + P.V);
+          const long long nw = (long long)P.V * P.bits_W;
+          for (long long i = tid; i < nw; i += blockDim.x) dbits[i] = __ldcg(&P.bits[i]);
+        }
+#endif
         __syncthreads();
         if (tid == 0) {
           const int2 meta = make_int2(bin_n, (int)trail_cnt);
@@ -2365,6 +2382,13 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
     // Snapshot::restore: domains <- label copy, re-activate the trail suffix (store.rs:319-323)
     const int2* src = B.stack + (long long)Lb * B.stack_stride;
     for (int v = tid; v < P.V; v += blockDim.x) P.dom[v] = __ldcg(&src[v]);
+#ifdef PCP_SET
+    {
+      const uint32_t* sbits = reinterpret_cast<const uint32_t*>(src + P.V);
+      const long long nw = (long long)P.V * P.bits_W;
+      for (long long i = tid; i < nw; i += blockDim.x) P.bits[i] = __ldcg(&sbits[i]);
+    }
+#endif
     const unsigned cnt = __ldcg(&ctl->trail_cnt);
     for (unsigned i = (unsigned)meta.y + tid; i < cnt; i += blockDim.x) {
       unsigned ref = __ldcg(&P.trail[i]);
@@ -2488,7 +2512,12 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     // CTA 0 does the bookkeeping of burst_host_step (trace, label, branch records, descriptor).
     fast = false;
     unsigned long long best = ~0ull;
-    if (SMEM && dec == D_FIXPOINT) {
+#ifdef PCP_SET
+    constexpr bool kFastDescent = false;  // FirstSmallestVar compares cardinalities: one pass over the bit sets, by CTA 0 only
+#else
+    constexpr bool kFastDescent = true;
+#endif
+    if (kFastDescent && SMEM && dec == D_FIXPOINT) {
       if (threadIdx.x == 0) s_tc = __ldcg(&ctl->trail_cnt);
       for (int v = threadIdx.x; v < P.V; v += blockDim.x) {
         const int2 d = st.sdom[v];

@@ -237,6 +237,7 @@ struct pcp_engine {
     DevBuf<int2> d_meta, d_bmeta;
     DevBuf<int> d_tstatus;
     DevBuf<int2> d_tdom;
+    DevBuf<uint32_t> d_tbits;       // IntervalSet engines: the bit sets of the traced nodes
     uint64_t trace_cap = 0;
     bool trace_dom = false;
     int all_solutions = 0;
@@ -920,6 +921,10 @@ const void* fixpoint_fn(bool bin_only, bool smem_dom) {
   if (bin_only) return smem_dom ? (const void*)binonly::pcp_fixpoint_kernel<true> : (const void*)binonly::pcp_fixpoint_kernel<false>;
   return smem_dom ? (const void*)full::pcp_fixpoint_kernel<true> : (const void*)full::pcp_fixpoint_kernel<false>;
 }
+const void* burst_set_fn(bool bin_only, bool smem_dom) {
+  if (bin_only) return smem_dom ? (const void*)binonly_set::pcp_burst_kernel<true> : (const void*)binonly_set::pcp_burst_kernel<false>;
+  return smem_dom ? (const void*)full_set::pcp_burst_kernel<true> : (const void*)full_set::pcp_burst_kernel<false>;
+}
 const void* burst_fn(bool bin_only, bool smem_dom) {
   if (bin_only) return smem_dom ? (const void*)binonly::pcp_burst_kernel<true> : (const void*)binonly::pcp_burst_kernel<false>;
   return smem_dom ? (const void*)full::pcp_burst_kernel<true> : (const void*)full::pcp_burst_kernel<false>;
@@ -1259,7 +1264,7 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     {
       // dynamic shared memory every persistent kernel may use = the opt-in maximum minus its own
       // static part; configured once (an engine never lowers what another engine relies on)
-      const void* fns[12] = {fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
+      const void* fns[16] = {burst_set_fn(false, false), burst_set_fn(false, true), burst_set_fn(true, false), burst_set_fn(true, true),fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
                              fixpoint_fn(true, false),  fixpoint_fn(true, true),  burst_fn(true, false),  burst_fn(true, true),
                              fixpoint_set_fn(false, false), fixpoint_set_fn(false, true), fixpoint_set_fn(true, false),
                              fixpoint_set_fn(true, true)};
@@ -1442,7 +1447,7 @@ void pcp_engine_destroy(pcp_engine* e) {
   e->d_dirty_bits.free(); e->d_seed_list.free(); e->d_trail.free(); e->d_stack.free(); e->d_bits.free();
   if (e->d_ctl) cudaFree(e->d_ctl);
   if (e->burst.d_bc) cudaFree(e->burst.d_bc);
-  e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_bmeta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free();
+  e->burst.d_branches.free(); e->burst.d_meta.free(); e->burst.d_bmeta.free(); e->burst.d_tstatus.free(); e->burst.d_tdom.free(); e->burst.d_tbits.free();
   if (e->d_block) cudaFree(e->d_block);
   if (e->h_block) cudaFreeHost(e->h_block);
   if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -1989,12 +1994,11 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
   if (cfg->var_sel != 0 || cfg->val_sel != 0 || cfg->distributor != 0 || cfg->bb_mode != 0) return 0;
   if (e->V == 0 || e->V > (size_t)(1 << 20)) return 0;
   if ((e->flags & PCP_FLAG_HOST_SEARCH)) return 0;
-  if (e->set_mode) return 0;  // IntervalSet engines: the host-driven node loop (sizes and bit sets per label)
   // the device search pre-reserves its whole label stack (burst_depth(e) slots of V domains):
   // a store too wide for that budget takes the host-driven node loop, which grows on demand
-  if (burst_depth(e) * e->V * sizeof(int2) > kBurstStackBudget) return 0;
+  if (burst_depth(e) * e->slot_stride() * sizeof(int2) > kBurstStackBudget) return 0;
   // the device trace keeps full domains for the traced nodes
-  if (trace_capacity * e->V * sizeof(int2) > (size_t)1 << 30) return 0;
+  if (trace_capacity * e->slot_stride() * sizeof(int2) > (size_t)1 << 30) return 0;
   return 1;
 }
 
@@ -2011,8 +2015,8 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
     // room for the search: label slots, branching constraints in the binary tail, trail
     const size_t depth = burst_depth(e);
     b.max_labels = (int)(e->labels.size() + depth);
-    e->stack_stride = V;
-    e->d_stack.reserve((size_t)b.max_labels * V, e->stream, e->labels.size() * V);
+    e->stack_stride = e->slot_stride();
+    e->d_stack.reserve((size_t)b.max_labels * e->stack_stride, e->stream, e->labels.size() * e->stack_stride);
     HostFamily& hb = e->fam[F_BIN];
     b.bin_cap = (int)(hb.n + depth);
     if (e->shared) {
@@ -2036,6 +2040,7 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
     if (trace_capacity) {
       b.d_tstatus.reserve(trace_capacity, e->stream);
       if (b.trace_dom) b.d_tdom.reserve(trace_capacity * V, e->stream);
+      if (b.trace_dom && e->set_mode) b.d_tbits.reserve(trace_capacity * V * (size_t)e->set_W, e->stream);
     }
     if (!b.d_bc) CUDA_CHECK(cudaMalloc(&b.d_bc, sizeof(BurstCtl)));
     BurstCtl bc;
@@ -2092,6 +2097,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     B.props_base = b.props_base;
     B.t_status = b.trace_cap ? b.d_tstatus.p : nullptr;
     B.t_dom = (b.trace_cap && b.trace_dom) ? b.d_tdom.p : nullptr;
+    B.t_bits = (b.trace_cap && b.trace_dom && e->set_mode) ? b.d_tbits.p : nullptr;
     B.t_cap = b.trace_cap;
     Params& P = b.P;
     P.max_iterations = e->max_iterations;
@@ -2116,7 +2122,7 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
         smem += bm_bytes;
       }
     }
-    const void* fn = burst_fn(bin_only_store(e), smem_dom);
+    const void* fn = e->set_mode ? burst_set_fn(bin_only_store(e), smem_dom) : burst_fn(bin_only_store(e), smem_dom);
     CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
     void* args[] = {&P, &B};
     launch_persistent(fn, grid, args, smem, e->stream);
@@ -2151,6 +2157,32 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     res->iterations = bc.iterations;
     res->propagations = r.propagations - b.props0;
     res->kernel_seconds = b.kernel_seconds;
+  });
+}
+
+// The bit sets of traced nodes [first, first + n) of an IntervalSet engine, re-based into the window
+// the caller asks for (as pcp_domains_read_bits does for the current domains).
+int pcp_internal_burst_trace_bits(pcp_engine* e, uint64_t first, uint64_t n, const int32_t* lo, const int32_t* hi, int32_t base,
+                                  int32_t words, uint32_t* out) {
+  if (!e) return PCP_ERR_INVALID;
+  return guarded(e, [&] {
+    auto& b = e->burst;
+    PCP_REQUIRE(b.open && e->set_mode && b.trace_dom && first + n <= b.trace_cap, "trace range out of bounds");
+    if (n == 0) return;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    const size_t V = e->V, W = (size_t)e->set_W;
+    std::vector<uint32_t> raw(n * V * W);
+    CUDA_CHECK(cudaMemcpyAsync(raw.data(), b.d_tbits.p + first * V * W, raw.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_CHECK(cudaStreamSynchronize(e->stream));
+    std::memset(out, 0, n * V * (size_t)words * 4);
+    for (size_t i = 0; i < n * V; ++i)
+      for (long long v = lo[i]; v <= hi[i]; ++v) {
+        const unsigned bb = (unsigned)(v - e->set_base);
+        if (!((raw[i * W + (bb >> 5)] >> (bb & 31)) & 1u)) continue;
+        const long long o = v - base;
+        PCP_REQUIRE(o >= 0 && o < (long long)words * 32, "value outside the requested bit window");
+        out[i * (size_t)words + (size_t)(o >> 5)] |= 1u << (o & 31);
+      }
   });
 }
 

@@ -26,6 +26,9 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
 int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result* res);
 /* copies the per-node trace of nodes [first, first+n): status and (if recorded) domains */
 int pcp_internal_burst_trace(pcp_engine* e, uint64_t first, uint64_t n, int32_t* status, int32_t* lo, int32_t* hi);
+/* IntervalSet engines: the value sets of traced nodes as bit windows [n * V, words] from `base` */
+int pcp_internal_burst_trace_bits(pcp_engine* e, uint64_t first, uint64_t n, const int32_t* lo, const int32_t* hi, int32_t base,
+                                  int32_t words, uint32_t* out);
 int pcp_internal_burst_end(pcp_engine* e);
 /* split-phase pcp_consistency: launch / non-blocking "result there?" / collect */
 int pcp_internal_consistency_begin(pcp_engine* e);

@@ -189,9 +189,20 @@ struct Driver {
       else if (t_hash) { blo.resize(n * (size_t)V); bhi.resize(n * (size_t)V); plo = blo.data(); phi = bhi.data(); }
       std::vector<int32_t> st(n);
       TRY(pcp_internal_burst_trace(e, a, n, st.data(), plo, phi));
+      const bool sets = pcp_internal_interval_set(e) != 0;
       for (uint64_t i = 0; i < n; ++i) {
         if (t_status) t_status[a + i] = st[i];
-        if (t_hash) t_hash[a + i] = st[i] == PCP_FALSE ? 0 : hash_domains(plo + i * (size_t)V, phi + i * (size_t)V, (size_t)V);
+        if (!t_hash) continue;
+        if (st[i] == PCP_FALSE) { t_hash[a + i] = 0; continue; }
+        const int32_t* l = plo + i * (size_t)V;
+        const int32_t* h = phi + i * (size_t)V;
+        if (!sets) { t_hash[a + i] = hash_domains(l, h, (size_t)V); continue; }
+        int32_t mn = l[0], mx = h[0];
+        for (int32_t v = 1; v < V; ++v) { mn = std::min(mn, l[v]); mx = std::max(mx, h[v]); }
+        const int32_t words = (int32_t)(((int64_t)mx - mn + 32) / 32);
+        bits.resize((size_t)V * (size_t)words);
+        TRY(pcp_internal_burst_trace_bits(e, a + i, 1, l, h, mn, words, bits.data()));
+        t_hash[a + i] = hash_domain_bits(l, h, (size_t)V, mn, words, bits.data());
       }
     }
     return PCP_OK;
