@@ -76,7 +76,7 @@ pub const PCP_UNKNOWN: i32 = 0;
 pub const PCP_TRUE: i32 = 1;
 
 pub const PCP_VAR_CONSTANT: i32 = -1;
-pub fn pcp_var_sum(sum_id: i32) -> i32 {
+pub fn var_sum(sum_id: i32) -> i32 {
     -2 - sum_id
 }
 
@@ -105,6 +105,7 @@ pub const PCP_FLAG_INTERVAL_SET: u32 = 4;
 #[link(name = "pcp_b200")]
 extern "C" {
     pub fn pcp_engine_create(cfg: *const PcpConfig, out: *mut *mut PcpEngine) -> c_int;
+    pub fn pcp_engine_fork(parent: *mut PcpEngine, out: *mut *mut PcpEngine) -> c_int;
     pub fn pcp_engine_destroy(e: *mut PcpEngine);
     pub fn pcp_last_error(e: *const PcpEngine) -> *const c_char;
     pub fn pcp_set_timing(e: *mut PcpEngine, enabled: i32) -> c_int;

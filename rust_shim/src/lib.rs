@@ -331,7 +331,7 @@ impl<Domain: DeviceDomain> GpuCStore<Domain> {
                             lowering::ViewDesc::Sum { terms, off } => {
                                 let mut id = 0i32;
                                 engine.check(unsafe { pcp_sum_alloc(engine.raw, terms.as_ptr(), terms.len() as i32, &mut id) });
-                                PcpOperand { var: pcp_var_sum(id), off: *off }
+                                PcpOperand { var: var_sum(id), off: *off }
                             }
                         })
                         .collect();

@@ -25,6 +25,30 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
 
 
+def test_rust_shim_binds_every_symbol_and_constant():
+    """rust_shim/src/ffi.rs (source only: no Rust toolchain here) declares every entry point of the
+    header with the same arity, and the same constants."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "pcp_b200.h")).read(), flags=re.S)
+    ffi = open(os.path.join(ROOT, "rust_shim", "src", "ffi.rs")).read()
+    c_fns = {m.group(1): m.group(2) for m in re.finditer(r"\b(pcp_[a-z_]+)\s*\(([^;{]*?)\)\s*;", hdr)}
+    r_fns = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (pcp_[a-z_]+)\(([^;]*?)\)(?:\s*->\s*[^;]+)?;", ffi, flags=re.S)}
+    assert sorted(c_fns) == sorted(_declared_symbols())
+    assert sorted(r_fns) == sorted(c_fns), sorted(set(c_fns) ^ set(r_fns))
+    for name, args in c_fns.items():
+        n_c = 0 if args.strip() in ("", "void") else args.count(",") + 1
+        n_r = r_fns[name].count(":")
+        assert n_c == n_r, name
+    for m in re.finditer(r"#define\s+(PCP_[A-Z_0-9]+)\s+\(?(-?\d+)u?\)?\s", hdr):
+        name, val = m.group(1), int(m.group(2))
+        if name in ("PCP_NUM_KINDS", "PCP_F_MAX_NODES", "PCP_F_MAX_VARS"):
+            continue
+        r = re.search(r"pub const %s: \w+ = (-?\d+);" % name, ffi)
+        assert r and int(r.group(1)) == val, name
+    for m in re.finditer(r"\b(PCP_[A-Z_]+)\s*=\s*(\d+)", hdr):   # enum pcp_prop_kind
+        r = re.search(r"pub const %s: i32 = (\d+);" % m.group(1), ffi)
+        assert r and int(r.group(1)) == int(m.group(2)), m.group(1)
+
+
 def test_struct_layouts_match_header():
     import ctypes as C
     from pcp_b200 import _capi
