@@ -1205,6 +1205,7 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
         else if (iter + 1 >= P.max_iterations) dec = D_ITER_CAP;
       }
       if (!decide) node_prologue_finish(P);  // prologue barrier: every CTA has read trail_cnt by now
+      else ctl->trail_at_decision = *(volatile unsigned*)&ctl->trail_cnt;
       ctl->bar_count = 0;
       unsigned rel = ((gen + 1u) << kDecBits) | dec;
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&ctl->bar_gen), "r"(rel) : "memory");
@@ -1660,6 +1661,7 @@ struct CtaState {
   int fam_g0[3], fam_cnt[3];
   int pipe_pos;      // chunks this CTA has pushed through the ring so far (all sweeps, all nodes)
   unsigned gen;      // barrier generation
+  unsigned rot;      // rotation of the three dirty sets: iteration i of a node works on sets (rot + i) % 3 ...
 };
 
 __device__ __forceinline__ FamSweep fam_sweep(const Params& P, const CtaState& st, int fam, int seq_off, int pre) {
@@ -1712,6 +1714,7 @@ __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* sm
     off += m.nch[f];
   }
   st.pipe_pos = 0;
+  st.rot = 0u;
 }
 
 // Producer: issue the first chunks of the coming sweep (thread 0 only).  Stages that still
@@ -1878,9 +1881,9 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
   unsigned iter = 0, dec, nprop = 0;
   int cur_buf = 0, next_buf = 1;
   while (true) {
-    cur_buf = iter % 3;
-    next_buf = (iter + 1) % 3;
-    const int spare_buf = (iter + 2) % 3;
+    cur_buf = (int)((st.rot + iter) % 3u);
+    next_buf = (int)((st.rot + iter + 1u) % 3u);
+    const int spare_buf = (int)((st.rot + iter + 2u) % 3u);
     const unsigned cur_epoch = epoch0 + iter;
     const uint32_t* cur_bits = P.dirty_bits + (size_t)cur_buf * W;
     if (threadIdx.x == 0) {
@@ -1891,8 +1894,10 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
     }
     __syncthreads();
     trace_mark1(P, iter, 0);
-    // the spare set was read in the previous iteration and is written in the next one
-    if (iter > 0 && blockIdx.x == 0)
+    // the spare set was read in the previous iteration (of this node, or -- when the device search
+    // went straight on to the next node -- the last one of the previous node) and is written in the
+    // next one: cleared here, before this iteration's barrier
+    if (blockIdx.x == 0)
       for (int w = threadIdx.x; w < W; w += blockDim.x) P.dirty_bits[(size_t)spare_buf * W + w] = 0u;
 
     // Incremental launch (no schedule-everything sweep): the variables of the posted propagators go
@@ -2101,14 +2106,22 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
     ++iter;
     if (dec != D_CONTINUE) break;
   }
-  // leave the dirty sets empty: the spare one was cleared during the last iteration
-  if (blockIdx.x == 0)
-    for (int w = threadIdx.x; w < W; w += blockDim.x) {
-      P.dirty_bits[(size_t)cur_buf * W + w] = 0u;
-      P.dirty_bits[(size_t)next_buf * W + w] = 0u;
-    }
+  // The sets this node leaves behind: `cur` (read in the last iteration) still holds the marks of the
+  // iteration before, `next` is empty at a fixpoint (nobody narrowed anything) and holds marks after a
+  // failure.  The caller either clears them (dirty_sets_reset: single-node launches, and a device
+  // search that meets at a barrier before the next node) or -- fast descent, fixpoints only -- lets the
+  // rotation run on: `next` becomes the next node's current set, `cur` its spare, cleared by CTA 0 in
+  // that node's first iteration before anybody writes it.  (Clearing them here raced with the CTAs that
+  // had already started the next node: a late CTA 0 wiped their first marks.)
+  st.rot = (st.rot + iter) % 3u;  // = the index of the last iteration's `next`
   iters_out = iter;
   return dec;
+}
+// every thread of CTA 0; the other CTAs only realign their rotation
+__device__ __forceinline__ void dirty_sets_reset(const Params& P, CtaState& st) {
+  if (blockIdx.x == 0)
+    for (int w = threadIdx.x; w < 3 * P.dirty_words; w += blockDim.x) P.dirty_bits[w] = 0u;
+  st.rot = 0u;
 }
 
 template <bool SMEM>
@@ -2164,6 +2177,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   const unsigned dec = fixpoint_node<SMEM>(P, PS, st, epoch0, P.fam[F_BIN].n, P.n_inline, P.inl, P.full_sweep != 0,
                                            P.seed_dirty, P.full_sweep != 0, iters);
 
+  dirty_sets_reset(P, st);  // the sets are empty between launches
   trace_mark(P, 6);
 #ifdef PCP_SET
   // the label copy of the bit sets: every CTA takes a slice (at a fixpoint nobody writes them any more)
@@ -2261,8 +2275,11 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (have_node && dec == D_ITER_CAP) { if (tid == 0) L->err = 2; have_node = false; }
   if (have_node) {
-    // ---- close the node: status, trace, branching, label
-    const unsigned trail_cnt = __ldcg(&ctl->trail_cnt);
+    // ---- close the node: status, trace, branching, label.  The trail length is the one published with
+    // the node's decision: in a fast descent the other CTAs are already running the left child, and what
+    // they find entailed there must not count as entailed at this node (its label would then leave those
+    // propagators switched off in the right subtree).
+    const unsigned trail_cnt = __ldcg(&ctl->trail_at_decision);
     const int bin_n = L->bin_n;
     const unsigned long long n = L->nodes;
     unsigned long long best = ~0ull;
@@ -2367,7 +2384,9 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
   }
   __syncthreads();
   if (!L->run) return;
-  if (L->root_pending) {
+  const bool root = L->root_pending != 0;
+  __syncthreads();  // (everybody has read the flag thread 0 clears below)
+  if (root) {
     if (tid == 0) {
       L->root_pending = 0; L->cur_label = -1; bc->inl_slot = -1; bc->bin_n = L->bin_n; bc->cmd = 0;
       bc->n_labels = L->n_labels; bc->n_branch = L->n_branch; bc->nodes = L->nodes;  // the other CTAs' mirrors
@@ -2378,7 +2397,9 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
   const int4 br = s_pop;
   const int2 meta = s_pop_meta;
   const int Lb = br.x;
-  if (L->cur_label != Lb) {
+  const int cur_label = L->cur_label;
+  __syncthreads();  // (everybody has read what thread 0 resets below)
+  if (cur_label != Lb) {
     // Snapshot::restore: domains <- label copy, re-activate the trail suffix (store.rs:319-323)
     const int2* src = B.stack + (long long)Lb * B.stack_stride;
     for (int v = tid; v < P.V; v += blockDim.x) P.dom[v] = __ldcg(&src[v]);
@@ -2512,13 +2533,13 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     // CTA 0 does the bookkeeping of burst_host_step (trace, label, branch records, descriptor).
     fast = false;
     unsigned long long best = ~0ull;
-#ifdef PCP_SET
+#if defined(PCP_SET) || defined(PCP_DEBUG_NO_FAST)
     constexpr bool kFastDescent = false;  // FirstSmallestVar compares cardinalities: one pass over the bit sets, by CTA 0 only
 #else
     constexpr bool kFastDescent = true;
 #endif
     if (kFastDescent && SMEM && dec == D_FIXPOINT) {
-      if (threadIdx.x == 0) s_tc = __ldcg(&ctl->trail_cnt);
+      if (threadIdx.x == 0) s_tc = __ldcg(&ctl->trail_at_decision);
       for (int v = threadIdx.x; v < P.V; v += blockDim.x) {
         const int2 d = st.sdom[v];
         const unsigned size = (unsigned)(d.y - d.x) + 1u;
@@ -2534,6 +2555,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
       fast = unknown && best != ~0ull && !stop && done < B.node_budget && s_mlabels < B.max_labels &&
              s_mbranch + 2 <= B.max_branches && s_mbin < B.bin_cap;
     }
+    if (!fast) dirty_sets_reset(P, st);  // (a device barrier follows before anybody marks a variable again)
     if (blockIdx.x == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, true, dec, iters, done);
     if (fast) {
       __syncthreads();  // everybody has read the mirrors (and CTA 0 is done with its snapshot)

@@ -64,7 +64,9 @@ struct Control {
   unsigned epoch;        // next unused epoch (stamps < epoch are stale)
   int failed;
   unsigned trail_cnt;    // number of deactivated (entailed) propagators on the trail
-  int pad0[3];
+  unsigned trail_at_decision;  // trail_cnt as the last CTA to arrive at a deciding barrier saw it: the node's own
+                               // entailments, all flushed, none of the next node's (the device search may run ahead)
+  int pad0[2];
   unsigned long long propagations;  // cumulative
   unsigned iterations;   // of the last launch
   unsigned last_decision;
