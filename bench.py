@@ -339,6 +339,12 @@ def run_ours(args):
         res["incremental"] = device_timed_pass(engines, args.steps, args.warmup, True, torch, device)
         barrier()
         close_all(engines)
+        if K > 1:  # and the headline's own protocol (K contexts per round, L2 flushed) on incremental engines
+            engines = contexts(K, incremental=True)
+            barrier()
+            res["incremental_batch"] = device_timed_pass(engines, args.steps, args.warmup, True, torch, device, skip=args.skip_nodes)
+            barrier()
+            close_all(engines)
 
         # e2e through the C++ driver over the C ABI with host buffers, twice: the host-driven node
         # loop (what a libpcp host does per node: restore, post one descriptor, fixpoint, status +
@@ -405,6 +411,9 @@ def run_ours(args):
     inc = res.get("incremental")
     if inc is not None:
         i_props, i_nodes, i_ms = reduce_sum(inc["propagations"]), reduce_sum(inc["nodes"]), reduce_max(inc["ms"])
+    incb = res.get("incremental_batch")
+    if incb is not None:
+        ib_props, ib_nodes, ib_ms = reduce_sum(incb["propagations"]), reduce_sum(incb["nodes"]), reduce_max(incb["ms"])
     e_props, e_nodes, e_s = reduce_sum(e2e["propagations"]), reduce_sum(e2e["nodes"]), reduce_max(e2e["seconds"])
     if e2e_dev is not None:
         d_props, d_nodes, d_s = (reduce_sum(e2e_dev["propagations"]), reduce_sum(e2e_dev["nodes"]),
@@ -456,7 +465,14 @@ def run_ours(args):
                 "nodes_per_s": i_nodes / (i_ms * 1e-3) if i_ms > 0 else 0.0, "ms_per_step": i_ms / max(inc["rounds"], 1),
                 "propagations_per_node": inc["propagations"] / max(inc["nodes"], 1),
                 "note": "PCP_FLAG_INCREMENTAL, one context: no schedule-everything first sweep when the restored state "
-                        "was a fixpoint; same domains and statuses, L2 flushed between steps"}),
+                        "was a fixpoint; same domains and statuses, L2 flushed between steps",
+                "batch": (None if incb is None else {
+                    "contexts_per_gpu": K, "nodes_per_s": ib_nodes / (ib_ms * 1e-3) if ib_ms > 0 else 0.0,
+                    "ms_per_step": ib_ms / max(incb["rounds"], 1), "us_per_node": 1e3 * ib_ms * world / max(ib_nodes, 1),
+                    "propagations_per_node": ib_props / max(ib_nodes, 1),
+                    "note": "the headline's protocol (one round of K nodes per step through pcp_consistency_batch, L2 flushed "
+                            "before every round, CUDA events) on PCP_FLAG_INCREMENTAL engines: compare ms_per_step with the "
+                            "line's own"})}),
             "e2e": {"value": e_props / e_s if e_s > 0 else 0.0, "unit": "propagations/s",
                     "nodes_per_s": e_nodes / e_s if e_s > 0 else 0.0, "us_per_node": 1e6 * e_s * world / max(e_nodes, 1),
                     "ms_per_step": 1e3 * e_s / max(args.steps, 1), "contexts_per_gpu": e2e.get("contexts", 1),

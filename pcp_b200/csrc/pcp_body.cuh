@@ -246,16 +246,20 @@ __device__ __forceinline__ void ring_advance(RingPos& r) {
 // fire-and-forget reductions straight from registers.  Entailment (rare) stays out of line.
 __device__ __forceinline__ bool sweep_upd(const Ctx& c, int var, int off, IV o, IV n) {
   const bool lo = n.lo > o.lo, hi = n.hi < o.hi;
+#ifndef PCP_EXP_NO_RED
   if (lo) atomicMax(&c.dom_w[var].x, n.lo - off);
   if (hi) atomicMin(&c.dom_w[var].y, n.hi - off);
+#endif
   // the variable is queued: in the CTA's bitmap (one coalesced flush into the dirty set after
   // the sweep instead of a scattered reduction per narrowing), else directly.  (Looking the bit
   // up first was measured slower: the look is a dependent load on the update path.)
+#ifndef PCP_EXP_NO_MARK
   if (lo || hi) {
     const uint32_t dbm_s = c.dbm_s;
     if (dbm_s) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(dbm_s + 4u * (unsigned)(var >> 5)), "r"(1u << (var & 31)) : "memory");
     else atomicOr(&c.next_bits[var >> 5], 1u << (var & 31));
   }
+#endif
   return lo || hi;
 }
 __device__ __forceinline__ void sweep_ter_eq_update(const Ctx& c, const FamSweep& a, int slot, int4 d, int2 e, IV x0, IV y0, IV z0) {
