@@ -154,7 +154,7 @@ def device_timed_pass(engines, steps, warmup, flush, torch, device, skip=0):
     (fork after the optional L2 flush on the lead stream, join after the last kernel)."""
     import pcp_b200
     dfs = [PyDfs(e) for e in engines]
-    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=device) if flush else None
+    flush_buf = torch.empty(int(os.environ.get("PCP_BENCH_FLUSH_MIB", "512")) << 20, dtype=torch.uint8, device=device) if flush else None
     # the flush runs on the lead engine's own stream, directly before the timed launches: the
     # events then bracket the kernels, not the host's launch latency on an idle stream
     ext = torch.cuda.ExternalStream(engines[0].cuda_stream(), device=device)
@@ -177,7 +177,7 @@ def device_timed_pass(engines, steps, warmup, flush, torch, device, skip=0):
             iters += sum(int(s.iterations) for s in stats)
             ms += float(stats[0].kernel_ms)   # the whole round: first launch to last completion
             nodes += len(live)
-            launches += len(live)             # one pcp_fixpoint_kernel per node (restore, posted constraint, label copy inside)
+            launches += sum(int(s.launches) for s in stats)  # one launch per round when the batch shares one, else one per node
         for i, st in zip(live, sts):
             dfs[i].after_fixpoint(st)
         n += 1
@@ -501,7 +501,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "pcp_fixpoint_kernel (node prologue, TMA sweep, worklist iterations, label snapshot)"
-                                   + (f", {K} launches side by side per step" if K > 1 else ""),
+                                   + (f"; the {K} contexts of a step share one launch (pcp_fixpoint_batch_kernel, {K} groups of CTAs)" if K > 1 else ""),
                          "algorithmic_bytes_per_propagation": bpp,
                          "streamed_bytes_per_propagation": STREAM_BYTES.get(workload, bpp),
                          "streamed_frac": ((f["propagations"] * STREAM_BYTES.get(workload, bpp)) / (f["ms"] * 1e-3) / 1e9 / peak) if f["ms"] > 0 else None,

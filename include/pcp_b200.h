@@ -105,7 +105,8 @@ typedef struct pcp_stats {
   uint32_t active_props; /* propagators still active (not entailed) after the call      */
   float kernel_ms;       /* device time of the fixpoint kernel (CUDA events); 0 unless
                             timing was enabled with pcp_set_timing                      */
-  uint32_t reserved;
+  uint32_t launches;     /* persistent-kernel launches this call made for this engine (1; in a
+                            batch served by one launch: 1 in stats[0], 0 in the others)    */
 } pcp_stats;
 
 int pcp_engine_create(const pcp_config* cfg, pcp_engine** out);
@@ -185,7 +186,11 @@ int pcp_consistency(pcp_engine* e, int32_t* status, pcp_stats* stats /* may be N
  * worklist iterations of one node overlap the sweeps of the others).  status / stats have n
  * entries (stats may be NULL).  Engines without a pcp_set_grid_limit get an equal share of the
  * SMs for the call.  With timing enabled on engines[0], stats[0].kernel_ms is the device time of
- * the whole batch (first launch to last completion). */
+ * the whole batch (first launch to last completion).
+ * Engines that run the same kernel with the same geometry (forks of one model, snapshot of the
+ * domains in shared memory, same grid limit, together no more CTAs than the device has SMs) are
+ * served by ONE launch: consecutive groups of CTAs take one engine each.  K launches on K streams
+ * start about 3 us apart on the device; the batch starts every engine's node at once. */
 int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status, pcp_stats* stats);
 
 /* Index<usize> on the variable store (variable/store.rs:175-181), batched. */

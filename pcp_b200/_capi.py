@@ -38,7 +38,7 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("propagations", C.c_uint64), ("iterations", C.c_uint32), ("active_props", C.c_uint32),
-                ("kernel_ms", C.c_float), ("reserved", C.c_uint32)]
+                ("kernel_ms", C.c_float), ("launches", C.c_uint32)]
 
 
 class SearchConfig(C.Structure):

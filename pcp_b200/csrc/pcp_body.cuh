@@ -12,10 +12,22 @@
 
 #include "pcp_eval.cuh"
 
+// The CTA's place among the CTAs that serve its engine.  A launch for one engine: (blockIdx.x,
+// gridDim.x).  A batched launch (pcp_fixpoint_batch_kernel) serves one engine per group of
+// consecutive CTAs: rank and count are then relative to the group, and so is everything that
+// deals work out by CTA or meets at the engine's barrier.  Set by thread 0 at kernel entry,
+// read after the first block-wide barrier.
+__shared__ unsigned s_cta_rank_, s_cta_count_;
+__device__ __forceinline__ unsigned cta_rank() { return s_cta_rank_; }
+__device__ __forceinline__ unsigned cta_count() { return s_cta_count_; }
+__device__ __forceinline__ void cta_place(unsigned rank, unsigned count) {
+  if (threadIdx.x == 0) { s_cta_rank_ = rank; s_cta_count_ = count; }
+  __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------------
 // iteration 0: the streaming sweep.  A chunk = up to kChunk* propagators of one family;
-// chunk g belongs to CTA g % gridDim.x.  Warp 0 (one lane) is the producer: it arms the
+// chunk g belongs to CTA g % cta_count().  Warp 0 (one lane) is the producer: it arms the
 // stage's `full` mbarrier with the byte count and issues the TMA bulk copies; the 31
 // consumer warps wait on `full`, evaluate from shared memory and release the stage through
 // the `empty` mbarrier.
@@ -1201,7 +1213,7 @@ __device__ __forceinline__ unsigned grid_barrier(const Params& P, unsigned& gen,
     unsigned old;
     asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(&ctl->bar_count), "r"(add) : "memory");
     unsigned now = old + add;
-    if ((now & 1023u) == gridDim.x) {
+    if ((now & 1023u) == cta_count()) {
       unsigned dec = D_CONTINUE;
       if (decide) {
         if ((now >> 20) & 1023u) dec = D_FAILED;
@@ -1410,7 +1422,7 @@ __device__ __forceinline__ unsigned expand_rows_local(const Params& P, Ctx& c, c
   const int lane = threadIdx.x & 31;
   unsigned nprop = 0;
   if (threadIdx.x == 0) c.mirror = SMEM;  // (ordered by the barrier that opens every row)
-  for (int e = blockIdx.x; e < n_dirty; e += gridDim.x) {
+  for (int e = cta_rank(); e < n_dirty; e += cta_count()) {
     const int v = list[e];
     const int rb = __ldg(&P.adj_ptr[v]), re = __ldg(&P.adj_ptr[v + 1]);
     const bool staged = re - rb <= kRowCap;
@@ -1550,10 +1562,10 @@ __device__ __forceinline__ unsigned expand_rows_local(const Params& P, Ctx& c, c
 
 template <bool SMEM>
 __device__ __forceinline__ unsigned expand_dirty_rows(const Params& P, Ctx& c, const int* list, int n_dirty, unsigned cur_epoch, char* ring, TrailBuf* tb) {
-  if (n_dirty <= (int)gridDim.x) return expand_rows_local<SMEM>(P, c, list, n_dirty, cur_epoch, ring, tb);
+  if (n_dirty <= (int)cta_count()) return expand_rows_local<SMEM>(P, c, list, n_dirty, cur_epoch, ring, tb);
   const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * kWarps;
+  const long long warp = (long long)cta_rank() * kWarps + (threadIdx.x >> 5);
+  const long long nwarps = (long long)cta_count() * kWarps;
   const long long S = max(1LL, nwarps / n_dirty);  // segments per row (upper bound)
   const long long items = (long long)n_dirty * S;
   unsigned nprop = 0;
@@ -1700,8 +1712,8 @@ __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* sm
   // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
   // by the other CTAs so that nobody waits for it at the barrier
   const ChunkMap m = chunk_map(P);
-  st.workers = gridDim.x > 1 ? (int)gridDim.x - 1 : 1;
-  st.wid = gridDim.x > 1 ? (int)blockIdx.x - 1 : 0;
+  st.workers = cta_count() > 1 ? (int)cta_count() - 1 : 1;
+  st.wid = cta_count() > 1 ? (int)cta_rank() - 1 : 0;
   st.my_chunks = 0;
   int off = 0;
   for (int f = 0; f < 3; ++f) {
@@ -1763,7 +1775,7 @@ __device__ __noinline__ unsigned nary_outlined(const Params* PS, const Ctx* c, c
   unsigned n = 0;
   // dealt from the last CTA backwards: CTA 0 (prologue, posted and tail propagators) is the
   // last to get one
-  for (int s = (int)gridDim.x - 1 - (int)blockIdx.x; s < P.n_nary; s += gridDim.x) {
+  for (int s = (int)cta_count() - 1 - (int)cta_rank(); s < P.n_nary; s += cta_count()) {
     if (!((__ldcg(&P.nary_active[s >> 5]) >> (s & 31)) & 1u)) continue;
     const int kind = __ldg(&P.nary_kind[s]);
     unsigned ev;
@@ -1901,7 +1913,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
     // the spare set was read in the previous iteration (of this node, or -- when the device search
     // went straight on to the next node -- the last one of the previous node) and is written in the
     // next one: cleared here, before this iteration's barrier
-    if (blockIdx.x == 0)
+    if (cta_rank() == 0)
       for (int w = threadIdx.x; w < W; w += blockDim.x) P.dirty_bits[(size_t)spare_buf * W + w] = 0u;
 
     // Incremental launch (no schedule-everything sweep): the variables of the posted propagators go
@@ -1932,11 +1944,11 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
         for (int i = 0; i < n_inline; ++i)
           if (inl[i].fam != F_BIN || ((unsigned)inl[i].q[0].x >> 28) != B_LESS) c.mark_dirty = true;
 #endif
-        if (blockIdx.x == 0 || !SMEM) {  // the global store: counted and book-kept by CTA 0
-          c.bookkeep = blockIdx.x == 0;
+        if (cta_rank() == 0 || !SMEM) {  // the global store: counted and book-kept by CTA 0
+          c.bookkeep = cta_rank() == 0;
           for (int i = 0; i < n_inline; ++i)
             eval_full<false>(c, inl[i].fam, inl[i].slot, inl[i].q[0], inl[i].q[1], inl[i].q[2]);
-          if (blockIdx.x == 0) nprop += n_inline;
+          if (cta_rank() == 0) nprop += n_inline;
           if (!SMEM) __threadfence();
         }
         if (SMEM) {
@@ -1988,8 +2000,8 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
       // grid)
       int bad = 0;
       if (sweep_now) {
-        const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
-        const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
+        const int r0 = SMEM ? threadIdx.x : cta_rank() * blockDim.x + threadIdx.x;
+        const int rs = SMEM ? blockDim.x : cta_count() * blockDim.x;
         for (int v = r0; v < P.V; v += rs) {  // coalesced re-read of everything beats gathers
           int2 d = ldcg_dom(&P.dom[v]);
 #ifdef PCP_SET
@@ -1999,8 +2011,8 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
           bad |= d.x > d.y;
         }
       } else {
-        const int r0 = SMEM ? threadIdx.x : blockIdx.x * blockDim.x + threadIdx.x;
-        const int rs = SMEM ? blockDim.x : gridDim.x * blockDim.x;
+        const int r0 = SMEM ? threadIdx.x : cta_rank() * blockDim.x + threadIdx.x;
+        const int rs = SMEM ? blockDim.x : cta_count() * blockDim.x;
         for (int i = r0; i < n_refresh; i += rs) {
           int v = list[i];
           int2 d = ldcg_dom(&P.dom[v]);
@@ -2030,7 +2042,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
       trace_mark1(P, iter, 2);
       if (!skip && !sweep_now && n_dirty > 0) nprop += rows_outlined<SMEM>(PS, &c, list, n_dirty, cur_epoch, st.ring, st.tbuf);
     }
-    if (blockIdx.x == 0 && !skip && (P.fam[0].n_static < bin_n || P.fam[1].n_static < P.fam[1].n || P.fam[2].n_static < P.fam[2].n))
+    if (cta_rank() == 0 && !skip && (P.fam[0].n_static < bin_n || P.fam[1].n_static < P.fam[1].n || P.fam[2].n_static < P.fam[2].n))
       nprop += tail_outlined<SMEM>(PS, &c, bin_n, iter == 0, n_inline, inl);
     if (sweep_now && !skip && st.my_chunks > 0) {
       // ---- the streaming sweep over the static descriptor arrays (ring positions keep
@@ -2100,7 +2112,7 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
     dec = grid_barrier(P, st.gen, bp, true, st.flags, iter);
     if (iter == 0) trace_mark(P, 5);
     trace_mark1(P, iter, 5);
-    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0 && iter < 32) {  // per-iteration record
+    if (P.trace && cta_rank() == 0 && threadIdx.x == 0 && iter < 32) {  // per-iteration record
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[8 * 256 + iter * 4 + 0] = t;
@@ -2123,24 +2135,18 @@ __device__ __forceinline__ unsigned fixpoint_node(const Params& P, const Params*
 }
 // every thread of CTA 0; the other CTAs only realign their rotation
 __device__ __forceinline__ void dirty_sets_reset(const Params& P, CtaState& st) {
-  if (blockIdx.x == 0)
+  if (cta_rank() == 0)
     for (int w = threadIdx.x; w < 3 * P.dirty_words; w += blockDim.x) P.dirty_bits[w] = 0u;
   st.rot = 0u;
 }
 
+// One node of one engine: prologue (restore, posted propagators), the fixpoint, the epilogue (label
+// copy, result header, zero-copy mirror).  `P`: the launch parameters where the hot loops read them
+// (the kernel's own parameter space, or shared memory in a batched launch); `PS`: their copy in
+// shared memory for the out-of-line cold sections.
 template <bool SMEM>
-__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_constant__ Params P) {
-  extern __shared__ __align__(128) char smem[];
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
-  __shared__ int s_flags[2];
-  // layout: [ring | n-ary staging (aliased)] [domain snapshot]
-  __shared__ Params s_P;  // copy of the launch parameters for the out-of-line cold sections
-  {
-    const unsigned* src = reinterpret_cast<const unsigned*>(&P);
-    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
-    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = src[i];  // (ordered by the barrier below)
-  }
-  const Params* PS = &s_P;
+__device__ __forceinline__ void fixpoint_launch_body(const Params& P, const Params* PS, char* smem, uint64_t* s_full,
+                                                     uint64_t* s_empty, int* s_flags) {
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
@@ -2165,13 +2171,13 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   trace_mark(P, 0);
 
   if (P.sync0) {
-    prologue_outlined(PS, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+    prologue_outlined(PS, cta_rank() * blockDim.x + threadIdx.x, cta_count() * blockDim.x);
     grid_barrier(P, st.gen, 0, false, s_flags, 0);  // its last arriver resets trail_cnt (nobody pushes yet)
     if (SMEM) {
       for (int v = threadIdx.x; v < P.V; v += blockDim.x) st.sdom[v] = ldcg_dom(&P.dom[v]);
       __syncthreads();
     }
-  } else if (blockIdx.x == 0) {
+  } else if (cta_rank() == 0) {
     prologue_outlined(PS, threadIdx.x, blockDim.x);  // CTA-local effects only (posted propagators)
     __syncthreads();
   }
@@ -2188,11 +2194,11 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
   if (P.snapshot_to && dec == D_FIXPOINT) {
     uint32_t* dst = reinterpret_cast<uint32_t*>(P.snapshot_to + P.V);
     const long long nw = (long long)P.V * P.bits_W;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x)
+    for (long long i = (long long)cta_rank() * blockDim.x + threadIdx.x; i < nw; i += (long long)cta_count() * blockDim.x)
       dst[i] = __ldcg(&P.bits[i]);
   }
 #endif
-  if (blockIdx.x == 0) {
+  if (cta_rank() == 0) {
     // Branch::distribute takes a label right after an Unknown node (branch.rs:36-49): leave the
     // copy of the fixpoint domains in the next label slot so that pcp_label is free.
     // (the last iteration of a fixpoint narrowed nothing anywhere, so this CTA's snapshot --
@@ -2238,6 +2244,44 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_
       }
     }
   }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_kernel(const __grid_constant__ Params P) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ int s_flags[2];
+  // layout: [ring | n-ary staging (aliased)] [domain snapshot]
+  __shared__ Params s_P;  // copy of the launch parameters for the out-of-line cold sections
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&P);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  cta_place(blockIdx.x, gridDim.x);  // (its barrier also orders the copy above)
+  fixpoint_launch_body<SMEM>(P, &s_P, smem, s_full, s_empty, s_flags);
+}
+
+// One node of each of several engines in ONE launch (pcp_consistency_batch on engines that run
+// the same kernel variant with the same geometry: forks of one model, each in its own subtree).
+// CTAs [k * group, (k + 1) * group) serve engine k with the launch parameters batch[k]; every
+// engine keeps its own barrier word, counters, dirty sets and result block, so the groups never
+// meet.  Same work per engine as pcp_fixpoint_kernel; what the batch removes is the launch per
+// engine: K cooperative launches on K streams start about 3 us apart on the device (70 us for
+// K = 24, as long as a node of a 6-CTA group itself takes).
+__global__ void __launch_bounds__(kThreads, 1) pcp_fixpoint_batch_kernel(const Params* __restrict__ batch, int group) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
+  __shared__ int s_flags[2];
+  __shared__ Params s_P;
+  const unsigned k = blockIdx.x / (unsigned)group;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(batch + k);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = __ldg(&src[i]);
+  }
+  cta_place(blockIdx.x - k * (unsigned)group, (unsigned)group);
+  fixpoint_launch_body<true>(s_P, &s_P, smem, s_full, s_empty, s_flags);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -2467,6 +2511,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     unsigned* dst = reinterpret_cast<unsigned*>(&s_B);
     for (int i = threadIdx.x; i < (int)(sizeof(BurstParams) / 4); i += blockDim.x) dst[i] = src[i];
   }
+  cta_place(blockIdx.x, gridDim.x);
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
@@ -2480,7 +2525,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (!B.incremental) pre_issue(P, st);  // descriptors never depend on the node
   } else if (threadIdx.x == 32) {
-    if (blockIdx.x == 0) burst_load(bc, &s_local);
+    if (cta_rank() == 0) burst_load(bc, &s_local);
   }
   __syncthreads();
   st.gen = P.gen0;
@@ -2492,7 +2537,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
   __shared__ unsigned long long s_mnodes, s_sel[kWarps];
   __shared__ unsigned s_tc;
   unsigned long long done = 0;
-  if (blockIdx.x == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, false, 0, 0, done);
+  if (cta_rank() == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, false, 0, 0, done);
   bool fast = false;  // uniform across the grid
   while (true) {
     if (!fast) {
@@ -2560,7 +2605,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
              s_mbranch + 2 <= B.max_branches && s_mbin < B.bin_cap;
     }
     if (!fast) dirty_sets_reset(P, st);  // (a device barrier follows before anybody marks a variable again)
-    if (blockIdx.x == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, true, dec, iters, done);
+    if (cta_rank() == 0) burst_host_step(s_P, s_B, &s_local, st.sdom, true, dec, iters, done);
     if (fast) {
       __syncthreads();  // everybody has read the mirrors (and CTA 0 is done with its snapshot)
       if (threadIdx.x == 0) {
@@ -2568,7 +2613,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
         const int2 d = st.sdom[var];
         const int val = (d.x + d.y) / 2;  // MiddleVal: truncating division
         s_inl.q[0] = make_int4((int)((B_LESS << 28) | (unsigned)var), 0, -1, val + 1);  // x <= val
-        if (blockIdx.x == 0) {  // what the bookkeeper posted must be what everybody derived
+        if (cta_rank() == 0) {  // what the bookkeeper posted must be what everybody derived
           const int4 posted = __ldcg(&bc->inl_desc);
           const int4 mine = s_inl.q[0];
           if (!s_local.run || *(volatile int*)&bc->inl_slot != s_mbin || posted.x != mine.x || posted.y != mine.y ||
@@ -2596,7 +2641,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
       mbar_wait(&s_full[s], (q / kStages) & 1);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (cta_rank() == 0 && threadIdx.x == 0) {
     burst_store(bc, &s_local);
     ctl->epoch = epoch + 1;
     Result r;

@@ -144,6 +144,9 @@ struct pcp_engine {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_sleep = nullptr;   // cudaEventBlockingSync: waits that put the host thread to sleep
   cudaEvent_t ev_done = nullptr, ev_batch0 = nullptr, ev_batch1 = nullptr;  // pcp_consistency_batch: fork / join across engines' streams
+  Params* d_batch = nullptr;  // pcp_consistency_batch, one launch for several engines: their launch parameters
+  Params* h_batch = nullptr;  // (pinned staging of the same)
+  int batch_cap = 0;
   bool timing = false;
   int num_sms = 0;
   int grid_limit = 0;               // pcp_set_grid_limit: CTAs a launch of this engine may use (0 = all SMs)
@@ -257,6 +260,7 @@ struct pcp_engine {
     size_t smem = 0;
     int grid = 0;
     bool want_snapshot = false, eager_dom = false, zero_copy = false;
+    bool fused = false;  // launched as one group of a batched launch (no events of its own)
     double hp0 = 0, hp1 = 0, hp2 = 0, hp3 = 0;
   } inflight;
 
@@ -624,12 +628,12 @@ void build_csr(pcp_engine* e) {
   {
     HostFamily& hb = e->fam[F_BIN];
     hb.n_cdesc = 0;
-    static const bool no_compact = std::getenv("PCP_NO_COMPACT") != nullptr;  // measurement switch
-    // (only where the descriptor stream does not stay L2-resident between nodes: for a store
-    // that does -- C2, 24 MB -- the extra unpacking costs more than the halved L2 traffic saves,
-    // measured +0.7 us per node; C5, 600 MB, gains 20 %)
-    const bool big = hb.n * sizeof(int4) > (size_t)64 << 20 || std::getenv("PCP_FORCE_COMPACT") != nullptr;
-    bool ok = !no_compact && big && hb.n > 0 && V <= 65536 && hb.first_nonplain >= hb.n &&
+    const bool no_compact = std::getenv("PCP_NO_COMPACT") != nullptr;  // measurement / test switch (read at every reactor build)
+    // (C5, 600 MB of descriptors: -20 % per node.  C2, 24 MB and L2-resident: a node alone on the GPU
+    // loses 0.7 us to the unpacking, the contexts of a batched launch -- every SM sweeping at once --
+    // gain 4-6 % from the halved L2 traffic; the batch is the configuration that counts.  Interval
+    // domains only: the IntervalSet sweep has its witness probe in the 16-byte loop.)
+    bool ok = !no_compact && !e->set_mode && hb.n > 0 && V <= 65536 && hb.first_nonplain >= hb.n &&
               hb.static_kind_mask == (1 << B_NEQ);
     std::vector<uint2> cd;
     if (ok) {
@@ -921,6 +925,10 @@ const void* fixpoint_fn(bool bin_only, bool smem_dom) {
   if (bin_only) return smem_dom ? (const void*)binonly::pcp_fixpoint_kernel<true> : (const void*)binonly::pcp_fixpoint_kernel<false>;
   return smem_dom ? (const void*)full::pcp_fixpoint_kernel<true> : (const void*)full::pcp_fixpoint_kernel<false>;
 }
+const void* fixpoint_batch_fn(bool set_mode, bool bin_only) {
+  if (set_mode) return bin_only ? (const void*)binonly_set::pcp_fixpoint_batch_kernel : (const void*)full_set::pcp_fixpoint_batch_kernel;
+  return bin_only ? (const void*)binonly::pcp_fixpoint_batch_kernel : (const void*)full::pcp_fixpoint_batch_kernel;
+}
 const void* burst_set_fn(bool bin_only, bool smem_dom) {
   if (bin_only) return smem_dom ? (const void*)binonly_set::pcp_burst_kernel<true> : (const void*)binonly_set::pcp_burst_kernel<false>;
   return smem_dom ? (const void*)full_set::pcp_burst_kernel<true> : (const void*)full_set::pcp_burst_kernel<false>;
@@ -1055,6 +1063,7 @@ void fixpoint_prepare(pcp_engine* e) {
   e->sizes_valid = false;
   pcp_engine::Inflight& f = e->inflight;
   f.prepared = true;
+  f.fused = false;
   f.P = P;
   f.fn = fn;
   f.smem = smem;
@@ -1138,7 +1147,8 @@ void fixpoint_wait(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     }
     unsigned long long t0 = ~0ull;
     for (int b = 0; b < grid; ++b) t0 = std::min(t0, t[b * 8]);
-    std::fprintf(stderr, "[pcp trace] grid=%d sync0=%d iters=%u; per phase: min/avg/max ns since first CTA start\n", grid, P.sync0, e->h_result()->iterations);
+    std::fprintf(stderr, "[pcp trace] grid=%d sync0=%d iters=%u (first CTA start at globaltimer %llu ns); per phase: min/avg/max ns since first CTA start\n",
+                 grid, P.sync0, e->h_result()->iterations, t0);
     const char* names[7] = {"start", "after_prologue_sync", "snapshot+inline_done", "sweep_done", "barrier_arrive", "barrier_leave", "exit"};
     for (int k = 0; k < 7; ++k) {
       unsigned long long mn = ~0ull, mx = 0, sum = 0;
@@ -1193,11 +1203,75 @@ void fixpoint_wait(pcp_engine* e, int32_t* status, pcp_stats* stats) {
     stats->propagations = props;
     stats->iterations = r.iterations;
     stats->active_props = (uint32_t)(e->num_props() - r.trail_cnt);
-    if (e->timing) {
+    stats->launches = f.fused ? 0u : 1u;
+    if (e->timing && !f.fused) {
       float ms = 0;
       CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
       stats->kernel_ms = ms;
     }
+  }
+}
+
+// pcp_consistency_batch: can these prepared fixpoints share one launch?  Same kernel variant, same
+// geometry, snapshot mode, one device, and room for every group at one CTA per SM.
+bool batch_fusable(pcp_engine* const* engines, int n) {
+  const char* sw = std::getenv("PCP_BATCH");  // measurement / test switch
+  const bool off = sw && std::strcmp(sw, "unfused") == 0;
+  static const bool trace_on = std::getenv("PCP_TRACE") != nullptr;
+  if (off || trace_on || n < 2) return false;
+  const pcp_engine* lead = engines[0];
+  const pcp_engine::Inflight& f0 = lead->inflight;
+  if (!f0.P.smem_dom || (long long)n * f0.grid > lead->num_sms) return false;
+  for (int i = 0; i < n; ++i) {
+    const pcp_engine* e = engines[i];
+    const pcp_engine::Inflight& f = e->inflight;
+    if (e->device != lead->device || f.fn != f0.fn || f.smem != f0.smem || f.grid != f0.grid || !f.prepared) return false;
+    for (int j = 0; j < i; ++j)
+      if (engines[j] == e) return false;
+  }
+  return true;
+}
+
+// the one launch for all of them, on the lead engine's stream; the other engines' streams are ordered
+// before it (their uploads) and after it (their result copies)
+void fire_fused(pcp_engine* const* engines, int n, bool timed) {
+  pcp_engine* lead = engines[0];
+  if (lead->batch_cap < n) {
+    if (lead->d_batch) cudaFree(lead->d_batch);
+    if (lead->h_batch) cudaFreeHost(lead->h_batch);
+    lead->d_batch = lead->h_batch = nullptr;
+    lead->batch_cap = 0;
+    const int cap = std::max(n, 32);
+    CUDA_CHECK(cudaMalloc(&lead->d_batch, (size_t)cap * sizeof(Params)));
+    CUDA_CHECK(cudaHostAlloc(&lead->h_batch, (size_t)cap * sizeof(Params), cudaHostAllocDefault));
+    lead->batch_cap = cap;
+  }
+  const double t0 = now_s();
+  for (int i = 0; i < n; ++i) lead->h_batch[i] = engines[i]->inflight.P;
+  for (int i = 1; i < n; ++i) {
+    CUDA_CHECK(cudaEventRecord(engines[i]->ev_done, engines[i]->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(lead->stream, engines[i]->ev_done, 0));
+  }
+  CUDA_CHECK(cudaMemcpyAsync(lead->d_batch, lead->h_batch, (size_t)n * sizeof(Params), cudaMemcpyHostToDevice, lead->stream));
+  const pcp_engine::Inflight& f0 = lead->inflight;
+  const void* fn = fixpoint_batch_fn(lead->set_mode, bin_only_store(lead));
+  const Params* batch = lead->d_batch;
+  int group = f0.grid;
+  void* args[] = {(void*)&batch, (void*)&group};
+  if (timed) CUDA_CHECK(cudaEventRecord(lead->ev_batch0, lead->stream));
+  launch_persistent(fn, n * group, args, f0.smem, lead->stream);
+  if (timed) CUDA_CHECK(cudaEventRecord(lead->ev_batch1, lead->stream));
+  CUDA_CHECK(cudaEventRecord(lead->ev_done, lead->stream));
+  const double t1 = now_s();
+  for (int i = 0; i < n; ++i) {
+    pcp_engine* e = engines[i];
+    if (i > 0) CUDA_CHECK(cudaStreamWaitEvent(e->stream, lead->ev_done, 0));
+    pcp_engine::Inflight& f = e->inflight;
+    f.hp2 = t0; f.hp3 = t1;
+    ++e->dom_version;
+    f.prepared = false;
+    f.active = true;
+    f.fused = true;
   }
 }
 
@@ -1264,7 +1338,8 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     {
       // dynamic shared memory every persistent kernel may use = the opt-in maximum minus its own
       // static part; configured once (an engine never lowers what another engine relies on)
-      const void* fns[16] = {burst_set_fn(false, false), burst_set_fn(false, true), burst_set_fn(true, false), burst_set_fn(true, true),fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
+      const void* fns[20] = {fixpoint_batch_fn(false, false), fixpoint_batch_fn(false, true), fixpoint_batch_fn(true, false), fixpoint_batch_fn(true, true),
+                             burst_set_fn(false, false), burst_set_fn(false, true), burst_set_fn(true, false), burst_set_fn(true, true),fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
                              fixpoint_fn(true, false),  fixpoint_fn(true, true),  burst_fn(true, false),  burst_fn(true, true),
                              fixpoint_set_fn(false, false), fixpoint_set_fn(false, true), fixpoint_set_fn(true, false),
                              fixpoint_set_fn(true, true)};
@@ -1453,6 +1528,8 @@ void pcp_engine_destroy(pcp_engine* e) {
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->d_batch) cudaFree(e->d_batch);
+  if (e->h_batch) cudaFreeHost(e->h_batch);
   if (e->ev_done) cudaEventDestroy(e->ev_done);
   if (e->ev_sleep) cudaEventDestroy(e->ev_sleep);
   if (e->ev_batch0) cudaEventDestroy(e->ev_batch0);
@@ -1593,7 +1670,16 @@ int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status
   // pending restore / uploads and must run, so the call goes on for them and reports the error)
   const int first_rc = rc;
   rc = PCP_OK;
-  for (int i = 0; i < prepared && rc == PCP_OK; ++i) {
+  bool fused = false;
+  if (prepared == n && batch_fusable(engines, n)) {
+    rc = guarded(lead, [&] {
+      CUDA_CHECK(cudaSetDevice(lead->device));
+      fire_fused(engines, n, timed);
+    });
+    fused = rc == PCP_OK;
+    if (fused) launched = n;
+  }
+  for (int i = 0; i < prepared && rc == PCP_OK && !fused; ++i) {
     pcp_engine* e = engines[i];
     rc = guarded(e, [&] {
       CUDA_CHECK(cudaSetDevice(e->device));
@@ -1607,7 +1693,7 @@ int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status
     });
     if (rc == PCP_OK) ++launched;
   }
-  if (timed && launched == n) {
+  if (timed && launched == n && !fused) {
     int r2 = guarded(lead, [&] { CUDA_CHECK(cudaSetDevice(lead->device)); CUDA_CHECK(cudaEventRecord(lead->ev_batch1, lead->stream)); });
     if (rc == PCP_OK) rc = r2;
   }
@@ -1629,6 +1715,7 @@ int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status
       stats[0].kernel_ms = ms;  // the whole batch: first launch to last completion
     });
   }
+  if (fused && stats) stats[0].launches = 1;
   return rc;
 }
 

@@ -28,7 +28,7 @@ pub struct PcpStats {
     pub iterations: u32,
     pub active_props: u32,
     pub kernel_ms: f32,
-    pub reserved: u32,
+    pub launches: u32,
 }
 
 #[repr(C)]

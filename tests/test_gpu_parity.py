@@ -672,21 +672,29 @@ def test_sharded_search_two_gpus_nccl():
     assert res[0]["bb"]["incumbent"] == res[1]["bb"]["incumbent"] == ref.bb_value
 
 
-@pytest.mark.parametrize("k", [2, 5])
-def test_consistency_batch_matches_lone_engines(k):
+@pytest.mark.parametrize("k,mode,fused", [(2, "interval", True), (5, "interval", True), (5, "interval", False),
+                                          (4, "set", True), (6, "incremental", True), (3, "distinct", True)])
+def test_consistency_batch_matches_lone_engines(k, mode, fused, monkeypatch):
     """pcp_consistency_batch: k engines, each on its own subtree of n-queens N=120, advance a
     host-driven DFS in lockstep (the k fixpoints of a round are launched together and run side
     by side on the GPU); after every round each engine's status, domains and `active` set equal
-    those of the oracle replaying the same subtree alone."""
+    those of the oracle replaying the same subtree alone.  Engines with the same kernel and geometry
+    share ONE launch (pcp_fixpoint_batch_kernel, a group of CTAs per engine); PCP_BATCH=unfused keeps
+    one launch per engine on its own stream.  Both, on Interval and IntervalSet domains, with the
+    incremental flag, and with an n-ary Distinct in the store (the `full` kernel variant)."""
     import pcp_b200
     from pcp_b200 import parallel
-    m = models.nqueens(120)
-    probe = _engine()
+    from oracle.oracle_api import SET, TUNED
+    if not fused:
+        monkeypatch.setenv("PCP_BATCH", "unfused")
+    m = models.nqueens(40, "distinct") if mode == "distinct" else models.nqueens(120)
+    kw = {"interval_set": True} if mode == "set" else ({"incremental": True} if mode == "incremental" else {})
+    probe = _engine(**kw)
     m.load_into(probe)
     paths = parallel.expand_frontier(probe, parts=k)[:k]
     devs, oras, stacks = [], [], []
     for p in paths:
-        d, o = _engine(), _oracle(2)
+        d, o = _engine(**kw), _oracle(SET + TUNED if mode == "set" else 2)
         for e in (d, o):
             m.load_into(e)
             e.consistency()
@@ -709,6 +717,7 @@ def test_consistency_batch_matches_lone_engines(k):
             parallel.post_decision(devs[i], dec)
             parallel.post_decision(oras[i], dec)
         sts, stats = pcp_b200.consistency_batch([devs[i] for i in live])
+        assert sum(int(s.launches) for s in stats) == (1 if fused and len(live) > 1 else len(live))
         for i, st in zip(live, sts):
             assert st == oras[i].consistency()[0], (rnd, i)
             if st == -1:
@@ -862,13 +871,16 @@ def test_all_equal_classes_with_distinct_representatives():
     _compare_search(m, 200)
 
 
-def test_compact_descriptor_stream_forced(monkeypatch):
-    """The compact 8-byte descriptor stream is only built for stores whose descriptors exceed the
-    L2 working set (C5); PCP_FORCE_COMPACT builds it for any all-XNeqY store, so that the sweep
-    over it is also checked node by node at a size the oracle handles (n-queens N=200 and 64)."""
-    monkeypatch.setenv("PCP_FORCE_COMPACT", "1")
-    _compare_search(models.nqueens(200), 150)
-    _compare_search(models.nqueens(64, "distinct"), 200)
+def test_compact_and_wide_descriptor_streams(monkeypatch):
+    """An all-XNeqY store over plain variables with 16-bit ids and offsets (n-queens, pairwise
+    distinct) is swept from the compact 8-byte copy of its descriptors; PCP_NO_COMPACT keeps the
+    16-byte stream (what every other store uses).  Both sweeps are checked node by node at sizes
+    the oracle handles, and against each other."""
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("PCP_NO_COMPACT", env)
+        _compare_search(models.nqueens(200), 150)
+        _compare_search(models.nqueens(64, "distinct"), 200)
 
 
 def test_result_paths_agree():
