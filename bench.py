@@ -41,8 +41,9 @@ import numpy as np  # noqa: E402
 
 BYTES_PER_PROP = {"c2": 32, "c5": 32, "c4": 48, "c3": 32}  # SURVEY 8d "algorithmic bytes per propagation"
 # what a sweep actually streams per propagation (the domains come from shared memory / L2):
-# 16-byte binary descriptors, the compact 8-byte stream at C5, 24-byte ternary descriptors
-STREAM_BYTES = {"c2": 16, "c5": 8, "c4": 24, "c3": 16}
+# 16-byte binary descriptors, the compact 8-byte stream of the all-XNeqY stores on Interval domains (C2, C5),
+# 24-byte ternary descriptors
+STREAM_BYTES = {"c2": 8, "c5": 8, "c4": 24, "c3": 16}
 
 
 def build_model(workload: str):
@@ -385,7 +386,7 @@ def run_ours(args):
             close_all(engines)
             return out
         e2e = e2e_pass(True, K_e2e)
-        e2e_dev = e2e_pass(False, K_dev)
+        e2e_dev = e2e_pass(False, K_dev, steps=max(args.steps, 200))  # (a 20-node window is two launches per context: too short to time)
         # PCP_FLAG_INCREMENTAL with the device-resident searches: nodes below the root evaluate their
         # posted constraint and the row of its variable instead of scheduling every propagator
         # (same statuses and domains: tests/); far fewer propagations per node, so nodes/s is its number
@@ -437,6 +438,7 @@ def run_ours(args):
             except Exception:
                 traffic = None
         rounds = max(f["rounds"], 1)
+        stream_b = 16 if (set_domains and workload in ("c2", "c5")) else STREAM_BYTES.get(workload, bpp)  # (IntervalSet: the 16-byte loop)
         line = {
             "metric": "propagations/s (and nodes/s) of the per-node propagation fixpoint",
             "value": value, "unit": "propagations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -502,9 +504,15 @@ def run_ours(args):
                          "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "kernel": "pcp_fixpoint_kernel (node prologue, TMA sweep, worklist iterations, label snapshot)"
                                    + (f"; the {K} contexts of a step share one launch (pcp_fixpoint_batch_kernel, {K} groups of CTAs)" if K > 1 else ""),
+                         "dram_frac": ((traffic * f["launches"]) / (f["ms"] * 1e-3) / 1e9 / peak) if traffic and f["ms"] > 0 and peak else None,
+                         "note": ("frac counts the algorithmic 32 B per propagation of every context; the contexts of a launch read "
+                                  "ONE copy of the descriptors (HBM once, then L2) and keep their domains in shared memory, so frac "
+                                  "can exceed 1: HBM moves `traffic` bytes per launch (dram_frac of the peak) and the launch is bound "
+                                  "by the sweep's issue rate (profiles/r2_c2_batch_fixpoint_*)" if K > 1 else
+                                  "frac: algorithmic bytes per propagation over the launch duration against the measured HBM peak"),
                          "algorithmic_bytes_per_propagation": bpp,
-                         "streamed_bytes_per_propagation": STREAM_BYTES.get(workload, bpp),
-                         "streamed_frac": ((f["propagations"] * STREAM_BYTES.get(workload, bpp)) / (f["ms"] * 1e-3) / 1e9 / peak) if f["ms"] > 0 else None,
+                         "streamed_bytes_per_propagation": stream_b,
+                         "streamed_frac": ((f["propagations"] * stream_b) / (f["ms"] * 1e-3) / 1e9 / peak) if f["ms"] > 0 else None,
                          "warm_frac": ((w["propagations"] * bpp) / (w["ms"] * 1e-3) / 1e9 / peak) if w["ms"] > 0 else None},
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -704,7 +712,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c2 (default) | c3 | c4 | c5 | nq<N>")
     ap.add_argument("--contexts", type=int, default=0, help="engines side by side per GPU in the device-timed rounds (0 = default: 24 for c2/c3, 1 for c4/c5)")
-    ap.add_argument("--e2e-contexts", type=int, default=12, help="contexts of the host-driven e2e loop (one host thread each)")
+    ap.add_argument("--e2e-contexts", type=int, default=24, help="contexts of the host-driven e2e loop (one host thread each)")
     ap.add_argument("--domains", default="interval", choices=["interval", "set"], help="Interval<i32> (VStoreFD) or IntervalSet<i32> (FDSpace) domains")
     ap.add_argument("--skip-nodes", type=int, default=0, help="advance every context by this many DFS nodes before the timed window (deep nodes)")
     ap.add_argument("--sync-every", type=int, default=8, help="multi-GPU e2e: nodes per context between two exchanges of the stop word")
