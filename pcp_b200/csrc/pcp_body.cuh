@@ -1709,11 +1709,14 @@ __device__ __forceinline__ void cta_init(const Params& P, CtaState& st, char* sm
   st.full = s_full;
   st.empty = s_empty;
   st.flags = s_flags;
-  // CTA 0 keeps the books (prologue, posted + tail propagators, result); the sweep is shared
-  // by the other CTAs so that nobody waits for it at the barrier
+  // CTA 0 keeps the books (prologue, posted + tail propagators, result); in a large group the sweep
+  // is shared by the other CTAs so that nobody waits for it at the barrier.  In a small group (the
+  // contexts of a batched launch: 6 CTAs each) a CTA's share of the sweep is tens of microseconds and
+  // the books are a few: there CTA 0 sweeps like everybody else instead of idling a sixth of the SMs.
   const ChunkMap m = chunk_map(P);
-  st.workers = cta_count() > 1 ? (int)cta_count() - 1 : 1;
-  st.wid = cta_count() > 1 ? (int)cta_rank() - 1 : 0;
+  const bool everybody = cta_count() <= (unsigned)kSweepAllCtas;
+  st.workers = cta_count() > 1 && !everybody ? (int)cta_count() - 1 : (int)cta_count();
+  st.wid = cta_count() > 1 && !everybody ? (int)cta_rank() - 1 : (int)cta_rank();
   st.my_chunks = 0;
   int off = 0;
   for (int f = 0; f < 3; ++f) {

@@ -22,6 +22,7 @@ constexpr int kChunkBin = kConsumerWarps * 32 * kGroupsBin;  // 1920 * 16 B = 30
 constexpr int kChunkTer = kConsumerWarps * 32 * kGroupsTer;  // 960 * 16 B + 960 * 8 B
 constexpr int kGroupsBinC = 8;           // compact 8-byte binary descriptors (Family::cdesc): twice the groups per stage
 constexpr int kChunkBinC = kConsumerWarps * 32 * kGroupsBinC;  // 3840 * 8 B = 30720 B
+constexpr int kSweepAllCtas = 32;       // groups up to this many CTAs: CTA 0 takes a share of the sweep too
 constexpr int kChunkDj = 480;           // 480 * 48 B = 23040 B
 static_assert(kChunkBin * 16 <= kStageBytes && kChunkTer * 16 <= 16384 && kChunkTer * 8 <= kStageBytes - 16384, "stage too small");
 constexpr int kTerPlaneB = 16384;       // offset of the z plane inside a stage
