@@ -209,16 +209,17 @@ def run_ours(args):
         desc += " -- IntervalSet<i32> domains (FDSpace, as example/src/nqueens.rs allocates them)"
     # contexts per GPU: engines side by side, each on its own subtree.  The streaming-bound
     # stores (C5: DRAM-bound sweep, C4: one fixpoint) gain nothing from it.
-    multi = workload in ("c2", "c3") or workload.startswith("nq")
-    K = args.contexts if args.contexts > 0 else (24 if multi else 1)
+    multi = workload in ("c2", "c3") or workload.startswith("nq") or args.contexts > 1
+    K = args.contexts if args.contexts > 0 else (74 if multi else (37 if workload == "c5" else 1))
+    multi = multi or K > 1
     # the host-driven loop runs one host thread per context, the device-resident searches one blocked
     # thread: their best context counts differ from the device-timed rounds' (measured: DESIGN 6)
     K_e2e = max(1, min(K, args.e2e_contexts)) if multi else 1
     # host threads of the host-driven loop: the rank's share of the cores; each thread pipelines its
     # share of the contexts (pcp_search_step_many)
     os.environ.setdefault("PCP_SEARCH_THREADS", str(max(1, min(K_e2e, 6, (os.cpu_count() or 8) // max(world, 1) - 1))))
-    K_dev = min(max(K, 1), 20) if multi else 1
-    K_inc = 30 if multi and args.contexts == 0 else K
+    K_dev = (args.dev_contexts or min(max(K, 1), 20)) if multi else 1
+    K_inc = (args.inc_contexts or (30 if args.contexts == 0 else K)) if multi else K
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -260,7 +261,7 @@ def run_ours(args):
         engines = [first] + [first.fork() for _ in range(k - 1)]
         for i, e in enumerate(engines):
             if k > 1:
-                e.set_grid_limit(max(2, sms // k))
+                e.set_grid_limit(max(1, sms // k))
             root = e.label()
             parallel.enter_subtree(e, root, paths[(rank * k + i) % len(paths)])
         return engines
@@ -711,8 +712,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, help="c2 (default) | c3 | c4 | c5 | nq<N>")
-    ap.add_argument("--contexts", type=int, default=0, help="engines side by side per GPU in the device-timed rounds (0 = default: 24 for c2/c3, 1 for c4/c5)")
-    ap.add_argument("--e2e-contexts", type=int, default=24, help="contexts of the host-driven e2e loop (one host thread each)")
+    ap.add_argument("--contexts", type=int, default=0, help="engines side by side per GPU in the device-timed rounds (0 = default: 74 for c2/c3 -- two CTAs each --, 37 for c5, 1 for c4)")
+    ap.add_argument("--e2e-contexts", type=int, default=74, help="contexts of the host-driven e2e loop (shared by PCP_SEARCH_THREADS host threads)")
+    ap.add_argument("--dev-contexts", type=int, default=0, help="contexts of the device-resident searches (0 = default)")
+    ap.add_argument("--inc-contexts", type=int, default=0, help="contexts of the incremental device-resident searches (0 = default)")
     ap.add_argument("--domains", default="interval", choices=["interval", "set"], help="Interval<i32> (VStoreFD) or IntervalSet<i32> (FDSpace) domains")
     ap.add_argument("--skip-nodes", type=int, default=0, help="advance every context by this many DFS nodes before the timed window (deep nodes)")
     ap.add_argument("--sync-every", type=int, default=8, help="multi-GPU e2e: nodes per context between two exchanges of the stop word")

@@ -955,7 +955,7 @@ int launch_ctas(const pcp_engine* e) {
   int n = e->num_sms;
   if (e->grid_limit > 0) n = std::min(n, e->grid_limit);
   if (env > 0) n = std::min(n, env);
-  return std::max(n, 2);  // (CTA 0 keeps the books, the others sweep)
+  return std::max(n, 1);
 }
 
 struct HostProf {
@@ -1661,7 +1661,7 @@ int pcp_consistency_batch(pcp_engine* const* engines, int32_t n, int32_t* status
     rc = guarded(e, [&] {
       PCP_REQUIRE_NO_BURST(e);
       CUDA_CHECK(cudaSetDevice(e->device));
-      if (e->grid_limit == 0 && n > 1) e->grid_limit = std::max(2, e->num_sms / n);
+      if (e->grid_limit == 0 && n > 1) e->grid_limit = std::max(1, e->num_sms / n);
       fixpoint_prepare(e);
     });
     if (rc == PCP_OK) ++prepared;

@@ -232,7 +232,7 @@ class SubtreeContexts:
         self.paths = []
         for i, e in enumerate(self.engines):
             if k > 1:
-                e.set_grid_limit(max(2, device_sms // k))
+                e.set_grid_limit(max(1, device_sms // k))
             root = e.label()
             path = frontier[i % len(frontier)]
             enter_subtree(e, root, path)
