@@ -521,24 +521,29 @@ __device__ __noinline__ unsigned sweep_bin_compact(const Ctx& c, const FamSweep 
         d[g] = make_int2(0, 0);
         if (aw.w[h + g] & lane_bit) d[g] = lds_dom(d_s + 256u * (h + g));
       }
+      // word 0: the byte offsets of the two domains (variable index * 8); word 1: x's view offset and
+      // the DIFFERENCE of the two view offsets.  The no-op test of an XNeqY -- both sides unassigned,
+      // views overlapping (bin_is_noop) -- needs no view arithmetic then: x.hi < y.lo  <=>
+      // dx.hi - dy.lo < yoff - xoff, y.hi < x.lo  <=>  dx.lo - dy.hi > yoff - xoff.
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        dx[g] = rd_plain<SMEM>(a.sdom_s, a.dom, (int)((unsigned)d[g].x & 0xffffu));
-        dy[g] = rd_plain<SMEM>(a.sdom_s, a.dom, (int)((unsigned)d[g].x >> 16));
+        const unsigned bx = (unsigned)d[g].x & 0xffffu, by = (unsigned)d[g].x >> 16;
+        dx[g] = SMEM ? lds_dom(a.sdom_s + bx) : ldcg_dom(reinterpret_cast<const int2*>(reinterpret_cast<const char*>(a.dom) + bx));
+        dy[g] = SMEM ? lds_dom(a.sdom_s + by) : ldcg_dom(reinterpret_cast<const int2*>(reinterpret_cast<const char*>(a.dom) + by));
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const int xo = (int)(short)((unsigned)d[g].y & 0xffffu), yo = d[g].y >> 16;
-        const IV x{dx[g].x + xo, dx[g].y + xo}, y{dy[g].x + yo, dy[g].y + yo};
-        if ((aw.w[h + g] & lane_bit) && !bin_is_noop(B_NEQ, x, y)) need |= 1u << g;
+        const int delta = d[g].y >> 16;
+        const bool noop = dx[g].x != dx[g].y && dy[g].x != dy[g].y && !(dx[g].y - dy[g].x < delta || dx[g].x - dy[g].y > delta);
+        if ((aw.w[h + g] & lane_bit) && !noop) need |= 1u << g;
       }
       if (need) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (!((need >> g) & 1u)) continue;
-          const int xo = (int)(short)((unsigned)d[g].y & 0xffffu), yo = d[g].y >> 16;
+          const int xo = (int)(short)((unsigned)d[g].y & 0xffffu), yo = xo + (d[g].y >> 16);
           const IV x{dx[g].x + xo, dx[g].y + xo}, y{dy[g].x + yo, dy[g].y + yo};
-          const int4 full = make_int4((int)((B_NEQ << 28) | ((unsigned)d[g].x & 0xffffu)), xo, (int)((unsigned)d[g].x >> 16), yo);
+          const int4 full = make_int4((int)((B_NEQ << 28) | (((unsigned)d[g].x & 0xffffu) >> 3)), xo, (int)((unsigned)d[g].x >> 19), yo);
           sweep_neq_update(c, a, base + 32 * (h + g) + lane, full, x, y);
         }
       }

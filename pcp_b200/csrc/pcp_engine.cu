@@ -633,15 +633,19 @@ void build_csr(pcp_engine* e) {
     // loses 0.7 us to the unpacking, the contexts of a batched launch -- every SM sweeping at once --
     // gain 4-6 % from the halved L2 traffic; the batch is the configuration that counts.  Interval
     // domains only: the IntervalSet sweep has its witness probe in the 16-byte loop.)
-    bool ok = !no_compact && !e->set_mode && hb.n > 0 && V <= 65536 && hb.first_nonplain >= hb.n &&
+    // word 0 = (xvar * 8) | (yvar * 8) << 16 (byte offsets into the domain array: V < 8192, which every
+    // store with a shared-memory snapshot satisfies); word 1 = (u16) xoff | (yoff - xoff) << 16
+    bool ok = !no_compact && !e->set_mode && hb.n > 0 && V < 8192 && hb.first_nonplain >= hb.n &&
               hb.static_kind_mask == (1 << B_NEQ);
     std::vector<uint2> cd;
     if (ok) {
       cd.resize(hb.n);
       for (size_t i = 0; i < hb.n && ok; ++i) {
         const int4& d = hb.desc[i];
-        ok = d.y >= -32768 && d.y <= 32767 && d.w >= -32768 && d.w <= 32767;
-        cd[i] = make_uint2(((unsigned)d.x & 0xffffu) | ((unsigned)d.z << 16), ((unsigned)d.y & 0xffffu) | ((unsigned)d.w << 16));
+        const long long delta = (long long)d.w - (long long)d.y;
+        ok = d.y >= -32768 && d.y <= 32767 && delta >= -32768 && delta <= 32767;
+        const unsigned xv = (unsigned)d.x & 0xffffu, yv = (unsigned)d.z & 0xffffu;
+        cd[i] = make_uint2((xv * 8u) | ((yv * 8u) << 16), ((unsigned)d.y & 0xffffu) | ((unsigned)(int)delta << 16));
       }
     }
     if (ok) {
