@@ -2497,29 +2497,18 @@ __device__ __noinline__ void burst_host_step(const Params& P, const BurstParams&
   __syncthreads();
 }
 
+// A slice of one engine's device-resident search.  `P`, `B`: the launch parameters where the hot
+// loops read them (the kernel's parameter space, or shared memory in a batched launch); `s_P`,
+// `s_B`: their copies in shared memory for the out-of-line sections.
 template <bool SMEM>
-__global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_constant__ Params P,
-                                                                const __grid_constant__ BurstParams B) {
-  extern __shared__ __align__(128) char smem[];
+__device__ __forceinline__ void burst_launch_body(const Params& P, const BurstParams& B, const Params& s_P, const BurstParams& s_B,
+                                                  char* smem) {
   __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages];
   __shared__ int s_flags[2];
   __shared__ int s_cmd, s_slot, s_bin_n;
   __shared__ InlineProp s_inl;
   __shared__ BurstLocal s_local;
-  __shared__ Params s_P;  // copy of the launch parameters for the out-of-line cold sections
-  {
-    const unsigned* src = reinterpret_cast<const unsigned*>(&P);
-    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
-    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = src[i];  // (ordered by the barrier below)
-  }
   const Params* PS = &s_P;
-  __shared__ BurstParams s_B;
-  {
-    const unsigned* src = reinterpret_cast<const unsigned*>(&B);
-    unsigned* dst = reinterpret_cast<unsigned*>(&s_B);
-    for (int i = threadIdx.x; i < (int)(sizeof(BurstParams) / 4); i += blockDim.x) dst[i] = src[i];
-  }
-  cta_place(blockIdx.x, gridDim.x);
   CtaState st;
   cta_init(P, st, smem, s_full, s_empty, s_flags, SMEM);
   if (st.dbm) for (int w = threadIdx.x; w < P.dirty_words; w += blockDim.x) st.dbm[w] = 0u;  // (ordered by the barrier below)
@@ -2662,5 +2651,49 @@ __global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_con
     r.gen = st.gen;
     *P.result = r;
   }
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(kThreads, 1) pcp_burst_kernel(const __grid_constant__ Params P,
+                                                                const __grid_constant__ BurstParams B) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ Params s_P;  // copies of the launch parameters for the out-of-line cold sections
+  __shared__ BurstParams s_B;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&P);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&B);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_B);
+    for (int i = threadIdx.x; i < (int)(sizeof(BurstParams) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  cta_place(blockIdx.x, gridDim.x);  // (its barrier also orders the copies above)
+  burst_launch_body<SMEM>(P, B, s_P, s_B, smem);
+}
+
+// Slices of several engines' device-resident searches in ONE launch (pcp_search_step_many on
+// searches whose engines run the same kernel variant with the same geometry): CTAs
+// [k * group, (k + 1) * group) run engine k's search with batchP[k] / batchB[k].  The groups never
+// meet: every search runs through its own node budget at its own pace.
+__global__ void __launch_bounds__(kThreads, 1) pcp_burst_batch_kernel(const Params* __restrict__ batchP,
+                                                                     const BurstParams* __restrict__ batchB, int group) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ Params s_P;
+  __shared__ BurstParams s_B;
+  const unsigned k = blockIdx.x / (unsigned)group;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(batchP + k);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_P);
+    for (int i = threadIdx.x; i < (int)(sizeof(Params) / 4); i += blockDim.x) dst[i] = __ldg(&src[i]);
+  }
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(batchB + k);
+    unsigned* dst = reinterpret_cast<unsigned*>(&s_B);
+    for (int i = threadIdx.x; i < (int)(sizeof(BurstParams) / 4); i += blockDim.x) dst[i] = __ldg(&src[i]);
+  }
+  cta_place(blockIdx.x - k * (unsigned)group, (unsigned)group);
+  burst_launch_body<true>(s_P, s_B, s_P, s_B, smem);
 }
 

@@ -147,6 +147,9 @@ struct pcp_engine {
   Params* d_batch = nullptr;  // pcp_consistency_batch, one launch for several engines: their launch parameters
   Params* h_batch = nullptr;  // (pinned staging of the same)
   int batch_cap = 0;
+  void* d_bbatch = nullptr;   // pcp_search_step_many, one launch for several device searches: parameters + results
+  void* h_bbatch = nullptr;
+  int burst_batch_cap = 0;
   bool timing = false;
   int num_sms = 0;
   int grid_limit = 0;               // pcp_set_grid_limit: CTAs a launch of this engine may use (0 = all SMs)
@@ -1342,7 +1345,9 @@ int pcp_engine_create(const pcp_config* cfg, pcp_engine** out) {
     {
       // dynamic shared memory every persistent kernel may use = the opt-in maximum minus its own
       // static part; configured once (an engine never lowers what another engine relies on)
-      const void* fns[20] = {fixpoint_batch_fn(false, false), fixpoint_batch_fn(false, true), fixpoint_batch_fn(true, false), fixpoint_batch_fn(true, true),
+      const void* fns[24] = {(const void*)binonly::pcp_burst_batch_kernel, (const void*)full::pcp_burst_batch_kernel,
+                             (const void*)binonly_set::pcp_burst_batch_kernel, (const void*)full_set::pcp_burst_batch_kernel,
+                             fixpoint_batch_fn(false, false), fixpoint_batch_fn(false, true), fixpoint_batch_fn(true, false), fixpoint_batch_fn(true, true),
                              burst_set_fn(false, false), burst_set_fn(false, true), burst_set_fn(true, false), burst_set_fn(true, true),fixpoint_fn(false, false), fixpoint_fn(false, true), burst_fn(false, false), burst_fn(false, true),
                              fixpoint_fn(true, false),  fixpoint_fn(true, true),  burst_fn(true, false),  burst_fn(true, true),
                              fixpoint_set_fn(false, false), fixpoint_set_fn(false, true), fixpoint_set_fn(true, false),
@@ -1532,6 +1537,8 @@ void pcp_engine_destroy(pcp_engine* e) {
   if (e->h_stage) cudaFreeHost(e->h_stage);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->d_bbatch) cudaFree(e->d_bbatch);
+  if (e->h_bbatch) cudaFreeHost(e->h_bbatch);
   if (e->d_batch) cudaFree(e->d_batch);
   if (e->h_batch) cudaFreeHost(e->h_batch);
   if (e->ev_done) cudaEventDestroy(e->ev_done);
@@ -2163,60 +2170,102 @@ int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node
   return rc;
 }
 
+namespace {
+struct BurstLaunch {
+  BurstParams B;
+  const void* fn = nullptr;
+  int grid = 0;
+  size_t smem = 0;
+  bool smem_dom = false;
+};
+
+// launch parameters of the next slice of e's device search (e->burst.P is completed in place)
+void burst_prepare(pcp_engine* e, uint64_t max_nodes, BurstLaunch& L) {
+  auto& b = e->burst;
+  PCP_REQUIRE(b.open, "no device search is open");
+  const size_t V = e->V;
+  BurstParams& B = L.B;
+  std::memset(&B, 0, sizeof(B));
+  B.bc = b.d_bc;
+  B.branches = b.d_branches.p;
+  B.label_meta = b.d_meta.p;
+  B.branch_meta = b.d_bmeta.p;
+  B.stack = e->d_stack.p;
+  B.stack_stride = (long long)e->stack_stride;
+  B.max_labels = b.max_labels;
+  B.max_branches = (int)b.d_branches.cap;
+  B.bin_cap = b.bin_cap;
+  B.all_solutions = b.all_solutions;
+  B.incremental = (e->flags & PCP_FLAG_INCREMENTAL) ? 1 : 0;
+  B.node_budget = max_nodes ? max_nodes : ~0ull;
+  B.node_limit = b.node_limit;
+  B.props_base = b.props_base;
+  B.t_status = b.trace_cap ? b.d_tstatus.p : nullptr;
+  B.t_dom = (b.trace_cap && b.trace_dom) ? b.d_tdom.p : nullptr;
+  B.t_bits = (b.trace_cap && b.trace_dom && e->set_mode) ? b.d_tbits.p : nullptr;
+  B.t_cap = b.trace_cap;
+  Params& P = b.P;
+  P.max_iterations = e->max_iterations;
+  if (e->epoch > 0x70000000u) {  // epoch wrap, as in run_fixpoint
+    for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
+    e->epoch = 1;
+  }
+  P.gen0 = e->bar_gen;
+  P.epoch0 = e->epoch;
+  size_t total = e->n_nary * 4096;
+  for (int f = 0; f < 3; ++f) total += e->fam[f].n;
+  L.grid = (int)std::min<size_t>((size_t)launch_ctas(e), std::max<size_t>(1, (total + 4095) / 4096));
+  size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
+  L.smem_dom = (size_t)kRingBytes + dom_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin;
+  L.smem = (size_t)kRingBytes + (L.smem_dom ? dom_bytes : 0);
+  P.smem_dom = L.smem_dom ? 1 : 0;
+  {
+    const size_t bm_bytes = (e->dirty_words * 4 + 15) & ~size_t(15);
+    P.dirty_bm_off = 0;
+    if (!L.smem_dom && L.smem + bm_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin) {
+      P.dirty_bm_off = (int)L.smem;
+      L.smem += bm_bytes;
+    }
+  }
+  L.fn = e->set_mode ? burst_set_fn(bin_only_store(e), L.smem_dom) : burst_fn(bin_only_store(e), L.smem_dom);
+}
+
+// host bookkeeping after a slice: `bc` and the result header have been copied back
+void burst_finish(pcp_engine* e, const BurstCtl& bc, pcp_burst_result* res) {
+  auto& b = e->burst;
+  const Result& r = *e->h_result();
+  e->epoch = r.epoch;
+  e->bar_gen = r.gen;
+  e->trail_len = r.trail_cnt;
+  e->props_total = r.propagations;
+  e->mirror_valid = false;
+  e->snapshot_valid = false;
+  e->at_fixpoint = false;
+  ++e->dom_version;
+  if (bc.err == 2) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
+  if (bc.err == 3) PCP_FAIL(PCP_ERR_CUDA, "device search: the bookkeeping CTA and the grid derived different branching decisions");
+  if (bc.err) PCP_FAIL(PCP_ERR_NOMEM, "device search: label / branch / tail capacity exceeded (pcp_config.max_labels)");
+  res->status = bc.status;
+  res->err = bc.err;
+  res->nodes = bc.nodes;
+  res->solutions = bc.solutions;
+  res->failures = bc.failures;
+  res->iterations = bc.iterations;
+  res->propagations = r.propagations - b.props0;
+  res->kernel_seconds = b.kernel_seconds;
+}
+}  // namespace
+
 int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result* res) {
   if (!e || !res) return PCP_ERR_INVALID;
   return guarded(e, [&] {
     auto& b = e->burst;
-    PCP_REQUIRE(b.open, "no device search is open");
     CUDA_CHECK(cudaSetDevice(e->device));
-    const size_t V = e->V;
-    BurstParams B;
-    std::memset(&B, 0, sizeof(B));
-    B.bc = b.d_bc;
-    B.branches = b.d_branches.p;
-    B.label_meta = b.d_meta.p;
-    B.branch_meta = b.d_bmeta.p;
-    B.stack = e->d_stack.p;
-    B.stack_stride = (long long)e->stack_stride;
-    B.max_labels = b.max_labels;
-    B.max_branches = (int)b.d_branches.cap;
-    B.bin_cap = b.bin_cap;
-    B.all_solutions = b.all_solutions;
-    B.incremental = (e->flags & PCP_FLAG_INCREMENTAL) ? 1 : 0;
-    B.node_budget = max_nodes ? max_nodes : ~0ull;
-    B.node_limit = b.node_limit;
-    B.props_base = b.props_base;
-    B.t_status = b.trace_cap ? b.d_tstatus.p : nullptr;
-    B.t_dom = (b.trace_cap && b.trace_dom) ? b.d_tdom.p : nullptr;
-    B.t_bits = (b.trace_cap && b.trace_dom && e->set_mode) ? b.d_tbits.p : nullptr;
-    B.t_cap = b.trace_cap;
-    Params& P = b.P;
-    P.max_iterations = e->max_iterations;
-    if (e->epoch > 0x70000000u) {  // epoch wrap, as in run_fixpoint
-      for (int f = 0; f < 3; ++f) fill_u32(e, e->fam[f].d_stamp.p, 0u, e->fam[f].d_stamp.cap);
-      e->epoch = 1;
-    }
-    P.gen0 = e->bar_gen;
-    P.epoch0 = e->epoch;
-    size_t total = e->n_nary * 4096;
-    for (int f = 0; f < 3; ++f) total += e->fam[f].n;
-    int grid = (int)std::min<size_t>((size_t)launch_ctas(e), std::max<size_t>(1, (total + 4095) / 4096));
-    size_t dom_bytes = (V * 8 + 15) & ~size_t(15);
-    bool smem_dom = (size_t)kRingBytes + dom_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin;
-    size_t smem = (size_t)kRingBytes + (smem_dom ? dom_bytes : 0);
-    P.smem_dom = smem_dom ? 1 : 0;
-    {
-      const size_t bm_bytes = (e->dirty_words * 4 + 15) & ~size_t(15);
-      P.dirty_bm_off = 0;
-      if (!smem_dom && smem + bm_bytes + e->static_smem + 256 <= (size_t)e->max_smem_optin) {
-        P.dirty_bm_off = (int)smem;
-        smem += bm_bytes;
-      }
-    }
-    const void* fn = e->set_mode ? burst_set_fn(bin_only_store(e), smem_dom) : burst_fn(bin_only_store(e), smem_dom);
+    BurstLaunch L;
+    burst_prepare(e, max_nodes, L);
     CUDA_CHECK(cudaEventRecord(e->ev0, e->stream));
-    void* args[] = {&P, &B};
-    launch_persistent(fn, grid, args, smem, e->stream);
+    void* args[] = {&b.P, &L.B};
+    launch_persistent(L.fn, L.grid, args, L.smem, e->stream);
     CUDA_CHECK(cudaEventRecord(e->ev1, e->stream));
     BurstCtl bc;
     CUDA_CHECK(cudaMemcpyAsync(&bc, b.d_bc, sizeof(bc), cudaMemcpyDeviceToHost, e->stream));
@@ -2228,27 +2277,99 @@ int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result*
     float ms = 0;
     CUDA_CHECK(cudaEventElapsedTime(&ms, e->ev0, e->ev1));
     b.kernel_seconds += ms * 1e-3;
-    const Result& r = *e->h_result();
-    e->epoch = r.epoch;
-    e->bar_gen = r.gen;
-    e->trail_len = r.trail_cnt;
-    e->props_total = r.propagations;
-    e->mirror_valid = false;
-    e->snapshot_valid = false;
-    e->at_fixpoint = false;
-    ++e->dom_version;
-    if (bc.err == 2) PCP_FAIL(PCP_ERR_CUDA, "fixpoint iteration cap reached");
-    if (bc.err == 3) PCP_FAIL(PCP_ERR_CUDA, "device search: the bookkeeping CTA and the grid derived different branching decisions");
-    if (bc.err) PCP_FAIL(PCP_ERR_NOMEM, "device search: label / branch / tail capacity exceeded (pcp_config.max_labels)");
-    res->status = bc.status;
-    res->err = bc.err;
-    res->nodes = bc.nodes;
-    res->solutions = bc.solutions;
-    res->failures = bc.failures;
-    res->iterations = bc.iterations;
-    res->propagations = r.propagations - b.props0;
-    res->kernel_seconds = b.kernel_seconds;
+    burst_finish(e, bc, res);
   });
+}
+
+// The next slice of several device searches in ONE launch (pcp_burst_batch_kernel: a group of CTAs
+// per search).  *fused = 0 and nothing done when the engines cannot share a launch (different kernel
+// variants or geometries, no shared-memory snapshot, more CTAs than SMs): the caller then steps them
+// one by one.  budgets[i] = node budget of search i for this slice.
+int pcp_internal_burst_step_many(pcp_engine* const* es, int32_t n, const uint64_t* budgets, pcp_burst_result* res, int32_t* fused) {
+  if (!es || n <= 0 || !budgets || !res || !fused) return PCP_ERR_INVALID;
+  *fused = 0;
+  pcp_engine* lead = es[0];
+  std::vector<BurstLaunch> Ls((size_t)n);
+  int rc = PCP_OK;
+  {
+    const char* sw = std::getenv("PCP_BATCH");  // measurement / test switch
+    if (sw && std::strcmp(sw, "unfused") == 0) return PCP_OK;
+  }
+  // can they share a launch?  (decided before anything is changed)
+  for (int i = 0; i < n; ++i) {
+    pcp_engine* e = es[i];
+    if (!e || !e->burst.open || e->device != lead->device || e->set_mode != lead->set_mode ||
+        bin_only_store(e) != bin_only_store(lead))
+      return PCP_OK;
+    for (int j = 0; j < i; ++j)
+      if (es[j] == e) return PCP_OK;
+  }
+  for (int i = 0; i < n && rc == PCP_OK; ++i) {
+    pcp_engine* e = es[i];
+    rc = guarded(e, [&] {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      burst_prepare(e, budgets[i], Ls[(size_t)i]);  // (idempotent: nothing is consumed before the launch)
+    });
+  }
+  if (rc != PCP_OK) return rc;
+  for (int i = 0; i < n; ++i)
+    if (!Ls[(size_t)i].smem_dom || Ls[(size_t)i].grid != Ls[0].grid || Ls[(size_t)i].smem != Ls[0].smem) return PCP_OK;
+  if ((long long)n * Ls[0].grid > lead->num_sms) return PCP_OK;
+  rc = guarded(lead, [&] {
+    const size_t bytes_p = (size_t)n * sizeof(Params), bytes_b = (size_t)n * sizeof(BurstParams);
+    if (lead->burst_batch_cap < n) {
+      if (lead->d_bbatch) cudaFree(lead->d_bbatch);
+      if (lead->h_bbatch) cudaFreeHost(lead->h_bbatch);
+      lead->d_bbatch = lead->h_bbatch = nullptr;
+      lead->burst_batch_cap = 0;
+      const size_t cap = (size_t)std::max(n, 32);
+      CUDA_CHECK(cudaMalloc(&lead->d_bbatch, cap * (sizeof(Params) + sizeof(BurstParams)) + cap * (sizeof(BurstCtl) + sizeof(Result))));
+      CUDA_CHECK(cudaHostAlloc(&lead->h_bbatch, cap * (sizeof(Params) + sizeof(BurstParams)) + cap * (sizeof(BurstCtl) + sizeof(Result)), cudaHostAllocDefault));
+      lead->burst_batch_cap = (int)cap;
+    }
+    const size_t cap = (size_t)lead->burst_batch_cap;
+    char* hb = static_cast<char*>(lead->h_bbatch);
+    char* db = static_cast<char*>(lead->d_bbatch);
+    Params* hP = reinterpret_cast<Params*>(hb);
+    BurstParams* hB = reinterpret_cast<BurstParams*>(hb + cap * sizeof(Params));
+    const Params* dP = reinterpret_cast<const Params*>(db);
+    const BurstParams* dB = reinterpret_cast<const BurstParams*>(db + cap * sizeof(Params));
+    BurstCtl* hbc = reinterpret_cast<BurstCtl*>(hb + cap * (sizeof(Params) + sizeof(BurstParams)));
+    for (int i = 0; i < n; ++i) { hP[i] = es[i]->burst.P; hB[i] = Ls[(size_t)i].B; }
+    for (int i = 1; i < n; ++i) {
+      CUDA_CHECK(cudaEventRecord(es[i]->ev_done, es[i]->stream));
+      CUDA_CHECK(cudaStreamWaitEvent(lead->stream, es[i]->ev_done, 0));
+    }
+    CUDA_CHECK(cudaMemcpyAsync(db, hb, bytes_p, cudaMemcpyHostToDevice, lead->stream));
+    CUDA_CHECK(cudaMemcpyAsync(db + cap * sizeof(Params), hb + cap * sizeof(Params), bytes_b, cudaMemcpyHostToDevice, lead->stream));
+    const void* fn = lead->set_mode ? (bin_only_store(lead) ? (const void*)binonly_set::pcp_burst_batch_kernel : (const void*)full_set::pcp_burst_batch_kernel)
+                                    : (bin_only_store(lead) ? (const void*)binonly::pcp_burst_batch_kernel : (const void*)full::pcp_burst_batch_kernel);
+    int group = Ls[0].grid;
+    void* args[] = {(void*)&dP, (void*)&dB, (void*)&group};
+    CUDA_CHECK(cudaEventRecord(lead->ev0, lead->stream));
+    launch_persistent(fn, n * group, args, Ls[0].smem, lead->stream);
+    CUDA_CHECK(cudaEventRecord(lead->ev1, lead->stream));
+    for (int i = 0; i < n; ++i) {
+      CUDA_CHECK(cudaMemcpyAsync(&hbc[i], es[i]->burst.d_bc, sizeof(BurstCtl), cudaMemcpyDeviceToHost, lead->stream));
+      CUDA_CHECK(cudaMemcpyAsync(es[i]->h_block, es[i]->d_block, sizeof(Result), cudaMemcpyDeviceToHost, lead->stream));
+    }
+    CUDA_CHECK(cudaEventRecord(lead->ev_done, lead->stream));
+    for (int i = 1; i < n; ++i) CUDA_CHECK(cudaStreamWaitEvent(es[i]->stream, lead->ev_done, 0));
+    CUDA_CHECK(cudaEventRecord(lead->ev_sleep, lead->stream));
+    CUDA_CHECK(cudaEventSynchronize(lead->ev_sleep));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, lead->ev0, lead->ev1));
+    for (int i = 0; i < n; ++i) es[i]->burst.kernel_seconds += ms * 1e-3 / n;  // (the launch's time, shared out)
+  });
+  if (rc != PCP_OK) return rc;
+  *fused = 1;
+  const BurstCtl* hbc = reinterpret_cast<const BurstCtl*>(static_cast<char*>(lead->h_bbatch) +
+                                                         (size_t)lead->burst_batch_cap * (sizeof(Params) + sizeof(BurstParams)));
+  for (int i = 0; i < n; ++i) {
+    int r2 = guarded(es[i], [&] { burst_finish(es[i], hbc[i], &res[i]); });
+    if (rc == PCP_OK) rc = r2;
+  }
+  return rc;
 }
 
 // The bit sets of traced nodes [first, first + n) of an IntervalSet engine, re-based into the window

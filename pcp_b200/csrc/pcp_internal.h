@@ -24,6 +24,9 @@ int pcp_internal_burst_supported(pcp_engine* e, const pcp_search_config* cfg, ui
 int pcp_internal_burst_begin(pcp_engine* e, int32_t all_solutions, uint64_t node_limit, uint64_t trace_capacity,
                              int32_t trace_domains);
 int pcp_internal_burst_step(pcp_engine* e, uint64_t max_nodes, pcp_burst_result* res);
+/* the next slice of n device searches in one launch (a group of CTAs per search); *fused = 0 and
+ * nothing done when their engines cannot share a launch */
+int pcp_internal_burst_step_many(pcp_engine* const* es, int32_t n, const uint64_t* budgets, pcp_burst_result* res, int32_t* fused);
 /* copies the per-node trace of nodes [first, first+n): status and (if recorded) domains */
 int pcp_internal_burst_trace(pcp_engine* e, uint64_t first, uint64_t n, int32_t* status, int32_t* lo, int32_t* hi);
 /* IntervalSet engines: the value sets of traced nodes as bit windows [n * V, words] from `base` */

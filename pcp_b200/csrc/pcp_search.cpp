@@ -208,40 +208,55 @@ struct Driver {
     return PCP_OK;
   }
 
-  int step_burst(uint64_t max_nodes, int* out) {
+  // The device search in slices.  burst_slice_pre: open it on first use and size the next slice
+  // (the warm-up nodes end a slice of their own); burst_slice_post: account for what the slice ran;
+  // *finished when the call's budget is used up or the search reported a status.
+  int burst_slice_pre(uint64_t remaining, uint64_t* budget, bool* timed) {
     if (!burst_begun) {
       TRY(pcp_num_vars(e, &V));
       TRY(pcp_internal_burst_begin(e, cfg->all_solutions, cfg->node_limit, t_cap, cfg->trace_domains));
       burst_begun = true;
     }
+    const uint64_t warm = (uint64_t)cfg->warmup_nodes;
+    *timed = res->num_nodes >= warm;
+    *budget = remaining;
+    if (!*timed) *budget = std::min<uint64_t>(*budget, warm - res->num_nodes);
+    return PCP_OK;
+  }
+  int burst_slice_post(const pcp_burst_result& br, double dt, bool timed, bool unlimited, uint64_t* remaining, int* out, bool* finished) {
+    const uint64_t ran = br.nodes - br_prev.nodes;
+    if (timed) {
+      res->seconds += dt;
+      res->propagations += br.propagations - br_prev.propagations;
+      res->iterations += br.iterations - br_prev.iterations;
+      res->kernel_seconds += br.kernel_seconds - br_prev.kernel_seconds;
+    }
+    if (t_cap && br_prev.nodes < t_cap) TRY(copy_burst_trace(br_prev.nodes, br.nodes));
+    res->num_nodes = br.nodes;
+    res->num_solution = br.solutions;
+    res->num_failed_node = br.failures;
+    br_prev = br;
+    *finished = false;
+    if (br.status != 0) { *out = br.status; if (br.status == 2) stopped = true; *finished = true; return PCP_OK; }
+    if (!unlimited) {
+      *remaining -= std::min(*remaining, ran);
+      if (*remaining == 0) { *out = 0; *finished = true; }
+    }
+    return PCP_OK;
+  }
+  int step_burst(uint64_t max_nodes, int* out) {
     uint64_t remaining = max_nodes;
     const bool unlimited = max_nodes == ~0ull;
     while (true) {
-      uint64_t budget = remaining;
-      const uint64_t warm = (uint64_t)cfg->warmup_nodes;
-      const bool timed = res->num_nodes >= warm;
-      if (!timed) budget = std::min<uint64_t>(budget, warm - res->num_nodes);
+      uint64_t budget = 0;
+      bool timed = false, finished = false;
+      TRY(burst_slice_pre(remaining, &budget, &timed));
       pcp_burst_result br{};
       auto t0 = std::chrono::steady_clock::now();
       TRY(pcp_internal_burst_step(e, budget, &br));
       double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      const uint64_t ran = br.nodes - br_prev.nodes;
-      if (timed) {
-        res->seconds += dt;
-        res->propagations += br.propagations - br_prev.propagations;
-        res->iterations += br.iterations - br_prev.iterations;
-        res->kernel_seconds += br.kernel_seconds - br_prev.kernel_seconds;
-      }
-      if (t_cap && br_prev.nodes < t_cap) TRY(copy_burst_trace(br_prev.nodes, br.nodes));
-      res->num_nodes = br.nodes;
-      res->num_solution = br.solutions;
-      res->num_failed_node = br.failures;
-      br_prev = br;
-      if (br.status != 0) { *out = br.status; if (br.status == 2) stopped = true; return PCP_OK; }
-      if (!unlimited) {
-        remaining -= std::min(remaining, ran);
-        if (remaining == 0) { *out = 0; return PCP_OK; }
-      }
+      TRY(burst_slice_post(br, dt, timed, unlimited, &remaining, out, &finished));
+      if (finished) return PCP_OK;
     }
   }
 
@@ -436,6 +451,61 @@ int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, p
   // its own worker thread, so that a search that needs a worklist iteration does not hold up the
   // round and the host work of one node (post, launch, read back, branch) overlaps the others'.
   static const bool lockstep = [] { const char* v = std::getenv("PCP_SEARCH_LOCKSTEP"); return v && v[0] == '1'; }();
+  if (all_burst && n > 1) {
+    // Device-resident searches whose engines can share a launch (forks of one model: same kernel, same
+    // geometry) advance slice by slice in ONE launch -- a group of CTAs per search, no host thread per
+    // search, every search free-running through its budget inside the launch.
+    const bool unlimited = budget == ~0ull;
+    std::vector<uint64_t> remaining((size_t)n, budget), budgets;
+    std::vector<char> fin((size_t)n, 0), timed;
+    std::vector<int> who, outs((size_t)n, 0);
+    std::vector<pcp_engine*> es;
+    std::vector<pcp_burst_result> brs;
+    bool first = true, fell_back = false;
+    while (true) {
+      who.clear(); es.clear(); budgets.clear(); timed.clear();
+      for (int i = 0; i < n; ++i) {
+        if (fin[(size_t)i]) continue;
+        Driver& d = ss[i]->d;
+        if (d.stopped) { outs[(size_t)i] = 2; fin[(size_t)i] = 1; continue; }
+        uint64_t b = 0;
+        bool t = false;
+        TRY(d.burst_slice_pre(remaining[(size_t)i], &b, &t));
+        who.push_back(i); es.push_back(d.e); budgets.push_back(b); timed.push_back(t ? 1 : 0);
+      }
+      if (who.empty()) break;
+      if (who.size() == 1 && !first) {  // a straggler: its own launch with the whole grid share it has
+        Driver& d = ss[who[0]]->d;
+        int o = 0;
+        TRY(d.step_burst(remaining[(size_t)who[0]], &o));
+        outs[(size_t)who[0]] = o;
+        fin[(size_t)who[0]] = 1;
+        continue;
+      }
+      brs.assign(who.size(), pcp_burst_result{});
+      int32_t fused = 0;
+      auto t0 = std::chrono::steady_clock::now();
+      TRY(pcp_internal_burst_step_many(es.data(), (int32_t)es.size(), budgets.data(), brs.data(), &fused));
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (!fused) { fell_back = first; if (!first) return PCP_ERR_INVALID; break; }
+      first = false;
+      for (size_t k = 0; k < who.size(); ++k) {
+        Driver& d = ss[who[k]]->d;
+        bool f = false;
+        int o = 0;
+        TRY(d.burst_slice_post(brs[k], dt, timed[k] != 0, unlimited, &remaining[(size_t)who[k]], &o, &f));
+        if (f) { outs[(size_t)who[k]] = o; fin[(size_t)who[k]] = 1; }
+      }
+    }
+    if (!fell_back) {
+      for (int i = 0; i < n; ++i) {
+        ss[i]->d.res->status = outs[(size_t)i];
+        ss[i]->res.status = outs[(size_t)i];
+        if (res) res[i] = ss[i]->res;
+      }
+      return PCP_OK;
+    }
+  }
   if (all_burst || (!lockstep && n > 1)) {
     // device-resident searches: one (sleeping) thread each.  Host-driven searches: T threads, each
     // pipelining its share of the searches; T = PCP_SEARCH_THREADS, else what the machine has.

@@ -791,15 +791,21 @@ def test_fork_shares_the_static_model_and_lets_go_of_it():
     assert rf.num_nodes == rb.num_nodes and (tf["status"] == tb["status"]).all() and (tf["hash"] == tb["hash"]).all()
 
 
-@pytest.mark.parametrize("host_search", [False, True], ids=["device-search", "host-lockstep"])
-def test_search_step_many_matches_lone_searches(host_search):
-    """pcp_search_step_many over 4 subtree contexts (device-resident searches on one host thread
-    each / host-driven searches in lockstep): every context counts the nodes, failures and
-    solutions of a lone search of its subtree, and together they hold every solution of n-queens
-    N=9 (352, all_solution.rs:67-74)."""
+@pytest.mark.parametrize("host_search,fused,kw", [(False, True, {}), (False, False, {}), (True, True, {}),
+                                                  (False, True, {"interval_set": True}), (False, True, {"incremental": True})],
+                         ids=["device-search-one-launch", "device-search-threads", "host-pipelined", "device-search-set",
+                              "device-search-incremental"])
+def test_search_step_many_matches_lone_searches(host_search, fused, kw, monkeypatch):
+    """pcp_search_step_many over 4 subtree contexts -- device-resident searches sharing one launch per
+    slice (pcp_burst_batch_kernel: a group of CTAs per search), the same on one host thread and launch
+    each (PCP_BATCH=unfused), host-driven searches pipelined over host threads: every context counts
+    the nodes, failures and solutions of a lone search of its subtree, and together they hold every
+    solution of n-queens N=9 (352, all_solution.rs:67-74)."""
     from pcp_b200 import Engine, parallel
+    if not fused:
+        monkeypatch.setenv("PCP_BATCH", "unfused")
     m = models.nqueens(9)
-    ctx = parallel.SubtreeContexts(lambda: Engine(host_search=host_search), m, 4)
+    ctx = parallel.SubtreeContexts(lambda: Engine(host_search=host_search, **kw), m, 4)
     ctx.open(all_solutions=True)
     res = None
     for _ in range(100000):
@@ -808,7 +814,8 @@ def test_search_step_many_matches_lone_searches(host_search):
             break
     assert sum(r.num_solution for r in res) == 352
     for path, r in zip(ctx.paths, res):
-        lone = _oracle(2)
+        from oracle.oracle_api import SET, TUNED
+        lone = _oracle(SET + TUNED if kw.get("interval_set") else 2)
         m.load_into(lone)
         lone.consistency()
         parallel.enter_subtree(lone, lone.label(), path)
