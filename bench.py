@@ -218,8 +218,13 @@ def run_ours(args):
     # host threads of the host-driven loop: the rank's share of the cores; each thread pipelines its
     # share of the contexts (pcp_search_step_many)
     os.environ.setdefault("PCP_SEARCH_THREADS", str(max(1, min(K_e2e, 6, (os.cpu_count() or 8) // max(world, 1) - 1))))
-    K_dev = (args.dev_contexts or min(max(K, 1), 20)) if multi else 1
-    K_inc = (args.inc_contexts or (30 if args.contexts == 0 else K)) if multi else K
+    # device-resident searches share one launch per slice: one CTA per search fills the GPU (stores whose
+    # label stacks are small enough for 148 of them; else as many as the device-timed rounds use)
+    # (a device search reserves its whole label stack up front: max_labels x V x 8 B on Interval engines,
+    # x 136 B per variable for C2's bit sets on IntervalSet engines -- 2.2 GB per search)
+    small = (workload in ("c2", "c3") or workload.startswith("nq")) and not set_domains
+    K_dev = (args.dev_contexts or (148 if small and args.contexts == 0 else min(K, 20))) if multi else 1
+    K_inc = (args.inc_contexts or (148 if small and args.contexts == 0 else min(K, 30))) if multi else K
 
     def barrier():
         torch.cuda.synchronize(device)
@@ -490,8 +495,9 @@ def run_ours(args):
                 "value": d_props / d_s if d_s > 0 else 0.0, "unit": "propagations/s",
                 "nodes_per_s": d_nodes / d_s if d_s > 0 else 0.0, "us_per_node": 1e6 * d_s * world / max(d_nodes, 1),
                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "contexts_per_gpu": e2e_dev.get("contexts"),
-                "path": f"pcp_search_step_many over {K_dev} device-resident searches (pcp_burst_kernel: branching, label/restore and "
-                        "the fixpoints in one launch per budget slice and context); counters copied back when a slice ends"}),
+                "path": f"pcp_search_step_many over {K_dev} device-resident searches (branching, label/restore and the fixpoints on "
+                        "the device; one launch per budget slice shared by all of them -- pcp_burst_batch_kernel, a group of CTAs "
+                        "per search); counters copied back when a slice ends"}),
             "incremental_device_search": (None if e2e_inc is None else {
                 "nodes_per_s": n_nodes / n_s if n_s > 0 else 0.0, "us_per_node": 1e6 * n_s * world / max(n_nodes, 1),
                 "value": n_props / n_s if n_s > 0 else 0.0, "unit": "propagations/s",

@@ -129,10 +129,18 @@ def consistency_batch(engines):
     status = (C.c_int32 * n)()
     stats = (Stats * n)()
     rc = engines[0]._lib.pcp_consistency_batch(hs, n, status, stats)
-    for e in engines:
-        if rc != 0:
-            e._check(rc)
+    if rc != 0:
+        _raise_from(engines, rc)
     return [int(x) for x in status], list(stats)
+
+
+def _raise_from(engines, rc):
+    """the error text lives in the engine that failed: report that one"""
+    for e in engines:
+        msg = e._fn("last_error")(e._h)
+        if msg:
+            e._check(rc)
+    engines[0]._check(rc)
 
 
 def search_step_many(handles, max_nodes: int = 0):
@@ -142,8 +150,7 @@ def search_step_many(handles, max_nodes: int = 0):
     res = (SearchResult * n)()
     rc = handles[0]._lib.pcp_search_step_many(hs, n, max_nodes, res)
     if rc != 0:
-        for h in handles:
-            h._engine._check(rc)
+        _raise_from([h._engine for h in handles], rc)
     return list(res)
 
 
