@@ -487,7 +487,17 @@ int pcp_search_step_many(pcp_search* const* ss, int32_t n, uint64_t max_nodes, p
       auto t0 = std::chrono::steady_clock::now();
       TRY(pcp_internal_burst_step_many(es.data(), (int32_t)es.size(), budgets.data(), brs.data(), &fused));
       const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      if (!fused) { fell_back = first; if (!first) return PCP_ERR_INVALID; break; }
+      if (!fused) {
+        if (first) { fell_back = true; break; }  // never could: one thread and one launch per search below
+        // they no longer can (a search's tail grew past a launch-geometry step): finish this call one by one
+        for (size_t k = 0; k < who.size(); ++k) {
+          int o = 0;
+          TRY(ss[who[k]]->d.step_burst(remaining[(size_t)who[k]], &o));
+          outs[(size_t)who[k]] = o;
+          fin[(size_t)who[k]] = 1;
+        }
+        continue;
+      }
       first = false;
       for (size_t k = 0; k < who.size(); ++k) {
         Driver& d = ss[who[k]]->d;

@@ -732,6 +732,54 @@ def test_consistency_batch_matches_lone_engines(k, mode, fused, monkeypatch):
         assert all(s.propagations > 0 for s in stats)
 
 
+def test_batched_launch_at_c2_size():
+    """The bench's configuration at full size: forks of one n-queens N=1000 engine, two CTAs each, one
+    batched launch per round (compact descriptor stream, CTA 0 sweeping with the others); after every
+    round each context's status and domains equal those of an oracle replaying the same subtree."""
+    import pcp_b200
+    from pcp_b200 import parallel
+    k = 4
+    m = models.nqueens(1000)
+    first = _engine()
+    m.load_into(first)
+    paths = parallel.expand_frontier(first, parts=k)[:k]
+    devs = [first] + [first.fork() for _ in range(k - 1)]
+    oras, stacks = [], []
+    for d, p in zip(devs, paths):
+        o = _oracle(2)
+        m.load_into(o)
+        o.consistency()
+        d.set_grid_limit(2)
+        for e in (d, o):
+            parallel.enter_subtree(e, e.label(), p)
+        oras.append(o)
+        stacks.append(None)
+    for rnd in range(6):
+        for i in range(k):
+            if stacks[i] is None:
+                stacks[i] = []
+                continue
+            assert stacks[i], "the first nodes of n-queens 1000 do not fail"
+            (dl, ol), dec = stacks[i].pop()
+            devs[i].restore(dl)
+            oras[i].restore(ol)
+            parallel.post_decision(devs[i], dec)
+            parallel.post_decision(oras[i], dec)
+        sts, stats = pcp_b200.consistency_batch(devs)
+        assert sum(int(s.launches) for s in stats) == 1
+        for i, st in enumerate(sts):
+            assert st == oras[i].consistency()[0], (rnd, i)
+            assert st == 0
+            _assert_same_state(devs[i], oras[i])
+            lo, hi = devs[i].domains()
+            var, val = parallel.select_branch(lo, hi)
+            labels = (devs[i].label(), oras[i].label())
+            stacks[i].append((labels, (var, val, 1)))
+            stacks[i].append((labels, (var, val, 0)))
+    for d in devs[1:]:
+        d.close()
+
+
 def test_fork_shares_the_static_model_and_lets_go_of_it():
     """pcp_engine_fork: the child starts in the parent's state and shares its descriptors and
     reactor on the device; both then go their own way (own tail, domains, `active`, trail, labels).
@@ -792,9 +840,10 @@ def test_fork_shares_the_static_model_and_lets_go_of_it():
 
 
 @pytest.mark.parametrize("host_search,fused,kw", [(False, True, {}), (False, False, {}), (True, True, {}),
-                                                  (False, True, {"interval_set": True}), (False, True, {"incremental": True})],
+                                                  (False, True, {"interval_set": True}), (False, True, {"incremental": True}),
+                                                  (False, True, {"flavour": "distinct"})],
                          ids=["device-search-one-launch", "device-search-threads", "host-pipelined", "device-search-set",
-                              "device-search-incremental"])
+                              "device-search-incremental", "device-search-nary"])
 def test_search_step_many_matches_lone_searches(host_search, fused, kw, monkeypatch):
     """pcp_search_step_many over 4 subtree contexts -- device-resident searches sharing one launch per
     slice (pcp_burst_batch_kernel: a group of CTAs per search), the same on one host thread and launch
@@ -804,7 +853,8 @@ def test_search_step_many_matches_lone_searches(host_search, fused, kw, monkeypa
     from pcp_b200 import Engine, parallel
     if not fused:
         monkeypatch.setenv("PCP_BATCH", "unfused")
-    m = models.nqueens(9)
+    kw = dict(kw)
+    m = models.nqueens(9, kw.pop("flavour", "example"))   # "distinct": n-ary Distinct, the `full` kernel variant
     ctx = parallel.SubtreeContexts(lambda: Engine(host_search=host_search, **kw), m, 4)
     ctx.open(all_solutions=True)
     res = None
