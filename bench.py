@@ -1,22 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- propagations/s and search-nodes/s of the propagation fixpoint (BASELINE.json).
 
-A *step* is one search node: one pass of the hot path (`Consistency::consistency`,
-reference src/libpcp/propagation/store.rs:247-257) over the propagator store, at the node
-the reference's own search (OneSolution o Propagation o Brancher(FirstSmallestVar, MiddleVal,
-BinarySplit), search/mod.rs:45-52) visits next.  Default workload: BASELINE configs[1],
-n-queens N=1000 (V=1000, P=1,498,500 XNeqY descriptors, example/src/nqueens.rs:27-50).
+A *step* is one round of search nodes, one per subtree context of the GPU (74 by default): each a
+pass of the hot path (`Consistency::consistency`, reference src/libpcp/propagation/store.rs:247-257)
+over the propagator store, at the node the reference's own search (OneSolution o Propagation o
+Brancher(FirstSmallestVar, MiddleVal, BinarySplit), search/mod.rs:45-52) visits next in that
+context's subtree; the K fixpoints of a round share one batched launch (pcp_consistency_batch).
+Default workload: BASELINE configs[1], n-queens N=1000 (V=1000, P=1,498,500 XNeqY descriptors,
+example/src/nqueens.rs:27-50).
 
     python bench.py --gpus N --steps K --warmup W            # our arm
     python bench.py --impl reference --steps K --warmup W    # CPU arm (oracle port, all cores)
 
 Numbers on the JSON line (our arm):
-  value       propagations/s, device-timed (CUDA events on the engine's stream around the node
-              prologue + fixpoint kernel of each step, max over ranks), L2 flushed between steps
-  warm        the same without the flush (descriptors, 24 MB, stay L2-resident between nodes)
+  value       propagations/s, device-timed (CUDA events on the lead engine's stream around the
+              batched launch of each step, max over ranks), L2 flushed between steps
+  warm        the same without the flush (the descriptors stay L2-resident between rounds)
   e2e         the same metric through the C ABI with host buffers: the C++ search driver calls
               pcp_restore / pcp_prop_alloc / pcp_consistency / pcp_domains_read / pcp_label per
-              node; wall clock, H2D of the posted descriptor and D2H of status + domains inside
+              node and context (host threads pipelining their share of the contexts); wall clock,
+              H2D of the posted descriptor and D2H of status + domains inside
   roofline    algorithmic bytes (32 B per binary propagation) / device time of the
               fixpoint launches (CUDA events, measured live in this run) vs the
               measured HBM copy bandwidth (MEASURED_PEAKS.json)

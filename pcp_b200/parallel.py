@@ -207,8 +207,10 @@ class SubtreeContexts:
     (SURVEY 8e applied inside a device).  One fixpoint of n-queens N=1000 leaves most of a B200
     idle between its phases (launch, prologue, device barriers, worklist iterations: 23 us per
     node of which the sweep is 4); K contexts on num_sms / K CTAs each overlap those phases of
-    one node with the sweeps of the others.  Every context is an ordinary (vstore, cstore) pair
-    behind the C ABI -- per-node results are exactly those of a lone engine on that subtree."""
+    one node with the sweeps of the others, and forks of one engine share one launch per round
+    (consistency_batch) or per slice of their searches (step).  Every context is an ordinary
+    (vstore, cstore) pair behind the C ABI -- per-node results are exactly those of a lone
+    engine on that subtree."""
 
     def __init__(self, make_engine, model, k: int, paths: Sequence[List[Decision]] = None, device_sms: int = 148,
                  fork: bool = True):
