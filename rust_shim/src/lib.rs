@@ -401,6 +401,41 @@ impl<Domain: DeviceDomain> Consistency<GpuVStore<Domain>> for GpuCStore<Domain> 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Several nodes at once (no counterpart in libpcp, which is single-threaded; sibling subtrees are
+// independent: search/branching/branch.rs:36-55).  `fork_space` = `Space::clone` for a sibling
+// subtree without a second copy of the model on the device (pcp_engine_fork); `consistency_many` =
+// `Consistency::consistency` of several such pairs, served by ONE launch when the pairs are forks of
+// one model (pcp_consistency_batch: a group of CTAs per pair).
+// ---------------------------------------------------------------------------------------------
+pub fn fork_space<Domain: DeviceDomain>(vstore: &GpuVStore<Domain>, cstore: &mut GpuCStore<Domain>) -> (GpuVStore<Domain>, GpuCStore<Domain>) {
+    let engine = vstore.engine().clone();
+    cstore.push_pending(&engine);
+    let mut raw = std::ptr::null_mut();
+    engine.check(unsafe { pcp_engine_fork(engine.raw, &mut raw) });
+    vstore.sync();
+    let child = GpuVStore { engine: Rc::new(Engine { raw }), mirror: RefCell::new(vstore.mirror.borrow().clone()), stale: RefCell::new(false) };
+    (child, GpuCStore { propagators: cstore.propagators.iter().map(|p| p.bclone()).collect(), pending: vec![], pushed: cstore.pushed })
+}
+
+pub fn consistency_many<Domain: DeviceDomain>(spaces: &mut [(&mut GpuVStore<Domain>, &mut GpuCStore<Domain>)]) -> Vec<SKleene> {
+    let mut raws = Vec::with_capacity(spaces.len());
+    for (v, c) in spaces.iter_mut() {
+        let engine = v.engine().clone();
+        c.push_pending(&engine);
+        raws.push(engine.raw);
+    }
+    let mut status = vec![0i32; spaces.len()];
+    let rc = unsafe { pcp_consistency_batch(raws.as_ptr(), raws.len() as i32, status.as_mut_ptr(), std::ptr::null_mut()) };
+    for (v, _) in spaces.iter_mut() {
+        if rc != 0 {
+            v.engine().check(rc);
+        }
+        v.invalidate();
+    }
+    status.iter().map(|&s| match s { PCP_FALSE => SKleene::False, PCP_TRUE => SKleene::True, _ => SKleene::Unknown }).collect()
+}
+
 impl<Domain> Clone for GpuCStore<Domain> {
     fn clone(&self) -> Self {
         // store.rs:260-272 clones the boxed propagators; the device state belongs to the engine of
