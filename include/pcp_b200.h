@@ -273,10 +273,13 @@ int pcp_search_open(pcp_engine* e, const pcp_search_config* cfg, int32_t* trace_
                     uint64_t trace_capacity, pcp_search** out);
 int pcp_search_step(pcp_search* s, uint64_t max_nodes, pcp_search_result* res);
 /* pcp_search_step for `n` searches at once -- independent subtrees of one model, each opened on its
- * own engine (SURVEY 8e inside one GPU): the device-resident searches run concurrently; host-driven
- * searches advance in lockstep, one node per search and round, with the fixpoints of a round
- * launched together (pcp_consistency_batch).  res has n entries (may be NULL); a search that is
- * finished or has used up `max_nodes` simply sits out the remaining rounds. */
+ * own engine (SURVEY 8e inside one GPU).  Device-resident searches whose engines run the same kernel
+ * with the same geometry (forks of one model) share ONE launch per slice of nodes, a group of CTAs
+ * each, every search running through its own budget at its own pace; otherwise one launch and one
+ * host thread each.  Host-driven searches are shared out over PCP_SEARCH_THREADS host threads, each
+ * keeping the next fixpoint of every search it drives in flight (PCP_SEARCH_LOCKSTEP=1: rounds of one
+ * node per search through pcp_consistency_batch on the calling thread).  res has n entries (may be
+ * NULL); a search that is finished or has used up `max_nodes` sits out the rest of the call. */
 int pcp_search_step_many(pcp_search* const* searches, int32_t n, uint64_t max_nodes, pcp_search_result* res);
 /* BranchAndBound's incumbent (search/branch_and_bound.rs:69-94) seen from outside: between two
  * pcp_search_step slices a rank adopts the best objective value any rank has found (the one-word
